@@ -1,0 +1,90 @@
+// CUDAPathIntegrator — the reference-side half of the drop-in.
+//
+// A pbr::Integrator (core/Integrator.h:17-23) with the constructor signature of
+// PathIntegrator (integrators/PathIntegrator.h:17-20).  Swapping
+//     std::make_shared<PathIntegrator>(5, camera, sampler, bounds, fb)
+// for
+//     std::make_shared<gnx::CUDAPathIntegrator>(5, camera, sampler, bounds, fb)
+// in ui/RenderThread.cpp:163-164 is the whole integration.  Render() flattens
+// the existing pbr::Scene into the plain buffers of include/gnxrt.h, hands them to libgnxrt.so
+// and writes the result into the FrameBuffer through the same setters the reference uses
+// (core/Integrator.cpp:307-310).
+//
+// This translation unit is the only one compiled against the reference's headers; it contains no
+// rendering code.
+#ifndef GNX_CUDA_PATH_INTEGRATOR_H
+#define GNX_CUDA_PATH_INTEGRATOR_H
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "core/Integrator.h"
+#include "gnxrt.h"
+
+namespace gnx {
+
+// Owns the host copies that a gnx_scene_desc points into.
+struct FlatScene {
+    gnx_scene_desc desc;
+    std::vector<gnx_bvh_node> nodes;
+    std::vector<float> prim_p, prim_uv, prim_n;
+    std::vector<uint8_t> prim_has_n, prim_is_transition, prim_flags;
+    std::vector<int32_t> prim_material, prim_light, prim_medium_in, prim_medium_out, prim_id;
+    std::vector<gnx_material> materials;
+    std::vector<gnx_texture> textures;
+    std::vector<std::vector<float>> texture_texels;
+    std::vector<gnx_light> lights;
+    std::vector<float> env_texels, env_cond_func, env_cond_cdf, env_cond_int, env_marg_func, env_marg_cdf;
+    std::vector<gnx_medium> media;
+    std::vector<std::vector<float>> media_density;
+    std::vector<uint16_t> perms;
+    std::vector<const void *> prim_ptr;  // ordered pbr::Primitive* (parity hook: pointer -> ordered index)
+    std::string error;                   // non-empty when the scene uses something outside the hot path
+};
+
+// Reads the private state of Scene/BVHAccel/Triangle/Material/Light/Camera/Sampler
+// into `out`.  Returns false (and sets out->error) for unsupported content.
+bool FlattenScene(const pbr::Scene &scene, const pbr::Camera &camera, const pbr::Sampler &sampler,
+                  FlatScene *out);
+
+class CUDAPathIntegrator : public pbr::Integrator {
+  public:
+    CUDAPathIntegrator(int maxDepth, std::shared_ptr<const pbr::Camera> camera,
+                       std::shared_ptr<pbr::Sampler> sampler, const pbr::Bounds2i &pixelBounds,
+                       FrameBuffer *pFrameBuffer, pbr::Float rrThreshold = 1,
+                       const std::string &lightSampleStrategy = "spatial", bool volumetric = false,
+                       int device = 0);
+    ~CUDAPathIntegrator() override;
+
+    // Integrator interface.  Synchronous like the reference: the FrameBuffer is complete on return.
+    void Render(const pbr::Scene &scene, double &timeConsume) override;
+
+    // Extras for tests / measurement (not part of pbr::Integrator).
+    bool ok() const { return ctx_ != nullptr && error_.empty(); }
+    const std::string &error() const { return error_; }
+    const gnx_stats &lastStats() const { return stats_; }
+    bool PrimaryHits(const pbr::Scene &scene, int sample, std::vector<int32_t> *orderedPrimIndex);
+    const FlatScene *flat() const { return flat_.get(); }
+    gnx_render_params MakeParams() const;
+
+  private:
+    bool EnsureUploaded(const pbr::Scene &scene);
+
+    const int maxDepth_;
+    std::shared_ptr<const pbr::Camera> camera_;
+    std::shared_ptr<pbr::Sampler> sampler_;
+    const pbr::Bounds2i pixelBounds_;
+    FrameBuffer *fb_;
+    const pbr::Float rrThreshold_;
+    const std::string lightSampleStrategy_;
+    const bool volumetric_;
+    gnx_ctx *ctx_ = nullptr;
+    const pbr::Scene *uploaded_ = nullptr;
+    std::unique_ptr<FlatScene> flat_;
+    gnx_stats stats_{};
+    std::string error_;
+};
+
+}  // namespace gnx
+#endif

@@ -1,0 +1,344 @@
+// gnx_path.cuh — what ONE path does in each wavefront stage, as __host__ __device__ functions.
+// The kernels in gnx_kernels.cuh are thin wrappers (pick the slot, call these, push to the queues
+// with warp-aggregated atomics); tests/emul runs the very same functions sequentially on the CPU
+// to check the logic against the reference without a GPU.
+//
+//   raygen_slot    GetCameraSample + GenerateRayDifferential          (Sampler.cpp:14-20, Perspective.cpp:62-112)
+//   extend_slot    scene.Intersect; escaped rays pick up InfiniteAreaLight::Le (PathIntegrator.cpp:98-117)
+//   shade_slot     Le at the vertex, material -> lobes, UniformSampleOneLight / EstimateDirect sample
+//                  generation, BSDF sampling, Russian roulette              (PathIntegrator.cpp:101-204)
+//   shadow_item    VisibilityTester::Unoccluded, and the "ray escapes" half of MIS for the environment
+//   probe_item     closest-hit MIS probe for area lights                    (core/Integrator.cpp:191-207)
+#pragma once
+#include "gnx_shade.cuh"
+
+namespace gnx {
+
+struct RenderConsts {
+    int width, height, npix;
+    int max_depth;
+    float rr_threshold;
+    int batch_spp;       // samples per pixel in this batch
+    int first_sample;    // sample number of the batch's first sample
+    int capacity;        // path slots
+};
+
+// Camera ray for (pixel, halton index): Sampler::GetCameraSample + PerspectiveCamera::GenerateRay +
+// Transform::operator()(Ray) (core/Transform.h:230-244).
+GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *o, V3 *d, float *tMax) {
+    float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+    V3 pFilm((float)px + u0, (float)py + u1, 0.f);
+    V3 pCamera = xform_point(sc.cam.r2c, pFilm);
+    V3 ro(0.f, 0.f, 0.f);
+    V3 rd = normalize(pCamera);
+    if (sc.cam.lens_radius > 0) {
+        float l0 = halton_sample_dimension(sc.smp, hidx, 3), l1 = halton_sample_dimension(sc.smp, hidx, 4);
+        float lx, ly;
+        concentric_sample_disk(l0, l1, &lx, &ly);
+        lx *= sc.cam.lens_radius; ly *= sc.cam.lens_radius;
+        float ft = sc.cam.focal_distance / rd.z;
+        V3 pFocus = ro + rd * ft;
+        ro = V3(lx, ly, 0);
+        rd = normalize(pFocus - ro);
+    }
+    V3 oErr;
+    V3 wo = xform_point_err(sc.cam.c2w, ro, &oErr);
+    V3 wd = xform_vector(sc.cam.c2w, rd);
+    float lsq = length_sq(wd);
+    float tm = GNX_INF;
+    if (lsq > 0) {
+        float dt = dot(vabs(wd), oErr) / lsq;
+        wo = wo + wd * dt;
+        tm -= dt;
+    }
+    *o = wo; *d = wd; *tMax = tm;
+}
+
+GNX_D void raygen_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot) {
+    int pixel = slot % rc.npix, s = rc.first_sample + slot / rc.npix;
+    int px = pixel % rc.width, py = pixel / rc.width;
+    uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)s * (uint64_t)sc.smp.stride;
+    V3 o, d;
+    float tMax;
+    camera_ray(sc, px, py, hidx, &o, &d, &tMax);
+    ps.ray_o[slot] = make_float4(o.x, o.y, o.z, tMax);
+    ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 1.f);  // w: etaScale = 1
+    ps.beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+    ps.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ps.hidx[slot] = (uint32_t)hidx;
+    ps.meta[slot] = 5u;  // dimension 5 (film 0-1, time 2, lens 3-4), bounces 0, flags 0
+}
+
+GNX_D int shade_type_of(unsigned matWord) { return (int)((matWord >> 20) & 0xfu); }
+
+// Returns the shade-queue type of the hit, or -1 when the path ends here.
+GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, int *stack, int stride,
+                      TraversalCounters &cnt) {
+    const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+    const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
+    int prim = -1;
+    TriHit h;
+    const bool hit = traverse<false>(sc, o, d, ro.w, stack, stride, &prim, &h, cnt);
+    const uint32_t meta = ps.meta[slot];
+    const int bounces = (meta >> 16) & 0xff;
+    const bool emitOk = bounces == 0 || ((meta >> 24) & kFlagSpecular);
+    if (hit) {
+        // beyond maxDepth only the emission term is left (PathIntegrator.cpp:101-117)
+        if (bounces >= rc.max_depth && !emitOk) return -1;
+        const unsigned matWord = f2u(ldg(&sc.tris[3 * prim + 2].y));
+        ps.hit[slot] = make_float4(h.b0, h.b1, h.b2, i2f(prim));
+        return shade_type_of(matWord);
+    }
+    if (emitOk && sc.env.present) {
+        // for (light : scene.infiniteLights) L += beta * light->Le(ray)
+        const float4 b = ps.beta[slot];
+        float4 L = ps.L[slot];
+        V3 add = V3(b.x, b.y, b.z) * env_Le(sc.env, d);
+        L.x += add.x; L.y += add.y; L.z += add.z;
+        ps.L[slot] = L;
+    }
+    return -1;
+}
+
+// Surfaces without a material are medium boundaries: PathIntegrator re-spawns the ray in the same
+// direction and does not count the bounce (PathIntegrator.cpp:121-126).  Returns "still alive".
+GNX_D bool shade_null_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot) {
+    const float4 rd = ps.ray_d[slot], hit = ps.hit[slot];
+    const V3 d(rd.x, rd.y, rd.z);
+    Surface s = make_surface(sc, f2i(hit.w), hit.x, hit.y, hit.z, d);
+    const uint32_t meta = ps.meta[slot];
+    const int bounces = (meta >> 16) & 0xff;
+    const bool emitOk = bounces == 0 || ((meta >> 24) & kFlagSpecular);
+    if (emitOk && s.light >= 0) {
+        const float4 b = ps.beta[slot];
+        float4 L = ps.L[slot];
+        V3 add = V3(b.x, b.y, b.z) * area_light_L(sc.lights[s.light], s.n, -d);
+        L.x += add.x; L.y += add.y; L.z += add.z;
+        ps.L[slot] = L;
+    }
+    if (bounces >= rc.max_depth) return false;
+    V3 o = offset_ray_origin(s.p, s.pError, s.n, d);
+    ps.ray_o[slot] = make_float4(o.x, o.y, o.z, GNX_INF);
+    return true;
+}
+
+struct ShadeOut {
+    bool alive, haveShadowA, haveShadowB, haveProbe;
+    ShadowItem shA, shB;
+    ProbeItem pr;
+};
+
+template <int MAXL>
+GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, ShadeOut &out) {
+    const int kNonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+    out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
+    const float4 rd4 = ps.ray_d[slot], hit = ps.hit[slot], b4 = ps.beta[slot];
+    const V3 rayD(rd4.x, rd4.y, rd4.z);
+    V3 beta(b4.x, b4.y, b4.z);
+    float etaScale = rd4.w;
+    const uint32_t meta = ps.meta[slot];
+    const int bounces = (meta >> 16) & 0xff;
+    const bool specularBounce = ((meta >> 24) & kFlagSpecular) != 0;
+    PathSampler smp(sc.smp, (uint64_t)ps.hidx[slot], (int)(meta & 0xffff));
+    Surface s = make_surface(sc, f2i(hit.w), hit.x, hit.y, hit.z, rayD);
+    // ---- emitted light at the vertex (PathIntegrator.cpp:101-111)
+    if ((bounces == 0 || specularBounce) && s.light >= 0) {
+        float4 L4 = ps.L[slot];
+        V3 add = beta * area_light_L(sc.lights[s.light], s.n, -rayD);
+        L4.x += add.x; L4.y += add.y; L4.z += add.z;
+        ps.L[slot] = L4;
+    }
+    if (bounces >= rc.max_depth) return;
+    const gnx_material &mat = sc.materials[s.material];
+    Bsdf<MAXL> bsdf;
+    build_bsdf<MAXL>(sc, mat, s, bsdf);
+    const V3 ns = bsdf.ns;
+    // ---- UniformSampleOneLight (core/Integrator.cpp:57-79)
+    if (bsdf.num_components(kNonSpec) > 0 && sc.n_lights > 0) {
+        float selPdf;
+        const int lightNum = choose_light(sc, s.p, smp.get1d(), &selPdf);
+        if (selPdf != 0) {
+            float ul0, ul1, us0, us1;
+            smp.get2d(&ul0, &ul1);
+            smp.get2d(&us0, &us1);
+            const gnx_light &light = sc.lights[lightNum];
+            const bool isEnv = light.type == GNX_LIGHT_INFINITE;
+            // ---- EstimateDirect, light-sampling half (core/Integrator.cpp:107-160)
+            LightSample ls;
+            bool ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
+            if (ok && ls.pdf > 0 && !is_black(ls.Li)) {
+                V3 f = bsdf_f(bsdf, s.wo, ls.wi, kNonSpec) * absdot(ls.wi, ns);
+                float scatteringPdf = bsdf_pdf(bsdf, s.wo, ls.wi, kNonSpec);
+                if (!is_black(f)) {
+                    V3 origin, dirv;
+                    if (isEnv) {
+                        // VisibilityTester(ref, Interaction(ref.p + wi * (2 * worldRadius), ...)): the far
+                        // point has neither normal nor error bound, so SpawnRayTo's target is the point itself
+                        V3 p1 = s.p + ls.wi * (2 * sc.env.world_radius);
+                        origin = offset_ray_origin(s.p, s.pError, s.n, p1 - s.p);
+                        dirv = p1 - origin;
+                    } else {
+                        origin = offset_ray_origin(s.p, s.pError, s.n, ls.pl - s.p);
+                        V3 target = offset_ray_origin(ls.pl, ls.plError, ls.nl, origin - ls.pl);
+                        dirv = target - origin;
+                    }
+                    float weight = (ls.pdf * ls.pdf) / (ls.pdf * ls.pdf + scatteringPdf * scatteringPdf);
+                    V3 Ld = div_each(f * ls.Li * weight, ls.pdf);
+                    V3 c = beta * div_each(Ld, selPdf);
+                    out.shA.o_tmax = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
+                    out.shA.d_path = make_float4(dirv.x, dirv.y, dirv.z, i2f(slot));
+                    out.shA.contrib = make_float4(c.x, c.y, c.z, 0.f);
+                    out.haveShadowA = true;
+                }
+            }
+            // ---- EstimateDirect, BSDF-sampling half (core/Integrator.cpp:163-208)
+            V3 wi;
+            float scatteringPdf;
+            int sampledType;
+            V3 f = bsdf_sample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, kNonSpec, &sampledType);
+            f = f * absdot(wi, ns);
+            if (!is_black(f) && scatteringPdf > 0) {
+                V3 o = offset_ray_origin(s.p, s.pError, s.n, wi);
+                float lightPdf = isEnv ? env_pdf_li(sc.env, wi) : area_pdf_li(sc, light, s.p, o, wi);
+                if (lightPdf != 0) {
+                    float weight = (scatteringPdf * scatteringPdf) / (scatteringPdf * scatteringPdf + lightPdf * lightPdf);
+                    if (isEnv) {
+                        // light.Le(ray) depends on the direction only: the probe just has to find no surface
+                        V3 Li = env_Le(sc.env, wi);
+                        if (!is_black(Li)) {
+                            V3 Ld = div_each(f * Li * weight, scatteringPdf);
+                            V3 c = beta * div_each(Ld, selPdf);
+                            out.shB.o_tmax = make_float4(o.x, o.y, o.z, GNX_INF);
+                            out.shB.d_path = make_float4(wi.x, wi.y, wi.z, i2f(slot));
+                            out.shB.contrib = make_float4(c.x, c.y, c.z, 0.f);
+                            out.haveShadowB = true;
+                        }
+                    } else {
+                        // lightIsect.Le(-wi), counted only if the closest hit is this light's triangle
+                        const TriVerts lt = load_tri(sc.tris, light.prim);
+                        V3 nl = normalize(cross(lt.p0 - lt.p2, lt.p1 - lt.p2));
+                        V3 Li = area_light_L(light, nl, -wi);
+                        if (!is_black(Li)) {
+                            V3 Ld = div_each(f * Li * weight, scatteringPdf);
+                            V3 c = beta * div_each(Ld, selPdf);
+                            out.pr.o_tmax = make_float4(o.x, o.y, o.z, GNX_INF);
+                            out.pr.d_path = make_float4(wi.x, wi.y, wi.z, i2f(slot));
+                            out.pr.contrib_expect = make_float4(c.x, c.y, c.z, i2f(light.prim));
+                            out.haveProbe = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- sample the BSDF for the next direction (PathIntegrator.cpp:143-163)
+    const V3 wo = -rayD;
+    V3 wi;
+    float pdf, u0, u1;
+    int flags;
+    smp.get2d(&u0, &u1);
+    V3 f = bsdf_sample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
+    if (is_black(f) || pdf == 0.f) return;
+    beta *= div_each(f * absdot(wi, ns), pdf);
+    const bool spec = (flags & BSDF_SPECULAR) != 0;
+    if (spec && (flags & BSDF_TRANSMISSION)) {
+        float eta = bsdf.eta;
+        etaScale *= (dot(wo, s.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+    }
+    V3 o = offset_ray_origin(s.p, s.pError, s.n, wi);
+    // ---- Russian roulette (PathIntegrator.cpp:198-204)
+    V3 rrBeta = beta * etaScale;
+    float mx = max_component(rrBeta);
+    if (mx < rc.rr_threshold && bounces > 3) {
+        float qq = fmaxf(.05f, 1 - mx);
+        if (smp.get1d() < qq) return;
+        beta = div_each(beta, 1 - qq);
+    }
+    out.alive = true;
+    ps.ray_o[slot] = make_float4(o.x, o.y, o.z, GNX_INF);
+    ps.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, etaScale);
+    ps.beta[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
+    ps.meta[slot] = (uint32_t)(smp.dim & 0xffff) | ((uint32_t)(bounces + 1) << 16) | ((spec ? kFlagSpecular : 0u) << 24);
+}
+
+GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int *stack, int stride,
+                       TraversalCounters &cnt) {
+    const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path);
+    int prim;
+    TriHit h;
+    const bool hit = traverse<true>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w, stack, stride, &prim, &h, cnt);
+    if (!hit) {
+        const float4 c = ldg(&item->contrib);
+        const int slot = f2i(d4.w);
+        float4 L = ps.L[slot];
+        L.x += c.x; L.y += c.y; L.z += c.z;
+        ps.L[slot] = L;
+    }
+}
+
+GNX_D void probe_item(const DeviceScene &sc, const PathState &ps, const ProbeItem *item, int *stack, int stride,
+                      TraversalCounters &cnt) {
+    const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path), c = ldg(&item->contrib_expect);
+    int prim = -1;
+    TriHit h;
+    const bool hit = traverse<false>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w, stack, stride, &prim, &h, cnt);
+    if (hit && prim == f2i(c.w)) {
+        const int slot = f2i(d4.w);
+        float4 L = ps.L[slot];
+        L.x += c.x; L.y += c.y; L.z += c.z;
+        ps.L[slot] = L;
+    }
+}
+
+GNX_D int primary_hit_id(const DeviceScene &sc, int px, int py, int sample, int *stack, int stride) {
+    uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    V3 o, d;
+    float tMax;
+    camera_ray(sc, px, py, hidx, &o, &d, &tMax);
+    int prim = -1;
+    TriHit h;
+    TraversalCounters cnt{0, 0};
+    bool hit = traverse<false>(sc, o, d, tMax, stack, stride, &prim, &h, cnt);
+    return hit ? f2i(ldg(&sc.tris[3 * prim + 2].w)) : -1;
+}
+
+// SpatialLightDistribution::ComputeDistribution for one voxel (core/LightDistribution.cpp:206-274):
+// 128 Halton points, each light's Li.y()/pdf summed, floor at 0.1% of the mean, then the
+// Distribution1D construction of core/Sampling.h:22-35.
+GNX_D void build_spatial_voxel(const DeviceScene &sc, int vox, float *func, float *cdf, float *fint) {
+    const int nL = sc.n_lights;
+    const int pi[3] = {vox % sc.ld.nvox[0], (vox / sc.ld.nvox[0]) % sc.ld.nvox[1], vox / (sc.ld.nvox[0] * sc.ld.nvox[1])};
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        float t0 = (float)pi[a] / (float)sc.ld.nvox[a], t1 = (float)(pi[a] + 1) / (float)sc.ld.nvox[a];
+        lo[a] = lerpf(t0, sc.wb_min[a], sc.wb_max[a]);
+        hi[a] = lerpf(t1, sc.wb_min[a], sc.wb_max[a]);
+    }
+    float *fv = func + (size_t)vox * nL;
+    for (int j = 0; j < nL; ++j) fv[j] = 0.f;
+    for (int i = 0; i < 128; ++i) {
+        float r0 = radical_inverse(sc.smp, 0, i), r1 = radical_inverse(sc.smp, 1, i), r2 = radical_inverse(sc.smp, 2, i);
+        V3 po(lerpf(r0, lo[0], hi[0]), lerpf(r1, lo[1], hi[1]), lerpf(r2, lo[2], hi[2]));
+        float u0 = radical_inverse(sc.smp, 3, i), u1 = radical_inverse(sc.smp, 4, i);
+        for (int j = 0; j < nL; ++j) {
+            const gnx_light &l = sc.lights[j];
+            LightSample ls;
+            bool ok = l.type == GNX_LIGHT_INFINITE ? env_sample_li(sc.env, u0, u1, &ls) : area_sample_li(sc, l, po, u0, u1, &ls);
+            if (ok && ls.pdf > 0) fv[j] += lum_y(ls.Li) / ls.pdf;
+        }
+    }
+    float sum = 0.f;
+    for (int j = 0; j < nL; ++j) sum += fv[j];
+    float avg = sum / (128 * nL);
+    float minContrib = (avg > 0) ? .001f * avg : 1;
+    for (int j = 0; j < nL; ++j) fv[j] = fmaxf(fv[j], minContrib);
+    float *cv = cdf + (size_t)vox * (nL + 1);
+    cv[0] = 0;
+    for (int j = 1; j < nL + 1; ++j) cv[j] = cv[j - 1] + fv[j - 1] / nL;
+    float funcInt = cv[nL];
+    if (funcInt == 0) for (int j = 1; j < nL + 1; ++j) cv[j] = (float)j / (float)nL;
+    else for (int j = 1; j < nL + 1; ++j) cv[j] /= funcInt;
+    fint[vox] = funcInt;
+}
+
+}  // namespace gnx

@@ -1,0 +1,577 @@
+// gnx_render.cu — the C ABI of include/gnxrt.h: context, scene upload (host SoA -> HBM layout),
+// the wavefront render loop and the parity hooks.  All compute is in gnx_kernels.cuh; there is no
+// CPU code path for any of it.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gnx_kernels.cuh"
+#include "gnx_pack.h"
+
+using namespace gnx;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct gnx_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    // scene
+    bool has_scene = false;
+    DeviceScene sc{};
+    std::vector<void *> scene_allocs;
+    unsigned shade_type_mask = 0;  // which k_shade variants the scene needs
+    bool spatial_built = false;
+    int n_lights_host = 0;
+    float wb[6]{};
+    // wavefront buffers
+    int capacity = 0;
+    PathState ps{};
+    Queues q{};
+    std::vector<void *> wave_allocs;
+    float4 *accum = nullptr, *rgba = nullptr;
+    int film_pixels = 0;
+    DevStats *d_stats = nullptr;
+    bool stage_timers = false;
+};
+
+#define GNX_CUDA(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            return GNX_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+static int fail(gnx_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+template <typename T>
+static int dupload(gnx_ctx *ctx, std::vector<void *> &pool, const T *host, size_t n, T **out) {
+    *out = nullptr;
+    if (n == 0) return GNX_OK;
+    void *p = nullptr;
+    GNX_CUDA(ctx, cudaMalloc(&p, n * sizeof(T)));
+    pool.push_back(p);
+    if (host) GNX_CUDA(ctx, cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    else GNX_CUDA(ctx, cudaMemset(p, 0, n * sizeof(T)));
+    *out = (T *)p;
+    return GNX_OK;
+}
+
+static void free_pool(std::vector<void *> &pool) {
+    for (void *p : pool) cudaFree(p);
+    pool.clear();
+}
+
+extern "C" {
+
+int gnx_abi_version(void) { return GNX_ABI_VERSION; }
+
+int gnx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *gnx_last_error(const gnx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gnx_create(gnx_ctx **out, int device) {
+    if (!out) { g_create_error = "gnx_create: out is NULL"; return GNX_ERR_INVALID; }
+    *out = nullptr;
+    int n = gnx_device_count();
+    if (n <= 0) {
+        g_create_error = "no usable CUDA device (libgnxrt has no CPU fallback)";
+        return GNX_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return GNX_ERR_INVALID; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GNX_ERR_CUDA; }
+    gnx_ctx *ctx = new gnx_ctx;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->d_stats, sizeof(DevStats))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete ctx;
+        return GNX_ERR_CUDA;
+    }
+    const char *t = getenv("GNX_STAGE_TIMERS");
+    ctx->stage_timers = t && t[0] == '1';
+    *out = ctx;
+    return GNX_OK;
+}
+
+void gnx_destroy(gnx_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_pool(ctx->scene_allocs);
+    free_pool(ctx->wave_allocs);
+    if (ctx->accum) cudaFree(ctx->accum);
+    if (ctx->rgba) cudaFree(ctx->rgba);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
+    if (!ctx || !d) return GNX_ERR_INVALID;
+    if (d->abi_version != GNX_ABI_VERSION) return fail(ctx, GNX_ERR_INVALID, "abi_version mismatch");
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_pool(ctx->scene_allocs);
+    ctx->has_scene = false;
+    ctx->spatial_built = false;
+    DeviceScene sc{};
+    std::vector<void *> &pool = ctx->scene_allocs;
+    const gnx_geometry &g = d->geom;
+    if (g.n_prims < 0 || g.n_nodes < 0 || (g.n_prims > 0 && (!g.nodes || !g.prim_p || !g.prim_material)))
+        return fail(ctx, GNX_ERR_INVALID, "geometry arrays missing");
+    if (d->n_materials > (1 << 20) - 2) return fail(ctx, GNX_ERR_UNSUPPORTED, "too many materials");
+    for (int i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].type < 0 || d->materials[i].type > GNX_MAT_DISNEY)
+            return fail(ctx, GNX_ERR_INVALID, "unknown material type");
+
+    // ---- nodes: bit-identical copy (two float4 per node)
+    static_assert(sizeof(gnx_bvh_node) == 32, "node size");
+    int rc;
+    gnx_bvh_node *dn;
+    if ((rc = dupload(ctx, pool, g.nodes, (size_t)g.n_nodes, &dn))) return rc;
+    sc.nodes = (const float4 *)dn;
+    sc.n_nodes = g.n_nodes;
+    sc.n_prims = g.n_prims;
+
+    // ---- triangles: 48-byte records
+    unsigned typeMask = 0;
+    {
+        std::vector<float4> tris;
+        std::string perr;
+        if (!pack_triangles(*d, tris, &typeMask, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        float4 *dt;
+        if ((rc = dupload(ctx, pool, tris.data(), tris.size(), &dt))) return rc;
+        sc.tris = dt;
+    }
+    ctx->shade_type_mask = typeMask;
+    float *df;
+    uint8_t *du8;
+    if (g.prim_uv) { if ((rc = dupload(ctx, pool, g.prim_uv, (size_t)g.n_prims * 6, &df))) return rc; sc.tri_uv = df; }
+    if (g.prim_n && g.prim_has_n) {
+        if ((rc = dupload(ctx, pool, g.prim_n, (size_t)g.n_prims * 9, &df))) return rc;
+        sc.tri_n = df;
+        if ((rc = dupload(ctx, pool, g.prim_has_n, (size_t)g.n_prims, &du8))) return rc;
+        sc.tri_has_n = du8;
+    }
+    if (g.prim_medium_in && g.prim_medium_out) {
+        std::vector<int2> med((size_t)g.n_prims);
+        for (int k = 0; k < g.n_prims; ++k) med[k] = make_int2(g.prim_medium_in[k], g.prim_medium_out[k]);
+        int2 *dm;
+        if ((rc = dupload(ctx, pool, med.data(), med.size(), &dm))) return rc;
+        sc.tri_media = dm;
+        if (g.prim_is_transition) {
+            if ((rc = dupload(ctx, pool, g.prim_is_transition, (size_t)g.n_prims, &du8))) return rc;
+            sc.tri_transition = du8;
+        }
+    }
+    for (int c = 0; c < 3; ++c) { sc.wb_min[c] = g.world_bound[c]; sc.wb_max[c] = g.world_bound[3 + c]; }
+    memcpy(ctx->wb, g.world_bound, sizeof(ctx->wb));
+
+    // ---- materials, textures
+    gnx_material *dm;
+    if ((rc = dupload(ctx, pool, d->materials, (size_t)d->n_materials, &dm))) return rc;
+    sc.materials = dm;
+    sc.n_materials = d->n_materials;
+    {
+        std::vector<DevTexture> tex((size_t)d->n_textures);
+        for (int i = 0; i < d->n_textures; ++i) {
+            const gnx_texture &t = d->textures[i];
+            if (t.width <= 0 || t.height <= 0 || (t.n_channels != 1 && t.n_channels != 3) || !t.texels)
+                return fail(ctx, GNX_ERR_INVALID, "bad texture descriptor");
+            float *dtex;
+            if ((rc = dupload(ctx, pool, t.texels, (size_t)t.width * t.height * t.n_channels, &dtex))) return rc;
+            tex[i] = DevTexture{t.width, t.height, t.n_channels, t.wrap, t.su, t.sv, t.du, t.dv, dtex};
+        }
+        DevTexture *dt;
+        if ((rc = dupload(ctx, pool, tex.data(), tex.size(), &dt))) return rc;
+        sc.textures = dt;
+        for (int i = 0; i < d->n_materials; ++i) {
+            for (int s = 0; s < GNX_MAT_MAX_RGB; ++s)
+                if (d->materials[i].rgb_tex[s] >= d->n_textures) return fail(ctx, GNX_ERR_INVALID, "texture index out of range");
+            for (int s = 0; s < GNX_MAT_MAX_F; ++s)
+                if (d->materials[i].f_tex[s] >= d->n_textures) return fail(ctx, GNX_ERR_INVALID, "texture index out of range");
+        }
+    }
+
+    // ---- lights
+    for (int i = 0; i < d->n_lights; ++i) {
+        const gnx_light &l = d->lights[i];
+        if (l.type == GNX_LIGHT_AREA_TRI) {
+            if (l.prim < 0 || l.prim >= g.n_prims) return fail(ctx, GNX_ERR_INVALID, "area light primitive out of range");
+        } else if (l.type == GNX_LIGHT_INFINITE) {
+            if (!d->env.present || d->env.light_index != i) return fail(ctx, GNX_ERR_INVALID, "infinite light without envmap record");
+        } else {
+            return fail(ctx, GNX_ERR_UNSUPPORTED, "light type outside the hot path (area, infinite)");
+        }
+    }
+    gnx_light *dl;
+    if ((rc = dupload(ctx, pool, d->lights, (size_t)d->n_lights, &dl))) return rc;
+    sc.lights = dl;
+    sc.n_lights = d->n_lights;
+    ctx->n_lights_host = d->n_lights;
+    if (d->env.present) {
+        const gnx_envmap &e = d->env;
+        if (!e.texels || !e.cond_func || !e.cond_cdf || !e.cond_int || !e.marg_func || !e.marg_cdf)
+            return fail(ctx, GNX_ERR_INVALID, "envmap arrays missing");
+        DevEnv &de = sc.env;
+        de.present = 1; de.light_index = e.light_index;
+        de.w = e.width; de.h = e.height; de.dw = e.dist_w; de.dh = e.dist_h;
+        if ((rc = dupload(ctx, pool, e.texels, (size_t)e.width * e.height * 3, &df))) return rc; de.texels = df;
+        if ((rc = dupload(ctx, pool, e.cond_func, (size_t)e.dist_w * e.dist_h, &df))) return rc; de.cond_func = df;
+        if ((rc = dupload(ctx, pool, e.cond_cdf, (size_t)(e.dist_w + 1) * e.dist_h, &df))) return rc; de.cond_cdf = df;
+        if ((rc = dupload(ctx, pool, e.cond_int, (size_t)e.dist_h, &df))) return rc; de.cond_int = df;
+        if ((rc = dupload(ctx, pool, e.marg_func, (size_t)e.dist_h, &df))) return rc; de.marg_func = df;
+        if ((rc = dupload(ctx, pool, e.marg_cdf, (size_t)e.dist_h + 1, &df))) return rc; de.marg_cdf = df;
+        de.marg_int = e.marg_int;
+        memcpy(de.l2w.m, e.light_to_world, 64);
+        memcpy(de.w2l.m, e.world_to_light, 64);
+        de.world_radius = e.world_radius;
+    }
+    // uniform light distribution: Distribution1D over n ones (core/LightDistribution.cpp:35-38)
+    if (d->n_lights > 0) {
+        std::vector<float> func, cdf;
+        float funcInt = uniform_light_distribution(d->n_lights, func, cdf);
+        if ((rc = dupload(ctx, pool, func.data(), func.size(), &df))) return rc; sc.ld.uni_func = df;
+        if ((rc = dupload(ctx, pool, cdf.data(), cdf.size(), &df))) return rc; sc.ld.uni_cdf = df;
+        sc.ld.uni_int = funcInt;
+    }
+    sc.ld.mode = GNX_LIGHTS_UNIFORM;
+
+    // ---- media (records only; the volumetric kernels validate them at render time)
+    if (d->n_media > 0) {
+        std::vector<DevMedium> med((size_t)d->n_media);
+        for (int i = 0; i < d->n_media; ++i) {
+            const gnx_medium &m = d->media[i];
+            DevMedium &dmv = med[i];
+            memset(&dmv, 0, sizeof(dmv));
+            dmv.type = m.type;
+            for (int c = 0; c < 3; ++c) {
+                dmv.sigma_a[c] = m.sigma_a[c]; dmv.sigma_s[c] = m.sigma_s[c];
+                dmv.sigma_t[c] = m.sigma_s[c] + m.sigma_a[c];  // HomogeneousMedium: sigma_s + sigma_a
+            }
+            dmv.g = m.g;
+            if (m.type == GNX_MEDIUM_GRID) {
+                if (!m.density || m.nx <= 0 || m.ny <= 0 || m.nz <= 0) return fail(ctx, GNX_ERR_INVALID, "grid medium without density");
+                dmv.nx = m.nx; dmv.ny = m.ny; dmv.nz = m.nz;
+                if ((rc = dupload(ctx, pool, m.density, (size_t)m.nx * m.ny * m.nz, &df))) return rc;
+                dmv.density = df;
+                memcpy(dmv.w2m.m, m.world_to_medium, 64);
+                dmv.inv_max_density = m.inv_max_density;
+                dmv.sigma_t_scalar = m.sigma_a[0] + m.sigma_s[0];  // (sigma_a + sigma_s)[0]
+            }
+        }
+        DevMedium *dmed;
+        if ((rc = dupload(ctx, pool, med.data(), med.size(), &dmed))) return rc;
+        sc.media = dmed;
+        sc.n_media = d->n_media;
+    }
+
+    // ---- camera
+    memcpy(sc.cam.r2c.m, d->camera.raster_to_camera, 64);
+    memcpy(sc.cam.c2w.m, d->camera.camera_to_world, 64);
+    sc.cam.lens_radius = d->camera.lens_radius;
+    sc.cam.focal_distance = d->camera.focal_distance;
+    sc.cam.medium = d->camera.medium;
+
+    // ---- sampler
+    const gnx_sampler &s = d->sampler;
+    if (s.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "only the Halton sampler is implemented");
+    if (s.base_scales[0] <= 0 || s.base_scales[1] <= 0 || s.sample_stride <= 0) return fail(ctx, GNX_ERR_INVALID, "bad Halton parameters");
+    sc.smp.type = s.type;
+    sc.smp.base_scale0 = s.base_scales[0]; sc.smp.base_scale1 = s.base_scales[1];
+    sc.smp.base_exp0 = s.base_exponents[0]; sc.smp.base_exp1 = s.base_exponents[1];
+    sc.smp.stride = s.sample_stride;
+    sc.smp.mult_inv0 = s.mult_inverse[0]; sc.smp.mult_inv1 = s.mult_inverse[1];
+    sc.smp.at_center = s.sample_at_pixel_center;
+    {
+        std::vector<int> primes, sums;
+        make_primes(primes, sums);
+        std::vector<uint16_t> perms;
+        const uint16_t *hp = s.perms;
+        size_t np = (size_t)s.n_perm_entries;
+        if (!hp) { make_permutations(primes, perms); hp = perms.data(); np = perms.size(); }
+        size_t need = (size_t)sums.back() + primes.back();
+        if (np < need) return fail(ctx, GNX_ERR_INVALID, "Halton permutation table too short");
+        uint16_t *dp; int *di;
+        if ((rc = dupload(ctx, pool, hp, np, &dp))) return rc; sc.smp.perms = dp;
+        if ((rc = dupload(ctx, pool, primes.data(), primes.size(), &di))) return rc; sc.smp.primes = di;
+        if ((rc = dupload(ctx, pool, sums.data(), sums.size(), &di))) return rc; sc.smp.prime_sums = di;
+        sc.smp.n_primes = (int)primes.size();
+    }
+    ctx->sc = sc;
+    ctx->has_scene = true;
+    return GNX_OK;
+}
+
+}  // extern "C"
+
+// SpatialLightDistribution ctor: voxel resolution (core/LightDistribution.cpp:70-87) + dense tables.
+static int ensure_light_distribution(gnx_ctx *ctx, int strategy) {
+    DeviceScene &sc = ctx->sc;
+    // CreateLightSampleDistribution: uniform when asked for or when exactly one light exists
+    if (strategy == GNX_LIGHTS_POWER) return fail(ctx, GNX_ERR_UNSUPPORTED, "power light distribution is not on the hot path");
+    if (strategy == GNX_LIGHTS_UNIFORM || sc.n_lights <= 1) { sc.ld.mode = GNX_LIGHTS_UNIFORM; return GNX_OK; }
+    if (!ctx->spatial_built) {
+        size_t nv = spatial_voxel_resolution(ctx->wb, sc.ld.nvox);
+        if (nv * (size_t)sc.n_lights > ((size_t)1 << 28))
+            return fail(ctx, GNX_ERR_UNSUPPORTED, "too many lights for dense spatial light tables");
+        float *f, *c, *fi;
+        int rc;
+        if ((rc = dupload<float>(ctx, ctx->scene_allocs, nullptr, nv * sc.n_lights, &f))) return rc;
+        if ((rc = dupload<float>(ctx, ctx->scene_allocs, nullptr, nv * (sc.n_lights + 1), &c))) return rc;
+        if ((rc = dupload<float>(ctx, ctx->scene_allocs, nullptr, nv, &fi))) return rc;
+        sc.ld.sp_func = f; sc.ld.sp_cdf = c; sc.ld.sp_int = fi;
+        sc.ld.mode = GNX_LIGHTS_SPATIAL;
+        int blocks = (int)std::min<size_t>((nv + 127) / 128, (size_t)ctx->sm_count * 16);
+        k_build_spatial<<<blocks, 128, 0, ctx->stream>>>(sc, f, c, fi);
+        GNX_CUDA(ctx, cudaGetLastError());
+        GNX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->spatial_built = true;
+    }
+    sc.ld.mode = GNX_LIGHTS_SPATIAL;
+    return GNX_OK;
+}
+
+static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix) {
+    if (capacity > ctx->capacity) {
+        free_pool(ctx->wave_allocs);
+        ctx->capacity = 0;
+        std::vector<void *> &pool = ctx->wave_allocs;
+        int rc;
+        size_t n = (size_t)capacity;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.ray_o))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.ray_d))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.beta))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.L))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.hit))) return rc;
+        if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.hidx))) return rc;
+        if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.meta))) return rc;
+        if ((rc = dupload<int32_t>(ctx, pool, nullptr, n, &ctx->ps.medium))) return rc;
+        if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[0]))) return rc;
+        if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[1]))) return rc;
+        if ((rc = dupload<int>(ctx, pool, nullptr, n * kNumShadeTypes, &ctx->q.shade_q))) return rc;
+        if ((rc = dupload<ShadowItem>(ctx, pool, nullptr, n * 2, &ctx->q.shadow_q))) return rc;
+        if ((rc = dupload<ProbeItem>(ctx, pool, nullptr, n, &ctx->q.probe_q))) return rc;
+        if ((rc = dupload<int>(ctx, pool, nullptr, kNumCounters, &ctx->q.counts))) return rc;
+        ctx->q.capacity = capacity;
+        ctx->capacity = capacity;
+        GNX_CUDA(ctx, cudaDeviceSynchronize());
+    }
+    if (npix > ctx->film_pixels) {
+        if (ctx->accum) cudaFree(ctx->accum);
+        if (ctx->rgba) cudaFree(ctx->rgba);
+        ctx->accum = ctx->rgba = nullptr;
+        ctx->film_pixels = 0;
+        GNX_CUDA(ctx, cudaMalloc((void **)&ctx->accum, (size_t)npix * sizeof(float4)));
+        GNX_CUDA(ctx, cudaMalloc((void **)&ctx->rgba, (size_t)npix * sizeof(float4)));
+        ctx->film_pixels = npix;
+    }
+    return GNX_OK;
+}
+
+static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
+    if (!ctx->has_scene) return fail(ctx, GNX_ERR_NO_SCENE, "no scene uploaded");
+    if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
+        return fail(ctx, GNX_ERR_INVALID, "bad render parameters");
+    if ((long long)p->width * p->height > (1ll << 28)) return fail(ctx, GNX_ERR_INVALID, "image too large");
+    if (p->integrator != GNX_INTEGRATOR_PATH) return fail(ctx, GNX_ERR_UNSUPPORTED, "VolPathIntegrator is not implemented yet");
+    if (p->film != GNX_FILM_BOX) return fail(ctx, GNX_ERR_UNSUPPORTED, "only the box film of the reference is implemented");
+    // the Halton index must fit the 32-bit path state
+    unsigned long long maxIdx = (unsigned long long)(p->first_sample + p->spp) * (unsigned long long)ctx->sc.smp.stride;
+    if (maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
+    return GNX_OK;
+}
+
+static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats) {
+    int rc = validate_params(ctx, p);
+    if (rc) return rc;
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
+    const int npix = p->width * p->height;
+    int batch_spp = p->batch_spp > 0 ? p->batch_spp : std::max(1, (4 << 20) / npix);
+    batch_spp = std::min(batch_spp, p->spp);
+    if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / npix));
+    if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix))) return rc;
+
+    cudaStream_t st = userStream ? userStream : ctx->stream;
+    const DeviceScene &sc = ctx->sc;
+    const int gridTrace = ctx->sm_count * 8, gridShade = ctx->sm_count * 8, gridWide = ctx->sm_count * 16;
+    const bool hasNull = (ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u;
+    unsigned long long launches = 0;
+
+    GNX_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), st));
+    GNX_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    GNX_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)npix * sizeof(float4), st));
+
+    for (int done = 0; done < p->spp; done += batch_spp) {
+        RenderConsts rcn{};
+        rcn.width = p->width; rcn.height = p->height; rcn.npix = npix;
+        rcn.max_depth = p->max_depth;
+        rcn.rr_threshold = p->rr_threshold;
+        rcn.batch_spp = std::min(batch_spp, p->spp - done);
+        rcn.first_sample = p->first_sample + done;
+        rcn.capacity = ctx->capacity;
+        k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
+        k_raygen<<<gridWide, 256, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
+        launches += 2;
+        int in = 0;
+        // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
+        // have them keep iterating until the queue drains.
+        for (int iter = 0;; ++iter) {
+            const int out = 1 - in;
+            k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
+            k_extend<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
+            launches += 2;
+            for (int t = 0; t < kNumShadeTypes - 1; ++t) {
+                if (!((ctx->shade_type_mask >> t) & 1u)) continue;
+                if (t == GNX_MAT_DISNEY) k_shade<8><<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                else k_shade<2><<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                ++launches;
+            }
+            if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, out); ++launches; }
+            if (sc.n_lights > 0) {
+                k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 0, ctx->d_stats);
+                ++launches;
+                if (sc.env.present) { k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 1, ctx->d_stats); ++launches; }
+                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_probe<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, ctx->d_stats); ++launches; }
+            }
+            in = out;
+            if (iter >= p->max_depth) {
+                if (!hasNull) break;
+                int remaining = 0;
+                GNX_CUDA(ctx, cudaMemcpyAsync(&remaining, ctx->q.counts + in, sizeof(int), cudaMemcpyDeviceToHost, st));
+                GNX_CUDA(ctx, cudaStreamSynchronize(st));
+                if (remaining == 0 || iter > p->max_depth + 4096) break;
+            }
+        }
+        k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);
+        ++launches;
+    }
+    const float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
+    float4 *out = rgba_dev_out ? (float4 *)rgba_dev_out : ctx->rgba;
+    k_film<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, norm);
+    ++launches;
+    GNX_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    GNX_CUDA(ctx, cudaGetLastError());
+    if (stats || !rgba_dev_out) {
+        GNX_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        GNX_CUDA(ctx, cudaGetLastError());
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        DevStats hs;
+        GNX_CUDA(ctx, cudaMemcpy(&hs, ctx->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+        float ms = 0;
+        GNX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->paths = hs.paths;
+        stats->rays_extend = hs.rays_extend;
+        stats->rays_shadow = hs.rays_shadow;
+        stats->rays_mis = hs.rays_mis;
+        stats->nodes_visited = hs.nodes_visited;
+        stats->tris_tested = hs.tris_tested;
+        stats->device_ms = ms;
+        stats->kernel_launches = launches;
+        const unsigned long long rays = hs.rays_extend + hs.rays_shadow + hs.rays_mis;
+        // 32 B per node, 48 B per triangle, 32 B ray read + 16 B hit write per ray
+        stats->bytes_algorithmic = 32ull * hs.nodes_visited + 48ull * hs.tris_tested + 48ull * rays;
+    }
+    return GNX_OK;
+}
+
+extern "C" {
+
+int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, gnx_stats *stats) {
+    if (!ctx || !rgba_out) return GNX_ERR_INVALID;
+    int rc = render_impl(ctx, params, nullptr, nullptr, stats);
+    if (rc) return rc;
+    const size_t bytes = (size_t)params->width * params->height * sizeof(float4);
+    GNX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->rgba, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GNX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GNX_OK;
+}
+
+int gnx_render_device(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_dev, void *stream, gnx_stats *stats) {
+    if (!ctx || !rgba_dev) return GNX_ERR_INVALID;
+    return render_impl(ctx, params, rgba_dev, (cudaStream_t)stream, stats);
+}
+
+int gnx_primary_hits(gnx_ctx *ctx, const gnx_render_params *p, int32_t sample, int32_t *prim_id_out) {
+    if (!ctx || !prim_id_out) return GNX_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GNX_ERR_NO_SCENE, "no scene uploaded");
+    if (!p || p->width <= 0 || p->height <= 0 || sample < 0) return fail(ctx, GNX_ERR_INVALID, "bad parameters");
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int npix = p->width * p->height;
+    int *d = nullptr;
+    GNX_CUDA(ctx, cudaMalloc((void **)&d, (size_t)npix * sizeof(int)));
+    k_primary_hits<<<ctx->sm_count * 8, kBlock, 0, ctx->stream>>>(ctx->sc, p->width, p->height, sample, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prim_id_out, d, (size_t)npix * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, GNX_ERR_CUDA, cudaGetErrorString(e));
+    return GNX_OK;
+}
+
+int gnx_sample_dimensions(gnx_ctx *ctx, int32_t n, const int64_t *index, const int32_t *dim, float *out) {
+    if (!ctx || n < 0 || !index || !dim || !out) return GNX_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GNX_ERR_NO_SCENE, "no scene uploaded");
+    if (n == 0) return GNX_OK;
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    long long *di = nullptr; int *dd = nullptr; float *dout = nullptr;
+    cudaError_t e = cudaMalloc((void **)&di, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dd, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dout, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(di, index, (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dd, dim, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_sample_dims<<<std::min((n + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->sc, n, di, dd, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(di); cudaFree(dd); cudaFree(dout);
+    if (e != cudaSuccess) return fail(ctx, GNX_ERR_CUDA, cudaGetErrorString(e));
+    return GNX_OK;
+}
+
+int gnx_tonemap_rgba8(gnx_ctx *ctx, const float *rgba, int32_t n_pixels, uint8_t *rgba8_out) {
+    if (!ctx || !rgba || !rgba8_out || n_pixels < 0) return GNX_ERR_INVALID;
+    if (n_pixels == 0) return GNX_OK;
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    float4 *din = nullptr; uchar4 *dout = nullptr;
+    cudaError_t e = cudaMalloc((void **)&din, (size_t)n_pixels * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dout, (size_t)n_pixels * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(din, rgba, (size_t)n_pixels * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_tonemap<<<std::min((n_pixels + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(din, dout, n_pixels);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(rgba8_out, dout, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(ctx, GNX_ERR_CUDA, cudaGetErrorString(e));
+    return GNX_OK;
+}
+
+}  // extern "C"

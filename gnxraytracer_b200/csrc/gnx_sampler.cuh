@@ -1,0 +1,152 @@
+// gnx_sampler.cuh — HaltonSampler / GlobalSampler on the device.
+//
+// Follows samplers/HaltonSampler.cpp:63-94 (GetIndexForSample, SampleDimension),
+// samplers/LowDiscrepancy.cpp:358-405 (RadicalInverseSpecialized, ScrambledRadicalInverseSpecialized,
+// base-2 bit reversal in double) and samplers/LowDiscrepancy.h:47-56 (InverseRadicalInverse).
+// Integer work is exact; the float products are taken in the same order as the reference so the
+// sample values are bit-identical (tests/test_sampler_parity.py).
+#pragma once
+#include "gnx_scene.cuh"
+
+namespace gnx {
+
+constexpr int kMaxResolution = 128;  // samplers/HaltonSampler.cpp:11
+
+GNX_HD uint64_t inverse_radical_inverse(uint64_t inverse, int base, int nDigits) {
+    uint64_t index = 0;
+    for (int i = 0; i < nDigits; ++i) {
+        uint64_t digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
+}
+
+// HaltonSampler::GetIndexForSample(0) for pixel (px, py): the offset of the pixel's first sample.
+GNX_HD uint64_t halton_pixel_offset(const DevSampler &s, int px, int py) {
+    uint64_t offset = 0;
+    if (s.stride > 1) {
+        int pmx = px % kMaxResolution, pmy = py % kMaxResolution;  // Mod() of non-negative ints
+        uint64_t d0 = inverse_radical_inverse((uint64_t)pmx, 2, s.base_exp0);
+        uint64_t d1 = inverse_radical_inverse((uint64_t)pmy, 3, s.base_exp1);
+        offset += d0 * (uint64_t)(s.stride / s.base_scale0) * (uint64_t)s.mult_inv0;
+        offset += d1 * (uint64_t)(s.stride / s.base_scale1) * (uint64_t)s.mult_inv1;
+        offset %= (uint64_t)s.stride;
+    }
+    return offset;
+}
+
+// The digit loops run on 32-bit operands whenever the index fits (always, at the configs: the
+// largest index is 31 104 * 1024 + 31 103 < 2^25); the reversed-digit accumulator stays 64-bit.
+GNX_D float radical_inverse_base(uint64_t a64, uint32_t base) {
+    const float invBase = 1.0f / (float)base;
+    uint64_t reversed = 0;
+    float invBaseN = 1;
+    if (a64 <= 0xffffffffull) {
+        uint32_t a = (uint32_t)a64;
+        while (a) {
+            uint32_t next = a / base;
+            uint32_t digit = a - next * base;
+            reversed = reversed * base + digit;
+            invBaseN *= invBase;
+            a = next;
+        }
+    } else {
+        while (a64) {
+            uint64_t next = a64 / base;
+            uint64_t digit = a64 - next * base;
+            reversed = reversed * base + digit;
+            invBaseN *= invBase;
+            a64 = next;
+        }
+    }
+    return fminf((float)reversed * invBaseN, kOneMinusEpsilon);
+}
+
+GNX_D float scrambled_radical_inverse_base(uint64_t a64, uint32_t base, const uint16_t *perm) {
+    const float invBase = 1.0f / (float)base;
+    uint64_t reversed = 0;
+    float invBaseN = 1;
+    if (a64 <= 0xffffffffull) {
+        uint32_t a = (uint32_t)a64;
+        while (a) {
+            uint32_t next = a / base;
+            uint32_t digit = a - next * base;
+            reversed = reversed * base + ldg(perm + digit);
+            invBaseN *= invBase;
+            a = next;
+        }
+    } else {
+        while (a64) {
+            uint64_t next = a64 / base;
+            uint64_t digit = a64 - next * base;
+            reversed = reversed * base + ldg(perm + digit);
+            invBaseN *= invBase;
+            a64 = next;
+        }
+    }
+    float p0 = (float)ldg(perm);
+    return fminf(invBaseN * ((float)reversed + invBase * p0 / (1 - invBase)), kOneMinusEpsilon);
+}
+
+// RadicalInverse(0, a): ReverseBits64(a) * 2^-64 in double, narrowed (LowDiscrepancy.cpp:396-405)
+GNX_D float radical_inverse_base2(uint64_t a) {
+    uint64_t r = brev64(a);
+    return (float)((double)r * 5.4210108624275222e-20);
+}
+
+// Unscrambled RadicalInverse(baseIndex, a) for the first few bases (used by the spatial light
+// distribution, core/LightDistribution.cpp:230-236).
+GNX_D float radical_inverse(const DevSampler &s, int baseIndex, uint64_t a) {
+    if (baseIndex == 0) return radical_inverse_base2(a);
+    return radical_inverse_base(a, (uint32_t)ldg(s.primes + baseIndex));
+}
+
+// HaltonSampler::SampleDimension, samplers/HaltonSampler.cpp:85-94
+GNX_D float halton_sample_dimension(const DevSampler &s, uint64_t index, int dim) {
+    if (s.at_center && (dim == 0 || dim == 1)) return 0.5f;
+    if (dim == 0) return radical_inverse_base2(index >> s.base_exp0);
+    if (dim == 1) return radical_inverse_base(index / (uint64_t)s.base_scale1, 3u);
+    // ScrambledRadicalInverse returns 0 for base indices it has no case for (>= 1024); the
+    // reference's PrimeSums read at dim >= 1000 is out of range, we return 0.
+    if (dim >= s.n_primes) return 0.f;
+    uint32_t base = (uint32_t)ldg(s.primes + dim);
+    return scrambled_radical_inverse_base(index, base, s.perms + ldg(s.prime_sums + dim));
+}
+
+// PCG32 (core/RNG.h:30-110), used as the per-pixel stream when the sampler is not Halton.
+struct Pcg32 {
+    uint64_t state, inc;
+    GNX_HD void set_sequence(uint64_t seq) {
+        state = 0u;
+        inc = (seq << 1u) | 1u;
+        next_u32();
+        state += 0x853c49e6748fea9bULL;
+        next_u32();
+    }
+    GNX_HD uint32_t next_u32() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    GNX_HD float uniform_float() { return fminf(kOneMinusEpsilon, (float)(next_u32() * 2.3283064365386963e-10f)); }
+};
+
+// Sampler view of one path: GlobalSampler::Get1D/Get2D (core/Sampler.cpp:162-179).  arrayStartDim
+// is 5 and no sample arrays are ever requested by Path/VolPath, so the array-skip branch is inert.
+struct PathSampler {
+    const DevSampler &s;
+    uint64_t index;
+    int dim;
+    GNX_D PathSampler(const DevSampler &smp, uint64_t idx, int d) : s(smp), index(idx), dim(d) {}
+    GNX_D float get1d() { return halton_sample_dimension(s, index, dim++); }
+    GNX_D void get2d(float *a, float *b) {
+        *a = halton_sample_dimension(s, index, dim);
+        *b = halton_sample_dimension(s, index, dim + 1);
+        dim += 2;
+    }
+};
+
+}  // namespace gnx

@@ -1,0 +1,125 @@
+// gnx_scene.cuh — the flattened scene as the kernels see it (device pointers, passed by value as a
+// kernel parameter), plus the wavefront path state.  Layout in HBM is described in DESIGN.md §3.
+#pragma once
+#include "gnx_math.cuh"
+#include "gnxrt.h"
+
+namespace gnx {
+
+struct DevTexture {
+    int w, h, nch, wrap;
+    float su, sv, du, dv;
+    const float *texels;  // level 0, row-major
+};
+
+struct DevEnv {
+    int present, light_index;
+    int w, h;                 // Lmap level 0
+    const float *texels;      // [h][w][3]
+    int dw, dh;               // Distribution2D resolution
+    const float *cond_func, *cond_cdf, *cond_int, *marg_func, *marg_cdf;
+    float marg_int;
+    M44 l2w, w2l;
+    float world_radius;
+};
+
+struct DevLightDistrib {
+    int mode;                 // gnx_light_strategy actually in force
+    const float *uni_func, *uni_cdf;   // [nL], [nL+1]  (uniform / power: one table for the whole scene)
+    float uni_int;
+    int nvox[3];              // spatial
+    const float *sp_func, *sp_cdf, *sp_int;  // [nvoxels][nL], [nvoxels][nL+1], [nvoxels]
+};
+
+struct DevCamera {
+    M44 r2c, c2w;
+    float lens_radius, focal_distance;
+    int medium;
+};
+
+struct DevSampler {
+    int type;
+    int base_scale0, base_scale1, base_exp0, base_exp1;
+    int stride, mult_inv0, mult_inv1, at_center;
+    const uint16_t *perms;
+    const int *primes, *prime_sums;
+    int n_primes;
+};
+
+struct DevMedium {
+    int type;
+    float sigma_a[3], sigma_s[3], sigma_t[3];
+    float g;
+    int nx, ny, nz;
+    const float *density;
+    M44 w2m;
+    float inv_max_density, sigma_t_scalar;
+};
+
+struct DeviceScene {
+    // geometry: two float4 per node; three float4 per ordered primitive:
+    //   a = (p0.x p0.y p0.z p1.x)  b = (p1.y p1.z p2.x p2.y)  c = (p2.z, bits(material | flags<<24), bits(light), bits(prim_id))
+    const float4 *nodes;
+    const float4 *tris;
+    const float *tri_uv;          // [n][6] or null
+    const float *tri_n;           // [n][9] or null
+    const uint8_t *tri_has_n;     // [n] or null
+    const int2 *tri_media;        // [n] (inside, outside) or null
+    const uint8_t *tri_transition;
+    int n_nodes, n_prims;
+    float wb_min[3], wb_max[3];
+    const gnx_material *materials;
+    int n_materials;
+    const DevTexture *textures;
+    const gnx_light *lights;
+    int n_lights;
+    DevEnv env;
+    DevLightDistrib ld;
+    const DevMedium *media;
+    int n_media;
+    DevCamera cam;
+    DevSampler smp;
+};
+
+// ---- wavefront state: structure of arrays over the path slots of one batch ------------------------
+struct PathState {
+    float4 *ray_o;     // xyz origin, w = tMax
+    float4 *ray_d;     // xyz direction, w = etaScale
+    float4 *beta;      // xyz throughput, w unused
+    float4 *L;         // xyz radiance accumulated by this path
+    float4 *hit;       // b0 b1 b2 bits(prim) written by extend
+    uint32_t *hidx;    // Halton sample index (low 32 bits; the reference's int64 never exceeds 2^32 at the configs)
+    uint32_t *meta;    // dimension (16 bits) | bounces (8) | flags (8)
+    int32_t *medium;   // current ray medium (VolPath), -1 none
+};
+constexpr uint32_t kFlagSpecular = 1u;
+
+struct ShadowItem {      // 48 bytes: any-hit query "add contrib to path if nothing is hit"
+    float4 o_tmax;       // origin, tMax
+    float4 d_path;       // direction, bits(path slot)
+    float4 contrib;      // rgb, w unused
+};
+struct ProbeItem {       // closest-hit query "add contrib if the closest hit is primitive `expect`"
+    float4 o_tmax;
+    float4 d_path;
+    float4 contrib_expect;  // rgb, bits(expected ordered primitive)
+};
+
+struct Queues {
+    int *extend_q[2];        // ping-pong lists of path slots that need a closest-hit query
+    int *shade_q;            // [n_mat_types][capacity] lists per material type
+    ShadowItem *shadow_q;
+    ProbeItem *probe_q;
+    // counters: [0..1] extend ping/pong, [2..2+NT) shade per type, then shadow, probe
+    int *counts;
+    int capacity;
+};
+constexpr int kNumShadeTypes = 7;  // 6 gnx_material_type + "no material" (medium boundary)
+constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCntShade0 + kNumShadeTypes,
+              kCntProbe = kCntShadow + 1, kNumCounters = kCntProbe + 1;
+
+struct DevStats {
+    unsigned long long rays_extend, rays_shadow, rays_mis, nodes_visited, tris_tested, paths;
+};
+
+}  // namespace gnx

@@ -1,0 +1,373 @@
+// gnx_shade.cuh — device functions of the shade stage: rebuild the SurfaceInteraction of the final
+// hit, evaluate textures, build the lobe list of a material, sample lights.
+#pragma once
+#include "gnx_bsdf.cuh"
+#include "gnx_bvh.cuh"
+#include "gnx_sampler.cuh"
+
+namespace gnx {
+
+struct Surface {
+    V3 p, pError, n;        // geometric
+    V3 ns, dpdu_s, dpdv_s;  // shading.n, shading.dpdu, shading.dpdv
+    V3 wo;                  // Normalize(-ray.d)  (Interaction ctor, core/Interaction.h:24-32)
+    float u, v;
+    int material, light, prim;
+    unsigned flags;
+};
+
+// Triangle::Intersect from "Compute triangle partial derivatives" on (shape/Triangle.cpp:170-303),
+// for the accepted hit only.
+GNX_D Surface make_surface(const DeviceScene &sc, int prim, float b0, float b1, float b2, V3 rayD) {
+    float4 c;
+    const TriVerts tv = load_tri(sc.tris, prim, &c);
+    const unsigned mf = f2u(c.y);
+    Surface s;
+    s.prim = prim;
+    s.material = (int)(mf & 0xfffffu) - 1;  // bits 0-19: material index + 1 (0 = none), 20-23: shade type
+    s.flags = mf >> 24;
+    s.light = f2i(c.z);
+    const V3 p0 = tv.p0, p1 = tv.p1, p2 = tv.p2;
+    float uv0x = 0, uv0y = 0, uv1x = 1, uv1y = 0, uv2x = 1, uv2y = 1;  // shape/Triangle.h:60-74
+    if (sc.tri_uv) {
+        const float *q = sc.tri_uv + 6 * (size_t)prim;
+        uv0x = q[0]; uv0y = q[1]; uv1x = q[2]; uv1y = q[3]; uv2x = q[4]; uv2y = q[5];
+    }
+    const float duv02x = uv0x - uv2x, duv02y = uv0y - uv2y, duv12x = uv1x - uv2x, duv12y = uv1y - uv2y;
+    const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float determinant = duv02x * duv12y - duv02y * duv12x;
+    const bool degenerateUV = fabsf(determinant) < 1e-8f;
+    V3 dpdu, dpdv;
+    if (!degenerateUV) {
+        float invdet = 1 / determinant;
+        dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+    }
+    if (degenerateUV || length_sq(cross(dpdu, dpdv)) == 0) {
+        V3 ng = cross(p2 - p0, p1 - p0);
+        coordinate_system(normalize(ng), &dpdu, &dpdv);
+    }
+    const float xAbsSum = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x));
+    const float yAbsSum = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y));
+    const float zAbsSum = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z));
+    s.pError = gamma_n(7) * V3(xAbsSum, yAbsSum, zAbsSum);
+    s.u = b0 * uv0x + b1 * uv1x + b2 * uv2x;
+    s.v = b0 * uv0y + b1 * uv1y + b2 * uv2y;
+    s.p = b0 * p0 + b1 * p1 + b2 * p2;
+    s.wo = normalize(-rayD);
+    s.n = normalize(cross(dp02, dp12));
+    if (s.flags & GNX_PRIM_FLIP_N) s.n = -s.n;
+    s.ns = s.n;
+    s.dpdu_s = dpdu;
+    s.dpdv_s = dpdv;
+    if (sc.tri_has_n && sc.tri_has_n[prim]) {
+        const float *q = sc.tri_n + 9 * (size_t)prim;
+        V3 n0(q[0], q[1], q[2]), n1(q[3], q[4], q[5]), n2(q[6], q[7], q[8]);
+        V3 ns = (b0 * n0 + b1 * n1 + b2 * n2);
+        if (length_sq(ns) > 0) ns = normalize(ns); else ns = s.n;
+        V3 ss = normalize(dpdu);
+        V3 ts = cross(ss, ns);
+        if (length_sq(ts) > 0.f) { ts = normalize(ts); ss = cross(ts, ns); }
+        else coordinate_system(ns, &ss, &ts);
+        if (s.flags & GNX_PRIM_REVERSE_ORI) ts = -ts;
+        // SetShadingGeometry(ss, ts, ..., orientationIsAuthoritative = true), core/Interaction.cpp:36-54
+        s.ns = normalize(cross(ss, ts));
+        s.n = faceforward(s.n, s.ns);
+        s.dpdu_s = ss;
+        s.dpdv_s = ts;
+    }
+    return s;
+}
+
+// MIPMap::triangle(0, st) with MIPMap::Texel wrap handling (core/MIPMap.h:201-256); PathIntegrator
+// reaches no other branch of MIPMap::Lookup because its rays carry no differentials.
+GNX_D V3 texel_fetch(const DevTexture &t, int s, int tt) {
+    if (t.wrap == GNX_WRAP_REPEAT) {
+        s = s % t.w; if (s < 0) s += t.w;
+        tt = tt % t.h; if (tt < 0) tt += t.h;
+    } else if (t.wrap == GNX_WRAP_CLAMP) {
+        s = s < 0 ? 0 : (s > t.w - 1 ? t.w - 1 : s);
+        tt = tt < 0 ? 0 : (tt > t.h - 1 ? t.h - 1 : tt);
+    } else if (s < 0 || s >= t.w || tt < 0 || tt >= t.h) {
+        return V3(0.f);
+    }
+    const float *q = t.texels + ((size_t)tt * t.w + s) * t.nch;
+    return t.nch == 3 ? V3(ldg(q), ldg(q + 1), ldg(q + 2)) : V3(ldg(q));
+}
+GNX_D V3 texture_bilinear(const DevTexture &t, float su, float sv) {
+    float s = su * t.w - 0.5f, tt = sv * t.h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(tt);
+    float ds = s - s0, dt = tt - t0;
+    return (1 - ds) * (1 - dt) * texel_fetch(t, s0, t0) + (1 - ds) * dt * texel_fetch(t, s0, t0 + 1) +
+           ds * (1 - dt) * texel_fetch(t, s0 + 1, t0) + ds * dt * texel_fetch(t, s0 + 1, t0 + 1);
+}
+GNX_D V3 eval_rgb(const DeviceScene &sc, const gnx_material &m, int slot, const Surface &s) {
+    int tex = m.rgb_tex[slot];
+    if (tex < 0) return V3(m.rgb[slot][0], m.rgb[slot][1], m.rgb[slot][2]);
+    const DevTexture &t = sc.textures[tex];
+    return texture_bilinear(t, t.su * s.u + t.du, t.sv * s.v + t.dv);
+}
+GNX_D float eval_f(const DeviceScene &sc, const gnx_material &m, int slot, const Surface &s) {
+    int tex = m.f_tex[slot];
+    if (tex < 0) return m.f[slot];
+    const DevTexture &t = sc.textures[tex];
+    return texture_bilinear(t, t.su * s.u + t.du, t.sv * s.v + t.dv).x;
+}
+
+GNX_D Lobe make_lobe(int kind, int type, V3 R) {
+    Lobe l;
+    l.kind = kind; l.type = type; l.fresnel = FR_NOOP; l.distrib = DK_TROWBRIDGE;
+    l.R = R; l.a = V3(0.f); l.b = V3(0.f);
+    l.p0 = l.p1 = 0; l.e0 = l.e1 = 1;
+    return l;
+}
+GNX_D float clamp_alpha(float a) { return fmaxf(0.001f, a); }  // TrowbridgeReitzDistribution ctor, MicroFacet.h:82-83
+
+// <Material>::ComputeScatteringFunctions (materials/*.cpp), allowMultipleLobes == true,
+// TransportMode::Radiance.  Also applies Material::Bump's re-derivation of shading.n when a
+// (constant) bump map is attached, and fills the BSDF frame (core/Reflection.h:106-111).
+template <int MAXL>
+GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, Bsdf<MAXL> &b) {
+    if (m.flags & GNX_MATF_BUMP_IDENTITY) {
+        // SetShadingGeometry(dpdu, dpdv, ..., false) with unchanged dpdu/dpdv (core/Material.cpp:45-51)
+        s.ns = normalize(cross(s.dpdu_s, s.dpdv_s));
+        s.ns = faceforward(s.ns, s.n);
+    }
+    b.n = 0;
+    b.eta = 1;
+    b.ns = s.ns;
+    b.ng = s.n;
+    b.ss = normalize(s.dpdu_s);
+    b.ts = cross(b.ns, b.ss);
+    switch (m.type) {
+    case GNX_MAT_MATTE: {
+        V3 r = clamp0(eval_rgb(sc, m, 0, s));
+        float sig = clampf(eval_f(sc, m, 0, s), 0, 90);
+        if (!is_black(r)) {
+            if (sig == 0) b.add(make_lobe(LK_LAMBERT_R, BSDF_REFLECTION | BSDF_DIFFUSE, r));
+            else {
+                Lobe l = make_lobe(LK_OREN_NAYAR, BSDF_REFLECTION | BSDF_DIFFUSE, r);
+                float sg = (kPi / 180.f) * sig;  // Radians(), core/GNXRayTracer.h
+                float sigma2 = sg * sg;
+                l.p0 = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+                l.p1 = 0.45f * sigma2 / (sigma2 + 0.09f);
+                b.add(l);
+            }
+        }
+        break;
+    }
+    case GNX_MAT_MIRROR: {
+        V3 R = clamp0(eval_rgb(sc, m, 0, s));
+        if (!is_black(R)) b.add(make_lobe(LK_SPEC_R, BSDF_REFLECTION | BSDF_SPECULAR, R));
+        break;
+    }
+    case GNX_MAT_PLASTIC: {
+        V3 kd = clamp0(eval_rgb(sc, m, 0, s));
+        if (!is_black(kd)) b.add(make_lobe(LK_LAMBERT_R, BSDF_REFLECTION | BSDF_DIFFUSE, kd));
+        V3 ks = clamp0(eval_rgb(sc, m, 1, s));
+        if (!is_black(ks)) {
+            float rough = eval_f(sc, m, 0, s);
+            if (m.flags & GNX_MATF_REMAP_ROUGHNESS) rough = roughness_to_alpha(rough);
+            Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, ks);
+            l.fresnel = FR_DIELECTRIC; l.e0 = 1.5f; l.e1 = 1.f;
+            l.p0 = l.p1 = clamp_alpha(rough);
+            b.add(l);
+        }
+        break;
+    }
+    case GNX_MAT_METAL: {
+        float ur = eval_f(sc, m, 0, s), vr = eval_f(sc, m, 1, s);
+        if (m.flags & GNX_MATF_REMAP_ROUGHNESS) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+        Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, V3(1.f));
+        l.fresnel = FR_CONDUCTOR; l.e0 = 1.f;
+        l.a = eval_rgb(sc, m, 0, s);
+        l.b = eval_rgb(sc, m, 1, s);
+        l.p0 = clamp_alpha(ur); l.p1 = clamp_alpha(vr);
+        b.add(l);
+        break;
+    }
+    case GNX_MAT_GLASS: {
+        float eta = eval_f(sc, m, 2, s);
+        float ur = eval_f(sc, m, 0, s), vr = eval_f(sc, m, 1, s);
+        V3 R = clamp0(eval_rgb(sc, m, 0, s)), T = clamp0(eval_rgb(sc, m, 1, s));
+        b.eta = eta;
+        if (is_black(R) && is_black(T)) break;
+        bool isSpecular = ur == 0 && vr == 0;
+        if (isSpecular) {
+            Lobe l = make_lobe(LK_FRESNEL_SPEC, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, R);
+            l.a = T; l.e0 = 1.f; l.e1 = eta;
+            b.add(l);
+        } else {
+            if (m.flags & GNX_MATF_REMAP_ROUGHNESS) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+            if (!is_black(R)) {
+                Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, R);
+                l.fresnel = FR_DIELECTRIC; l.e0 = 1.f; l.e1 = eta;
+                l.p0 = clamp_alpha(ur); l.p1 = clamp_alpha(vr);
+                b.add(l);
+            }
+            if (!is_black(T)) {
+                Lobe l = make_lobe(LK_MICRO_T, BSDF_TRANSMISSION | BSDF_GLOSSY, T);
+                l.e0 = 1.f; l.e1 = eta;
+                l.p0 = clamp_alpha(ur); l.p1 = clamp_alpha(vr);
+                b.add(l);
+            }
+        }
+        break;
+    }
+    default: break;
+    }
+}
+
+// ---- lights ----------------------------------------------------------------------------------------------------
+struct LightSample {
+    V3 wi, Li;
+    float pdf;
+    V3 pl, nl, plError;  // point on the light, its normal and error bound (VisibilityTester p1)
+};
+
+// DiffuseAreaLight::L with the reference's bool truncation (lights/DiffuseAreaLight.h:22-27):
+// `bool dotNW = Dot(n, w)` is true for any non-zero dot product, so the light emits on both sides.
+GNX_D V3 area_light_L(const gnx_light &l, V3 n, V3 w) {
+    bool dotNW = dot(n, w) != 0.f;
+    return (l.two_sided || dotNW) ? V3(l.L[0], l.L[1], l.L[2]) : V3(0.f);
+}
+
+// DiffuseAreaLight::Sample_Li -> Shape::Sample(ref,u) -> Triangle::Sample(u)
+// (lights/DiffuseAreaLight.cpp:37-52, core/Shape.cpp:21-35, shape/Triangle.cpp:464-492)
+GNX_D bool area_sample_li(const DeviceScene &sc, const gnx_light &l, V3 refP, float u0, float u1, LightSample *ls) {
+    float4 c;
+    const TriVerts tv = load_tri(sc.tris, l.prim, &c);
+    const unsigned flags = f2u(c.y) >> 24;
+    float su0 = sqrtf(u0);
+    float bb0 = 1 - su0, bb1 = u1 * su0;
+    V3 p = bb0 * tv.p0 + bb1 * tv.p1 + (1 - bb0 - bb1) * tv.p2;
+    V3 n = normalize(cross(tv.p1 - tv.p0, tv.p2 - tv.p0));
+    if (sc.tri_has_n && sc.tri_has_n[l.prim]) {
+        const float *q = sc.tri_n + 9 * (size_t)l.prim;
+        V3 ns = bb0 * V3(q[0], q[1], q[2]) + bb1 * V3(q[3], q[4], q[5]) + (1 - bb0 - bb1) * V3(q[6], q[7], q[8]);
+        n = faceforward(n, ns);
+    } else if (flags & GNX_PRIM_FLIP_N) n = -n;
+    V3 pAbsSum = vabs(bb0 * tv.p0) + vabs(bb1 * tv.p1) + vabs((1 - bb0 - bb1) * tv.p2);
+    ls->plError = gamma_n(6) * pAbsSum;
+    float pdf = 1 / l.area;
+    V3 wi = p - refP;
+    if (length_sq(wi) == 0) pdf = 0;
+    else {
+        wi = normalize(wi);
+        V3 dd = refP - p;
+        pdf *= length_sq(dd) / absdot(n, -wi);
+        if (finf(pdf)) pdf = 0.f;
+    }
+    ls->pl = p; ls->nl = n;
+    if (pdf == 0 || length_sq(p - refP) == 0) { ls->pdf = 0; ls->Li = V3(0.f); return false; }
+    ls->wi = normalize(p - refP);
+    ls->pdf = pdf;
+    ls->Li = area_light_L(l, n, -ls->wi);
+    return true;
+}
+
+// DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi): intersects the light's own triangle
+// (core/Shape.cpp:37-53).  `o` is ref.SpawnRay(wi).o.
+GNX_D float area_pdf_li(const DeviceScene &sc, const gnx_light &l, V3 refP, V3 o, V3 wi) {
+    const TriVerts tv = load_tri(sc.tris, l.prim);
+    TriHit h;
+    const RayShear rs = make_shear(wi);
+    if (!intersect_tri(tv, o, rs, GNX_INF, &h) || tri_degenerate(tv)) return 0;
+    V3 pl = h.b0 * tv.p0 + h.b1 * tv.p1 + h.b2 * tv.p2;
+    V3 nl = normalize(cross(tv.p0 - tv.p2, tv.p1 - tv.p2));
+    V3 dd = refP - pl;
+    float pdf = length_sq(dd) / (absdot(nl, -wi) * l.area);
+    if (finf(pdf)) pdf = 0.f;
+    return pdf;
+}
+
+// InfiniteAreaLight (lights/InfiniteAreaLight.cpp:91-132) ------------------------------------------------
+GNX_D V3 env_lookup(const DevEnv &e, float su, float sv) {
+    // Lmap->Lookup(st) -> triangle(0, st), wrap Repeat (the MIPMap default)
+    float s = su * e.w - 0.5f, t = sv * e.h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(t);
+    float ds = s - s0, dt = t - t0;
+    auto tx = [&](int x, int y) {
+        x = x % e.w; if (x < 0) x += e.w;
+        y = y % e.h; if (y < 0) y += e.h;
+        const float *q = e.texels + ((size_t)y * e.w + x) * 3;
+        return V3(ldg(q), ldg(q + 1), ldg(q + 2));
+    };
+    return (1 - ds) * (1 - dt) * tx(s0, t0) + (1 - ds) * dt * tx(s0, t0 + 1) + ds * (1 - dt) * tx(s0 + 1, t0) +
+           ds * dt * tx(s0 + 1, t0 + 1);
+}
+GNX_D float spherical_theta(V3 v) { return acosf(clampf(v.z, -1, 1)); }
+GNX_D float spherical_phi(V3 v) { float p = atan2f(v.y, v.x); return (p < 0) ? (p + 2 * kPi) : p; }
+
+GNX_D V3 env_Le(const DevEnv &e, V3 rayD) {
+    V3 w = normalize(xform_vector(e.w2l, rayD));
+    return env_lookup(e, spherical_phi(w) * kInv2Pi, spherical_theta(w) * kInvPi);
+}
+// Distribution1D::SampleContinuous, core/Sampling.h:40-59
+GNX_D float dist1d_sample_continuous(const float *func, const float *cdf, float funcInt, int n, float u, float *pdf, int *off) {
+    int offset = find_interval_cdf(cdf, n + 1, u);
+    *off = offset;
+    float du = u - cdf[offset];
+    if ((cdf[offset + 1] - cdf[offset]) > 0) du /= (cdf[offset + 1] - cdf[offset]);
+    *pdf = (funcInt > 0) ? func[offset] / funcInt : 0;
+    return (offset + du) / n;
+}
+GNX_D bool env_sample_li(const DevEnv &e, float u0, float u1, LightSample *ls) {
+    float pdf1, pdf0;
+    int v, dummy;
+    float d1 = dist1d_sample_continuous(e.marg_func, e.marg_cdf, e.marg_int, e.dh, u1, &pdf1, &v);
+    float d0 = dist1d_sample_continuous(e.cond_func + (size_t)v * e.dw, e.cond_cdf + (size_t)v * (e.dw + 1),
+                                        e.cond_int[v], e.dw, u0, &pdf0, &dummy);
+    float mapPdf = pdf0 * pdf1;
+    ls->pdf = 0;
+    ls->Li = V3(0.f);
+    if (mapPdf == 0) return false;
+    float theta = d1 * kPi, phi = d0 * 2 * kPi;
+    float cosTheta = cosf(theta), sinTheta = sinf(theta);
+    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    ls->wi = xform_vector(e.l2w, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));
+    ls->pdf = mapPdf / (2 * kPi * kPi * sinTheta);
+    if (sinTheta == 0) ls->pdf = 0;
+    ls->Li = env_lookup(e, d0, d1);
+    return true;
+}
+GNX_D float env_pdf_li(const DevEnv &e, V3 w) {
+    V3 wi = xform_vector(e.w2l, w);
+    float theta = spherical_theta(wi), phi = spherical_phi(wi);
+    float sinTheta = sinf(theta);
+    if (sinTheta == 0) return 0;
+    float pu = phi * kInv2Pi, pv = theta * kInvPi;
+    int iu = (int)(pu * e.dw); iu = iu < 0 ? 0 : (iu > e.dw - 1 ? e.dw - 1 : iu);
+    int iv = (int)(pv * e.dh); iv = iv < 0 ? 0 : (iv > e.dh - 1 ? e.dh - 1 : iv);
+    return (e.cond_func[(size_t)iv * e.dw + iu] / e.marg_int) / (2 * kPi * kPi * sinTheta);
+}
+
+// Light choice: Distribution1D::SampleDiscrete over the distribution that LightDistribution::Lookup(p)
+// returns (core/Sampling.h:60-70, core/LightDistribution.cpp:109-204).
+GNX_D int choose_light(const DeviceScene &sc, V3 p, float u, float *pdf) {
+    const DevLightDistrib &ld = sc.ld;
+    const int n = sc.n_lights;
+    const float *func, *cdf;
+    float funcInt;
+    if (ld.mode == GNX_LIGHTS_SPATIAL) {
+        // Bounds3::Offset, core/Geometry.h
+        float o[3] = {p.x - sc.wb_min[0], p.y - sc.wb_min[1], p.z - sc.wb_min[2]};
+        int pi[3];
+        for (int i = 0; i < 3; ++i) {
+            if (sc.wb_max[i] > sc.wb_min[i]) o[i] /= sc.wb_max[i] - sc.wb_min[i];
+            int v = (int)(o[i] * ld.nvox[i]);
+            pi[i] = v < 0 ? 0 : (v > ld.nvox[i] - 1 ? ld.nvox[i] - 1 : v);
+        }
+        size_t vox = ((size_t)pi[2] * ld.nvox[1] + pi[1]) * ld.nvox[0] + pi[0];
+        func = ld.sp_func + vox * n;
+        cdf = ld.sp_cdf + vox * (n + 1);
+        funcInt = ld.sp_int[vox];
+    } else {
+        func = ld.uni_func; cdf = ld.uni_cdf; funcInt = ld.uni_int;
+    }
+    int offset = find_interval_cdf(cdf, n + 1, u);
+    *pdf = (funcInt > 0) ? func[offset] / (funcInt * n) : 0;
+    return offset;
+}
+
+}  // namespace gnx

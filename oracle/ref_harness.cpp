@@ -1,0 +1,356 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE ONLY (oracle side).
+//
+// Builds the BASELINE.json configs through the reference's own class API (the UI's scene code in
+// ui/ModelList.cpp, ui/MaterialList.cpp and ui/RenderThread.cpp cannot be compiled without Qt, so
+// its recipes are re-expressed here with the same numbers), renders them with the UNMODIFIED
+// reference integrators and exposes parity hooks over a small C interface used by tests/ and by
+// bench.py's cpu_baseline / --impl reference legs via ctypes.  It also instantiates the product's
+// CUDAPathIntegrator on the very same pbr::Scene, which is how the drop-in boundary is tested.
+//
+// Linked into oracle/_ref/libgnxref.so together with the reference objects (oracle/Makefile).
+// Nothing in the product library depends on this file.
+#include <dlfcn.h>
+#include <omp.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "accelerator/BVHAccel.h"
+#include "camera/Perspective.h"
+#include "core/Integrator.h"
+#include "core/Scene.h"
+#include "core/Transform.h"
+#include "integrators/PathIntegrator.h"
+#include "integrators/VolPathIntegrator.h"
+#include "lights/DiffuseAreaLight.h"
+#include "lights/InfiniteAreaLight.h"
+#include "materials/DisneyMaterial.h"
+#include "materials/GlassMaterial.h"
+#include "materials/MatteMaterial.h"
+#include "materials/MetalMaterial.h"
+#include "materials/MirrorMaterial.h"
+#include "materials/PlasticMaterial.h"
+#include "media/GridDensityMedium.h"
+#include "media/HomogeneousMedium.h"
+#include "samplers/HaltonSampler.h"
+#include "shape/Triangle.h"
+#include "textures/ConstantTexture.h"
+#include "textures/ImageTexture.h"
+
+#include "gnxraytracer_b200/bridge/CUDAPathIntegrator.h"
+#include "gnxraytracer_b200/host/scenekit_mesh.h"
+
+using namespace pbr;
+
+namespace {
+
+std::string ResourceDir() {
+    if (const char *e = getenv("GNX_RESOURCES")) return std::string(e) + "/";
+    Dl_info info;
+    if (dladdr((void *)&ResourceDir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.find_last_of('/');
+        return p.substr(0, s) + "/Resources/";
+    }
+    return "Resources/";
+}
+
+struct HarnessScene {
+    int width = 0, height = 0, spp = 0;
+    std::string name;
+    std::vector<std::unique_ptr<Transform>> transforms;  // Triangle keeps raw pointers to these
+    std::vector<std::shared_ptr<Primitive>> prims;       // original (pre-BVH) order
+    std::vector<std::shared_ptr<Light>> lights;
+    std::vector<std::shared_ptr<Medium>> media;
+    std::unique_ptr<Transform> cam2world;
+    std::unique_ptr<AnimatedTransform> animated;
+    std::shared_ptr<const Camera> camera;
+    std::shared_ptr<HaltonSampler> sampler;
+    std::unique_ptr<Scene> scene;
+    std::unique_ptr<FrameBuffer> fb;
+    std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
+    int cudaMaxDepth = -1;
+    std::unordered_map<const Primitive *, int> orderedIndex;  // BVH-ordered index of each primitive
+    std::string error;
+    double bvhSeconds = 0;
+
+    const Transform *keep(const Transform &t) {
+        transforms.emplace_back(new Transform(t));
+        return transforms.back().get();
+    }
+};
+
+std::shared_ptr<Texture<Spectrum>> ConstSpec(float r, float g, float b) {
+    Spectrum s;
+    s[0] = r; s[1] = g; s[2] = b;
+    return std::make_shared<ConstantTexture<Spectrum>>(s);
+}
+std::shared_ptr<Texture<Float>> ConstF(float v) { return std::make_shared<ConstantTexture<Float>>(v); }
+
+// TriangleMesh + one Triangle/GeometricPrimitive per face, as ui/ModelList.cpp:49-69 does.
+void AddMesh(HarnessScene &hs, const gnxsk::Mesh &m, const Transform &o2w, std::shared_ptr<Material> material,
+             const Spectrum *emit, const MediumInterface &mi = MediumInterface()) {
+    const Transform *O2W = hs.keep(o2w), *W2O = hs.keep(Inverse(o2w));
+    int nv = m.nVerts(), nt = m.nTris();
+    std::vector<Point3f> P(nv);
+    for (int i = 0; i < nv; ++i) P[i] = Point3f(m.P[3 * i], m.P[3 * i + 1], m.P[3 * i + 2]);
+    std::vector<Normal3f> N;
+    if (!m.N.empty()) {
+        N.resize(nv);
+        for (int i = 0; i < nv; ++i) N[i] = Normal3f(m.N[3 * i], m.N[3 * i + 1], m.N[3 * i + 2]);
+    }
+    std::vector<Point2f> UV;
+    if (!m.UV.empty()) {
+        UV.resize(nv);
+        for (int i = 0; i < nv; ++i) UV[i] = Point2f(m.UV[2 * i], m.UV[2 * i + 1]);
+    }
+    auto mesh = std::make_shared<TriangleMesh>(*O2W, nt, m.idx.data(), nv, P.data(), nullptr,
+                                               N.empty() ? nullptr : N.data(), UV.empty() ? nullptr : UV.data(), nullptr);
+    for (int i = 0; i < nt; ++i) {
+        std::shared_ptr<Shape> tri = std::make_shared<Triangle>(O2W, W2O, false, mesh, i);
+        std::shared_ptr<AreaLight> area;
+        if (emit) {
+            // one DiffuseAreaLight per triangle, nSamples 5, one-sided (ui/ModelList.cpp:140-146)
+            area = std::make_shared<DiffuseAreaLight>(*O2W, MediumInterface(), *emit, 5, tri, false);
+            hs.lights.push_back(area);
+        }
+        hs.prims.push_back(std::make_shared<GeometricPrimitive>(tri, material, area, mi));
+    }
+}
+
+void SetupCamera(HarnessScene &hs, const Point3f &eye, const Point3f &look) {
+    // ui/RenderThread.cpp:60-68
+    Transform lookat = LookAt(eye, look, Vector3f(0.0f, 1.0f, 0.0f));
+    hs.cam2world.reset(new Transform(Inverse(lookat)));
+    hs.animated.reset(new AnimatedTransform(hs.cam2world.get(), 0.0f, hs.cam2world.get(), 1.0f));
+    hs.camera = std::shared_ptr<Camera>(CreatePerspectiveCamera(hs.width, hs.height, *hs.animated));
+}
+
+void Finish(HarnessScene &hs) {
+    double t0 = omp_get_wtime();
+    auto bvh = std::make_shared<BVHAccel>(hs.prims, 1);  // ui/RenderThread.cpp:155
+    hs.bvhSeconds = omp_get_wtime() - t0;
+    hs.scene.reset(new Scene(bvh, hs.lights));
+    Bounds2i bounds(Point2i(0, 0), Point2i(hs.width, hs.height));
+    hs.sampler = std::make_shared<HaltonSampler>(hs.spp, bounds, false);  // ui/RenderThread.cpp:159
+    hs.fb.reset(new FrameBuffer);
+    hs.fb->InitBuffer(hs.width, hs.height, 4);
+}
+
+std::shared_ptr<Material> Matte(float r, float g, float b, float sigma) {
+    // constant-0 bump map, as every UI material has (ui/RenderThread.cpp:90-99)
+    return std::make_shared<MatteMaterial>(ConstSpec(r, g, b), ConstF(sigma), ConstF(0.0f));
+}
+
+// Config 1: Cornell box, two icospheres (Mirror, Glass), two-triangle area light.
+// variant: 0 = Lambert walls (sigma 0), 1 = the UI's Oren-Nayar sigma 60; sphere subdivision in p1.
+void BuildCornell(HarnessScene &hs, int variant, int subdiv) {
+    float sigma = variant == 1 ? 60.0f : 0.0f;
+    auto white = Matte(0.91f, 0.91f, 0.91f, sigma);
+    auto red = Matte(0.9f, 0.1f, 0.17f, sigma);
+    auto blue = Matte(0.14f, 0.21f, 0.87f, sigma);
+    if (subdiv >= 0) {
+        auto mirror = std::make_shared<MirrorMaterial>(ConstSpec(0.9f, 0.9f, 0.9f), ConstF(0.0f));
+        auto glass = std::make_shared<GlassMaterial>(ConstSpec(0.98f, 0.98f, 0.98f), ConstSpec(0.98f, 0.98f, 0.98f),
+                                                     ConstF(0.0f), ConstF(0.0f), ConstF(1.5f), ConstF(0.0f), false);
+        AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, -1.0f, -1.7f, -0.5f), Transform(), mirror, nullptr);
+        AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, 1.0f, -1.7f, 0.8f), Transform(), glass, nullptr);
+    }
+    // walls: triangles 6,7 red, 8,9 blue, others white (ui/ModelList.cpp:116-124)
+    gnxsk::Mesh walls = gnxsk::cornell_walls(5.0f);
+    Transform box2world = Translate(Vector3f(-2.5f, -2.5f, -2.5f));
+    for (int i = 0; i < 10; ++i) {
+        gnxsk::Mesh one;
+        for (int v = 0; v < 3; ++v) {
+            one.P.insert(one.P.end(), {walls.P[9 * i + 3 * v], walls.P[9 * i + 3 * v + 1], walls.P[9 * i + 3 * v + 2]});
+            one.idx.push_back(v);
+        }
+        AddMesh(hs, one, box2world, (i == 6 || i == 7) ? red : (i == 8 || i == 9) ? blue : white, nullptr);
+    }
+    Spectrum Le(5.0f);
+    AddMesh(hs, gnxsk::area_light_quad(1.4f), Translate(Vector3f(0.0f, 2.45f, 0.0f)), white, &Le);
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    Finish(hs);
+}
+
+std::shared_ptr<Material> PurplePlastic() {  // ui/MaterialList.cpp:48-56
+    return std::make_shared<PlasticMaterial>(ConstSpec(0.35f, 0.12f, 0.48f), ConstSpec(1.f - 0.35f, 1.f - 0.12f, 1.f - 0.48f),
+                                             ConstF(0.1f), ConstF(0.0f), true);
+}
+std::shared_ptr<Material> YellowMetal() {  // ui/MaterialList.cpp:58-69
+    return std::make_shared<MetalMaterial>(ConstSpec(0.2f, 0.2f, 0.8f), ConstSpec(0.11f, 0.11f, 0.11f), ConstF(0.15f),
+                                           ConstF(0.15f), ConstF(0.15f), ConstF(0.0f), false);
+}
+
+// Config 2: dragon-class mesh (torus knot stand-in for the stripped dragon.3d) under the MonValley
+// environment light.  variant 0 = Plastic, 1 = Metal; nu x nv quads.
+bool BuildDragon(HarnessScene &hs, int variant, int nu, int nv, const std::string &hdr) {
+    gnxsk::Mesh knot = gnxsk::torus_knot(nu, nv);
+    for (float &x : knot.P) x *= 20;  // plyInfo scales every vertex by 20 (shape/plyRead.h:38)
+    AddMesh(hs, knot, Translate(Vector3f(0.f, -2.9f, 0.f)), variant == 1 ? YellowMetal() : PurplePlastic(), nullptr);
+    std::string path = ResourceDir() + hdr;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { hs.error = "missing resource " + path; return false; }
+    fclose(f);
+    Transform l2w = RotateX(20) * RotateY(-90) * RotateX(-90);  // ui/ModelList.cpp:172-178
+    hs.lights.push_back(std::make_shared<InfiniteAreaLight>(l2w, Spectrum(1.0f), 10, path));
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    Finish(hs);
+    return true;
+}
+
+void IndexPrims(HarnessScene &hs) {
+    if (!hs.cuda || !hs.cuda->flat()) return;
+    const auto &ptrs = hs.cuda->flat()->prim_ptr;
+    hs.orderedIndex.clear();
+    for (size_t k = 0; k < ptrs.size(); ++k) hs.orderedIndex[(const Primitive *)ptrs[k]] = (int)k;
+}
+
+}  // namespace
+
+extern "C" {
+
+// name: "cornell" (p0 = variant, p1 = sphere subdivision, -1 = no spheres)
+//       "dragon"  (p0 = variant, p1 = nu, p2 = nv)
+void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0, int p1, int p2) {
+    auto *hs = new HarnessScene;
+    hs->name = name;
+    hs->width = width; hs->height = height; hs->spp = spp;
+    if (hs->name == "cornell") BuildCornell(*hs, p0, p1);
+    else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
+    else hs->error = "unknown scene";
+    return hs;
+}
+const char *gnxh_scene_error(void *h) { return ((HarnessScene *)h)->error.c_str(); }
+void gnxh_scene_destroy(void *h) { delete (HarnessScene *)h; }
+int gnxh_scene_num_prims(void *h) { return (int)((HarnessScene *)h)->prims.size(); }
+double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
+
+// The reference's own render: PathIntegrator::Render with `threads` OpenMP threads (0 = default).
+// rgba_out receives FrameBuffer's float buffer; *seconds the reference's own timeConsume.
+int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, double *seconds) {
+    auto *hs = (HarnessScene *)h;
+    if (!hs->scene) return -1;
+    if (threads > 0) omp_set_num_threads(threads);
+    hs->fb->InitBuffer(hs->width, hs->height, 4);
+    hs->fb->renderCountClear();
+    Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+    PathIntegrator integ(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    double t = 0;
+    integ.Render(*hs->scene, t);
+    if (seconds) *seconds = t;
+    if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * 4 * hs->width * hs->height);
+    return 0;
+}
+
+// Li of individual camera samples (pixel, sample number) straight from PathIntegrator::Li, and the
+// ordered primitive index of each sample's primary hit (-1 = miss).
+int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const int *py, const int *sample, float *rgb_out,
+                           int *prim_out) {
+    auto *hs = (HarnessScene *)h;
+    if (!hs->scene) return -1;
+    Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+    PathIntegrator integ(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    integ.Preprocess(*hs->scene, *hs->sampler);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        MemoryArena arena;
+        std::unique_ptr<Sampler> s = hs->sampler->Clone(0);
+        Point2i pixel(px[i], py[i]);
+        s->StartPixel(pixel);
+        s->SetSampleNumber(sample[i]);
+        CameraSample cs = s->GetCameraSample(pixel);
+        RayDifferential ray;
+        hs->camera->GenerateRayDifferential(cs, &ray);
+        ray.ScaleDifferentials(1 / std::sqrt((Float)s->samplesPerPixel));
+        if (prim_out) {
+            SurfaceInteraction isect;
+            Ray r(ray);
+            bool hit = hs->scene->Intersect(r, &isect);
+            int idx = -1;
+            if (hit) {
+                auto it = hs->orderedIndex.find(isect.primitive);
+                idx = it == hs->orderedIndex.end() ? -2 : it->second;
+            }
+            prim_out[i] = idx;
+        }
+        if (rgb_out) {
+            Spectrum L = integ.Li(ray, *hs->scene, *s, arena, 0);
+            rgb_out[3 * i] = L[0]; rgb_out[3 * i + 1] = L[1]; rgb_out[3 * i + 2] = L[2];
+        }
+    }
+    return 0;
+}
+
+int gnxh_reference_sample_dims(void *h, int n, const int64_t *index, const int *dim, float *out) {
+    auto *hs = (HarnessScene *)h;
+    for (int i = 0; i < n; ++i) out[i] = hs->sampler->SampleDimension(index[i], dim[i]);
+    return 0;
+}
+
+// HaltonSampler::GetIndexForSample(sample) for a pixel.
+int64_t gnxh_reference_sample_index(void *h, int px, int py, int sample) {
+    auto *hs = (HarnessScene *)h;
+    std::unique_ptr<Sampler> s = hs->sampler->Clone(0);
+    s->StartPixel(Point2i(px, py));
+    return static_cast<HaltonSampler *>(s.get())->GetIndexForSample(sample);
+}
+
+// ---- the product side, through the drop-in class -----------------------------------------------------
+static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
+    if (!hs->cuda || hs->cudaMaxDepth != maxDepth) {
+        Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
+        hs->cudaMaxDepth = maxDepth;
+    }
+    return hs->cuda.get();
+}
+
+// Flatten only (no GPU needed): returns the gnx_scene_desc the bridge would upload, or NULL.
+const gnx_scene_desc *gnxh_flatten(void *h) {
+    auto *hs = (HarnessScene *)h;
+    static thread_local std::unique_ptr<gnx::FlatScene> keep;
+    auto *flat = new gnx::FlatScene;
+    if (!gnx::FlattenScene(*hs->scene, *hs->camera, *hs->sampler, flat)) {
+        hs->error = flat->error;
+        delete flat;
+        return nullptr;
+    }
+    hs->orderedIndex.clear();
+    for (size_t k = 0; k < flat->prim_ptr.size(); ++k) hs->orderedIndex[(const Primitive *)flat->prim_ptr[k]] = (int)k;
+    keep.reset(flat);
+    return &flat->desc;
+}
+
+int gnxh_render_cuda(void *h, int maxDepth, float *rgba_out, double *seconds, gnx_stats *stats) {
+    auto *hs = (HarnessScene *)h;
+    gnx::CUDAPathIntegrator *c = EnsureCuda(hs, maxDepth);
+    hs->fb->InitBuffer(hs->width, hs->height, 4);
+    hs->fb->renderCountClear();
+    double t = 0;
+    c->Render(*hs->scene, t);
+    if (!c->error().empty()) { hs->error = c->error(); return -1; }
+    IndexPrims(*hs);
+    if (seconds) *seconds = t;
+    if (stats) *stats = c->lastStats();
+    if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * 4 * hs->width * hs->height);
+    return 0;
+}
+
+int gnxh_cuda_primary_hits(void *h, int sample, int *ordered_out) {
+    auto *hs = (HarnessScene *)h;
+    gnx::CUDAPathIntegrator *c = EnsureCuda(hs, hs->cudaMaxDepth < 0 ? 5 : hs->cudaMaxDepth);
+    std::vector<int32_t> v;
+    if (!c->PrimaryHits(*hs->scene, sample, &v)) { hs->error = c->error(); return -1; }
+    IndexPrims(*hs);
+    memcpy(ordered_out, v.data(), v.size() * sizeof(int));
+    return 0;
+}
+
+int gnxh_max_threads(void) { return omp_get_max_threads(); }
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// host_emul.cpp — TEST TOOL: runs the product's per-path device functions (gnx_path.cuh and below,
+// all __host__ __device__) sequentially on the CPU over a gnx_scene_desc.
+//
+// Purpose: the CPU-only test tier (`pytest -m "not gpu"`) can check the LOGIC of the kernels — Halton
+// indexing, camera rays, BVH traversal, BSDF/light sampling, MIS, Russian roulette — against the
+// reference without a GPU.  It is built with g++ (no nvcc) into tests/emul/_build/libgnxemul.so and
+// is loaded only by tests/.  The product library neither links nor loads it, and nothing here
+// is a fallback for libgnxrt.so.
+#include <omp.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "gnx_pack.h"
+#include "gnx_path.cuh"
+
+using namespace gnx;
+
+namespace {
+
+struct EmulScene {
+    DeviceScene sc{};
+    std::vector<float4> tris;
+    std::vector<int2> media;
+    std::vector<DevTexture> textures;
+    std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int;
+    std::vector<int> primes, sums;
+    std::vector<uint16_t> perms;
+    unsigned typeMask = 0;
+    float wb[6];
+    std::string err;
+};
+
+bool build(const gnx_scene_desc *d, EmulScene &e) {
+    DeviceScene &sc = e.sc;
+    const gnx_geometry &g = d->geom;
+    sc.nodes = (const float4 *)g.nodes;
+    sc.n_nodes = g.n_nodes;
+    sc.n_prims = g.n_prims;
+    if (!pack_triangles(*d, e.tris, &e.typeMask, &e.err)) return false;
+    sc.tris = e.tris.data();
+    sc.tri_uv = g.prim_uv;
+    sc.tri_n = (g.prim_n && g.prim_has_n) ? g.prim_n : nullptr;
+    sc.tri_has_n = (g.prim_n && g.prim_has_n) ? g.prim_has_n : nullptr;
+    for (int c = 0; c < 3; ++c) { sc.wb_min[c] = g.world_bound[c]; sc.wb_max[c] = g.world_bound[3 + c]; }
+    memcpy(e.wb, g.world_bound, sizeof(e.wb));
+    sc.materials = d->materials;
+    sc.n_materials = d->n_materials;
+    e.textures.resize(d->n_textures);
+    for (int i = 0; i < d->n_textures; ++i) {
+        const gnx_texture &t = d->textures[i];
+        e.textures[i] = DevTexture{t.width, t.height, t.n_channels, t.wrap, t.su, t.sv, t.du, t.dv, t.texels};
+    }
+    sc.textures = e.textures.data();
+    sc.lights = d->lights;
+    sc.n_lights = d->n_lights;
+    if (d->env.present) {
+        const gnx_envmap &v = d->env;
+        DevEnv &de = sc.env;
+        de.present = 1; de.light_index = v.light_index;
+        de.w = v.width; de.h = v.height; de.dw = v.dist_w; de.dh = v.dist_h;
+        de.texels = v.texels; de.cond_func = v.cond_func; de.cond_cdf = v.cond_cdf; de.cond_int = v.cond_int;
+        de.marg_func = v.marg_func; de.marg_cdf = v.marg_cdf; de.marg_int = v.marg_int;
+        memcpy(de.l2w.m, v.light_to_world, 64);
+        memcpy(de.w2l.m, v.world_to_light, 64);
+        de.world_radius = v.world_radius;
+    }
+    if (d->n_lights > 0) {
+        sc.ld.uni_int = uniform_light_distribution(d->n_lights, e.uni_func, e.uni_cdf);
+        sc.ld.uni_func = e.uni_func.data();
+        sc.ld.uni_cdf = e.uni_cdf.data();
+    }
+    sc.ld.mode = GNX_LIGHTS_UNIFORM;
+    memcpy(sc.cam.r2c.m, d->camera.raster_to_camera, 64);
+    memcpy(sc.cam.c2w.m, d->camera.camera_to_world, 64);
+    sc.cam.lens_radius = d->camera.lens_radius;
+    sc.cam.focal_distance = d->camera.focal_distance;
+    sc.cam.medium = d->camera.medium;
+    const gnx_sampler &s = d->sampler;
+    sc.smp.type = s.type;
+    sc.smp.base_scale0 = s.base_scales[0]; sc.smp.base_scale1 = s.base_scales[1];
+    sc.smp.base_exp0 = s.base_exponents[0]; sc.smp.base_exp1 = s.base_exponents[1];
+    sc.smp.stride = s.sample_stride;
+    sc.smp.mult_inv0 = s.mult_inverse[0]; sc.smp.mult_inv1 = s.mult_inverse[1];
+    sc.smp.at_center = s.sample_at_pixel_center;
+    make_primes(e.primes, e.sums);
+    if (s.perms) e.perms.assign(s.perms, s.perms + s.n_perm_entries);
+    else make_permutations(e.primes, e.perms);
+    sc.smp.perms = e.perms.data();
+    sc.smp.primes = e.primes.data();
+    sc.smp.prime_sums = e.sums.data();
+    sc.smp.n_primes = (int)e.primes.size();
+    return true;
+}
+
+void ensure_spatial(EmulScene &e, int strategy) {
+    DeviceScene &sc = e.sc;
+    if (strategy == GNX_LIGHTS_UNIFORM || sc.n_lights <= 1) { sc.ld.mode = GNX_LIGHTS_UNIFORM; return; }
+    size_t nv = spatial_voxel_resolution(e.wb, sc.ld.nvox);
+    e.sp_func.assign(nv * sc.n_lights, 0.f);
+    e.sp_cdf.assign(nv * (sc.n_lights + 1), 0.f);
+    e.sp_int.assign(nv, 0.f);
+    sc.ld.mode = GNX_LIGHTS_SPATIAL;
+    sc.ld.sp_func = e.sp_func.data(); sc.ld.sp_cdf = e.sp_cdf.data(); sc.ld.sp_int = e.sp_int.data();
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long v = 0; v < (long long)nv; ++v) build_spatial_voxel(sc, (int)v, e.sp_func.data(), e.sp_cdf.data(), e.sp_int.data());
+}
+
+// One camera sample carried through every wavefront stage, one slot.
+V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, int sample, TraversalCounters &cnt,
+                unsigned long long rays[3]) {
+    const DeviceScene &sc = e.sc;
+    float4 ray_o, ray_d, beta, L, hit;
+    uint32_t hidx, meta;
+    int32_t medium = -1;
+    PathState ps{&ray_o, &ray_d, &beta, &L, &hit, &hidx, &meta, &medium};
+    RenderConsts rc{};
+    rc.width = p.width; rc.height = p.height;
+    rc.npix = 1;  // slot 0 only: pixel/sample are injected through first_sample below
+    rc.max_depth = p.max_depth;
+    rc.rr_threshold = p.rr_threshold;
+    rc.batch_spp = 1;
+    // raygen_slot derives (pixel, sample) from the slot number; do its work by hand for one pixel
+    uint64_t hi = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    V3 o, d;
+    float tMax;
+    camera_ray(sc, px, py, hi, &o, &d, &tMax);
+    ray_o = make_float4(o.x, o.y, o.z, tMax);
+    ray_d = make_float4(d.x, d.y, d.z, 1.f);
+    beta = make_float4(1, 1, 1, 0);
+    L = make_float4(0, 0, 0, 0);
+    hidx = (uint32_t)hi;
+    meta = 5u;
+    int stack[kSmemStack];
+    for (int iter = 0; iter < 100000; ++iter) {
+        ++rays[0];
+        int type = extend_slot(sc, ps, rc, 0, stack, 1, cnt);
+        if (type < 0) break;
+        ShadeOut out;
+        out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
+        if (type == kNumShadeTypes - 1) out.alive = shade_null_slot(sc, ps, rc, 0);
+        else if (type == GNX_MAT_DISNEY) shade_slot<8>(sc, ps, rc, 0, out);
+        else shade_slot<2>(sc, ps, rc, 0, out);
+        if (out.haveShadowA) { ++rays[1]; shadow_item(sc, ps, &out.shA, stack, 1, cnt); }
+        if (out.haveShadowB) { ++rays[2]; shadow_item(sc, ps, &out.shB, stack, 1, cnt); }
+        if (out.haveProbe) { ++rays[2]; probe_item(sc, ps, &out.pr, stack, 1, cnt); }
+        if (!out.alive) break;
+    }
+    return V3(L.x, L.y, L.z);
+}
+
+}  // namespace
+
+extern "C" {
+
+void *gnxe_create(const gnx_scene_desc *d) {
+    auto *e = new EmulScene;
+    if (!build(d, *e)) fprintf(stderr, "[gnxe] %s\n", e->err.c_str());
+    return e;
+}
+void gnxe_destroy(void *h) { delete (EmulScene *)h; }
+
+int gnxe_render(void *h, const gnx_render_params *p, float *rgba_out, gnx_stats *stats) {
+    auto *e = (EmulScene *)h;
+    ensure_spatial(*e, p->light_strategy);
+    unsigned long long nodes = 0, tris = 0, r0 = 0, r1 = 0, r2 = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : nodes, tris, r0, r1, r2)
+    for (int pixel = 0; pixel < p->width * p->height; ++pixel) {
+        int px = pixel % p->width, py = pixel / p->width;
+        V3 sum(0.f);
+        TraversalCounters cnt{0, 0};
+        unsigned long long rays[3] = {0, 0, 0};
+        for (int s = 0; s < p->spp; ++s) sum += trace_sample(*e, *p, px, py, p->first_sample + s, cnt, rays);
+        float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
+        rgba_out[4 * pixel + 0] = sum.x / norm;
+        rgba_out[4 * pixel + 1] = sum.y / norm;
+        rgba_out[4 * pixel + 2] = sum.z / norm;
+        rgba_out[4 * pixel + 3] = 1.f;
+        nodes += cnt.nodes; tris += cnt.tris; r0 += rays[0]; r1 += rays[1]; r2 += rays[2];
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->paths = (uint64_t)p->width * p->height * p->spp;
+        stats->rays_extend = r0; stats->rays_shadow = r1; stats->rays_mis = r2;
+        stats->nodes_visited = nodes; stats->tris_tested = tris;
+    }
+    return 0;
+}
+
+int gnxe_samples(void *h, const gnx_render_params *p, int n, const int *px, const int *py, const int *sample, float *rgb_out) {
+    auto *e = (EmulScene *)h;
+    ensure_spatial(*e, p->light_strategy);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        TraversalCounters cnt{0, 0};
+        unsigned long long rays[3] = {0, 0, 0};
+        V3 L = trace_sample(*e, *p, px[i], py[i], sample[i], cnt, rays);
+        rgb_out[3 * i] = L.x; rgb_out[3 * i + 1] = L.y; rgb_out[3 * i + 2] = L.z;
+    }
+    return 0;
+}
+
+int gnxe_primary_hits(void *h, int width, int height, int sample, int *out) {
+    auto *e = (EmulScene *)h;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int pixel = 0; pixel < width * height; ++pixel) {
+        int stack[kSmemStack];
+        out[pixel] = primary_hit_id(e->sc, pixel % width, pixel / width, sample, stack, 1);
+    }
+    return 0;
+}
+
+int gnxe_sample_dims(void *h, int n, const int64_t *index, const int *dim, float *out) {
+    auto *e = (EmulScene *)h;
+    for (int i = 0; i < n; ++i) out[i] = halton_sample_dimension(e->sc.smp, (uint64_t)index[i], dim[i]);
+    return 0;
+}
+
+int64_t gnxe_sample_index(void *h, int px, int py, int sample) {
+    auto *e = (EmulScene *)h;
+    return (int64_t)(halton_pixel_offset(e->sc.smp, px, py) + (uint64_t)sample * (uint64_t)e->sc.smp.stride);
+}
+
+}  // extern "C"
