@@ -1,0 +1,242 @@
+"""ctypes bindings of include/gnxrt.h and include/gnx_scenekit.h.
+
+Plumbing only: every call lands in libgnxrt.so (CUDA).  If the library is missing, or no CUDA device
+is usable, the calls raise — there is no Python or CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .build import repo_root
+
+c_int32, c_float, c_u64, c_double, c_void_p = ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+
+LIGHTS_UNIFORM, LIGHTS_SPATIAL, LIGHTS_POWER = 0, 1, 2
+INTEGRATOR_PATH, INTEGRATOR_VOLPATH = 0, 1
+
+STATUS = {0: "GNX_OK", -1: "GNX_ERR_INVALID", -2: "GNX_ERR_NO_DEVICE", -3: "GNX_ERR_CUDA", -4: "GNX_ERR_UNSUPPORTED",
+          -5: "GNX_ERR_NO_SCENE"}
+
+
+class GnxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class RenderParams(ctypes.Structure):
+    """gnx_render_params (include/gnxrt.h)."""
+    _fields_ = [
+        ("width", c_int32), ("height", c_int32), ("spp", c_int32), ("first_sample", c_int32),
+        ("spp_normalize", c_int32), ("max_depth", c_int32), ("rr_threshold", c_float), ("integrator", c_int32),
+        ("light_strategy", c_int32), ("film", c_int32), ("filter_radius", c_float), ("filter_alpha", c_float),
+        ("batch_spp", c_int32),
+    ]
+
+    @classmethod
+    def make(cls, width, height, spp, max_depth=5, first_sample=0, spp_normalize=0, rr_threshold=1.0,
+             light_strategy=LIGHTS_SPATIAL, integrator=INTEGRATOR_PATH, batch_spp=0):
+        return cls(width, height, spp, first_sample, spp_normalize, max_depth, rr_threshold, integrator,
+                   light_strategy, 0, 0.0, 0.0, batch_spp)
+
+
+class Stats(ctypes.Structure):
+    """gnx_stats (include/gnxrt.h)."""
+    _fields_ = [
+        ("paths", c_u64), ("rays_extend", c_u64), ("rays_shadow", c_u64), ("rays_mis", c_u64),
+        ("nodes_visited", c_u64), ("tris_tested", c_u64), ("device_ms", c_double), ("ms_raygen", c_double),
+        ("ms_extend", c_double), ("ms_shade", c_double), ("ms_shadow", c_double), ("ms_film", c_double),
+        ("kernel_launches", c_u64), ("bytes_algorithmic", c_u64),
+        ("extend_nodes", c_u64), ("extend_tris", c_u64), ("extend_launches", c_u64), ("extend_bytes", c_u64),
+    ]
+
+    @property
+    def rays(self):
+        return self.rays_extend + self.rays_shadow + self.rays_mis
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["rays"] = self.rays
+        return d
+
+
+EXPORTS = ["gnx_abi_version", "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_upload_scene",
+           "gnx_render", "gnx_render_device", "gnx_primary_hits", "gnx_sample_dimensions", "gnx_tonemap_rgba8"]
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(repo_root(), "gnxraytracer_b200", "lib", "libgnxrt.so")
+
+
+def load_library():
+    """Loads libgnxrt.so; raises if it has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: the CUDA library must be built first (there is no fallback)")
+    lib = ctypes.CDLL(path)
+    lib.gnx_create.argtypes = [ctypes.POINTER(c_void_p), ctypes.c_int]
+    lib.gnx_destroy.argtypes = [c_void_p]
+    lib.gnx_destroy.restype = None
+    lib.gnx_last_error.argtypes = [c_void_p]
+    lib.gnx_last_error.restype = ctypes.c_char_p
+    lib.gnx_upload_scene.argtypes = [c_void_p, c_void_p]
+    lib.gnx_render.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_void_p, ctypes.POINTER(Stats)]
+    lib.gnx_render_device.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_void_p, c_void_p, ctypes.POINTER(Stats)]
+    lib.gnx_primary_hits.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_int32, c_void_p]
+    lib.gnx_sample_dimensions.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.gnx_tonemap_rgba8.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One gnx_ctx == one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = c_void_p()
+        rc = self.lib.gnx_create(ctypes.byref(self.h), device)
+        if rc != 0:
+            raise GnxError(rc, self.lib.gnx_last_error(None).decode())
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GnxError(rc, self.lib.gnx_last_error(self.h).decode())
+
+    def upload(self, desc_ptr):
+        """desc_ptr: address of a gnx_scene_desc (from SceneKit or from the bridge's FlattenScene)."""
+        self._check(self.lib.gnx_upload_scene(self.h, c_void_p(int(desc_ptr))))
+
+    def render(self, params, out=None, want_stats=True):
+        if out is None:
+            out = np.empty((params.height, params.width, 4), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == params.width * params.height * 4
+        st = Stats()
+        self._check(self.lib.gnx_render(self.h, ctypes.byref(params), out.ctypes.data, ctypes.byref(st) if want_stats else None))
+        return out, st
+
+    def render_host_ptr(self, params, host_ptr, want_stats=True):
+        """Like render(), into caller-owned (e.g. pinned) host memory."""
+        st = Stats()
+        self._check(self.lib.gnx_render(self.h, ctypes.byref(params), c_void_p(int(host_ptr)), ctypes.byref(st) if want_stats else None))
+        return st
+
+    def render_device(self, params, dev_ptr, stream=0, want_stats=True):
+        st = Stats()
+        self._check(self.lib.gnx_render_device(self.h, ctypes.byref(params), c_void_p(int(dev_ptr)), c_void_p(int(stream)),
+                                               ctypes.byref(st) if want_stats else None))
+        return st
+
+    def primary_hits(self, params, sample=0):
+        out = np.empty((params.height, params.width), np.int32)
+        self._check(self.lib.gnx_primary_hits(self.h, ctypes.byref(params), sample, out.ctypes.data))
+        return out
+
+    def sample_dimensions(self, index, dim):
+        index = np.ascontiguousarray(index, np.int64)
+        dim = np.ascontiguousarray(dim, np.int32)
+        out = np.empty(index.size, np.float32)
+        self._check(self.lib.gnx_sample_dimensions(self.h, index.size, index.ctypes.data, dim.ctypes.data, out.ctypes.data))
+        return out
+
+    def tonemap(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        out = np.empty(rgba.shape[:-1] + (4,), np.uint8)
+        self._check(self.lib.gnx_tonemap_rgba8(self.h, rgba.ctypes.data, rgba.size // 4, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.gnx_destroy(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- host-side scene kit (include/gnx_scenekit.h): builds gnx_scene_desc for the BASELINE configs ----
+SCENEKIT_EXPORTS = ["gnxsk_create", "gnxsk_destroy", "gnxsk_desc", "gnxsk_error", "gnxsk_num_prims", "gnxsk_build_seconds"]
+_sk = None
+
+
+def scenekit_path():
+    return os.path.join(repo_root(), "gnxraytracer_b200", "lib", "libgnxscenekit.so")
+
+
+def load_scenekit():
+    global _sk
+    if _sk is not None:
+        return _sk
+    path = scenekit_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it first")
+    sk = ctypes.CDLL(path)
+    sk.gnxsk_create.restype = c_void_p
+    sk.gnxsk_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_int, ctypes.c_char_p]
+    sk.gnxsk_destroy.argtypes = [c_void_p]
+    sk.gnxsk_destroy.restype = None
+    sk.gnxsk_desc.argtypes = [c_void_p]
+    sk.gnxsk_desc.restype = c_void_p
+    sk.gnxsk_error.argtypes = [c_void_p]
+    sk.gnxsk_error.restype = ctypes.c_char_p
+    sk.gnxsk_num_prims.argtypes = [c_void_p]
+    sk.gnxsk_build_seconds.argtypes = [c_void_p]
+    sk.gnxsk_build_seconds.restype = c_double
+    _sk = sk
+    return sk
+
+
+def resources_dir():
+    """Where the HDR environment maps live: GNX_RESOURCES, else the build-time copy next to the oracle
+    (oracle/_ref/Resources, filled by `make -C oracle ref` from the reference's Resources/)."""
+    env = os.environ.get("GNX_RESOURCES")
+    if env:
+        return env
+    return os.path.join(repo_root(), "oracle", "_ref", "Resources")
+
+
+class SceneKit:
+    """A scene built natively by the product's host-side kit (own BVH build, own env-map tables)."""
+
+    def __init__(self, name, width, height, spp, p0=0, p1=0, p2=0, resources=None):
+        self.sk = load_scenekit()
+        res = (resources or resources_dir()).encode()
+        self.h = self.sk.gnxsk_create(name.encode(), width, height, spp, p0, p1, p2, res)
+        err = self.sk.gnxsk_error(self.h).decode()
+        if err:
+            raise RuntimeError(f"scenekit({name}): {err}")
+        self.width, self.height, self.spp = width, height, spp
+
+    @property
+    def desc(self):
+        return self.sk.gnxsk_desc(self.h)
+
+    @property
+    def num_prims(self):
+        return self.sk.gnxsk_num_prims(self.h)
+
+    @property
+    def build_seconds(self):
+        return self.sk.gnxsk_build_seconds(self.h)
+
+    def close(self):
+        if self.h:
+            self.sk.gnxsk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -26,21 +26,16 @@ __device__ __forceinline__ int warp_push(int *counter, bool pred) {
     return pred ? base + __popc(m & ((1u << lane) - 1)) : -1;
 }
 
-__device__ __forceinline__ void flush_stats(DevStats *st, unsigned nodes, unsigned tris, unsigned raysE, unsigned raysS,
-                                            unsigned raysM) {
+__device__ __forceinline__ void flush_stats(DevStats *st, int kind, unsigned nodes, unsigned tris, unsigned rays) {
     for (int o = 16; o > 0; o >>= 1) {
         nodes += __shfl_down_sync(kFull, nodes, o);
         tris += __shfl_down_sync(kFull, tris, o);
-        raysE += __shfl_down_sync(kFull, raysE, o);
-        raysS += __shfl_down_sync(kFull, raysS, o);
-        raysM += __shfl_down_sync(kFull, raysM, o);
+        rays += __shfl_down_sync(kFull, rays, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (nodes) atomicAdd(&st->nodes_visited, (unsigned long long)nodes);
-        if (tris) atomicAdd(&st->tris_tested, (unsigned long long)tris);
-        if (raysE) atomicAdd(&st->rays_extend, (unsigned long long)raysE);
-        if (raysS) atomicAdd(&st->rays_shadow, (unsigned long long)raysS);
-        if (raysM) atomicAdd(&st->rays_mis, (unsigned long long)raysM);
+    if ((threadIdx.x & 31) == 0 && rays) {
+        atomicAdd(&st->nodes[kind], (unsigned long long)nodes);
+        atomicAdd(&st->tris[kind], (unsigned long long)tris);
+        atomicAdd(&st->rays[kind], (unsigned long long)rays);
     }
 }
 
@@ -85,7 +80,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(const DeviceScene sc, PathSta
             if (idx >= 0) q.shade_q[(size_t)t * q.capacity + idx] = slot;
         }
     }
-    flush_stats(st, cnt.nodes, cnt.tris, rays, 0, 0);
+    flush_stats(st, 0, cnt.nodes, cnt.tris, rays);
 }
 
 __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
@@ -146,7 +141,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(const DeviceScene sc, PathSta
         ++rays;
         shadow_item(sc, ps, items + i, stack, kBlock, cnt);
     }
-    flush_stats(st, cnt.nodes, cnt.tris, 0, which == 0 ? rays : 0, which == 1 ? rays : 0);
+    flush_stats(st, which == 0 ? 1 : 2, cnt.nodes, cnt.tris, rays);
 }
 
 __global__ void __launch_bounds__(kBlock) k_probe(const DeviceScene sc, PathState ps, Queues q, DevStats *st) {
@@ -160,7 +155,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DeviceScene sc, PathStat
         ++rays;
         probe_item(sc, ps, q.probe_q + i, stack, kBlock, cnt);
     }
-    flush_stats(st, cnt.nodes, cnt.tris, 0, 0, rays);
+    flush_stats(st, 2, cnt.nodes, cnt.tris, rays);
 }
 
 // colObj += Li(...) over the samples of the pixel, in sample order (core/Integrator.cpp:274-291)

@@ -40,6 +40,30 @@ struct gnx_ctx {
     int film_pixels = 0;
     DevStats *d_stats = nullptr;
     bool stage_timers = false;
+    // per-stage CUDA-event pairs (recorded on the render stream, read back after the render)
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;  // stage id of pair i (events 2i, 2i+1)
+    size_t ev_used = 0;
+};
+
+enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+
+// RAII-free helper: brackets the launches issued between begin() and end() with two events.
+struct StageTimer {
+    gnx_ctx *ctx; cudaStream_t st; bool on;
+    void begin(int stage) {
+        if (!on) return;
+        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+        }
+        ctx->ev_stage.push_back(stage);
+        cudaEventRecord(ctx->ev_pool[ctx->ev_used], st);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st);
+        ctx->ev_used += 2;
+    }
 };
 
 #define GNX_CUDA(ctx, call)                                                                         \
@@ -109,7 +133,7 @@ int gnx_create(gnx_ctx **out, int device) {
         return GNX_ERR_CUDA;
     }
     const char *t = getenv("GNX_STAGE_TIMERS");
-    ctx->stage_timers = t && t[0] == '1';
+    ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
     return GNX_OK;
 }
@@ -124,6 +148,7 @@ void gnx_destroy(gnx_ctx *ctx) {
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -421,6 +446,12 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     unsigned long long launches = 0;
 
     GNX_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), st));
+    // per-stage timers cost two event records per kernel group (~1 us each); on whenever the caller
+    // asks for stats, unless GNX_STAGE_TIMERS=0
+    StageTimer tm{ctx, st, stats != nullptr && ctx->stage_timers};
+    ctx->ev_used = 0;
+    ctx->ev_stage.clear();
+    unsigned long long extendLaunches = 0;
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     GNX_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)npix * sizeof(float4), st));
 
@@ -432,8 +463,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         rcn.batch_spp = std::min(batch_spp, p->spp - done);
         rcn.first_sample = p->first_sample + done;
         rcn.capacity = ctx->capacity;
+        tm.begin(ST_RAYGEN);
         k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
         k_raygen<<<gridWide, 256, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
+        tm.end();
         launches += 2;
         int in = 0;
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
@@ -441,8 +474,12 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         for (int iter = 0;; ++iter) {
             const int out = 1 - in;
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
+            tm.begin(ST_EXTEND);
             k_extend<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
+            tm.end();
             launches += 2;
+            ++extendLaunches;
+            tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
                 if (t == GNX_MAT_DISNEY) k_shade<8><<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
@@ -450,12 +487,15 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
                 ++launches;
             }
             if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, out); ++launches; }
+            tm.end();
+            tm.begin(ST_SHADOW);
             if (sc.n_lights > 0) {
                 k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 0, ctx->d_stats);
                 ++launches;
                 if (sc.env.present) { k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 1, ctx->d_stats); ++launches; }
                 if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_probe<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, ctx->d_stats); ++launches; }
             }
+            tm.end();
             in = out;
             if (iter >= p->max_depth) {
                 if (!hasNull) break;
@@ -465,7 +505,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
                 if (remaining == 0 || iter > p->max_depth + 4096) break;
             }
         }
+        tm.begin(ST_FILM);
         k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);
+        tm.end();
         ++launches;
     }
     const float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
@@ -485,16 +527,27 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         float ms = 0;
         GNX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->paths = hs.paths;
-        stats->rays_extend = hs.rays_extend;
-        stats->rays_shadow = hs.rays_shadow;
-        stats->rays_mis = hs.rays_mis;
-        stats->nodes_visited = hs.nodes_visited;
-        stats->tris_tested = hs.tris_tested;
+        stats->rays_extend = hs.rays[0];
+        stats->rays_shadow = hs.rays[1];
+        stats->rays_mis = hs.rays[2];
+        stats->nodes_visited = hs.nodes[0] + hs.nodes[1] + hs.nodes[2];
+        stats->tris_tested = hs.tris[0] + hs.tris[1] + hs.tris[2];
         stats->device_ms = ms;
         stats->kernel_launches = launches;
-        const unsigned long long rays = hs.rays_extend + hs.rays_shadow + hs.rays_mis;
+        const unsigned long long rays = hs.rays[0] + hs.rays[1] + hs.rays[2];
         // 32 B per node, 48 B per triangle, 32 B ray read + 16 B hit write per ray
-        stats->bytes_algorithmic = 32ull * hs.nodes_visited + 48ull * hs.tris_tested + 48ull * rays;
+        stats->bytes_algorithmic = 32ull * stats->nodes_visited + 48ull * stats->tris_tested + 48ull * rays;
+        stats->extend_nodes = hs.nodes[0];
+        stats->extend_tris = hs.tris[0];
+        stats->extend_launches = extendLaunches;
+        stats->extend_bytes = 32ull * hs.nodes[0] + 48ull * hs.tris[0] + 48ull * hs.rays[0];
+        double acc[ST_COUNT] = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i * 2 + 1 < ctx->ev_used + 0 && i < ctx->ev_stage.size(); ++i) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) == cudaSuccess) acc[ctx->ev_stage[i]] += t;
+        }
+        stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND]; stats->ms_shade = acc[ST_SHADE];
+        stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
     }
     return GNX_OK;
 }

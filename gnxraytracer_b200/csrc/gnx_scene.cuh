@@ -118,8 +118,8 @@ constexpr int kNumShadeTypes = 7;  // 6 gnx_material_type + "no material" (mediu
 constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCntShade0 + kNumShadeTypes,
               kCntProbe = kCntShadow + 1, kNumCounters = kCntProbe + 1;
 
-struct DevStats {
-    unsigned long long rays_extend, rays_shadow, rays_mis, nodes_visited, tris_tested, paths;
+struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
+    unsigned long long rays[3], nodes[3], tris[3], paths;
 };
 
 }  // namespace gnx

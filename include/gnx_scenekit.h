@@ -1,0 +1,40 @@
+/*
+ * gnx_scenekit.h — C ABI of the host-side scene kit (libgnxscenekit.so).
+ *
+ * The reference has no scene file format: its scenes are built in code by the Qt UI
+ * (ui/RenderThread.cpp:46-164, ui/ModelList.cpp:20-178, ui/MaterialList.cpp:31-92) and its BVH by
+ * BVHAccel's constructor (accelerator/BVHAccel.cpp:147-189).  When the host application is the
+ * reference itself, the bridge (gnxraytracer_b200/bridge) flattens that live scene.  The scene kit is
+ * the stand-alone counterpart: it builds the same BASELINE.json configs — geometry from
+ * host/scenekit_mesh.h, its own binned-SAH BVH, the InfiniteAreaLight importance tables
+ * (lights/InfiniteAreaLight.cpp:12-82), Halton parameters (samplers/HaltonSampler.cpp:33-61) and the
+ * perspective camera (camera/Perspective.cpp:114-135) — directly as a gnx_scene_desc, so that
+ * bench.py and smoke() need neither the reference nor the oracle.
+ */
+#ifndef GNX_SCENEKIT_H
+#define GNX_SCENEKIT_H
+
+#include "gnxrt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gnxsk_scene gnxsk_scene;
+
+/* name: "cornell" (p0: 0 = Lambert walls, 1 = Oren-Nayar sigma 60; p1: icosphere subdivision, -1 = none)
+ *       "dragon"  (p0: 0 = Plastic, 1 = Metal; p1 x p2: torus-knot quads, 0 = 2048 x 213)
+ * resources: directory holding MonValley1000.hdr (only read by "dragon").
+ * Never returns NULL; check gnxsk_error(). */
+gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int p0, int p1, int p2,
+                          const char *resources);
+void gnxsk_destroy(gnxsk_scene *s);
+const char *gnxsk_error(const gnxsk_scene *s);         /* "" when the scene is usable */
+const gnx_scene_desc *gnxsk_desc(const gnxsk_scene *s); /* valid until gnxsk_destroy   */
+int gnxsk_num_prims(const gnxsk_scene *s);
+double gnxsk_build_seconds(const gnxsk_scene *s);      /* BVH build wall time          */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -272,7 +272,11 @@ typedef struct gnx_stats {
     double device_ms;           /* CUDA-event time of the whole render (ray-gen .. film)          */
     double ms_raygen, ms_extend, ms_shade, ms_shadow, ms_film; /* per-stage CUDA-event sums       */
     uint64_t kernel_launches;   /* kernels launched by this call                                  */
-    uint64_t bytes_algorithmic; /* 32*nodes + 48*tris + per-ray/per-vertex bytes, see DESIGN.md   */
+    uint64_t bytes_algorithmic; /* 32*nodes + 48*tris + 48*rays over all traversal kernels */
+    /* the dominant kernel (k_extend) on its own, for the roofline line of bench.py */
+    uint64_t extend_nodes, extend_tris; /* BVH nodes popped / triangles tested by closest-hit extension rays */
+    uint64_t extend_launches;   /* number of k_extend launches; ms_extend is their CUDA-event sum   */
+    uint64_t extend_bytes;      /* 32*extend_nodes + 48*extend_tris + 48*rays_extend                */
 } gnx_stats;
 
 typedef struct gnx_ctx gnx_ctx;

@@ -75,6 +75,7 @@ struct HarnessScene {
     std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
     int cudaMaxDepth = -1;
     std::unordered_map<const Primitive *, int> orderedIndex;  // BVH-ordered index of each primitive
+    std::unordered_map<const Primitive *, int> originalIndex; // position in `prims` (the caller's order)
     std::string error;
     double bvhSeconds = 0;
 
@@ -139,6 +140,7 @@ void Finish(HarnessScene &hs) {
     hs.sampler = std::make_shared<HaltonSampler>(hs.spp, bounds, false);  // ui/RenderThread.cpp:159
     hs.fb.reset(new FrameBuffer);
     hs.fb->InitBuffer(hs.width, hs.height, 4);
+    for (size_t i = 0; i < hs.prims.size(); ++i) hs.originalIndex[hs.prims[i].get()] = (int)i;
 }
 
 std::shared_ptr<Material> Matte(float r, float g, float b, float sigma) {
@@ -248,7 +250,7 @@ int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, d
 }
 
 // Li of individual camera samples (pixel, sample number) straight from PathIntegrator::Li, and the
-// ordered primitive index of each sample's primary hit (-1 = miss).
+// index (in the scene's original primitive order) of each sample's primary hit (-1 = miss).
 int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const int *py, const int *sample, float *rgb_out,
                            int *prim_out) {
     auto *hs = (HarnessScene *)h;
@@ -273,8 +275,8 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
             bool hit = hs->scene->Intersect(r, &isect);
             int idx = -1;
             if (hit) {
-                auto it = hs->orderedIndex.find(isect.primitive);
-                idx = it == hs->orderedIndex.end() ? -2 : it->second;
+                auto it = hs->originalIndex.find(isect.primitive);
+                idx = it == hs->originalIndex.end() ? -2 : it->second;
             }
             prim_out[i] = idx;
         }
@@ -348,6 +350,19 @@ int gnxh_cuda_primary_hits(void *h, int sample, int *ordered_out) {
     if (!c->PrimaryHits(*hs->scene, sample, &v)) { hs->error = c->error(); return -1; }
     IndexPrims(*hs);
     memcpy(ordered_out, v.data(), v.size() * sizeof(int));
+    return 0;
+}
+
+// Maps BVH-ordered primitive indices (gnx_geometry::prim_id of a bridge-flattened scene) to the
+// scene's original primitive order; -1 stays -1.  Requires gnxh_flatten or a CUDA call before.
+int gnxh_ordered_to_original(void *h, int n, const int *ordered, int *original) {
+    auto *hs = (HarnessScene *)h;
+    std::vector<int> map(hs->orderedIndex.size(), -2);
+    for (auto &kv : hs->orderedIndex) {
+        auto it = hs->originalIndex.find(kv.first);
+        if (kv.second >= 0 && kv.second < (int)map.size() && it != hs->originalIndex.end()) map[kv.second] = it->second;
+    }
+    for (int i = 0; i < n; ++i) original[i] = ordered[i] < 0 ? -1 : (ordered[i] < (int)map.size() ? map[ordered[i]] : -2);
     return 0;
 }
 

@@ -1,0 +1,191 @@
+"""ctypes wrappers used by the tests only: the oracle (compiled reference + harness) and the CPU
+emulation of the product's device functions."""
+import ctypes
+import os
+
+import numpy as np
+
+from gnxraytracer_b200.api import RenderParams, Stats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgnxref.so")
+EMUL_LIB = os.path.join(ROOT, "tests", "emul", "_build", "libgnxemul.so")
+vp, ci = ctypes.c_void_p, ctypes.c_int
+
+# (scene name, p0, p1, p2) presets small enough for CPU tests
+SCENES = {
+    "cornell": ("cornell", 0, 2, 0),        # Lambert walls, mirror + glass icospheres (320 tris each)
+    "cornell_on": ("cornell", 1, 2, 0),     # the UI's Oren-Nayar sigma = 60 walls
+    "cornell_full": ("cornell", 0, 3, 0),   # BASELINE config 1 geometry (2 x 1280-triangle spheres)
+    "dragon": ("dragon", 0, 256, 32),       # Plastic knot, MonValley environment
+    "dragon_metal": ("dragon", 1, 256, 32),
+    "dragon_full": ("dragon", 0, 2048, 213),  # BASELINE config 2 geometry (872 448 triangles)
+}
+
+
+def grid(width, height):
+    ys, xs = np.mgrid[0:height, 0:width]
+    return xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)
+
+
+class RefScene:
+    def __init__(self, lib, h, width, height, spp):
+        self.lib, self.h, self.width, self.height, self.spp = lib, h, width, height, spp
+        self._desc = None
+
+    @property
+    def desc(self):
+        """gnx_scene_desc* produced by the bridge's FlattenScene from the live pbr::Scene."""
+        if self._desc is None:
+            self._desc = self.lib.gnxh_flatten(self.h)
+            if not self._desc:
+                raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
+        return self._desc
+
+    def render_reference(self, max_depth=5, threads=0):
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        sec = ctypes.c_double()
+        rc = self.lib.gnxh_render_reference(self.h, max_depth, threads, out.ctypes.data, ctypes.byref(sec))
+        assert rc == 0
+        return out, sec.value
+
+    def reference_samples(self, px, py, sample, max_depth=5, want_rgb=True, want_prim=True):
+        self.desc  # builds the pointer -> ordered-index map
+        n = px.size
+        rgb = np.zeros((n, 3), np.float32)
+        prim = np.zeros(n, np.int32)
+        rc = self.lib.gnxh_reference_samples(self.h, max_depth, n, px.ctypes.data, py.ctypes.data, sample.ctypes.data,
+                                             rgb.ctypes.data if want_rgb else None, prim.ctypes.data if want_prim else None)
+        assert rc == 0
+        return rgb, prim
+
+    def sample_dims(self, index, dim):
+        out = np.zeros(index.size, np.float32)
+        self.lib.gnxh_reference_sample_dims(self.h, index.size, index.ctypes.data, dim.ctypes.data, out.ctypes.data)
+        return out
+
+    def sample_index(self, x, y, s):
+        return self.lib.gnxh_reference_sample_index(self.h, int(x), int(y), int(s))
+
+    def render_cuda(self, max_depth=5):
+        """Through the drop-in class gnx::CUDAPathIntegrator::Render (needs a GPU)."""
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        sec = ctypes.c_double()
+        st = Stats()
+        rc = self.lib.gnxh_render_cuda(self.h, max_depth, out.ctypes.data, ctypes.byref(sec), ctypes.byref(st))
+        if rc != 0:
+            raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
+        return out, sec.value, st
+
+    def cuda_primary_hits(self, sample=0):
+        out = np.zeros(self.width * self.height, np.int32)
+        rc = self.lib.gnxh_cuda_primary_hits(self.h, sample, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
+        return out
+
+    def to_original(self, ordered):
+        """BVH-ordered primitive indices (a bridge-flattened scene's prim_id) -> original scene order."""
+        ordered = np.ascontiguousarray(ordered, np.int32).ravel()
+        out = np.zeros(ordered.size, np.int32)
+        self.lib.gnxh_ordered_to_original(self.h, ordered.size, ordered.ctypes.data, out.ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.gnxh_scene_destroy(self.h)
+            self.h = None
+
+
+class Ref:
+    def __init__(self):
+        l = ctypes.CDLL(REF_LIB)
+        l.gnxh_scene_create.restype = vp
+        l.gnxh_scene_create.argtypes = [ctypes.c_char_p] + [ci] * 6
+        l.gnxh_scene_error.restype = ctypes.c_char_p
+        l.gnxh_scene_error.argtypes = [vp]
+        l.gnxh_scene_destroy.argtypes = [vp]
+        l.gnxh_scene_num_prims.argtypes = [vp]
+        l.gnxh_scene_bvh_seconds.argtypes = [vp]
+        l.gnxh_scene_bvh_seconds.restype = ctypes.c_double
+        l.gnxh_flatten.restype = vp
+        l.gnxh_flatten.argtypes = [vp]
+        l.gnxh_render_reference.argtypes = [vp, ci, ci, vp, vp]
+        l.gnxh_reference_samples.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+        l.gnxh_reference_sample_dims.argtypes = [vp, ci, vp, vp, vp]
+        l.gnxh_reference_sample_index.restype = ctypes.c_int64
+        l.gnxh_reference_sample_index.argtypes = [vp, ci, ci, ci]
+        l.gnxh_render_cuda.argtypes = [vp, ci, vp, vp, vp]
+        l.gnxh_cuda_primary_hits.argtypes = [vp, ci, vp]
+        l.gnxh_ordered_to_original.argtypes = [vp, ci, vp, vp]
+        self.lib = l
+
+    def scene(self, preset, width, height, spp):
+        name, p0, p1, p2 = SCENES[preset]
+        h = self.lib.gnxh_scene_create(name.encode(), width, height, spp, p0, p1, p2)
+        err = self.lib.gnxh_scene_error(h).decode()
+        if err:
+            raise RuntimeError(err)
+        return RefScene(self.lib, h, width, height, spp)
+
+    def max_threads(self):
+        return self.lib.gnxh_max_threads()
+
+
+class EmulScene:
+    def __init__(self, lib, desc):
+        self.lib = lib
+        self.h = lib.gnxe_create(desc)
+
+    def render(self, params):
+        out = np.zeros((params.height, params.width, 4), np.float32)
+        st = Stats()
+        self.lib.gnxe_render(self.h, ctypes.byref(params), out.ctypes.data, ctypes.byref(st))
+        return out, st
+
+    def samples(self, params, px, py, sample):
+        rgb = np.zeros((px.size, 3), np.float32)
+        self.lib.gnxe_samples(self.h, ctypes.byref(params), px.size, px.ctypes.data, py.ctypes.data, sample.ctypes.data, rgb.ctypes.data)
+        return rgb
+
+    def primary_hits(self, width, height, sample=0):
+        out = np.zeros(width * height, np.int32)
+        self.lib.gnxe_primary_hits(self.h, width, height, sample, out.ctypes.data)
+        return out
+
+    def sample_dims(self, index, dim):
+        out = np.zeros(index.size, np.float32)
+        self.lib.gnxe_sample_dims(self.h, index.size, index.ctypes.data, dim.ctypes.data, out.ctypes.data)
+        return out
+
+    def sample_index(self, x, y, s):
+        return self.lib.gnxe_sample_index(self.h, int(x), int(y), int(s))
+
+    def close(self):
+        if self.h:
+            self.lib.gnxe_destroy(self.h)
+            self.h = None
+
+
+class Emul:
+    def __init__(self):
+        l = ctypes.CDLL(EMUL_LIB)
+        l.gnxe_create.restype = vp
+        l.gnxe_create.argtypes = [vp]
+        l.gnxe_destroy.argtypes = [vp]
+        l.gnxe_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, ctypes.POINTER(Stats)]
+        l.gnxe_samples.argtypes = [vp, ctypes.POINTER(RenderParams), ci, vp, vp, vp, vp]
+        l.gnxe_primary_hits.argtypes = [vp, ci, ci, ci, vp]
+        l.gnxe_sample_dims.argtypes = [vp, ci, vp, vp, vp]
+        l.gnxe_sample_index.restype = ctypes.c_int64
+        l.gnxe_sample_index.argtypes = [vp, ci, ci, ci]
+        self.lib = l
+
+    def scene(self, desc):
+        return EmulScene(self.lib, desc)
+
+
+def rel_mse(img, ref_img):
+    """Relative MSE as used for renderer comparisons: mean((a-b)^2 / (b^2 + eps)) over RGB."""
+    a, b = img[..., :3].astype(np.float64), ref_img[..., :3].astype(np.float64)
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))

@@ -1,0 +1,56 @@
+"""The N > 1 path on CPU: two gloo ranks shard the samples of every pixel, render their range (with
+the CPU emulation standing in for the GPU) and sum-reduce the framebuffer; rank 0 must hold the same
+image as a single-rank render.  Exercises first_sample / spp_normalize and gnxraytracer_b200.dist."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import _harness
+    from gnxraytracer_b200.api import RenderParams, SceneKit
+    from gnxraytracer_b200.dist import reduce_framebuffer, sample_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res, spp = 40, 6
+    sk = SceneKit("cornell", res, res, spp, 0, 1, 0)
+    es = _harness.Emul().scene(sk.desc)
+    first, count = sample_range(spp, rank, world)
+    img, _ = es.render(RenderParams.make(res, res, count, first_sample=first, spp_normalize=spp))
+    fb = torch.from_numpy(img)
+    reduce_framebuffer(fb, dst=0)
+    if rank == 0:
+        full, _ = es.render(RenderParams.make(res, res, spp))
+        np.savez(out_path, reduced=fb.numpy(), full=full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_reduce_to_the_single_rank_image(tmp_path, emul):
+    out = str(tmp_path / "out.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    d = np.load(out)
+    assert np.allclose(d["reduced"][..., :3], d["full"][..., :3], rtol=1e-5, atol=1e-6)
+    assert np.all(d["reduced"][..., 3] == 1.0)
+
+
+def test_sample_ranges_partition():
+    from gnxraytracer_b200.dist import sample_range, weak_sample_range
+    for spp in (1, 7, 64, 1024):
+        for world in (1, 2, 3, 8):
+            r = [sample_range(spp, k, world) for k in range(world)]
+            assert r[0][0] == 0 and sum(c for _, c in r) == spp
+            for (f0, c0), (f1, _) in zip(r, r[1:]):
+                assert f0 + c0 == f1
+    assert weak_sample_range(64, 3) == (192, 64)
