@@ -8,10 +8,10 @@
 // double-precision fallback for zero edge functions; the interaction itself is rebuilt once, for
 // the final hit only, in the shade stage.
 //
-// Layout: a node is two float4 (32 B, the reference's LinearBVHNode bit for bit), a triangle is three
-// float4 (48 B, vertices pre-gathered); both are read with 16-byte __ldg loads.  The traversal stack
-// lives in shared memory, one column per thread (stack[level][thread]: conflict-free), and spills
-// to a local array only beyond kSmemStack levels.
+// Layout: a device node is four float4 (64 B: an interior LinearBVHNode plus both children's bounds, see
+// "Node2" below), a triangle is three float4 (48 B, vertices pre-gathered); both are read with 16-byte
+// __ldg loads.  The traversal stack lives in shared memory, one column per thread (stack[level][thread]:
+// conflict-free), and spills to a local array only beyond kSmemStack levels.
 #pragma once
 #include "gnx_scene.cuh"
 
@@ -109,79 +109,133 @@ GNX_D bool tri_degenerate(const TriVerts &tv) {
 
 struct TraversalCounters { unsigned nodes, tris; };
 
-// Closest-hit (ANY=false) or any-hit (ANY=true).  `stack` is the calling thread's column of the
-// block's shared-memory stack: entry k lives at stack[k * stride].
-template <bool ANY>
-GNX_D bool traverse(const DeviceScene &sc, V3 o, V3 d, float tMax, int *stack, int stride, int *primOut,
-                    TriHit *hitOut, TraversalCounters &cnt) {
-    if (sc.n_nodes == 0) return false;
-    const V3 invDir(1.f / d.x, 1.f / d.y, 1.f / d.z);
-    const int neg0 = invDir.x < 0, neg1 = invDir.y < 0, neg2 = invDir.z < 0;
-    const RayShear rs = make_shear(d);
+// ---- traversal -------------------------------------------------------------------------------------
+// Device node ("Node2", 64 B = four float4): an INTERIOR node of the reference's LinearBVHNode array
+// together with the bounds of both of its children, so one fetch feeds two slab tests and the
+// dependent-load chain is half as long:
+//   n0 = (c0.lo.xyz, c0.hi.x)  n1 = (c0.hi.yz, c1.lo.xy)  n2 = (c1.lo.z, c1.hi.xyz)  n3 = (ref0, ref1, axis, -)
+// c0 is the reference's first child (index + 1), c1 its second child.  A child ref >= 0 is another
+// Node2; a negative ref is a leaf, ~ref = primitive offset | (count - 1) << 27.  axis 0..2 picks the near
+// child from the ray's sign exactly as BVHAccel::Intersect does; axis 3 means "c0 first" (chained
+// oversized leaves).  The order in which leaves are intersected is the reference's order, so the
+// closest hit is the same hit (not merely an equally close one).
+constexpr int kRefNone = 0x7fffffff;
+constexpr int kLeafMaxPrims = 16;
+GNX_HD int leaf_ref(int offset, int count) { return ~(offset | ((count - 1) << 27)); }
+
+struct Trav {
+    V3 o, invDir;
+    RayShear rs;
+    float tMax;
+    int cur, sp, neg;  // neg: bit k set when invDir[k] < 0
+    bool hit;
+    TriHit h;
+    int prim;
+    int2 spill[kSpillStack];
+};
+
+GNX_D void trav_init(const DeviceScene &sc, Trav &t, V3 o, V3 d, float tMax) {
+    t.o = o;
+    t.invDir = V3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    t.neg = (t.invDir.x < 0 ? 1 : 0) | (t.invDir.y < 0 ? 2 : 0) | (t.invDir.z < 0 ? 4 : 0);
+    t.rs = make_shear(d);
+    t.tMax = tMax;
+    t.sp = 0;
+    t.hit = false;
+    t.prim = -1;
+    t.cur = sc.n_nodes2 > 0 ? 0 : kRefNone;
+}
+
+// Bounds3::IntersectP(ray, invDir, dirIsNeg), core/Geometry.h:1380-1406; *tminOut is the entry distance
+// the reference compares with ray.tMax.
+GNX_D bool slab_test(const Trav &t, float lox, float loy, float loz, float hix, float hiy, float hiz, float *tminOut) {
     const float widen = 1 + 2 * gamma_n(3);
-    int spill[kSpillStack];
-    int sp = 0, cur = 0;
-    bool hit = false;
-    while (true) {
-        const float4 n0 = ldg(sc.nodes + 2 * cur), n1 = ldg(sc.nodes + 2 * cur + 1);
-        ++cnt.nodes;
-        // bounds[dirIsNeg] selects pMin (0) or pMax (1)
-        const float bx0 = neg0 ? n0.w : n0.x, bx1 = neg0 ? n0.x : n0.w;
-        const float by0 = neg1 ? n1.x : n0.y, by1 = neg1 ? n0.y : n1.x;
-        const float bz0 = neg2 ? n1.y : n0.z, bz1 = neg2 ? n0.z : n1.y;
-        float tmin = (bx0 - o.x) * invDir.x, tmax = (bx1 - o.x) * invDir.x;
-        float tymin = (by0 - o.y) * invDir.y, tymax = (by1 - o.y) * invDir.y;
-        tmax *= widen;
-        tymax *= widen;
-        bool inside = !(tmin > tymax || tymin > tmax);
-        if (inside) {
-            if (tymin > tmin) tmin = tymin;
-            if (tymax < tmax) tmax = tymax;
-            float tzmin = (bz0 - o.z) * invDir.z, tzmax = (bz1 - o.z) * invDir.z;
-            tzmax *= widen;
-            inside = !(tmin > tzmax || tzmin > tmax);
-            if (inside) {
-                if (tzmin > tmin) tmin = tzmin;
-                if (tzmax < tmax) tmax = tzmax;
-                inside = (tmin < tMax) && (tmax > 0);
-            }
+    const bool n0 = t.neg & 1, n1 = t.neg & 2, n2 = t.neg & 4;
+    float tmin = ((n0 ? hix : lox) - t.o.x) * t.invDir.x, tmax = ((n0 ? lox : hix) - t.o.x) * t.invDir.x;
+    float tymin = ((n1 ? hiy : loy) - t.o.y) * t.invDir.y, tymax = ((n1 ? loy : hiy) - t.o.y) * t.invDir.y;
+    tmax *= widen;
+    tymax *= widen;
+    if (tmin > tymax || tymin > tmax) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = ((n2 ? hiz : loz) - t.o.z) * t.invDir.z, tzmax = ((n2 ? loz : hiz) - t.o.z) * t.invDir.z;
+    tzmax *= widen;
+    if (tmin > tzmax || tzmin > tmax) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    *tminOut = tmin;
+    return (tmin < t.tMax) && (tmax > 0);
+}
+
+// One traversal step: tests both children of the current interior node, intersects whatever leaves come
+// next in the reference's visiting order, and stops at the next interior node.  Returns true when the
+// traversal is finished (t.hit / t.h / t.prim hold the result).  `stack` is the calling thread's column of
+// a shared-memory stack (entry k at stack[k * stride]); deeper levels spill into t.spill.
+template <bool ANY>
+GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
+    if (t.cur == kRefNone) return true;
+    const float4 *np = sc.nodes2 + 4 * (size_t)t.cur;
+    const float4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3);
+    const int ref0 = f2i(n3.x), ref1 = f2i(n3.y), axis = f2i(n3.z);
+    float tmin0 = 0, tmin1 = 0;
+    bool hit0 = false, hit1 = false;
+    if (ref0 != kRefNone) { ++cnt.nodes; hit0 = slab_test(t, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, &tmin0); }
+    if (ref1 != kRefNone) { ++cnt.nodes; hit1 = slab_test(t, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, &tmin1); }
+    const bool nearIs1 = axis < 3 && ((t.neg >> axis) & 1);
+    int refN = nearIs1 ? ref1 : ref0, refF = nearIs1 ? ref0 : ref1;
+    bool hitN = nearIs1 ? hit1 : hit0, hitF = nearIs1 ? hit0 : hit1;
+    const float tminF = nearIs1 ? tmin0 : tmin1;
+    int next;
+    if (hitN) {
+        next = refN;
+        if (hitF) {
+            const int2 e = make_int2(refF, f2i(tminF));
+            if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
+            ++t.sp;
         }
-        bool pop = true;
-        if (inside) {
-            const int offset = f2i(n1.z);
-            const unsigned meta = f2u(n1.w);
-            const int nPrims = (int)(meta & 0xffffu);
-            if (nPrims > 0) {
-                for (int i = 0; i < nPrims; ++i) {
-                    const int prim = offset + i;
-                    const TriVerts tv = load_tri(sc.tris, prim);
-                    ++cnt.tris;
-                    TriHit h;
-                    if (intersect_tri(tv, o, rs, tMax, &h) && !tri_degenerate(tv)) {
-                        if (ANY) return true;
-                        hit = true;
-                        tMax = h.t;
-                        *hitOut = h;
-                        *primOut = prim;
-                    }
-                }
-            } else {
-                const int axis = (int)((meta >> 16) & 0xffu);
-                const int negAxis = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
-                int far;
-                if (negAxis) { far = cur + 1; cur = offset; } else { far = offset; cur = cur + 1; }
-                if (sp < kSmemStack) stack[sp * stride] = far; else spill[sp - kSmemStack] = far;
-                ++sp;
-                pop = false;
-            }
-        }
-        if (pop) {
-            if (sp == 0) break;
-            --sp;
-            cur = sp < kSmemStack ? stack[sp * stride] : spill[sp - kSmemStack];
-        }
+    } else if (hitF) {
+        next = refF;
+    } else {
+        next = kRefNone;
     }
-    return hit;
+    while (true) {
+        if (next == kRefNone) {
+            // pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax)
+            while (true) {
+                if (t.sp == 0) { t.cur = kRefNone; return true; }
+                --t.sp;
+                const int2 e = t.sp < kSmemStack ? stack[t.sp * stride] : t.spill[t.sp - kSmemStack];
+                if (i2f(e.y) < t.tMax) { next = e.x; break; }
+            }
+        }
+        if (next >= 0) { t.cur = next; return false; }
+        const int x = ~next, offset = x & 0x7ffffff, count = (x >> 27) + 1;
+        for (int i = 0; i < count; ++i) {
+            const int prim = offset + i;
+            const TriVerts tv = load_tri(sc.tris, prim);
+            ++cnt.tris;
+            TriHit h;
+            if (intersect_tri(tv, t.o, t.rs, t.tMax, &h) && !tri_degenerate(tv)) {
+                t.hit = true;
+                t.tMax = h.t;
+                t.h = h;
+                t.prim = prim;
+                if (ANY) { t.cur = kRefNone; return true; }
+            }
+        }
+        next = kRefNone;
+    }
+}
+
+// Whole traversal in one call (parity hooks, light-table build, CPU emulation).
+template <bool ANY>
+GNX_D bool traverse(const DeviceScene &sc, V3 o, V3 d, float tMax, int2 *stack, int stride, int *primOut, TriHit *hitOut,
+                    TraversalCounters &cnt) {
+    Trav t;
+    trav_init(sc, t, o, d, tMax);
+    while (!trav_step<ANY>(sc, t, stack, stride, cnt)) {}
+    if (t.hit) { *primOut = t.prim; *hitOut = t.h; }
+    return t.hit;
 }
 
 }  // namespace gnx

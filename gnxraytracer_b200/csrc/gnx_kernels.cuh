@@ -2,10 +2,11 @@
 // walks its input queue with a block-uniform grid-stride loop so that every lane of a warp reaches
 // the warp-aggregated queue pushes (__ballot_sync + one atomicAdd per warp and queue).
 //
-//   k_raygen  -> k_extend -> k_shade<type> ... -> k_shadow x2, k_probe -> (next bounce) ... -> k_accumulate -> k_film
+//   k_raygen -> k_trace<0> -> k_shade<type> ... -> k_trace<1> x2, k_trace<2> -> (next bounce) ... -> k_accumulate -> k_film
 //
-// Grid sizes are multiples of the SM count (148 on B200); the traversal kernels keep their stacks
-// in shared memory (12 KB per 128-thread block).
+// Grids are sized from the occupancy query: SM count (148 on B200) x resident blocks per SM, so a
+// persistent kernel never has a partial second wave.  The traversal kernel keeps its stacks in shared
+// memory (24 KB per 128-thread block).
 #pragma once
 #include "gnx_path.cuh"
 
@@ -57,30 +58,80 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
     if (i < kNumCounters && i != (1 - outExtend)) counts[i] = 0;
 }
 
-__global__ void __launch_bounds__(kBlock) k_extend(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
-                                                    int inQ, DevStats *st) {
-    __shared__ int s_stack[kSmemStack * kBlock];
-    int *stack = s_stack + threadIdx.x;
-    const int n = q.counts[inQ];
-    const int *inList = q.extend_q[inQ];
+// ---- the traversal kernel --------------------------------------------------------------------------------
+// Persistent threads with dynamic ray fetch (Aila & Laine's while-while scheme): one block column of the
+// grid stays resident per SM slot; every lane owns at most one ray; lanes whose ray has finished pull the
+// next unprocessed queue entry through a warp-aggregated atomic on a global cursor as soon as fewer than
+// kRefetchBelow lanes of the warp are still traversing.  This replaces a static ray-per-thread mapping
+// whose SIMD efficiency profiled at 5-11 active lanes of 32 (profiles/r01_extend_static.txt).
+//   KIND 0: extension rays of the path slots in extend_q[arg]   -> hit record, env radiance, shade queues
+//   KIND 1: shadow_q half `arg` (any-hit)                        -> L += contrib when unoccluded
+//   KIND 2: probe_q (closest hit must be the light's triangle)   -> L += contrib
+constexpr int kRefetchBelow = 24;
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int arg,
+                                                      DevStats *st) {
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n = KIND == 0 ? q.counts[arg] : (KIND == 1 ? q.counts[kCntShadow + arg] : q.counts[kCntProbe]);
+    int *cursor = &q.counts[kCntFetch + (KIND == 0 ? 0 : (KIND == 1 ? 1 + arg : 3))];
+    const int *inList = KIND == 0 ? q.extend_q[arg] : nullptr;
+    const ShadowItem *shadowItems = q.shadow_q + (size_t)(KIND == 1 ? arg : 0) * q.capacity;
     TraversalCounters cnt{0, 0};
     unsigned rays = 0;
-    const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {
-        const int i = base + threadIdx.x;
-        int type = -1, slot = 0;
-        if (i < n) {
-            slot = inList[i];
-            ++rays;
-            type = extend_slot(sc, ps, rc, slot, stack, kBlock, cnt);
-        }
+    Trav t;
+    t.cur = kRefNone;
+    bool active = false, exhausted = false;
+    int item = 0;            // slot (KIND 0) or queue index (KIND 1, 2) of the lane's ray
+    int pendType = -1, pendSlot = 0;
+    while (true) {
+        if (KIND == 0) {
+            // shade-queue pushes of the rays that finished since the last visit, one atomic per warp and queue
+            const unsigned any = __ballot_sync(kFull, pendType >= 0);
+            if (any) {
 #pragma unroll
-        for (int t = 0; t < kNumShadeTypes; ++t) {
-            int idx = warp_push(&q.counts[kCntShade0 + t], type == t);
-            if (idx >= 0) q.shade_q[(size_t)t * q.capacity + idx] = slot;
+                for (int ty = 0; ty < kNumShadeTypes; ++ty) {
+                    int idx = warp_push(&q.counts[kCntShade0 + ty], pendType == ty);
+                    if (idx >= 0) q.shade_q[(size_t)ty * q.capacity + idx] = pendSlot;
+                }
+                pendType = -1;
+            }
         }
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(kFull, !active);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(cursor, __popc(idle));
+                base = __shfl_sync(kFull, base, leader);
+                if (!active) {
+                    const int i = base + __popc(idle & ((1u << lane) - 1));
+                    if (i < n) {
+                        if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
+                        else if (KIND == 1) { item = i; shadow_begin(sc, shadowItems + i, t); }
+                        else { item = i; probe_begin(sc, q.probe_q + i, t); }
+                        active = true;
+                        ++rays;
+                    }
+                }
+                exhausted = base + __popc(idle) >= n;
+            }
+        }
+        if (!__any_sync(kFull, active)) break;
+        while (active) {
+            if (trav_step<KIND == 1>(sc, t, stack, kBlock, cnt)) {
+                if (KIND == 0) { pendType = extend_finish(sc, ps, rc, item, t); pendSlot = item; }
+                else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
+                else probe_finish(ps, q.probe_q + item, t);
+                active = false;
+            }
+            if (!exhausted && __popc(__activemask()) < kRefetchBelow) break;
+        }
+        __syncwarp();
     }
-    flush_stats(st, 0, cnt.nodes, cnt.tris, rays);
+    flush_stats(st, KIND == 0 ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);
 }
 
 __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
@@ -127,37 +178,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(const DeviceScene sc, PathStat
     }
 }
 
-// which == 0: VisibilityTester rays; which == 1: the BSDF-sampled MIS ray toward the environment.
-// Two launches (not one mixed queue) keep the two additions into a path's L in a fixed order.
-__global__ void __launch_bounds__(kBlock) k_shadow(const DeviceScene sc, PathState ps, Queues q, int which, DevStats *st) {
-    __shared__ int s_stack[kSmemStack * kBlock];
-    int *stack = s_stack + threadIdx.x;
-    const int n = q.counts[kCntShadow + which];
-    const ShadowItem *items = q.shadow_q + (size_t)which * q.capacity;
-    TraversalCounters cnt{0, 0};
-    unsigned rays = 0;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        ++rays;
-        shadow_item(sc, ps, items + i, stack, kBlock, cnt);
-    }
-    flush_stats(st, which == 0 ? 1 : 2, cnt.nodes, cnt.tris, rays);
-}
-
-__global__ void __launch_bounds__(kBlock) k_probe(const DeviceScene sc, PathState ps, Queues q, DevStats *st) {
-    __shared__ int s_stack[kSmemStack * kBlock];
-    int *stack = s_stack + threadIdx.x;
-    const int n = q.counts[kCntProbe];
-    TraversalCounters cnt{0, 0};
-    unsigned rays = 0;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        ++rays;
-        probe_item(sc, ps, q.probe_q + i, stack, kBlock, cnt);
-    }
-    flush_stats(st, 2, cnt.nodes, cnt.tris, rays);
-}
-
 // colObj += Li(...) over the samples of the pixel, in sample order (core/Integrator.cpp:274-291)
 __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
@@ -179,8 +199,8 @@ __global__ void k_film(const float4 *accum, float4 *rgba, int npix, float spp) {
 }
 
 __global__ void __launch_bounds__(kBlock) k_primary_hits(const DeviceScene sc, int width, int height, int sample, int *out) {
-    __shared__ int s_stack[kSmemStack * kBlock];
-    int *stack = s_stack + threadIdx.x;
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
     const int npix = width * height;
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)
         out[pixel] = primary_hit_id(sc, pixel % width, pixel / width, sample, stack, kBlock);

@@ -10,6 +10,7 @@
 
 #include "gnx_scene.cuh"
 #include "gnx_sampler.cuh"
+#include "gnx_bvh.cuh"
 
 namespace gnx {
 
@@ -77,6 +78,70 @@ inline bool pack_triangles(const gnx_scene_desc &d, std::vector<float4> &tris, u
         tris[3 * (size_t)k + 0] = make_float4(p[0], p[1], p[2], p[3]);
         tris[3 * (size_t)k + 1] = make_float4(p[4], p[5], p[6], p[7]);
         tris[3 * (size_t)k + 2] = make_float4(p[8], fw, fl, fi);
+    }
+    return true;
+}
+
+// LinearBVHNode array (32 B nodes, depth-first, first child = index + 1) -> Node2 array (gnx_bvh.cuh): one
+// 64-byte record per INTERIOR node holding both children's bounds.  Leaves with more than
+// kLeafMaxPrims primitives (coincident centroids) become a chain of "c0 first" nodes.
+inline bool build_node2(const gnx_bvh_node *nodes, int n, std::vector<float4> &out, std::string *err) {
+    out.clear();
+    if (n <= 0) return true;
+    std::vector<int> id((size_t)n, -1);
+    int count = 0;
+    for (int i = 0; i < n; ++i) if (nodes[i].n_prims == 0) id[i] = count++;
+    struct N2 { float lo0[3], hi0[3], lo1[3], hi1[3]; int ref0, ref1, axis; };
+    std::vector<N2> v((size_t)count);
+    auto empty = [](float *lo, float *hi) { for (int c = 0; c < 3; ++c) { lo[c] = 0; hi[c] = 0; } };
+    // leaf reference, chaining oversized leaves through extra nodes appended at the end
+    auto leafRef = [&](const gnx_bvh_node &lf) -> int {
+        int offset = lf.offset, cnt = lf.n_prims;
+        if (cnt <= kLeafMaxPrims) return leaf_ref(offset, cnt);
+        int first = -1, prev = -1;
+        while (cnt > 0) {
+            int take = std::min(cnt, kLeafMaxPrims);
+            N2 c{};
+            memcpy(c.lo0, lf.bmin, 12); memcpy(c.hi0, lf.bmax, 12);
+            memcpy(c.lo1, lf.bmin, 12); memcpy(c.hi1, lf.bmax, 12);
+            c.ref0 = leaf_ref(offset, take); c.ref1 = kRefNone; c.axis = 3;
+            v.push_back(c);
+            int me = (int)v.size() - 1;
+            if (first < 0) first = me; else v[prev].ref1 = me;
+            prev = me; offset += take; cnt -= take;
+        }
+        return first;
+    };
+    if (nodes[0].n_prims > 0) {  // single-leaf tree
+        N2 r{};
+        memcpy(r.lo0, nodes[0].bmin, 12); memcpy(r.hi0, nodes[0].bmax, 12);
+        empty(r.lo1, r.hi1);
+        r.ref1 = kRefNone; r.axis = 3;
+        v.push_back(r);
+        int ref = leafRef(nodes[0]);
+        v[0].ref0 = ref;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (nodes[i].n_prims != 0) continue;
+        const int c0 = i + 1, c1 = nodes[i].offset;
+        if (c0 >= n || c1 <= i || c1 >= n) { *err = "malformed BVH node array"; return false; }
+        N2 r{};
+        memcpy(r.lo0, nodes[c0].bmin, 12); memcpy(r.hi0, nodes[c0].bmax, 12);
+        memcpy(r.lo1, nodes[c1].bmin, 12); memcpy(r.hi1, nodes[c1].bmax, 12);
+        r.axis = nodes[i].axis > 2 ? 0 : nodes[i].axis;
+        r.ref0 = nodes[c0].n_prims ? leafRef(nodes[c0]) : id[c0];
+        r.ref1 = nodes[c1].n_prims ? leafRef(nodes[c1]) : id[c1];
+        v[id[i]] = r;
+    }
+    out.resize(v.size() * 4);
+    for (size_t k = 0; k < v.size(); ++k) {
+        const N2 &r = v[k];
+        float f0, f1, fa;
+        memcpy(&f0, &r.ref0, 4); memcpy(&f1, &r.ref1, 4); memcpy(&fa, &r.axis, 4);
+        out[4 * k + 0] = make_float4(r.lo0[0], r.lo0[1], r.lo0[2], r.hi0[0]);
+        out[4 * k + 1] = make_float4(r.hi0[1], r.hi0[2], r.lo1[0], r.lo1[1]);
+        out[4 * k + 2] = make_float4(r.lo1[2], r.hi1[0], r.hi1[1], r.hi1[2]);
+        out[4 * k + 3] = make_float4(f0, f1, fa, 0.f);
     }
     return true;
 }

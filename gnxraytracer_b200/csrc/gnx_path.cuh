@@ -71,33 +71,39 @@ GNX_D void raygen_slot(const DeviceScene &sc, const PathState &ps, const RenderC
 
 GNX_D int shade_type_of(unsigned matWord) { return (int)((matWord >> 20) & 0xfu); }
 
-// Returns the shade-queue type of the hit, or -1 when the path ends here.
-GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, int *stack, int stride,
-                      TraversalCounters &cnt) {
+// Extension ray of a path slot: begin loads the ray and arms the traversal, finish consumes the result.
+GNX_D void extend_begin(const DeviceScene &sc, const PathState &ps, int slot, Trav &t) {
     const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
-    const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
-    int prim = -1;
-    TriHit h;
-    const bool hit = traverse<false>(sc, o, d, ro.w, stack, stride, &prim, &h, cnt);
+    trav_init(sc, t, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w);
+}
+// Returns the shade-queue type of the hit, or -1 when the path ends here.
+GNX_D int extend_finish(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, const Trav &t) {
     const uint32_t meta = ps.meta[slot];
     const int bounces = (meta >> 16) & 0xff;
     const bool emitOk = bounces == 0 || ((meta >> 24) & kFlagSpecular);
-    if (hit) {
+    if (t.hit) {
         // beyond maxDepth only the emission term is left (PathIntegrator.cpp:101-117)
         if (bounces >= rc.max_depth && !emitOk) return -1;
-        const unsigned matWord = f2u(ldg(&sc.tris[3 * prim + 2].y));
-        ps.hit[slot] = make_float4(h.b0, h.b1, h.b2, i2f(prim));
+        const unsigned matWord = f2u(ldg(&sc.tris[3 * t.prim + 2].y));
+        ps.hit[slot] = make_float4(t.h.b0, t.h.b1, t.h.b2, i2f(t.prim));
         return shade_type_of(matWord);
     }
     if (emitOk && sc.env.present) {
         // for (light : scene.infiniteLights) L += beta * light->Le(ray)
-        const float4 b = ps.beta[slot];
+        const float4 b = ps.beta[slot], rd = ps.ray_d[slot];
         float4 L = ps.L[slot];
-        V3 add = V3(b.x, b.y, b.z) * env_Le(sc.env, d);
+        V3 add = V3(b.x, b.y, b.z) * env_Le(sc.env, V3(rd.x, rd.y, rd.z));
         L.x += add.x; L.y += add.y; L.z += add.z;
         ps.L[slot] = L;
     }
     return -1;
+}
+GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, int2 *stack, int stride,
+                      TraversalCounters &cnt) {
+    Trav t;
+    extend_begin(sc, ps, slot, t);
+    while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
+    return extend_finish(sc, ps, rc, slot, t);
 }
 
 // Surfaces without a material are medium boundaries: PathIntegrator re-spawns the ray in the same
@@ -261,36 +267,49 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
     ps.meta[slot] = (uint32_t)(smp.dim & 0xffff) | ((uint32_t)(bounces + 1) << 16) | ((spec ? kFlagSpecular : 0u) << 24);
 }
 
-GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int *stack, int stride,
-                       TraversalCounters &cnt) {
+// Shadow / MIS-escape item (any-hit): the contribution is added when nothing is hit.
+GNX_D void shadow_begin(const DeviceScene &sc, const ShadowItem *item, Trav &t) {
     const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path);
-    int prim;
-    TriHit h;
-    const bool hit = traverse<true>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w, stack, stride, &prim, &h, cnt);
-    if (!hit) {
-        const float4 c = ldg(&item->contrib);
-        const int slot = f2i(d4.w);
-        float4 L = ps.L[slot];
-        L.x += c.x; L.y += c.y; L.z += c.z;
-        ps.L[slot] = L;
-    }
+    trav_init(sc, t, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w);
+}
+GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav &t) {
+    if (t.hit) return;
+    const float4 c = ldg(&item->contrib);
+    const int slot = f2i(ldg(&item->d_path).w);
+    float4 L = ps.L[slot];
+    L.x += c.x; L.y += c.y; L.z += c.z;
+    ps.L[slot] = L;
+}
+GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int2 *stack, int stride,
+                       TraversalCounters &cnt) {
+    Trav t;
+    shadow_begin(sc, item, t);
+    while (!trav_step<true>(sc, t, stack, stride, cnt)) {}
+    shadow_finish(ps, item, t);
 }
 
-GNX_D void probe_item(const DeviceScene &sc, const PathState &ps, const ProbeItem *item, int *stack, int stride,
+// Area-light MIS probe (closest hit): counted only if the closest hit is the sampled light's triangle.
+GNX_D void probe_begin(const DeviceScene &sc, const ProbeItem *item, Trav &t) {
+    const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path);
+    trav_init(sc, t, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w);
+}
+GNX_D void probe_finish(const PathState &ps, const ProbeItem *item, const Trav &t) {
+    const float4 c = ldg(&item->contrib_expect);
+    if (!(t.hit && t.prim == f2i(c.w))) return;
+    const int slot = f2i(ldg(&item->d_path).w);
+    float4 L = ps.L[slot];
+    L.x += c.x; L.y += c.y; L.z += c.z;
+    ps.L[slot] = L;
+}
+GNX_D void probe_item(const DeviceScene &sc, const PathState &ps, const ProbeItem *item, int2 *stack, int stride,
                       TraversalCounters &cnt) {
-    const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path), c = ldg(&item->contrib_expect);
-    int prim = -1;
-    TriHit h;
-    const bool hit = traverse<false>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w, stack, stride, &prim, &h, cnt);
-    if (hit && prim == f2i(c.w)) {
-        const int slot = f2i(d4.w);
-        float4 L = ps.L[slot];
-        L.x += c.x; L.y += c.y; L.z += c.z;
-        ps.L[slot] = L;
-    }
+    Trav t;
+    probe_begin(sc, item, t);
+    while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
+    probe_finish(ps, item, t);
 }
 
-GNX_D int primary_hit_id(const DeviceScene &sc, int px, int py, int sample, int *stack, int stride) {
+GNX_D int primary_hit_id(const DeviceScene &sc, int px, int py, int sample, int2 *stack, int stride) {
     uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
     V3 o, d;
     float tMax;

@@ -23,6 +23,7 @@ struct gnx_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    int grid_trace = 148 * 8, grid_shade = 148 * 4;  // SM count x resident blocks (occupancy query at create)
     // scene
     bool has_scene = false;
     DeviceScene sc{};
@@ -132,6 +133,11 @@ int gnx_create(gnx_ctx **out, int device) {
         delete ctx;
         return GNX_ERR_CUDA;
     }
+    {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
+    }
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
@@ -170,12 +176,18 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         if (d->materials[i].type < 0 || d->materials[i].type > GNX_MAT_DISNEY)
             return fail(ctx, GNX_ERR_INVALID, "unknown material type");
 
-    // ---- nodes: bit-identical copy (two float4 per node)
+    // ---- nodes: the reference's 32-byte LinearBVHNode array re-packed into 64-byte two-child records
     static_assert(sizeof(gnx_bvh_node) == 32, "node size");
     int rc;
-    gnx_bvh_node *dn;
-    if ((rc = dupload(ctx, pool, g.nodes, (size_t)g.n_nodes, &dn))) return rc;
-    sc.nodes = (const float4 *)dn;
+    {
+        std::vector<float4> n2;
+        std::string perr;
+        if (!build_node2(g.nodes, g.n_nodes, n2, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        float4 *dn;
+        if ((rc = dupload(ctx, pool, n2.data(), n2.size(), &dn))) return rc;
+        sc.nodes2 = dn;
+        sc.n_nodes2 = (int)(n2.size() / 4);
+    }
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
 
@@ -434,14 +446,27 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
     if ((rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
     const int npix = p->width * p->height;
-    int batch_spp = p->batch_spp > 0 ? p->batch_spp : std::max(1, (4 << 20) / npix);
+    // Paths in flight per wavefront batch.  Late bounces carry few rays and every launch has a tail, so
+    // the batch is made as large as memory comfortably allows (profiles/README.md: 4 M -> 64 M slots took
+    // C2 from 126 ms to 71 ms): up to 64 M slots, and never more than a quarter of the free HBM.
+    int batch_spp = p->batch_spp;
+    if (batch_spp <= 0) {
+        size_t freeB = 0, totalB = 0;
+        long long slots = 64ll << 20;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const long long bytesPerSlot = 288;  // PathState 92 B + queues 180 B, rounded up
+            long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
+            slots = std::max(1ll << 20, std::min(slots, avail));
+        }
+        batch_spp = (int)std::max(1ll, slots / npix);
+    }
     batch_spp = std::min(batch_spp, p->spp);
     if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / npix));
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix))) return rc;
 
     cudaStream_t st = userStream ? userStream : ctx->stream;
     const DeviceScene &sc = ctx->sc;
-    const int gridTrace = ctx->sm_count * 8, gridShade = ctx->sm_count * 8, gridWide = ctx->sm_count * 16;
+    const int gridTrace = ctx->grid_trace, gridShade = ctx->grid_shade, gridWide = ctx->sm_count * 16;
     const bool hasNull = (ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u;
     unsigned long long launches = 0;
 
@@ -475,7 +500,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             const int out = 1 - in;
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
             tm.begin(ST_EXTEND);
-            k_extend<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
+            k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
             ++extendLaunches;
@@ -490,10 +515,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             tm.end();
             tm.begin(ST_SHADOW);
             if (sc.n_lights > 0) {
-                k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 0, ctx->d_stats);
+                k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats);
                 ++launches;
-                if (sc.env.present) { k_shadow<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, 1, ctx->d_stats); ++launches; }
-                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_probe<<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, ctx->d_stats); ++launches; }
+                if (sc.env.present) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
+                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats); ++launches; }
             }
             tm.end();
             in = out;
@@ -577,7 +602,7 @@ int gnx_primary_hits(gnx_ctx *ctx, const gnx_render_params *p, int32_t sample, i
     const int npix = p->width * p->height;
     int *d = nullptr;
     GNX_CUDA(ctx, cudaMalloc((void **)&d, (size_t)npix * sizeof(int)));
-    k_primary_hits<<<ctx->sm_count * 8, kBlock, 0, ctx->stream>>>(ctx->sc, p->width, p->height, sample, d);
+    k_primary_hits<<<ctx->sm_count * 4, kBlock, 0, ctx->stream>>>(ctx->sc, p->width, p->height, sample, d);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(prim_id_out, d, (size_t)npix * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

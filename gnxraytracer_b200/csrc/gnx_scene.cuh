@@ -57,9 +57,10 @@ struct DevMedium {
 };
 
 struct DeviceScene {
-    // geometry: two float4 per node; three float4 per ordered primitive:
-    //   a = (p0.x p0.y p0.z p1.x)  b = (p1.y p1.z p2.x p2.y)  c = (p2.z, bits(material | flags<<24), bits(light), bits(prim_id))
-    const float4 *nodes;
+    // geometry: four float4 per interior node (gnx_bvh.cuh "Node2"); three float4 per ordered primitive:
+    //   a = (p0.x p0.y p0.z p1.x)  b = (p1.y p1.z p2.x p2.y)  c = (p2.z, bits(material | type<<20 | flags<<24), bits(light), bits(prim_id))
+    const float4 *nodes2;
+    int n_nodes2;
     const float4 *tris;
     const float *tri_uv;          // [n][6] or null
     const float *tri_n;           // [n][9] or null
@@ -115,8 +116,10 @@ struct Queues {
     int capacity;
 };
 constexpr int kNumShadeTypes = 7;  // 6 gnx_material_type + "no material" (medium boundary)
+// queue counters: extend ping/pong, one per shade type, shadow A (light samples), shadow B (environment MIS
+// probes), probe (area-light MIS probes); then the dynamic-fetch cursors of the four traversal launches
 constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCntShade0 + kNumShadeTypes,
-              kCntProbe = kCntShadow + 1, kNumCounters = kCntProbe + 1;
+              kCntProbe = kCntShadow + 2, kCntFetch = kCntProbe + 1, kNumCounters = kCntFetch + 4;
 
 struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
     unsigned long long rays[3], nodes[3], tris[3], paths;

@@ -21,7 +21,7 @@ namespace {
 
 struct EmulScene {
     DeviceScene sc{};
-    std::vector<float4> tris;
+    std::vector<float4> tris, nodes2;
     std::vector<int2> media;
     std::vector<DevTexture> textures;
     std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int;
@@ -35,7 +35,9 @@ struct EmulScene {
 bool build(const gnx_scene_desc *d, EmulScene &e) {
     DeviceScene &sc = e.sc;
     const gnx_geometry &g = d->geom;
-    sc.nodes = (const float4 *)g.nodes;
+    if (!build_node2(g.nodes, g.n_nodes, e.nodes2, &e.err)) return false;
+    sc.nodes2 = e.nodes2.data();
+    sc.n_nodes2 = (int)(e.nodes2.size() / 4);
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
     if (!pack_triangles(*d, e.tris, &e.typeMask, &e.err)) return false;
@@ -132,7 +134,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
     L = make_float4(0, 0, 0, 0);
     hidx = (uint32_t)hi;
     meta = 5u;
-    int stack[kSmemStack];
+    int2 stack[kSmemStack];
     for (int iter = 0; iter < 100000; ++iter) {
         ++rays[0];
         int type = extend_slot(sc, ps, rc, 0, stack, 1, cnt);
@@ -205,7 +207,7 @@ int gnxe_primary_hits(void *h, int width, int height, int sample, int *out) {
     auto *e = (EmulScene *)h;
 #pragma omp parallel for schedule(dynamic, 256)
     for (int pixel = 0; pixel < width * height; ++pixel) {
-        int stack[kSmemStack];
+        int2 stack[kSmemStack];
         out[pixel] = primary_hit_id(e->sc, pixel % width, pixel / width, sample, stack, 1);
     }
     return 0;

@@ -65,7 +65,8 @@ def test_bridge_render_matches_reference(ref, preset, res, spp):
     mean_gpu = img.reshape(-1, 4)[sel, :3]
     mean_ref = img_ref.reshape(-1, 4)[sel, :3]
     assert np.mean(np.abs(mean_gpu - mean_ref) <= 3 * sigma) >= 0.999
-    assert np.all(img[..., 3] == 1.0)
+    # FrameBuffer's float alpha is never written by Render (only the 8-bit one, core/Integrator.cpp:310)
+    assert np.array_equal(img[..., 3], img_ref[..., 3])
     rs.close()
 
 
