@@ -167,13 +167,26 @@ GNX_D bool slab_test(const Trav &t, float lox, float loy, float loz, float hix, 
     return (tmin < t.tMax) && (tmax > 0);
 }
 
-// One traversal step: tests both children of the current interior node, intersects whatever leaves come
-// next in the reference's visiting order, and stops at the next interior node.  Returns true when the
-// traversal is finished (t.hit / t.h / t.prim hold the result).  `stack` is the calling thread's column of
-// a shared-memory stack (entry k at stack[k * stride]); deeper levels spill into t.spill.
-template <bool ANY>
-GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
-    if (t.cur == kRefNone) return true;
+// The traversal is split the "while-while" way so that the lanes of a warp do the same kind of work at
+// the same time: trav_interior handles one interior node (two slab tests, push far, go near),
+// trav_leaf intersects one leaf and pops.  t.cur is an interior index (0 <= cur < kRefNone), a leaf
+// reference (negative) or kRefNone when the traversal is over.  `stack` is the calling thread's column
+// of a shared-memory stack (entry k at stack[k * stride]); deeper levels spill into t.spill.
+GNX_D bool trav_is_interior(const Trav &t) { return (unsigned)t.cur < (unsigned)kRefNone; }
+GNX_D bool trav_is_leaf(const Trav &t) { return t.cur < 0; }
+GNX_D bool trav_done(const Trav &t) { return t.cur == kRefNone; }
+
+// pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax)
+GNX_D void trav_pop(Trav &t, const int2 *stack, int stride) {
+    while (true) {
+        if (t.sp == 0) { t.cur = kRefNone; return; }
+        --t.sp;
+        const int2 e = t.sp < kSmemStack ? stack[t.sp * stride] : t.spill[t.sp - kSmemStack];
+        if (i2f(e.y) < t.tMax) { t.cur = e.x; return; }
+    }
+}
+
+GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
     const float4 *np = sc.nodes2 + 4 * (size_t)t.cur;
     const float4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3);
     const int ref0 = f2i(n3.x), ref1 = f2i(n3.y), axis = f2i(n3.z);
@@ -182,49 +195,48 @@ GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, Tr
     if (ref0 != kRefNone) { ++cnt.nodes; hit0 = slab_test(t, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, &tmin0); }
     if (ref1 != kRefNone) { ++cnt.nodes; hit1 = slab_test(t, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, &tmin1); }
     const bool nearIs1 = axis < 3 && ((t.neg >> axis) & 1);
-    int refN = nearIs1 ? ref1 : ref0, refF = nearIs1 ? ref0 : ref1;
-    bool hitN = nearIs1 ? hit1 : hit0, hitF = nearIs1 ? hit0 : hit1;
-    const float tminF = nearIs1 ? tmin0 : tmin1;
-    int next;
+    const int refN = nearIs1 ? ref1 : ref0, refF = nearIs1 ? ref0 : ref1;
+    const bool hitN = nearIs1 ? hit1 : hit0, hitF = nearIs1 ? hit0 : hit1;
     if (hitN) {
-        next = refN;
+        t.cur = refN;
         if (hitF) {
-            const int2 e = make_int2(refF, f2i(tminF));
+            const int2 e = make_int2(refF, f2i(nearIs1 ? tmin0 : tmin1));
             if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
             ++t.sp;
         }
     } else if (hitF) {
-        next = refF;
+        t.cur = refF;
     } else {
-        next = kRefNone;
+        trav_pop(t, stack, stride);
     }
-    while (true) {
-        if (next == kRefNone) {
-            // pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax)
-            while (true) {
-                if (t.sp == 0) { t.cur = kRefNone; return true; }
-                --t.sp;
-                const int2 e = t.sp < kSmemStack ? stack[t.sp * stride] : t.spill[t.sp - kSmemStack];
-                if (i2f(e.y) < t.tMax) { next = e.x; break; }
-            }
+}
+
+template <bool ANY>
+GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stride, TraversalCounters &cnt) {
+    const int x = ~t.cur, offset = x & 0x7ffffff, count = (x >> 27) + 1;
+    for (int i = 0; i < count; ++i) {
+        const int prim = offset + i;
+        const TriVerts tv = load_tri(sc.tris, prim);
+        ++cnt.tris;
+        TriHit h;
+        if (intersect_tri(tv, t.o, t.rs, t.tMax, &h) && !tri_degenerate(tv)) {
+            t.hit = true;
+            t.tMax = h.t;
+            t.h = h;
+            t.prim = prim;
+            if (ANY) { t.cur = kRefNone; return; }
         }
-        if (next >= 0) { t.cur = next; return false; }
-        const int x = ~next, offset = x & 0x7ffffff, count = (x >> 27) + 1;
-        for (int i = 0; i < count; ++i) {
-            const int prim = offset + i;
-            const TriVerts tv = load_tri(sc.tris, prim);
-            ++cnt.tris;
-            TriHit h;
-            if (intersect_tri(tv, t.o, t.rs, t.tMax, &h) && !tri_degenerate(tv)) {
-                t.hit = true;
-                t.tMax = h.t;
-                t.h = h;
-                t.prim = prim;
-                if (ANY) { t.cur = kRefNone; return true; }
-            }
-        }
-        next = kRefNone;
     }
+    trav_pop(t, stack, stride);
+}
+
+// One step for sequential callers: an interior node and whatever leaves follow it.  Returns true when
+// the traversal is finished (t.hit / t.h / t.prim hold the result).
+template <bool ANY>
+GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
+    if (trav_is_interior(t)) trav_interior(sc, t, stack, stride, cnt);
+    while (trav_is_leaf(t)) trav_leaf<ANY>(sc, t, stack, stride, cnt);
+    return trav_done(t);
 }
 
 // Whole traversal in one call (parity hooks, light-table build, CPU emulation).

@@ -2,7 +2,7 @@
 // walks its input queue with a block-uniform grid-stride loop so that every lane of a warp reaches
 // the warp-aggregated queue pushes (__ballot_sync + one atomicAdd per warp and queue).
 //
-//   k_raygen -> k_trace<0> -> k_shade<type> ... -> k_trace<1> x2, k_trace<2> -> (next bounce) ... -> k_accumulate -> k_film
+//   k_trace<3> (ray-gen + first extension) -> k_shade<type> ... -> k_trace<1> x2, k_trace<2> -> k_trace<0> -> k_shade ... -> k_trace<1> x2, k_trace<2> -> (next bounce) ... -> k_accumulate -> k_film
 //
 // Grids are sized from the occupancy query: SM count (148 on B200) x resident blocks per SM, so a
 // persistent kernel never has a partial second wave.  The traversal kernel keeps its stacks in shared
@@ -40,18 +40,6 @@ __device__ __forceinline__ void flush_stats(DevStats *st, int kind, unsigned nod
     }
 }
 
-__global__ void __launch_bounds__(256) k_raygen(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
-    const int n = rc.npix * rc.batch_spp;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-        raygen_slot(sc, ps, rc, slot);
-        q.extend_q[0][slot] = slot;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.counts[kCntExtend0] = n;
-        atomicAdd(&st->paths, (unsigned long long)n);
-    }
-}
-
 // Zeroes every queue counter except the extend queue that is about to be consumed.
 __global__ void k_reset_counts(int *counts, int outExtend) {
     int i = threadIdx.x;
@@ -59,14 +47,18 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
 }
 
 // ---- the traversal kernel --------------------------------------------------------------------------------
-// Persistent threads with dynamic ray fetch (Aila & Laine's while-while scheme): one block column of the
-// grid stays resident per SM slot; every lane owns at most one ray; lanes whose ray has finished pull the
-// next unprocessed queue entry through a warp-aggregated atomic on a global cursor as soon as fewer than
-// kRefetchBelow lanes of the warp are still traversing.  This replaces a static ray-per-thread mapping
-// whose SIMD efficiency profiled at 5-11 active lanes of 32 (profiles/r01_extend_static.txt).
+// Persistent threads with dynamic ray fetch (Aila & Laine's while-while scheme): the grid is exactly the
+// number of resident blocks; every lane owns at most one ray; lanes whose ray has finished pull the next
+// unprocessed queue entry through a warp-aggregated atomic on a global cursor as soon as fewer than
+// kRefetchBelow lanes of the warp are still traversing.  Inside, lanes first all descend interior nodes
+// (two slab tests per 64-byte fetch), then all intersect their pending leaf, so a warp executes one
+// kind of work at a time.  This replaced a static ray-per-thread mapping whose SIMD efficiency profiled
+// at 5-11 active lanes of 32 (profiles/r01_extend_static.txt).
 //   KIND 0: extension rays of the path slots in extend_q[arg]   -> hit record, env radiance, shade queues
 //   KIND 1: shadow_q half `arg` (any-hit)                        -> L += contrib when unoccluded
 //   KIND 2: probe_q (closest hit must be the light's triangle)   -> L += contrib
+//   KIND 3: camera rays of the batch, generated in registers (ray-gen fused with the first extension;
+//           path state is written only for rays that hit)      -> L = Le or hit record + shade queues
 constexpr int kRefetchBelow = 24;
 
 template <int KIND>
@@ -75,8 +67,10 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int n = KIND == 0 ? q.counts[arg] : (KIND == 1 ? q.counts[kCntShadow + arg] : q.counts[kCntProbe]);
-    int *cursor = &q.counts[kCntFetch + (KIND == 0 ? 0 : (KIND == 1 ? 1 + arg : 3))];
+    const bool kExtend = KIND == 0 || KIND == 3;
+    const int n = KIND == 3 ? rc.npix * rc.batch_spp
+                            : (KIND == 0 ? q.counts[arg] : (KIND == 1 ? q.counts[kCntShadow + arg] : q.counts[kCntProbe]));
+    int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? 1 + arg : 3))];
     const int *inList = KIND == 0 ? q.extend_q[arg] : nullptr;
     const ShadowItem *shadowItems = q.shadow_q + (size_t)(KIND == 1 ? arg : 0) * q.capacity;
     TraversalCounters cnt{0, 0};
@@ -84,13 +78,14 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
     Trav t;
     t.cur = kRefNone;
     bool active = false, exhausted = false;
-    int item = 0;            // slot (KIND 0) or queue index (KIND 1, 2) of the lane's ray
+    int item = 0;            // path slot (KIND 0, 3) or queue index (KIND 1, 2) of the lane's ray
     int pendType = -1, pendSlot = 0;
+    uint32_t hidx = 0;       // KIND 3 only
+    V3 camD;                 // KIND 3 only
     while (true) {
-        if (KIND == 0) {
+        if (kExtend) {
             // shade-queue pushes of the rays that finished since the last visit, one atomic per warp and queue
-            const unsigned any = __ballot_sync(kFull, pendType >= 0);
-            if (any) {
+            if (__any_sync(kFull, pendType >= 0)) {
 #pragma unroll
                 for (int ty = 0; ty < kNumShadeTypes; ++ty) {
                     int idx = warp_push(&q.counts[kCntShade0 + ty], pendType == ty);
@@ -109,7 +104,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
                 if (!active) {
                     const int i = base + __popc(idle & ((1u << lane) - 1));
                     if (i < n) {
-                        if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
+                        if (KIND == 3) {
+                            item = i;
+                            const int pixel = i % rc.npix;
+                            primary_begin(sc, pixel % rc.width, pixel / rc.width, rc.first_sample + i / rc.npix, &hidx, &camD, t);
+                        } else if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
                         else if (KIND == 1) { item = i; shadow_begin(sc, shadowItems + i, t); }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
                         active = true;
@@ -121,8 +120,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
         }
         if (!__any_sync(kFull, active)) break;
         while (active) {
+            // one interior node plus the (rare: ~1 leaf per 25 nodes) leaves that follow it.  A strict
+            // while-while split (all lanes descend until each holds a leaf) measured 15-35 % slower here.
             if (trav_step<KIND == 1>(sc, t, stack, kBlock, cnt)) {
-                if (KIND == 0) { pendType = extend_finish(sc, ps, rc, item, t); pendSlot = item; }
+                if (KIND == 3) { pendType = primary_finish(sc, ps, rc, item, hidx, camD, t); pendSlot = item; }
+                else if (KIND == 0) { pendType = extend_finish(sc, ps, rc, item, t); pendSlot = item; }
                 else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
                 else probe_finish(ps, q.probe_q + item, t);
                 active = false;
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
         }
         __syncwarp();
     }
-    flush_stats(st, KIND == 0 ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);
+    flush_stats(st, kExtend ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);
+    if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
 
 __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,

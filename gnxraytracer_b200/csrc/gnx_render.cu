@@ -488,11 +488,6 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         rcn.batch_spp = std::min(batch_spp, p->spp - done);
         rcn.first_sample = p->first_sample + done;
         rcn.capacity = ctx->capacity;
-        tm.begin(ST_RAYGEN);
-        k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
-        k_raygen<<<gridWide, 256, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
-        tm.end();
-        launches += 2;
         int in = 0;
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.
@@ -500,7 +495,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             const int out = 1 - in;
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
             tm.begin(ST_EXTEND);
-            k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
+            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats);  // ray-gen fused in
+            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
             ++extendLaunches;

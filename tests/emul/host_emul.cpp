@@ -123,22 +123,15 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
     rc.max_depth = p.max_depth;
     rc.rr_threshold = p.rr_threshold;
     rc.batch_spp = 1;
-    // raygen_slot derives (pixel, sample) from the slot number; do its work by hand for one pixel
-    uint64_t hi = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
-    V3 o, d;
-    float tMax;
-    camera_ray(sc, px, py, hi, &o, &d, &tMax);
-    ray_o = make_float4(o.x, o.y, o.z, tMax);
-    ray_d = make_float4(d.x, d.y, d.z, 1.f);
-    beta = make_float4(1, 1, 1, 0);
-    L = make_float4(0, 0, 0, 0);
-    hidx = (uint32_t)hi;
-    meta = 5u;
     int2 stack[kSmemStack];
-    for (int iter = 0; iter < 100000; ++iter) {
-        ++rays[0];
-        int type = extend_slot(sc, ps, rc, 0, stack, 1, cnt);
-        if (type < 0) break;
+    // camera ray: generated and traversed in registers, like the fused primary kernel
+    Trav t;
+    V3 d;
+    primary_begin(sc, px, py, sample, &hidx, &d, t);
+    ++rays[0];
+    while (!trav_step<false>(sc, t, stack, 1, cnt)) {}
+    int type = primary_finish(sc, ps, rc, 0, hidx, d, t);
+    for (int iter = 0; iter < 100000 && type >= 0; ++iter) {
         ShadeOut out;
         out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
         if (type == kNumShadeTypes - 1) out.alive = shade_null_slot(sc, ps, rc, 0);
@@ -148,6 +141,8 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         if (out.haveShadowB) { ++rays[2]; shadow_item(sc, ps, &out.shB, stack, 1, cnt); }
         if (out.haveProbe) { ++rays[2]; probe_item(sc, ps, &out.pr, stack, 1, cnt); }
         if (!out.alive) break;
+        ++rays[0];
+        type = extend_slot(sc, ps, rc, 0, stack, 1, cnt);
     }
     return V3(L.x, L.y, L.z);
 }
