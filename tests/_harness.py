@@ -189,3 +189,63 @@ def rel_mse(img, ref_img):
     """Relative MSE as used for renderer comparisons: mean((a-b)^2 / (b^2 + eps)) over RGB."""
     a, b = img[..., :3].astype(np.float64), ref_img[..., :3].astype(np.float64)
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+# ---- oracle/restate: independent plain-C++ restatement of the path (oracle/_build/libgnxrestate.so) ----
+RESTATE_LIB = os.path.join(ROOT, "oracle", "_build", "libgnxrestate.so")
+
+
+class RestateScene:
+    def __init__(self, lib, desc):
+        self.lib, self.h = lib, lib.gnxr_create(desc)
+
+    def render(self, params):
+        out = np.zeros((params.height, params.width, 4), np.float32)
+        counts = np.zeros(5, np.uint64)
+        rc = self.lib.gnxr_render(self.h, ctypes.byref(params), out.ctypes.data, counts.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"restatement does not cover this scene (rc={rc})")
+        return out, dict(zip(["rays_extend", "rays_shadow", "rays_mis", "nodes_visited", "tris_tested"], (int(c) for c in counts)))
+
+    def samples(self, params, px, py, sample):
+        rgb = np.zeros((px.size, 3), np.float32)
+        rc = self.lib.gnxr_samples(self.h, ctypes.byref(params), px.size, px.ctypes.data, py.ctypes.data, sample.ctypes.data, rgb.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"restatement does not cover this scene (rc={rc})")
+        return rgb
+
+    def primary_hits(self, width, height, sample=0):
+        out = np.zeros(width * height, np.int32)
+        self.lib.gnxr_primary_hits(self.h, width, height, sample, out.ctypes.data)
+        return out
+
+    def sample_dims(self, index, dim):
+        out = np.zeros(index.size, np.float32)
+        self.lib.gnxr_sample_dims(self.h, index.size, index.ctypes.data, dim.ctypes.data, out.ctypes.data)
+        return out
+
+    def sample_index(self, x, y, s):
+        return self.lib.gnxr_sample_index(self.h, int(x), int(y), int(s))
+
+    def close(self):
+        if self.h:
+            self.lib.gnxr_destroy(self.h)
+            self.h = None
+
+
+class Restate:
+    def __init__(self):
+        l = ctypes.CDLL(RESTATE_LIB)
+        l.gnxr_create.restype = vp
+        l.gnxr_create.argtypes = [vp]
+        l.gnxr_destroy.argtypes = [vp]
+        l.gnxr_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, vp]
+        l.gnxr_samples.argtypes = [vp, ctypes.POINTER(RenderParams), ci, vp, vp, vp, vp]
+        l.gnxr_primary_hits.argtypes = [vp, ci, ci, ci, vp]
+        l.gnxr_sample_dims.argtypes = [vp, ci, vp, vp, vp]
+        l.gnxr_sample_index.restype = ctypes.c_int64
+        l.gnxr_sample_index.argtypes = [vp, ci, ci, ci]
+        self.lib = l
+
+    def scene(self, desc):
+        return RestateScene(self.lib, desc)

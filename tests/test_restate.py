@@ -1,0 +1,77 @@
+"""Pins the independent CPU restatement (oracle/restate/gnx_restate.cpp): against the unmodified
+reference where oracle/_ref was built, and against the committed golden vectors everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+import _harness
+from _harness import grid, rel_mse
+from gnxraytracer_b200.api import RenderParams, SceneKit
+from gnxraytracer_b200.build import build_oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def restate():
+    if not os.path.exists(_harness.RESTATE_LIB):
+        build_oracle()
+    return _harness.Restate()
+
+
+def test_restate_halton_matches_golden_bit_exact(restate):
+    g = np.load(os.path.join(G, "halton_values.npz"))
+    sk = SceneKit("cornell", 96, 96, 4, 0, 2, 0)
+    rs = restate.scene(sk.desc)
+    v = rs.sample_dims(g["index"], g["dim"])
+    assert np.array_equal(v.view(np.uint32), g["value"].view(np.uint32))
+    for x, y, s, want in g["pixel_index"]:
+        assert rs.sample_index(x, y, s) == want
+    rs.close(); sk.close()
+
+
+@pytest.mark.parametrize("name,args", [("cornell", (0, 2, 0)), ("dragon", (0, 256, 32))])
+def test_restate_matches_golden_images(restate, name, args):
+    g = np.load(os.path.join(G, f"{name}_96x96_4spp.npz"))
+    sk = SceneKit(name, 96, 96, 4, *args)
+    rs = restate.scene(sk.desc)
+    assert np.mean(rs.primary_hits(96, 96, 0) == g["primary_hit"]) >= 0.999  # scene-kit camera: ulp-level ray differences
+    img, counts = rs.render(RenderParams.make(96, 96, 4, max_depth=5))
+    assert rel_mse(img, g["image"]) <= 1e-3
+    assert counts["rays_extend"] >= 96 * 96 * 4
+    rs.close(); sk.close()
+
+
+@pytest.mark.parametrize("preset,res", [("cornell", 64), ("cornell_on", 48), ("dragon", 96), ("dragon_metal", 64)])
+def test_restate_matches_live_reference(ref, restate, preset, res):
+    r = ref.scene(preset, res, res, 4)
+    rs = restate.scene(r.desc)
+    px, py = grid(res, res)
+    p = RenderParams.make(res, res, 4, max_depth=5)
+    for s in (0, 2):
+        sm = np.full(px.size, s, np.int32)
+        rgb, prim = r.reference_samples(px, py, sm)
+        assert np.array_equal(r.to_original(rs.primary_hits(res, res, s)), prim)
+        mine = rs.samples(p, px, py, sm)
+        scale = np.maximum(np.abs(rgb).max(axis=1), 1e-3)
+        rel = np.abs(mine - rgb).max(axis=1) / scale
+        assert np.mean(rel < 1e-5) >= 0.999, np.mean(rel < 1e-5)
+    r.close(); rs.close()
+
+
+def test_restate_and_emulated_kernels_agree_on_counters(ref, restate, emul):
+    """BVH nodes visited / triangles tested by the kernels' traversal must agree with the
+    reference-order traversal to < 1 %."""
+    r = ref.scene("cornell", 48, 48, 4)
+    p = RenderParams.make(48, 48, 4, max_depth=5)
+    a, ca = restate.scene(r.desc).render(p)
+    b, sb = emul.scene(r.desc).render(p)
+    assert rel_mse(b, a) <= 1e-6
+    assert ca["rays_extend"] == sb.rays_extend and ca["rays_shadow"] == sb.rays_shadow
+    assert ca["tris_tested"] == sb.tris_tested
+    # the two-child layout tests a node's box at its parent, so every box test of the reference order has
+    # its counterpart except the root's own (one per ray)
+    rays = int(sb.rays_extend + sb.rays_shadow + sb.rays_mis)
+    assert abs(ca["nodes_visited"] - (int(sb.nodes_visited) + rays)) <= 0.01 * ca["nodes_visited"]
+    r.close()
