@@ -31,6 +31,8 @@ WORKLOADS = {
     # name: (scene, p0, p1, p2, width, height, spp, max_depth, description)
     "c2": ("dragon", 0, 0, 0, 1024, 1024, 64, 5,
            "C2: dragon-class mesh 872448 tris (torus-knot stand-in for dragon.3d), Plastic, InfiniteAreaLight MonValley1000.hdr, 1024x1024, 64 spp, maxDepth 5, PathIntegrator+Halton"),
+    "c3": ("nano", 0, 0, 0, 1920, 1080, 128, 5,
+           "C3: UV-mapped smooth-shaded mesh (~90k tris, stand-in for nanosuit), DisneyMaterial + ImageTexture, InfiniteAreaLight TropicalRuins1000.hdr, 1920x1080, 128 spp, maxDepth 5"),
     "c1": ("cornell", 0, 3, 0, 512, 512, 16, 5,
            "C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
 }

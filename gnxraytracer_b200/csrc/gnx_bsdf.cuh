@@ -132,7 +132,7 @@ GNX_D V3 fr_schlick3(V3 R0, float cosTheta) {
     float w = schlick_weight(cosTheta);
     return (1 - w) * R0 + w * V3(1.f);
 }
-GNX_D float schlick_r0_from_eta(float eta) { float s = (eta - 1) / (eta + 1); return s * s; }
+GNX_D float schlick_r0_from_eta(float eta) { return ((eta - 1) * (eta - 1)) / ((eta + 1) * (eta + 1)); }
 
 GNX_D V3 lobe_fresnel(const Lobe &l, float cosI) {
     switch (l.fresnel) {

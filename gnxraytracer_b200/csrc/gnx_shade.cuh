@@ -214,6 +214,78 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
         }
         break;
     }
+    case GNX_MAT_DISNEY: {  // materials/DisneyMaterial.cpp:467-581
+        const V3 c = clamp0(eval_rgb(sc, m, 0, s));
+        const float metallicWeight = eval_f(sc, m, 0, s), e = eval_f(sc, m, 1, s), strans = eval_f(sc, m, 9, s);
+        const float diffuseWeight = (1 - metallicWeight) * (1 - strans);
+        const float dt = eval_f(sc, m, 11, s) / 2;
+        const float rough = eval_f(sc, m, 2, s);
+        const float lum = lum_y(c);
+        const V3 Ctint = lum > 0 ? div_each(c, lum) : V3(1.f);
+        const float sheenWeight = eval_f(sc, m, 5, s);
+        V3 Csheen(0.f);
+        if (sheenWeight > 0) { float stint = eval_f(sc, m, 6, s); Csheen = (1 - stint) * V3(1.f) + stint * Ctint; }
+        const bool thin = (m.flags & GNX_MATF_THIN) != 0;
+        if (diffuseWeight > 0) {
+            if (thin) {
+                float flat = eval_f(sc, m, 10, s);
+                b.add(make_lobe(LK_DISNEY_DIFFUSE, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * (1 - flat) * (1 - dt)) * c));
+                Lobe l = make_lobe(LK_DISNEY_FAKESS, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * flat * (1 - dt)) * c);
+                l.p0 = rough;
+                b.add(l);
+            } else {
+                V3 sd = eval_rgb(sc, m, 1, s);
+                if (is_black(sd)) b.add(make_lobe(LK_DISNEY_DIFFUSE, BSDF_REFLECTION | BSDF_DIFFUSE, diffuseWeight * c));
+                else {
+                    // the BSSRDF itself is compiled out of both integrators (PathIntegrator.cpp:165-192); the
+                    // SpecularTransmission lobe that goes with it is still added
+                    Lobe l = make_lobe(LK_SPEC_T, BSDF_TRANSMISSION | BSDF_SPECULAR, V3(1.f));
+                    l.e0 = 1.f; l.e1 = e;
+                    b.add(l);
+                }
+            }
+            Lobe r = make_lobe(LK_DISNEY_RETRO, BSDF_REFLECTION | BSDF_DIFFUSE, diffuseWeight * c);
+            r.p0 = rough;
+            b.add(r);
+            if (sheenWeight > 0) b.add(make_lobe(LK_DISNEY_SHEEN, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * sheenWeight) * Csheen));
+        }
+        const float aspect = (float)sqrt(1 - eval_f(sc, m, 4, s) * .9);
+        const float ax = fmaxf(.001f, (rough * rough) / aspect), ay = fmaxf(.001f, (rough * rough) * aspect);
+        const float specTint = eval_f(sc, m, 3, s);
+        const float r0 = ((e - 1) * (e - 1)) / ((e + 1) * (e + 1));  // SchlickR0FromEta
+        const V3 tintMix = (1 - specTint) * V3(1.f) + specTint * Ctint;
+        const V3 Cspec0 = (1 - metallicWeight) * (r0 * tintMix) + metallicWeight * c;
+        {
+            Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, V3(1.f));
+            l.fresnel = FR_DISNEY; l.distrib = DK_DISNEY;
+            l.a = Cspec0; l.e0 = metallicWeight; l.e1 = e;
+            l.p0 = clamp_alpha(ax); l.p1 = clamp_alpha(ay);
+            b.add(l);
+        }
+        const float cc = eval_f(sc, m, 7, s);
+        if (cc > 0) {
+            Lobe l = make_lobe(LK_DISNEY_CLEARCOAT, BSDF_REFLECTION | BSDF_GLOSSY, V3(0.f));
+            l.p0 = cc;
+            l.p1 = lerpf(eval_f(sc, m, 8, s), .1f, .001f);
+            b.add(l);
+        }
+        if (strans > 0) {
+            V3 T = strans * vsqrt(c);
+            Lobe l = make_lobe(LK_MICRO_T, BSDF_TRANSMISSION | BSDF_GLOSSY, T);
+            l.e0 = 1.f; l.e1 = e;
+            if (thin) {
+                float rscaled = (0.65f * e - 0.35f) * rough;
+                l.p0 = clamp_alpha(fmaxf(.001f, (rscaled * rscaled) / aspect));
+                l.p1 = clamp_alpha(fmaxf(.001f, (rscaled * rscaled) * aspect));
+            } else {
+                l.distrib = DK_DISNEY;
+                l.p0 = clamp_alpha(ax); l.p1 = clamp_alpha(ay);
+            }
+            b.add(l);
+        }
+        if (thin) b.add(make_lobe(LK_LAMBERT_T, BSDF_TRANSMISSION | BSDF_DIFFUSE, dt * c));
+        break;
+    }
     default: break;
     }
 }

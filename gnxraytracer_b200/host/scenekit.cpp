@@ -94,6 +94,15 @@ static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3],
         }
         s.material.push_back(material);
         s.light.push_back(-1);
+        // per-triangle copies of the optional vertex attributes (a pure translation leaves normals unchanged)
+        for (int v = 0; v < 3; ++v) {
+            int vi = m.idx[3 * f + v];
+            if (!m.UV.empty()) { s.uv.push_back(m.UV[2 * vi]); s.uv.push_back(m.UV[2 * vi + 1]); s.anyUV = true; }
+            else { const float d[3][2] = {{0, 0}, {1, 0}, {1, 1}}; s.uv.push_back(d[v][0]); s.uv.push_back(d[v][1]); }
+            for (int c = 0; c < 3; ++c) s.n.push_back(m.N.empty() ? 0.f : m.N[3 * vi + c]);
+        }
+        s.has_n.push_back(m.N.empty() ? 0 : 1);
+        if (!m.N.empty()) s.anyN = true;
     }
 }
 
@@ -375,6 +384,8 @@ struct gnxsk_scene {
     std::vector<uint8_t> prim_has_n, prim_flags;
     std::vector<int32_t> prim_material, prim_light, prim_id;
     std::vector<gnx_material> materials;
+    std::vector<gnx_texture> textures;
+    std::vector<float> texels;
     std::vector<gnx_light> lights;
     EnvTables env;
     double build_seconds = 0;
@@ -411,6 +422,15 @@ struct gnxsk_scene {
             prim_material[k] = soup.material[src];
             prim_id[k] = src;
         }
+        if (soup.anyUV) {
+            prim_uv.resize((size_t)n * 6);
+            for (int k = 0; k < n; ++k) memcpy(&prim_uv[(size_t)k * 6], &soup.uv[(size_t)bb.order[k] * 6], 24);
+        }
+        if (soup.anyN) {
+            prim_n.resize((size_t)n * 9);
+            prim_has_n.resize(n);
+            for (int k = 0; k < n; ++k) { memcpy(&prim_n[(size_t)k * 9], &soup.n[(size_t)bb.order[k] * 9], 36); prim_has_n[k] = soup.has_n[bb.order[k]]; }
+        }
         for (size_t i = 0; i < lights.size(); ++i)
             if (lights[i].type == GNX_LIGHT_AREA_TRI) {
                 lights[i].prim = newIndex[lights[i].prim];
@@ -421,6 +441,10 @@ struct gnxsk_scene {
         g.n_prims = n; g.prim_p = prim_p.data();
         g.prim_material = prim_material.data(); g.prim_light = prim_light.data();
         g.prim_flags = prim_flags.data(); g.prim_id = prim_id.data();
+        g.prim_uv = soup.anyUV ? prim_uv.data() : nullptr;
+        g.prim_n = soup.anyN ? prim_n.data() : nullptr;
+        g.prim_has_n = soup.anyN ? prim_has_n.data() : nullptr;
+        desc.n_textures = (int32_t)textures.size(); desc.textures = textures.data();
         memcpy(g.world_bound, wb.lo, 12); memcpy(g.world_bound + 3, wb.hi, 12);
         desc.abi_version = GNX_ABI_VERSION;
         desc.n_materials = (int32_t)materials.size(); desc.materials = materials.data();
@@ -551,6 +575,44 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
         int w0, h0;
         std::vector<float> rgb;
         std::string path = std::string(resources ? resources : ".") + "/MonValley1000.hdr";
+        if (!load_hdr(path, &w0, &h0, rgb, &sc->error)) return sc;
+        build_env(rgb, w0, h0, 1.0f, sc->env);
+        Mat4 l2w = mul(mul(rotate_axis(0, 20), rotate_axis(1, -90)), rotate_axis(0, -90));
+        sc->finalize(soup, width, height, spp, true, l2w);
+    } else if (nm == "nano") {
+        // config 3 stand-in, oracle/ref_harness.cpp::BuildNano: Disney material on a UV-mapped, smooth-shaded
+        // mesh under TropicalRuins1000.hdr.  The oracle side textures it with awesomeface.jpg through the
+        // reference's stb loader; the kit has no JPEG decoder, so it paints a procedural 512 x 512 colour map
+        // (same code path: ImageTexture level-0 bilinear, Repeat wrap).
+        const bool thin = p0 == 1;
+        gnx_material m = make_material(GNX_MAT_DISNEY, thin ? GNX_MATF_THIN : 0u);
+        m.rgb_tex[0] = 0;
+        const float fv[12] = {0.2f, 1.5f, 0.4f, 0.f, thin ? 0.3f : 0.f, 0.5f, 0.5f, 0.5f, 0.8f, thin ? 0.4f : 0.f, thin ? 0.3f : 0.f, thin ? 0.5f : 0.f};
+        memcpy(m.f, fv, sizeof(fv));
+        sc->materials.push_back(m);
+        const int TW = 512;
+        sc->texels.resize((size_t)TW * TW * 3);
+        for (int y = 0; y < TW; ++y)
+            for (int x = 0; x < TW; ++x) {
+                float u = (x + .5f) / TW, v = (y + .5f) / TW;
+                bool chk = ((x / 64) + (y / 64)) & 1;
+                float *q = &sc->texels[((size_t)y * TW + x) * 3];
+                q[0] = chk ? 0.9f : 0.15f + 0.5f * u;
+                q[1] = chk ? 0.75f * v + 0.1f : 0.6f;
+                q[2] = chk ? 0.1f : 0.8f * (1 - v);
+            }
+        gnx_texture t{};
+        t.width = t.height = TW; t.n_channels = 3; t.n_levels = 1; t.wrap = GNX_WRAP_REPEAT; t.max_aniso = 8.f;
+        t.su = t.sv = 1.f; t.texels = sc->texels.data();
+        sc->textures.push_back(t);
+        const int nu = p1 > 0 ? p1 : 320, nv = p2 > 0 ? p2 : 64;
+        const float T[3] = {0.f, -2.9f, 0.f};
+        add_mesh(soup, gnxsk::torus_knot(nu, nv, 1.0f, true, true), 20.f, T, 0);
+        add_mesh(soup, gnxsk::uv_sphere(std::max(8, nu / 4), std::max(6, nv), 0.9f, -2.6f, -1.2f, 0.6f), 1.f, zero, 0);
+        add_mesh(soup, gnxsk::uv_sphere(std::max(8, nu / 4), std::max(6, nv), 0.7f, 2.7f, 1.4f, -0.4f), 1.f, zero, 0);
+        int w0, h0;
+        std::vector<float> rgb;
+        std::string path = std::string(resources ? resources : ".") + "/TropicalRuins1000.hdr";
         if (!load_hdr(path, &w0, &h0, rgb, &sc->error)) return sc;
         build_env(rgb, w0, h0, 1.0f, sc->env);
         Mat4 l2w = mul(mul(rotate_axis(0, 20), rotate_axis(1, -90)), rotate_axis(0, -90));

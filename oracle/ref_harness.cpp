@@ -205,6 +205,38 @@ bool BuildDragon(HarnessScene &hs, int variant, int nu, int nv, const std::strin
     return true;
 }
 
+// Config 3: textured mesh with per-vertex UVs and normals (stand-in for the stripped nanosuit: there is no
+// OBJ loader in the reference), DisneyMaterial whose colour is an ImageTexture on awesomeface.jpg exactly
+// as getSmileFacePlasticMaterial builds it (ui/MaterialList.cpp:31-46), TropicalRuins environment.
+// variant 0 = the SURVEY §8d constants, 1 = thin surface with transmission lobes; nu x nv knot quads.
+bool BuildNano(HarnessScene &hs, int variant, int nu, int nv) {
+    std::string tex = ResourceDir() + "awesomeface.jpg", hdr = ResourceDir() + "TropicalRuins1000.hdr";
+    for (const std::string &f : {tex, hdr}) {
+        FILE *fp = fopen(f.c_str(), "rb");
+        if (!fp) { hs.error = "missing resource " + f; return false; }
+        fclose(fp);
+    }
+    std::unique_ptr<TextureMapping2D> map = std::make_unique<UVMapping2D>(1.f, 1.f, 0.f, 0.f);
+    std::shared_ptr<Texture<Spectrum>> color =
+        std::make_shared<ImageTexture<RGBSpectrum, Spectrum>>(std::move(map), tex, false, 8.f, ImageWrap::Repeat, 1.f, false);
+    bool thin = variant == 1;
+    auto disney = std::make_shared<DisneyMaterial>(
+        color, ConstF(0.2f) /*metallic*/, ConstF(1.5f) /*eta*/, ConstF(0.4f) /*roughness*/, ConstF(0.f) /*specularTint*/,
+        ConstF(thin ? 0.3f : 0.f) /*anisotropic*/, ConstF(0.5f) /*sheen*/, ConstF(0.5f) /*sheenTint*/, ConstF(0.5f) /*clearcoat*/,
+        ConstF(0.8f) /*clearcoatGloss*/, ConstF(thin ? 0.4f : 0.f) /*specTrans*/, ConstSpec(0.f, 0.f, 0.f) /*scatterDistance*/, thin,
+        ConstF(thin ? 0.3f : 0.f) /*flatness*/, ConstF(thin ? 0.5f : 0.f) /*diffTrans*/, nullptr /*bumpMap*/);
+    gnxsk::Mesh knot = gnxsk::torus_knot(nu, nv, 1.0f, true, true);
+    for (float &x : knot.P) x *= 20;
+    AddMesh(hs, knot, Translate(Vector3f(0.f, -2.9f, 0.f)), disney, nullptr);
+    AddMesh(hs, gnxsk::uv_sphere(std::max(8, nu / 4), std::max(6, nv), 0.9f, -2.6f, -1.2f, 0.6f), Transform(), disney, nullptr);
+    AddMesh(hs, gnxsk::uv_sphere(std::max(8, nu / 4), std::max(6, nv), 0.7f, 2.7f, 1.4f, -0.4f), Transform(), disney, nullptr);
+    Transform l2w = RotateX(20) * RotateY(-90) * RotateX(-90);
+    hs.lights.push_back(std::make_shared<InfiniteAreaLight>(l2w, Spectrum(1.0f), 10, hdr));
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    Finish(hs);
+    return true;
+}
+
 void IndexPrims(HarnessScene &hs) {
     if (!hs.cuda || !hs.cuda->flat()) return;
     const auto &ptrs = hs.cuda->flat()->prim_ptr;
@@ -218,12 +250,14 @@ extern "C" {
 
 // name: "cornell" (p0 = variant, p1 = sphere subdivision, -1 = no spheres)
 //       "dragon"  (p0 = variant, p1 = nu, p2 = nv)
+//       "nano"    (p0 = variant, p1 = nu, p2 = nv)
 void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0, int p1, int p2) {
     auto *hs = new HarnessScene;
     hs->name = name;
     hs->width = width; hs->height = height; hs->spp = spp;
     if (hs->name == "cornell") BuildCornell(*hs, p0, p1);
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
+    else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else hs->error = "unknown scene";
     return hs;
 }

@@ -20,6 +20,9 @@ SCENES = {
     "dragon": ("dragon", 0, 256, 32),       # Plastic knot, MonValley environment
     "dragon_metal": ("dragon", 1, 256, 32),
     "dragon_full": ("dragon", 0, 2048, 213),  # BASELINE config 2 geometry (872 448 triangles)
+    "nano": ("nano", 0, 96, 24),            # config 3 stand-in: Disney + ImageTexture + shading normals, small
+    "nano_thin": ("nano", 1, 96, 24),       # thin Disney surface: transmission lobes
+    "nano_full": ("nano", 0, 320, 64),      # ~ 90 k triangles
 }
 
 

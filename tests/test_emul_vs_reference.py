@@ -11,7 +11,8 @@ from _harness import grid, rel_mse
 from gnxraytracer_b200.api import RenderParams
 
 
-@pytest.mark.parametrize("preset,res", [("cornell", 64), ("cornell_on", 48), ("dragon", 96), ("dragon_metal", 64)])
+@pytest.mark.parametrize("preset,res", [("cornell", 64), ("cornell_on", 48), ("dragon", 96), ("dragon_metal", 64),
+                                        ("nano", 64), ("nano_thin", 64)])
 def test_primary_hits_and_radiance(ref, emul, preset, res):
     rs = ref.scene(preset, res, res, 4)
     es = emul.scene(rs.desc)

@@ -40,7 +40,7 @@ def test_sample_dimensions_bit_exact_on_device(ref, ctx):
 
 # ---- primary hits + image, through the drop-in class -----------------------------------------------------------
 @pytest.mark.parametrize("preset,res,spp", [("cornell_full", 256, 16), ("cornell_on", 128, 8), ("dragon", 256, 8),
-                                            ("dragon_metal", 192, 8)])
+                                            ("dragon_metal", 192, 8), ("nano", 192, 8), ("nano_thin", 128, 8)])
 def test_bridge_render_matches_reference(ref, preset, res, spp):
     rs = ref.scene(preset, res, res, spp)
     img_ref, _ = rs.render_reference(max_depth=5)
@@ -152,6 +152,41 @@ def test_uniform_light_strategy_and_depth_zero(ref, ctx):
     imgu, _ = ctx.render(RenderParams.make(res, res, 2, light_strategy=LIGHTS_UNIFORM))
     assert np.isfinite(imgu).all() and imgu[..., :3].mean() > 0
     rs.close()
+
+
+def test_gpu_counters_match_the_restated_reference_traversal(ref, ctx):
+    """nodes visited / triangles tested by the kernels agree with the reference-order
+    traversal (oracle/restate walks the reference's own 32-byte node array) to < 1 %."""
+    import os
+    import _harness
+    if not os.path.exists(_harness.RESTATE_LIB):
+        pytest.skip("oracle/_build/libgnxrestate.so not built")
+    res = 128
+    rs = ref.scene("dragon", res, res, 4)
+    ctx.upload(rs.desc)
+    p = RenderParams.make(res, res, 4, max_depth=5)
+    img, st = ctx.render(p)
+    ro = _harness.Restate().scene(rs.desc)
+    img_r, c = ro.render(p)
+    assert rel_mse(img, img_r) <= 1e-5
+    rays = int(st.rays)
+    assert abs(c["rays_extend"] - int(st.rays_extend)) <= 0.002 * c["rays_extend"]
+    assert abs(c["tris_tested"] - int(st.tris_tested)) <= 0.01 * c["tris_tested"]
+    # the reference also slab-tests the root once per ray; the two-child layout does that at the parent
+    assert abs(c["nodes_visited"] - (int(st.nodes_visited) + rays)) <= 0.01 * c["nodes_visited"]
+    rs.close(); ro.close()
+
+
+def test_config3_scene_kit_disney_textured(ctx, emul):
+    """Scene-kit config 3 (procedural colour map): GPU against the host build of the same code."""
+    res = 96
+    sk = SceneKit("nano", res, res, 4, 0, 96, 24)
+    ctx.upload(sk.desc)
+    p = RenderParams.make(res, res, 4)
+    a, _ = ctx.render(p)
+    b, _ = emul.scene(sk.desc).render(p)
+    assert rel_mse(a, b) <= 1e-4
+    sk.close()
 
 
 def test_errors_are_reported_not_swallowed(ctx):
