@@ -68,7 +68,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(repo_root(), "gnxraytracer_b200", "lib", "libgnxrt.so")
+    # GNX_LIB: another build of the same CUDA library (tuning experiments, tools/profile_step.py)
+    return os.environ.get("GNX_LIB") or os.path.join(repo_root(), "gnxraytracer_b200", "lib", "libgnxrt.so")
 
 
 def load_library():

@@ -17,7 +17,10 @@
 
 namespace gnx {
 
-constexpr int kSmemStack = 24;   // levels kept in shared memory
+#ifndef GNX_SMEM_STACK
+#define GNX_SMEM_STACK 24
+#endif
+constexpr int kSmemStack = GNX_SMEM_STACK;   // levels kept in shared memory
 constexpr int kSpillStack = 40;  // further levels in local memory (reference total: 64)
 
 struct TriHit {

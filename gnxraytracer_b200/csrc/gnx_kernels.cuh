@@ -60,9 +60,16 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
 //   KIND 3: camera rays of the batch, generated in registers (ray-gen fused with the first extension;
 //           path state is written only for rays that hit)      -> L = Le or hit record + shade queues
 constexpr int kRefetchBelow = 24;
+#ifndef GNX_LEAF_BATCH
+#define GNX_LEAF_BATCH 8
+#endif
+constexpr int kLeafBatch = GNX_LEAF_BATCH;  // parked lanes that trigger a joint triangle-test round
 
+#ifndef GNX_TRACE_BLOCKS
+#define GNX_TRACE_BLOCKS 8
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int arg,
+__global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int arg,
                                                       DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
@@ -119,19 +126,30 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(const DeviceScene sc, PathS
             }
         }
         if (!__any_sync(kFull, active)) break;
-        while (active) {
-            // one interior node plus the (rare: ~1 leaf per 25 nodes) leaves that follow it.  A strict
-            // while-while split (all lanes descend until each holds a leaf) measured 15-35 % slower here.
-            if (trav_step<KIND == 1>(sc, t, stack, kBlock, cnt)) {
+        // Warp-synchronous traversal rounds: all 32 lanes run the loop control together (full-mask votes
+        // force reconvergence every round), lanes without work are predicated off.
+        while (true) {
+            // A lane that reaches a leaf parks until kLeafBatch lanes of the warp hold one (or nobody can
+            // advance any more); then the warp runs the triangle test for all of them at once.  The
+            // kernel is issue-bound, leaves come up once per ~25 slab tests per lane, and the triangle
+            // test is ~3x an interior step: run on arrival it took 61 % of the issue slots at <= 3 active
+            // lanes (profiles/r01_trace_persistent.txt).  No speculation: node and triangle visits are
+            // exactly those of the reference order.
+            bool parked = active && trav_is_leaf(t);
+            if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt); parked = trav_is_leaf(t); }
+            const unsigned parkedMask = __ballot_sync(kFull, parked);
+            const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
+            if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
+            if (active && trav_done(t)) {
                 if (KIND == 3) { pendType = primary_finish(sc, ps, rc, item, hidx, camD, t); pendSlot = item; }
                 else if (KIND == 0) { pendType = extend_finish(sc, ps, rc, item, t); pendSlot = item; }
                 else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
                 else probe_finish(ps, q.probe_q + item, t);
                 active = false;
             }
-            if (!exhausted && __popc(__activemask()) < kRefetchBelow) break;
+            const unsigned actMask = __ballot_sync(kFull, active);
+            if (actMask == 0 || (!exhausted && __popc(actMask) < kRefetchBelow)) break;
         }
-        __syncwarp();
     }
     flush_stats(st, kExtend ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);
     if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);

@@ -23,6 +23,9 @@ struct gnx_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    void *geom_base = nullptr;
+    size_t geom_bytes = 0;
+    int l2_persist = 0;  // measured on B200/C2: 52.1 ms with the window vs 46.1 ms without (set-aside starves the rest)
     int grid_trace = 148 * 8, grid_shade = 148 * 4;  // SM count x resident blocks (occupancy query at create)
     // scene
     bool has_scene = false;
@@ -138,6 +141,7 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
     }
+    if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
@@ -179,28 +183,27 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
     // ---- nodes: the reference's 32-byte LinearBVHNode array re-packed into 64-byte two-child records
     static_assert(sizeof(gnx_bvh_node) == 32, "node size");
     int rc;
+    // ---- BVH nodes (64-byte two-child records re-packed from the reference's LinearBVHNode array) and
+    // 48-byte triangle records, in ONE allocation so that a single L2 access-policy window can keep the
+    // traversal working set resident while path state and queues stream through (see set_l2_window).
+    unsigned typeMask = 0;
     {
-        std::vector<float4> n2;
+        std::vector<float4> n2, tris;
         std::string perr;
         if (!build_node2(g.nodes, g.n_nodes, n2, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        if (!pack_triangles(*d, tris, &typeMask, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        std::vector<float4> both(n2);
+        both.insert(both.end(), tris.begin(), tris.end());
         float4 *dn;
-        if ((rc = dupload(ctx, pool, n2.data(), n2.size(), &dn))) return rc;
+        if ((rc = dupload(ctx, pool, both.data(), both.size(), &dn))) return rc;
         sc.nodes2 = dn;
         sc.n_nodes2 = (int)(n2.size() / 4);
+        sc.tris = dn + n2.size();
+        ctx->geom_base = dn;
+        ctx->geom_bytes = both.size() * sizeof(float4);
     }
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
-
-    // ---- triangles: 48-byte records
-    unsigned typeMask = 0;
-    {
-        std::vector<float4> tris;
-        std::string perr;
-        if (!pack_triangles(*d, tris, &typeMask, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
-        float4 *dt;
-        if ((rc = dupload(ctx, pool, tris.data(), tris.size(), &dt))) return rc;
-        sc.tris = dt;
-    }
     ctx->shade_type_mask = typeMask;
     float *df;
     uint8_t *du8;
@@ -440,6 +443,26 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     return GNX_OK;
 }
 
+// Marks the node + triangle arrays as persisting in L2 for work launched on `st`: the random gathers of
+// the traversal then compete less with the streaming path-state / queue traffic (C2: 98 MB of geometry
+// against ~1 GB of state per bounce, 126 MB of L2).
+static void set_l2_window(gnx_ctx *ctx, cudaStream_t st) {
+    if (!ctx->l2_persist || !ctx->geom_base) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
+    size_t setAside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, ctx->geom_bytes);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
+    cudaStreamAttrValue attr{};
+    size_t win = std::min<size_t>(ctx->geom_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = ctx->geom_base;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win > 0 ? std::min(1.0f, (float)setAside / (float)win) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+
 static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats) {
     int rc = validate_params(ctx, p);
     if (rc) return rc;
@@ -465,6 +488,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix))) return rc;
 
     cudaStream_t st = userStream ? userStream : ctx->stream;
+    set_l2_window(ctx, st);
     const DeviceScene &sc = ctx->sc;
     const int gridTrace = ctx->grid_trace, gridShade = ctx->grid_shade, gridWide = ctx->sm_count * 16;
     const bool hasNull = (ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u;
