@@ -33,6 +33,8 @@ WORKLOADS = {
            "C2: dragon-class mesh 872448 tris (torus-knot stand-in for dragon.3d), Plastic, InfiniteAreaLight MonValley1000.hdr, 1024x1024, 64 spp, maxDepth 5, PathIntegrator+Halton"),
     "c3": ("nano", 0, 0, 0, 1920, 1080, 128, 5,
            "C3: UV-mapped smooth-shaded mesh (~90k tris, stand-in for nanosuit), DisneyMaterial + ImageTexture, InfiniteAreaLight TropicalRuins1000.hdr, 1920x1080, 128 spp, maxDepth 5"),
+    "c4": ("smoke", 0, 0, 0, 1024, 1024, 64, 5,
+           "C4: VolPathIntegrator, GridDensityMedium density_render.70.volume inside HomogeneousMedium fog, Matte ground, MonValley env, 1024x1024, 64 spp, maxDepth 5, PCG32 stream sampler"),
     "c1": ("cornell", 0, 3, 0, 512, 512, 16, 5,
            "C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
 }
@@ -189,7 +191,8 @@ def run_ours(args, wl):
     t_upload = time.time() - t0
 
     first, count = weak_sample_range(spp, rank)
-    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world)
+    integ = 1 if scene == "smoke" else 0  # VolPathIntegrator for the participating-media config
+    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world, integrator=integ)
     fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
@@ -281,7 +284,7 @@ def run_ours(args, wl):
                 line["cpu_baseline"] = info
                 rs, img_ref, n = extra
                 # parity at the baseline's spp: same scene through the bridge-free scene kit
-                img, _ = ctx.render(RenderParams.make(W, H, n, max_depth=depth))
+                img, _ = ctx.render(RenderParams.make(W, H, n, max_depth=depth, integrator=integ))
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 import _harness
                 line["rel_mse_vs_cpu_ref"] = _harness.rel_mse(img, img_ref)

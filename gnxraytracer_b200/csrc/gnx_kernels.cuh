@@ -8,7 +8,7 @@
 // persistent kernel never has a partial second wave.  The traversal kernel keeps its stacks in shared
 // memory (24 KB per 128-thread block).
 #pragma once
-#include "gnx_path.cuh"
+#include "gnx_volpath.cuh"
 
 namespace gnx {
 
@@ -199,6 +199,37 @@ __global__ void __launch_bounds__(kBlock) k_shade(const DeviceScene sc, PathStat
     }
 }
 
+// VolPathIntegrator: one path per lane from camera to termination (gnx_volpath.cuh explains why this
+// integrator is not cut into wavefront stages).  Lanes pull camera samples through a warp-aggregated cursor.
+__global__ void __launch_bounds__(kBlock) k_volpath(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
+    const int n = rc.npix * rc.batch_spp;
+    const int lane = threadIdx.x & 31;
+    int *cursor = &q.counts[kCntFetch];
+    TraversalCounters cnt{0, 0};
+    VolCounters vc{0, 0, 0};
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        const int slot = base + lane;
+        if (slot < n) {
+            const int pixel = slot % rc.npix;
+            V3 L = volpath_li(sc, rc, pixel % rc.width, pixel / rc.width, rc.first_sample + slot / rc.npix, stack, kBlock, cnt, vc);
+            ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+        __syncwarp();
+    }
+    // all traversal work is booked under the ray kind that issued it
+    unsigned nodes = cnt.nodes, tris = cnt.tris;
+    flush_stats(st, 0, nodes, tris, vc.extend);
+    flush_stats(st, 1, 0, 0, vc.shadow);
+    flush_stats(st, 2, 0, 0, vc.mis);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+}
+
 // colObj += Li(...) over the samples of the pixel, in sample order (core/Integrator.cpp:274-291)
 __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
@@ -224,7 +255,7 @@ __global__ void __launch_bounds__(kBlock) k_primary_hits(const DeviceScene sc, i
     int2 *stack = s_stack + threadIdx.x;
     const int npix = width * height;
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)
-        out[pixel] = primary_hit_id(sc, pixel % width, pixel / width, sample, stack, kBlock);
+        out[pixel] = primary_hit_id(sc, width, pixel % width, pixel / width, sample, stack, kBlock);
 }
 
 __global__ void k_sample_dims(const DeviceScene sc, int n, const long long *index, const int *dim, float *out) {

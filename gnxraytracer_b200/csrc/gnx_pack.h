@@ -146,6 +146,24 @@ inline bool build_node2(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
     return true;
 }
 
+// gnx_medium -> DevMedium (density pointer supplied by the caller: host for the emulation, device for upload)
+inline void fill_dev_medium(const gnx_medium &m, const float *density, DevMedium &dm) {
+    memset(&dm, 0, sizeof(dm));
+    dm.type = m.type;
+    for (int c = 0; c < 3; ++c) {
+        dm.sigma_a[c] = m.sigma_a[c]; dm.sigma_s[c] = m.sigma_s[c];
+        dm.sigma_t[c] = m.sigma_s[c] + m.sigma_a[c];  // HomogeneousMedium: sigma_s + sigma_a (media/HomogeneousMedium.h)
+    }
+    dm.g = m.g;
+    if (m.type == GNX_MEDIUM_GRID) {
+        dm.nx = m.nx; dm.ny = m.ny; dm.nz = m.nz;
+        dm.density = density;
+        memcpy(dm.w2m.m, m.world_to_medium, 64);
+        dm.inv_max_density = m.inv_max_density;
+        dm.sigma_t_scalar = m.sigma_a[0] + m.sigma_s[0];  // (sigma_a + sigma_s)[0], media/GridDensityMedium.h:32
+    }
+}
+
 // UniformLightDistribution: Distribution1D over n ones (core/LightDistribution.cpp:35-38, core/Sampling.h:22-35)
 inline float uniform_light_distribution(int n, std::vector<float> &func, std::vector<float> &cdf) {
     func.assign((size_t)n, 1.f);

@@ -25,14 +25,13 @@ struct RenderConsts {
 
 // Camera ray for (pixel, halton index): Sampler::GetCameraSample + PerspectiveCamera::GenerateRay +
 // Transform::operator()(Ray) (core/Transform.h:230-244).
-GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *o, V3 *d, float *tMax) {
-    float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+GNX_D void camera_ray_uv(const DeviceScene &sc, int px, int py, float u0, float u1, float l0, float l1, V3 *o, V3 *d,
+                         float *tMax) {
     V3 pFilm((float)px + u0, (float)py + u1, 0.f);
     V3 pCamera = xform_point(sc.cam.r2c, pFilm);
     V3 ro(0.f, 0.f, 0.f);
     V3 rd = normalize(pCamera);
     if (sc.cam.lens_radius > 0) {
-        float l0 = halton_sample_dimension(sc.smp, hidx, 3), l1 = halton_sample_dimension(sc.smp, hidx, 4);
         float lx, ly;
         concentric_sample_disk(l0, l1, &lx, &ly);
         lx *= sc.cam.lens_radius; ly *= sc.cam.lens_radius;
@@ -52,6 +51,12 @@ GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *
         tm -= dt;
     }
     *o = wo; *d = wd; *tMax = tm;
+}
+GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *o, V3 *d, float *tMax) {
+    float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+    float l0 = 0, l1 = 0;
+    if (sc.cam.lens_radius > 0) { l0 = halton_sample_dimension(sc.smp, hidx, 3); l1 = halton_sample_dimension(sc.smp, hidx, 4); }
+    camera_ray_uv(sc, px, py, u0, u1, l0, l1, o, d, tMax);
 }
 
 GNX_D int shade_type_of(unsigned matWord) { return (int)((matWord >> 20) & 0xfu); }
@@ -325,11 +330,20 @@ GNX_D void probe_item(const DeviceScene &sc, const PathState &ps, const ProbeIte
     probe_finish(ps, item, t);
 }
 
-GNX_D int primary_hit_id(const DeviceScene &sc, int px, int py, int sample, int2 *stack, int stride) {
-    uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+GNX_D int primary_hit_id(const DeviceScene &sc, int width, int px, int py, int sample, int2 *stack, int stride) {
     V3 o, d;
     float tMax;
-    camera_ray(sc, px, py, hidx, &o, &d, &tMax);
+    if (sc.smp.type == GNX_SAMPLER_PCG32) {
+        PathSampler smp = PathSampler::stream(sc.smp, ((uint64_t)(width * py + px) << 20) | (uint64_t)sample);
+        float u0, u1, l0, l1;
+        smp.get2d(&u0, &u1);
+        smp.get1d();
+        smp.get2d(&l0, &l1);
+        camera_ray_uv(sc, px, py, u0, u1, l0, l1, &o, &d, &tMax);
+    } else {
+        uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+        camera_ray(sc, px, py, hidx, &o, &d, &tMax);
+    }
     int prim = -1;
     TriHit h;
     TraversalCounters cnt{0, 0};

@@ -26,14 +26,14 @@ struct gnx_ctx {
     void *geom_base = nullptr;
     size_t geom_bytes = 0;
     int l2_persist = 0;  // measured on B200/C2: 52.1 ms with the window vs 46.1 ms without (set-aside starves the rest)
-    int grid_trace = 148 * 8, grid_shade = 148 * 4;  // SM count x resident blocks (occupancy query at create)
+    int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_volpath = 148 * 2;  // SM count x resident blocks (occupancy query at create)
     // scene
     bool has_scene = false;
     DeviceScene sc{};
     std::vector<void *> scene_allocs;
     unsigned shade_type_mask = 0;  // which k_shade variants the scene needs
     bool spatial_built = false;
-    int n_lights_host = 0;
+    int n_lights_host = 0, n_textures_host = 0;
     float wb[6]{};
     // wavefront buffers
     int capacity = 0;
@@ -140,6 +140,7 @@ int gnx_create(gnx_ctx **out, int device) {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
@@ -233,6 +234,7 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
     if ((rc = dupload(ctx, pool, d->materials, (size_t)d->n_materials, &dm))) return rc;
     sc.materials = dm;
     sc.n_materials = d->n_materials;
+    ctx->n_textures_host = d->n_textures;
     {
         std::vector<DevTexture> tex((size_t)d->n_textures);
         for (int i = 0; i < d->n_textures; ++i) {
@@ -304,22 +306,13 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         for (int i = 0; i < d->n_media; ++i) {
             const gnx_medium &m = d->media[i];
             DevMedium &dmv = med[i];
-            memset(&dmv, 0, sizeof(dmv));
-            dmv.type = m.type;
-            for (int c = 0; c < 3; ++c) {
-                dmv.sigma_a[c] = m.sigma_a[c]; dmv.sigma_s[c] = m.sigma_s[c];
-                dmv.sigma_t[c] = m.sigma_s[c] + m.sigma_a[c];  // HomogeneousMedium: sigma_s + sigma_a
-            }
-            dmv.g = m.g;
+            const float *ddens = nullptr;
             if (m.type == GNX_MEDIUM_GRID) {
                 if (!m.density || m.nx <= 0 || m.ny <= 0 || m.nz <= 0) return fail(ctx, GNX_ERR_INVALID, "grid medium without density");
-                dmv.nx = m.nx; dmv.ny = m.ny; dmv.nz = m.nz;
                 if ((rc = dupload(ctx, pool, m.density, (size_t)m.nx * m.ny * m.nz, &df))) return rc;
-                dmv.density = df;
-                memcpy(dmv.w2m.m, m.world_to_medium, 64);
-                dmv.inv_max_density = m.inv_max_density;
-                dmv.sigma_t_scalar = m.sigma_a[0] + m.sigma_s[0];  // (sigma_a + sigma_s)[0]
+                ddens = df;
             }
+            fill_dev_medium(m, ddens, dmv);
         }
         DevMedium *dmed;
         if ((rc = dupload(ctx, pool, med.data(), med.size(), &dmed))) return rc;
@@ -336,8 +329,9 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
 
     // ---- sampler
     const gnx_sampler &s = d->sampler;
-    if (s.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "only the Halton sampler is implemented");
-    if (s.base_scales[0] <= 0 || s.base_scales[1] <= 0 || s.sample_stride <= 0) return fail(ctx, GNX_ERR_INVALID, "bad Halton parameters");
+    if (s.type != GNX_SAMPLER_HALTON && s.type != GNX_SAMPLER_PCG32) return fail(ctx, GNX_ERR_INVALID, "unknown sampler type");
+    if (s.type == GNX_SAMPLER_HALTON && (s.base_scales[0] <= 0 || s.base_scales[1] <= 0 || s.sample_stride <= 0))
+        return fail(ctx, GNX_ERR_INVALID, "bad Halton parameters");
     sc.smp.type = s.type;
     sc.smp.base_scale0 = s.base_scales[0]; sc.smp.base_scale1 = s.base_scales[1];
     sc.smp.base_exp0 = s.base_exponents[0]; sc.smp.base_exp1 = s.base_exponents[1];
@@ -435,11 +429,18 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
         return fail(ctx, GNX_ERR_INVALID, "bad render parameters");
     if ((long long)p->width * p->height > (1ll << 28)) return fail(ctx, GNX_ERR_INVALID, "image too large");
-    if (p->integrator != GNX_INTEGRATOR_PATH) return fail(ctx, GNX_ERR_UNSUPPORTED, "VolPathIntegrator is not implemented yet");
+    if (p->integrator != GNX_INTEGRATOR_PATH && p->integrator != GNX_INTEGRATOR_VOLPATH) return fail(ctx, GNX_ERR_INVALID, "unknown integrator");
+    if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.smp.type != GNX_SAMPLER_HALTON)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "the wavefront PathIntegrator keeps a Halton (index, dimension) per path; the PCG32 stream sampler is for VolPath");
+    if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.n_media > 0)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "scene has participating media: use GNX_INTEGRATOR_VOLPATH (PathIntegrator ignores media)");
+    if (p->integrator == GNX_INTEGRATOR_VOLPATH && ctx->n_textures_host > 0)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "VolPath with image textures needs ray-differential (EWA) filtering at the camera vertex, which is not implemented");
     if (p->film != GNX_FILM_BOX) return fail(ctx, GNX_ERR_UNSUPPORTED, "only the box film of the reference is implemented");
     // the Halton index must fit the 32-bit path state
     unsigned long long maxIdx = (unsigned long long)(p->first_sample + p->spp) * (unsigned long long)ctx->sc.smp.stride;
-    if (maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
+    if (ctx->sc.smp.type == GNX_SAMPLER_HALTON && maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
+    if (ctx->sc.smp.type == GNX_SAMPLER_PCG32 && p->first_sample + p->spp >= (1 << 20)) return fail(ctx, GNX_ERR_UNSUPPORTED, "PCG32 stream ids hold 20 bits of sample number");
     return GNX_OK;
 }
 
@@ -512,6 +513,18 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         rcn.batch_spp = std::min(batch_spp, p->spp - done);
         rcn.first_sample = p->first_sample + done;
         rcn.capacity = ctx->capacity;
+        if (p->integrator == GNX_INTEGRATOR_VOLPATH) {
+            k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
+            tm.begin(ST_EXTEND);
+            k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
+            tm.end();
+            tm.begin(ST_FILM);
+            k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);
+            tm.end();
+            launches += 3;
+            ++extendLaunches;
+            continue;
+        }
         int in = 0;
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.

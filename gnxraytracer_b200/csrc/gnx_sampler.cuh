@@ -134,15 +134,32 @@ struct Pcg32 {
     GNX_HD float uniform_float() { return fminf(kOneMinusEpsilon, (float)(next_u32() * 2.3283064365386963e-10f)); }
 };
 
-// Sampler view of one path: GlobalSampler::Get1D/Get2D (core/Sampler.cpp:162-179).  arrayStartDim
-// is 5 and no sample arrays are ever requested by Path/VolPath, so the array-skip branch is inert.
+// Sampler view of one path.
+//   Halton: GlobalSampler::Get1D/Get2D (core/Sampler.cpp:162-179).  arrayStartDim is 5 and no sample arrays
+//   are ever requested by Path/VolPath, so the array-skip branch is inert.
+//   PCG32:  one stream per camera sample, sequence id = (W * py + px) << 20 | sampleNumber — the
+//   convention of the harness's Sampler subclass (oracle/ref_harness.cpp, PcgStreamSampler), which the
+//   unbounded delta-tracking loops of GridDensityMedium need (the reference's Halton tables stop at
+//   dimension 1000 and read out of range beyond).
 struct PathSampler {
     const DevSampler &s;
     uint64_t index;
     int dim;
-    GNX_D PathSampler(const DevSampler &smp, uint64_t idx, int d) : s(smp), index(idx), dim(d) {}
-    GNX_D float get1d() { return halton_sample_dimension(s, index, dim++); }
+    bool pcg;
+    Pcg32 rng;
+    GNX_D PathSampler(const DevSampler &smp, uint64_t idx, int d) : s(smp), index(idx), dim(d), pcg(false) {}
+    GNX_D static PathSampler stream(const DevSampler &smp, uint64_t sequence) {
+        PathSampler p(smp, 0, 0);
+        p.pcg = true;
+        p.rng.set_sequence(sequence);
+        return p;
+    }
+    GNX_D float get1d() {
+        if (pcg) { ++dim; return rng.uniform_float(); }
+        return halton_sample_dimension(s, index, dim++);
+    }
     GNX_D void get2d(float *a, float *b) {
+        if (pcg) { *a = rng.uniform_float(); *b = rng.uniform_float(); dim += 2; return; }
         *a = halton_sample_dimension(s, index, dim);
         *b = halton_sample_dimension(s, index, dim + 1);
         dim += 2;

@@ -74,15 +74,16 @@ struct Soup {
     std::vector<float> p;          // 9 per triangle
     std::vector<float> uv, n;      // 6 / 9 per triangle (may stay empty)
     std::vector<uint8_t> has_n;
-    std::vector<int32_t> material, light;
-    bool anyUV = false, anyN = false;
+    std::vector<int32_t> material, light, med_in, med_out;
+    std::vector<uint8_t> transition;
+    bool anyUV = false, anyN = false, anyMedia = false;
     int count() const { return (int)material.size(); }
 };
 
 // Appends a mesh after the float operations the reference applies to it: an optional uniform
 // pre-scale (plyInfo's x20, shape/plyRead.h:38) and a translation (TriangleMesh's ObjectToWorld,
 // shape/Triangle.cpp:24-29: with a pure translation the 4x4 product reduces to x + tx).
-static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3], int material) {
+static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3], int material, int medIn = -1, int medOut = -1) {
     for (int f = 0; f < m.nTris(); ++f) {
         for (int v = 0; v < 3; ++v) {
             int vi = m.idx[3 * f + v];
@@ -94,6 +95,8 @@ static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3],
         }
         s.material.push_back(material);
         s.light.push_back(-1);
+        s.med_in.push_back(medIn); s.med_out.push_back(medOut); s.transition.push_back(medIn != medOut);
+        if (medIn >= 0 || medOut >= 0) s.anyMedia = true;
         // per-triangle copies of the optional vertex attributes (a pure translation leaves normals unchanged)
         for (int v = 0; v < 3; ++v) {
             int vi = m.idx[3 * f + v];
@@ -382,7 +385,11 @@ struct gnxsk_scene {
     std::vector<gnx_bvh_node> nodes;
     std::vector<float> prim_p, prim_uv, prim_n;
     std::vector<uint8_t> prim_has_n, prim_flags;
-    std::vector<int32_t> prim_material, prim_light, prim_id;
+    std::vector<int32_t> prim_material, prim_light, prim_id, prim_med_in, prim_med_out;
+    std::vector<uint8_t> prim_transition;
+    std::vector<gnx_medium> media;
+    std::vector<float> density;
+    bool pcgSampler = false;
     std::vector<gnx_material> materials;
     std::vector<gnx_texture> textures;
     std::vector<float> texels;
@@ -422,6 +429,10 @@ struct gnxsk_scene {
             prim_material[k] = soup.material[src];
             prim_id[k] = src;
         }
+        if (soup.anyMedia) {
+            prim_med_in.resize(n); prim_med_out.resize(n); prim_transition.resize(n);
+            for (int k = 0; k < n; ++k) { int src = bb.order[k]; prim_med_in[k] = soup.med_in[src]; prim_med_out[k] = soup.med_out[src]; prim_transition[k] = soup.transition[src]; }
+        }
         if (soup.anyUV) {
             prim_uv.resize((size_t)n * 6);
             for (int k = 0; k < n; ++k) memcpy(&prim_uv[(size_t)k * 6], &soup.uv[(size_t)bb.order[k] * 6], 24);
@@ -441,6 +452,10 @@ struct gnxsk_scene {
         g.n_prims = n; g.prim_p = prim_p.data();
         g.prim_material = prim_material.data(); g.prim_light = prim_light.data();
         g.prim_flags = prim_flags.data(); g.prim_id = prim_id.data();
+        g.prim_medium_in = soup.anyMedia ? prim_med_in.data() : nullptr;
+        g.prim_medium_out = soup.anyMedia ? prim_med_out.data() : nullptr;
+        g.prim_is_transition = soup.anyMedia ? prim_transition.data() : nullptr;
+        desc.n_media = (int32_t)media.size(); desc.media = media.data();
         g.prim_uv = soup.anyUV ? prim_uv.data() : nullptr;
         g.prim_n = soup.anyN ? prim_n.data() : nullptr;
         g.prim_has_n = soup.anyN ? prim_has_n.data() : nullptr;
@@ -493,7 +508,7 @@ struct gnxsk_scene {
         desc.camera.medium = -1;
         // ---- Halton parameters (samplers/HaltonSampler.cpp:33-61): scales >= min(res, 128)
         gnx_sampler &s = desc.sampler;
-        s.type = GNX_SAMPLER_HALTON; s.samples_per_pixel = spp;
+        s.type = pcgSampler ? GNX_SAMPLER_PCG32 : GNX_SAMPLER_HALTON; s.samples_per_pixel = spp;
         const int res[2] = {width, height};
         for (int i = 0; i < 2; ++i) {
             int base = i == 0 ? 2 : 3, sc = 1, ex = 0;
@@ -614,6 +629,55 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
         std::vector<float> rgb;
         std::string path = std::string(resources ? resources : ".") + "/TropicalRuins1000.hdr";
         if (!load_hdr(path, &w0, &h0, rgb, &sc->error)) return sc;
+        build_env(rgb, w0, h0, 1.0f, sc->env);
+        Mat4 l2w = mul(mul(rotate_axis(0, 20), rotate_axis(1, -90)), rotate_axis(0, -90));
+        sc->finalize(soup, width, height, spp, true, l2w);
+    } else if (nm == "smoke") {
+        // config 4, oracle/ref_harness.cpp::BuildSmoke: GridDensityMedium (density_render.70.volume) inside a
+        // HomogeneousMedium fog box, material-less boundary triangles, Matte ground, MonValley environment.
+        // p0: 0 = grid + fog with the PCG32 stream sampler, 1 = fog only with Halton.
+        const std::string res = resources ? resources : ".";
+        gnx_medium fog{};
+        fog.type = GNX_MEDIUM_HOMOGENEOUS;
+        for (int c = 0; c < 3; ++c) { fog.sigma_a[c] = 0.02f; fog.sigma_s[c] = 0.08f; }
+        fog.g = 0.5f;
+        sc->media.push_back(fog);
+        if (p0 == 0) {
+            std::ifstream f(res + "/density_render.70.volume");
+            if (!f) { sc->error = "cannot open " + res + "/density_render.70.volume"; return sc; }
+            std::string tok;
+            int nx = 0, ny = 0, nz = 0;
+            float q0[3], q1[3], sa[3], ss[3];
+            f >> tok >> nx >> tok >> ny >> tok >> nz;
+            f >> tok >> q0[0] >> q0[1] >> q0[2] >> tok >> q1[0] >> q1[1] >> q1[2];
+            f >> tok >> sa[0] >> sa[1] >> sa[2] >> tok >> ss[0] >> ss[1] >> ss[2];
+            sc->density.resize((size_t)nx * ny * nz);
+            float mx = 0;
+            for (float &d : sc->density) { f >> d; mx = std::max(mx, d); }
+            if (!f || nx <= 0) { sc->error = "cannot parse the .volume file"; return sc; }
+            gnx_medium grid{};
+            grid.type = GNX_MEDIUM_GRID;
+            for (int c = 0; c < 3; ++c) { grid.sigma_a[c] = sa[0]; grid.sigma_s[c] = ss[0]; }
+            grid.g = 0.f; grid.nx = nx; grid.ny = ny; grid.nz = nz;
+            grid.density = sc->density.data();
+            grid.inv_max_density = 1 / mx;
+            Mat4 m2w = mul(mul(translate(-1, -1, -0.4f), translate(q0[0], q0[1], q0[2])), scale(q1[0] - q0[0], q1[1] - q0[1], q1[2] - q0[2]));
+            to_float16(inverse(m2w), grid.world_to_medium);
+            sc->media.push_back(grid);
+            const float lo[3] = {-1.f + q0[0] - 0.01f, -1.f + q0[1] - 0.01f, -0.4f + q0[2] - 0.01f};
+            const float hi[3] = {-1.f + q1[0] + 0.01f, -1.f + q1[1] + 0.01f, -0.4f + q1[2] + 0.01f};
+            add_mesh(soup, gnxsk::box(lo, hi), 1.f, zero, -1, 1, 0);
+            sc->pcgSampler = true;
+        }
+        const float flo[3] = {-2.4f, -2.4f, -2.4f}, fhi[3] = {2.4f, 2.4f, 2.4f};
+        add_mesh(soup, gnxsk::box(flo, fhi), 1.f, zero, -1, 0, -1);
+        gnx_material m = make_material(GNX_MAT_MATTE, GNX_MATF_BUMP_IDENTITY);
+        set_rgb(m, 0, 0.5f, 0.5f, 0.5f);
+        sc->materials.push_back(m);
+        add_mesh(soup, gnxsk::ground_quad(2.2f, -1.5f), 1.f, zero, 0, 0, 0);
+        int w0, h0;
+        std::vector<float> rgb;
+        if (!load_hdr(res + "/MonValley1000.hdr", &w0, &h0, rgb, &sc->error)) return sc;
         build_env(rgb, w0, h0, 1.0f, sc->env);
         Mat4 l2w = mul(mul(rotate_axis(0, 20), rotate_axis(1, -90)), rotate_axis(0, -90));
         sc->finalize(soup, width, height, spp, true, l2w);

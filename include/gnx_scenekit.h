@@ -25,6 +25,8 @@ typedef struct gnxsk_scene gnxsk_scene;
 /* name: "cornell" (p0: 0 = Lambert walls, 1 = Oren-Nayar sigma 60; p1: icosphere subdivision, -1 = none)
  *       "dragon"  (p0: 0 = Plastic, 1 = Metal; p1 x p2: torus-knot quads, 0 = 2048 x 213)
  *       "nano"    (p0: 0 = Disney, 1 = thin Disney; p1 x p2: knot quads, 0 = 320 x 64; textured, smooth-shaded)
+ *       "smoke"   (p0: 0 = grid density medium in fog, PCG32 stream sampler; 1 = fog only, Halton) -> render with
+ *                 GNX_INTEGRATOR_VOLPATH
  * resources: directory holding MonValley1000.hdr (only read by "dragon").
  * Never returns NULL; check gnxsk_error(). */
 gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int p0, int p1, int p2,

@@ -14,6 +14,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -69,7 +70,8 @@ struct HarnessScene {
     std::unique_ptr<Transform> cam2world;
     std::unique_ptr<AnimatedTransform> animated;
     std::shared_ptr<const Camera> camera;
-    std::shared_ptr<HaltonSampler> sampler;
+    std::shared_ptr<Sampler> sampler;
+    int integrator = 0;  // 0 = PathIntegrator, 1 = VolPathIntegrator
     std::unique_ptr<Scene> scene;
     std::unique_ptr<FrameBuffer> fb;
     std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
@@ -83,6 +85,27 @@ struct HarnessScene {
         transforms.emplace_back(new Transform(t));
         return transforms.back().get();
     }
+};
+
+// A Sampler for integrators whose number of draws per sample is unbounded (VolPath + GridDensityMedium:
+// the reference's Halton tables stop at dimension 1000 and are read out of range beyond that, SURVEY.md
+// §8a-14).  One PCG32 stream (core/RNG.h) per camera sample, sequence id = (seed << 20) | sampleNumber where
+// seed is what SamplerIntegrator::Render passes to Clone(): W * y + x (core/Integrator.cpp:264,268).
+// The product's GNX_SAMPLER_PCG32 uses the same convention (gnx_sampler.cuh, PathSampler::stream).
+class PcgStreamSampler : public Sampler {
+  public:
+    PcgStreamSampler(int64_t spp, int seed = 0) : Sampler(spp), base(seed) {}
+    void StartPixel(const Point2i &p) override { Sampler::StartPixel(p); Reseed(0); }
+    bool StartNextSample() override { bool more = Sampler::StartNextSample(); Reseed(currentPixelSampleIndex); return more; }
+    bool SetSampleNumber(int64_t n) override { bool ok = Sampler::SetSampleNumber(n); Reseed(n); return ok; }
+    Float Get1D() override { return rng.UniformFloat(); }
+    Point2f Get2D() override { Float a = rng.UniformFloat(); Float b = rng.UniformFloat(); return Point2f(a, b); }
+    std::unique_ptr<Sampler> Clone(int seed) override { return std::unique_ptr<Sampler>(new PcgStreamSampler(samplesPerPixel, seed)); }
+
+  private:
+    void Reseed(int64_t s) { rng.SetSequence(((uint64_t)base << 20) | (uint64_t)s); }
+    int base;
+    RNG rng;
 };
 
 std::shared_ptr<Texture<Spectrum>> ConstSpec(float r, float g, float b) {
@@ -131,13 +154,14 @@ void SetupCamera(HarnessScene &hs, const Point3f &eye, const Point3f &look) {
     hs.camera = std::shared_ptr<Camera>(CreatePerspectiveCamera(hs.width, hs.height, *hs.animated));
 }
 
-void Finish(HarnessScene &hs) {
+void Finish(HarnessScene &hs, bool pcgSampler = false) {
     double t0 = omp_get_wtime();
     auto bvh = std::make_shared<BVHAccel>(hs.prims, 1);  // ui/RenderThread.cpp:155
     hs.bvhSeconds = omp_get_wtime() - t0;
     hs.scene.reset(new Scene(bvh, hs.lights));
     Bounds2i bounds(Point2i(0, 0), Point2i(hs.width, hs.height));
-    hs.sampler = std::make_shared<HaltonSampler>(hs.spp, bounds, false);  // ui/RenderThread.cpp:159
+    if (pcgSampler) hs.sampler = std::make_shared<PcgStreamSampler>(hs.spp);
+    else hs.sampler = std::make_shared<HaltonSampler>(hs.spp, bounds, false);  // ui/RenderThread.cpp:159
     hs.fb.reset(new FrameBuffer);
     hs.fb->InitBuffer(hs.width, hs.height, 4);
     for (size_t i = 0; i < hs.prims.size(); ++i) hs.originalIndex[hs.prims[i].get()] = (int)i;
@@ -237,6 +261,51 @@ bool BuildNano(HarnessScene &hs, int variant, int nu, int nv) {
     return true;
 }
 
+// Config 4: VolPathIntegrator, GridDensityMedium(density_render.70.volume) inside a HomogeneousMedium "fog"
+// box, both bounded by material-less triangles carrying MediumInterfaces, a Matte ground quad, MonValley
+// environment.  There is no .volume loader in the reference: the text file is parsed here (header tokens
+// nx ny nz / p0 / p1 / sigma_a / sigma_s, then nx*ny*nz floats, x fastest).
+// variant 0 = grid + fog (PCG stream sampler), 1 = fog only with the Halton sampler (bounded dimensions).
+bool BuildSmoke(HarnessScene &hs, int variant) {
+    std::string hdr = ResourceDir() + "MonValley1000.hdr", vol = ResourceDir() + "density_render.70.volume";
+    FILE *fp = fopen(hdr.c_str(), "rb");
+    if (!fp) { hs.error = "missing resource " + hdr; return false; }
+    fclose(fp);
+    auto fog = std::make_shared<HomogeneousMedium>(Spectrum(0.02f), Spectrum(0.08f), 0.5f);
+    hs.media.push_back(fog);
+    const Medium *inner = fog.get();
+    if (variant == 0) {
+        std::ifstream f(vol);
+        if (!f) { hs.error = "missing resource " + vol; return false; }
+        std::string tok;
+        int nx = 0, ny = 0, nz = 0;
+        float p0[3], p1[3], sa[3], ss[3];
+        f >> tok >> nx >> tok >> ny >> tok >> nz;
+        f >> tok >> p0[0] >> p0[1] >> p0[2] >> tok >> p1[0] >> p1[1] >> p1[2];
+        f >> tok >> sa[0] >> sa[1] >> sa[2] >> tok >> ss[0] >> ss[1] >> ss[2];
+        std::vector<Float> dens((size_t)nx * ny * nz);
+        for (Float &d : dens) f >> d;
+        if (!f || nx <= 0) { hs.error = "cannot parse " + vol; return false; }
+        // centre the medium box on the origin
+        Transform m2w = Translate(Vector3f(-1.f, -1.f, -0.4f)) * Translate(Vector3f(p0[0], p0[1], p0[2])) *
+                        Scale(p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]);
+        auto grid = std::make_shared<GridDensityMedium>(Spectrum(sa[0]), Spectrum(ss[0]), 0.f, nx, ny, nz, m2w, dens.data());
+        hs.media.push_back(grid);
+        const float lo[3] = {-1.f + p0[0] - 0.01f, -1.f + p0[1] - 0.01f, -0.4f + p0[2] - 0.01f};
+        const float hi[3] = {-1.f + p1[0] + 0.01f, -1.f + p1[1] + 0.01f, -0.4f + p1[2] + 0.01f};
+        AddMesh(hs, gnxsk::box(lo, hi), Transform(), nullptr, nullptr, MediumInterface(grid.get(), fog.get()));
+    }
+    const float flo[3] = {-2.4f, -2.4f, -2.4f}, fhi[3] = {2.4f, 2.4f, 2.4f};
+    AddMesh(hs, gnxsk::box(flo, fhi), Transform(), nullptr, nullptr, MediumInterface(inner, nullptr));
+    AddMesh(hs, gnxsk::ground_quad(2.2f, -1.5f), Transform(), Matte(0.5f, 0.5f, 0.5f, 0.f), nullptr, MediumInterface(inner));
+    Transform l2w = RotateX(20) * RotateY(-90) * RotateX(-90);
+    hs.lights.push_back(std::make_shared<InfiniteAreaLight>(l2w, Spectrum(1.0f), 10, hdr));
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    hs.integrator = 1;
+    Finish(hs, variant == 0);
+    return true;
+}
+
 void IndexPrims(HarnessScene &hs) {
     if (!hs.cuda || !hs.cuda->flat()) return;
     const auto &ptrs = hs.cuda->flat()->prim_ptr;
@@ -251,6 +320,7 @@ extern "C" {
 // name: "cornell" (p0 = variant, p1 = sphere subdivision, -1 = no spheres)
 //       "dragon"  (p0 = variant, p1 = nu, p2 = nv)
 //       "nano"    (p0 = variant, p1 = nu, p2 = nv)
+//       "smoke"   (p0 = variant)   -> VolPathIntegrator
 void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0, int p1, int p2) {
     auto *hs = new HarnessScene;
     hs->name = name;
@@ -258,6 +328,7 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     if (hs->name == "cornell") BuildCornell(*hs, p0, p1);
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
+    else if (hs->name == "smoke") BuildSmoke(*hs, p0);
     else hs->error = "unknown scene";
     return hs;
 }
@@ -275,9 +346,11 @@ int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, d
     hs->fb->InitBuffer(hs->width, hs->height, 4);
     hs->fb->renderCountClear();
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-    PathIntegrator integ(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    std::unique_ptr<SamplerIntegrator> integ;
+    if (hs->integrator == 1) integ.reset(new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get()));
+    else integ.reset(new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
     double t = 0;
-    integ.Render(*hs->scene, t);
+    integ->Render(*hs->scene, t);
     if (seconds) *seconds = t;
     if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * 4 * hs->width * hs->height);
     return 0;
@@ -290,12 +363,15 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
     auto *hs = (HarnessScene *)h;
     if (!hs->scene) return -1;
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-    PathIntegrator integ(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    std::unique_ptr<SamplerIntegrator> integp;
+    if (hs->integrator == 1) integp.reset(new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get()));
+    else integp.reset(new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
+    SamplerIntegrator &integ = *integp;
     integ.Preprocess(*hs->scene, *hs->sampler);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < n; ++i) {
         MemoryArena arena;
-        std::unique_ptr<Sampler> s = hs->sampler->Clone(0);
+        std::unique_ptr<Sampler> s = hs->sampler->Clone(hs->width * py[i] + px[i]);
         Point2i pixel(px[i], py[i]);
         s->StartPixel(pixel);
         s->SetSampleNumber(sample[i]);
@@ -324,7 +400,9 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
 
 int gnxh_reference_sample_dims(void *h, int n, const int64_t *index, const int *dim, float *out) {
     auto *hs = (HarnessScene *)h;
-    for (int i = 0; i < n; ++i) out[i] = hs->sampler->SampleDimension(index[i], dim[i]);
+    auto *hal = dynamic_cast<HaltonSampler *>(hs->sampler.get());
+    if (!hal) return -1;
+    for (int i = 0; i < n; ++i) out[i] = hal->SampleDimension(index[i], dim[i]);
     return 0;
 }
 
@@ -333,14 +411,16 @@ int64_t gnxh_reference_sample_index(void *h, int px, int py, int sample) {
     auto *hs = (HarnessScene *)h;
     std::unique_ptr<Sampler> s = hs->sampler->Clone(0);
     s->StartPixel(Point2i(px, py));
-    return static_cast<HaltonSampler *>(s.get())->GetIndexForSample(sample);
+    auto *hal = dynamic_cast<HaltonSampler *>(s.get());
+    return hal ? hal->GetIndexForSample(sample) : -1;
 }
 
 // ---- the product side, through the drop-in class -----------------------------------------------------
 static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
     if (!hs->cuda || hs->cudaMaxDepth != maxDepth) {
         Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
+        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial",
+                                                   hs->integrator == 1));
         hs->cudaMaxDepth = maxDepth;
     }
     return hs->cuda.get();

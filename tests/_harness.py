@@ -23,6 +23,8 @@ SCENES = {
     "nano": ("nano", 0, 96, 24),            # config 3 stand-in: Disney + ImageTexture + shading normals, small
     "nano_thin": ("nano", 1, 96, 24),       # thin Disney surface: transmission lobes
     "nano_full": ("nano", 0, 320, 64),      # ~ 90 k triangles
+    "smoke": ("smoke", 0, 0, 0),            # config 4: VolPath, grid density medium in homogeneous fog, PCG stream sampler
+    "fog": ("smoke", 1, 0, 0),              # VolPath, homogeneous fog only, Halton sampler
 }
 
 

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "gnx_pack.h"
-#include "gnx_path.cuh"
+#include "gnx_volpath.cuh"
 
 using namespace gnx;
 
@@ -23,6 +23,7 @@ struct EmulScene {
     DeviceScene sc{};
     std::vector<float4> tris, nodes2;
     std::vector<int2> media;
+    std::vector<DevMedium> dev_media;
     std::vector<DevTexture> textures;
     std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int;
     std::vector<int> primes, sums;
@@ -57,6 +58,16 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.textures = e.textures.data();
     sc.lights = d->lights;
     sc.n_lights = d->n_lights;
+    if (g.prim_medium_in && g.prim_medium_out) {
+        e.media.resize(g.n_prims);
+        for (int k = 0; k < g.n_prims; ++k) e.media[k] = make_int2(g.prim_medium_in[k], g.prim_medium_out[k]);
+        sc.tri_media = e.media.data();
+        sc.tri_transition = g.prim_is_transition;
+    }
+    e.dev_media.resize(d->n_media);
+    for (int i = 0; i < d->n_media; ++i) fill_dev_medium(d->media[i], d->media[i].density, e.dev_media[i]);
+    sc.media = e.dev_media.data();
+    sc.n_media = d->n_media;
     if (d->env.present) {
         const gnx_envmap &v = d->env;
         DevEnv &de = sc.env;
@@ -113,6 +124,15 @@ void ensure_spatial(EmulScene &e, int strategy) {
 V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, int sample, TraversalCounters &cnt,
                 unsigned long long rays[3]) {
     const DeviceScene &sc = e.sc;
+    if (p.integrator == GNX_INTEGRATOR_VOLPATH) {
+        RenderConsts rcv{};
+        rcv.width = p.width; rcv.height = p.height; rcv.max_depth = p.max_depth; rcv.rr_threshold = p.rr_threshold;
+        int2 vstack[kSmemStack];
+        VolCounters vc{0, 0, 0};
+        V3 Lv = volpath_li(sc, rcv, px, py, sample, vstack, 1, cnt, vc);
+        rays[0] += vc.extend; rays[1] += vc.shadow; rays[2] += vc.mis;
+        return Lv;
+    }
     float4 ray_o, ray_d, beta, L, hit;
     uint32_t hidx, meta;
     int32_t medium = -1;
@@ -203,7 +223,7 @@ int gnxe_primary_hits(void *h, int width, int height, int sample, int *out) {
 #pragma omp parallel for schedule(dynamic, 256)
     for (int pixel = 0; pixel < width * height; ++pixel) {
         int2 stack[kSmemStack];
-        out[pixel] = primary_hit_id(e->sc, pixel % width, pixel / width, sample, stack, 1);
+        out[pixel] = primary_hit_id(e->sc, width, pixel % width, pixel / width, sample, stack, 1);
     }
     return 0;
 }

@@ -193,6 +193,39 @@ def test_config3_scene_kit_disney_textured(ctx, emul):
     sk.close()
 
 
+@pytest.mark.parametrize("preset,res,spp", [("fog", 128, 8), ("smoke", 128, 8)])
+def test_volpath_bridge_render_matches_reference(ref, preset, res, spp):
+    """Config 4: VolPathIntegrator through the drop-in class (volumetric = true) against the reference's
+    VolPathIntegrator::Render on the same pbr::Scene with media."""
+    rs = ref.scene(preset, res, res, spp)
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, seconds, st = rs.render_cuda(max_depth=5)
+    assert st.paths == res * res * spp and st.rays_shadow > 0
+    r = rel_mse(img, img_ref)
+    assert r <= 1e-3, f"rel-MSE {r}"
+    px, py = grid(res, res)
+    sel = np.random.default_rng(9).choice(px.size, 512, replace=False)
+    samples = np.stack([rs.reference_samples(px[sel], py[sel], np.full(sel.size, s, np.int32), want_prim=False)[0] for s in range(spp)])
+    sigma = samples.std(axis=0, ddof=1) / np.sqrt(spp) + 1e-4
+    assert np.mean(np.abs(img.reshape(-1, 4)[sel, :3] - img_ref.reshape(-1, 4)[sel, :3]) <= 3 * sigma) >= 0.999
+    rs.close()
+
+
+def test_volpath_scene_kit_and_integrator_rules(ctx, emul):
+    from gnxraytracer_b200.api import GnxError
+    res = 64
+    sk = SceneKit("smoke", res, res, 4, 0, 0, 0)
+    ctx.upload(sk.desc)
+    p = RenderParams.make(res, res, 4, integrator=1)
+    a, _ = ctx.render(p)
+    b, _ = emul.scene(sk.desc).render(p)
+    assert rel_mse(a, b) <= 1e-4
+    with pytest.raises(GnxError) as e:   # PathIntegrator ignores media: refused rather than silently wrong
+        ctx.render(RenderParams.make(res, res, 4, integrator=0))
+    assert e.value.code == -4
+    sk.close()
+
+
 def test_errors_are_reported_not_swallowed(ctx):
     from gnxraytracer_b200.api import GnxError
     fresh = Context(0)
@@ -204,8 +237,8 @@ def test_errors_are_reported_not_swallowed(ctx):
     with pytest.raises(GnxError):
         fresh.render(RenderParams.make(0, 8, 1))
     with pytest.raises(GnxError) as e:
-        fresh.render(RenderParams.make(8, 8, 1, integrator=1))
-    assert e.value.code == -4
+        fresh.render(RenderParams.make(8, 8, 1, integrator=7))
+    assert e.value.code == -1
     fresh.close(); sk.close()
 
 

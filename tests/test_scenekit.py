@@ -7,11 +7,13 @@ from _harness import grid, rel_mse
 from gnxraytracer_b200.api import RenderParams, SceneKit
 
 
-@pytest.mark.parametrize("preset,args", [("cornell", (0, 2, 0)), ("dragon", (0, 256, 32)), ("dragon_metal", (1, 256, 32))])
+@pytest.mark.parametrize("preset,args", [("cornell", (0, 2, 0)), ("dragon", (0, 256, 32)), ("dragon_metal", (1, 256, 32)),
+                                         ("smoke", (0, 0, 0)), ("fog", (1, 0, 0))])
 def test_scenekit_scene_renders_like_the_reference(ref, emul, preset, args):
     res, spp = 48, 4
     rs = ref.scene(preset, res, res, spp)
-    sk = SceneKit(preset.split("_")[0], res, res, spp, *args)
+    sk = SceneKit({"fog": "smoke"}.get(preset, preset.split("_")[0]), res, res, spp, *args)
+    integ = 1 if preset in ("smoke", "fog") else 0
     assert sk.num_prims == rs.lib.gnxh_scene_num_prims(rs.h)
     es = emul.scene(sk.desc)
     px, py = grid(res, res)
@@ -20,7 +22,7 @@ def test_scenekit_scene_renders_like_the_reference(ref, emul, preset, args):
     hits = es.primary_hits(res, res, 0)  # scene-kit prim_id is already the original order
     assert np.mean(hits == prim) >= 0.999
     img_ref, _ = rs.render_reference(max_depth=5)
-    img, _ = es.render(RenderParams.make(res, res, spp, max_depth=5))
+    img, _ = es.render(RenderParams.make(res, res, spp, max_depth=5, integrator=integ))
     assert rel_mse(img, img_ref) <= 1e-3
     rs.close(); es.close(); sk.close()
 
