@@ -21,7 +21,10 @@ namespace gnx {
 #define GNX_SMEM_STACK 24
 #endif
 constexpr int kSmemStack = GNX_SMEM_STACK;   // levels kept in shared memory
-constexpr int kSpillStack = 40;  // further levels in local memory (reference total: 64)
+#ifndef GNX_BVH_WIDTH
+#define GNX_BVH_WIDTH 2  // 4 measured no faster (profiles/README.md)
+#endif
+constexpr int kSpillStack = GNX_BVH_WIDTH == 4 ? 72 : 40;  // further levels in local memory (reference total: 64; a 4-wide node pushes up to 3)
 
 struct TriHit {
     float t, b0, b1, b2;
@@ -189,9 +192,58 @@ GNX_D void trav_pop(Trav &t, const int2 *stack, int stride) {
     }
 }
 
+#if GNX_BVH_WIDTH == 4
+// Node4 (128 B = eight float4): lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4] (axTop, ax0, ax1, -).
+// Slots 0-1 are the children of the source node's first child, slots 2-3 of its second child (a child
+// that is a leaf occupies the first slot of its pair).  Visiting order = the reference's depth-first order:
+// near pair first by the sign on axTop, near slot first inside a pair by ax0 / ax1 (axis 3: slot order).
+GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
+    const float4 *np = sc.nodes2 + 8 * (size_t)t.cur;
+    const float4 lx = ldg(np), ly = ldg(np + 1), lz = ldg(np + 2), hx = ldg(np + 3), hy = ldg(np + 4), hz = ldg(np + 5);
+    const float4 rf = ldg(np + 6), ax = ldg(np + 7);
+    const int ref[4] = {f2i(rf.x), f2i(rf.y), f2i(rf.z), f2i(rf.w)};
+    const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+    const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+    float tmin[4];
+    bool hit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        hit[k] = false;
+        tmin[k] = 0;
+        if (ref[k] != kRefNone) { ++cnt.nodes; hit[k] = slab_test(t, lox[k], loy[k], loz[k], hix[k], hiy[k], hiz[k], &tmin[k]); }
+    }
+    const int axTop = f2i(ax.x), ax0 = f2i(ax.y), ax1 = f2i(ax.z);
+    const int swapTop = axTop < 3 && ((t.neg >> axTop) & 1);
+    const int swap0 = ax0 < 3 && ((t.neg >> ax0) & 1), swap1 = ax1 < 3 && ((t.neg >> ax1) & 1);
+    // visiting order of the four slots
+    int order[4];
+    order[swapTop ? 2 : 0] = swap0 ? 1 : 0;
+    order[swapTop ? 3 : 1] = swap0 ? 0 : 1;
+    order[swapTop ? 0 : 2] = swap1 ? 3 : 2;
+    order[swapTop ? 1 : 3] = swap1 ? 2 : 3;
+    // push the hit slots in reverse visiting order, then continue with the first one
+    int first = -1;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        const int sl = order[k];
+        if (hit[sl]) {
+            if (first >= 0) {
+                const int2 e = make_int2(ref[first], f2i(tmin[first]));
+                if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
+                ++t.sp;
+            }
+            first = sl;
+        }
+    }
+    if (first >= 0) t.cur = ref[first];
+    else trav_pop(t, stack, stride);
+}
+#else
 GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
     const float4 *np = sc.nodes2 + 4 * (size_t)t.cur;
-    const float4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3);
+    float4 n0, n1, n2, n3;
+    ldg256(np, &n0, &n1);
+    ldg256(np + 2, &n2, &n3);
     const int ref0 = f2i(n3.x), ref1 = f2i(n3.y), axis = f2i(n3.z);
     float tmin0 = 0, tmin1 = 0;
     bool hit0 = false, hit1 = false;
@@ -213,6 +265,8 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
         trav_pop(t, stack, stride);
     }
 }
+
+#endif
 
 template <bool ANY>
 GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stride, TraversalCounters &cnt) {

@@ -55,6 +55,18 @@ GNX_HD T ldg(const T *p) {
     return *p;
 #endif
 }
+// 32-byte read-only load (LDG.E.256 on sm_100a; the pointer must be 32-byte aligned).  A traversal step
+// gathers a 64-byte node per lane from unrelated addresses, so the L1 wavefront count — not bytes — is what
+// the load path pays for: two 256-bit loads cost half the wavefronts of four 128-bit ones.
+GNX_HD void ldg256(const float4 *p, float4 *a, float4 *b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+                 : "l"(p));
+#else
+    *a = p[0]; *b = p[1];
+#endif
+}
 GNX_HD uint64_t brev64(uint64_t n) {
 #ifdef __CUDA_ARCH__
     return __brevll(n);

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -143,6 +144,95 @@ inline bool build_node2(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
         out[4 * k + 2] = make_float4(r.lo1[2], r.hi1[0], r.hi1[1], r.hi1[2]);
         out[4 * k + 3] = make_float4(f0, f1, fa, 0.f);
     }
+    return true;
+}
+
+// Same input, 4-wide: every Node4 (gnx_bvh.cuh) covers an interior LinearBVHNode X and its two children, i.e.
+// holds the bounds of X's (up to) four grandchildren, slots 0-1 under X's first child and slots 2-3 under its
+// second child; a child that is itself a leaf takes one slot of its pair.  Halves the dependent fetches of
+// the two-child layout without changing which leaves are visited or in which order.
+inline bool build_node4(const gnx_bvh_node *nodes, int n, std::vector<float4> &out, std::string *err) {
+    out.clear();
+    if (n <= 0) return true;
+    struct N4 { float lo[3][4], hi[3][4]; int ref[4]; int axTop, ax0, ax1; };
+    std::vector<N4> v;
+    auto blank = [] { N4 r{}; for (int k = 0; k < 4; ++k) r.ref[k] = kRefNone; r.axTop = r.ax0 = r.ax1 = 3; return r; };
+    auto setBox = [](N4 &r, int slot, const gnx_bvh_node &b) { for (int c = 0; c < 3; ++c) { r.lo[c][slot] = b.bmin[c]; r.hi[c][slot] = b.bmax[c]; } };
+    // chain of "slot order" nodes for a leaf with more than kLeafMaxPrims primitives; returns a child reference
+    std::function<int(const gnx_bvh_node &, int, int)> leafRef = [&](const gnx_bvh_node &lf, int offset, int cnt) -> int {
+        if (cnt <= kLeafMaxPrims) return leaf_ref(offset, cnt);
+        int me = (int)v.size();
+        v.push_back(blank());
+        setBox(v[me], 0, lf); setBox(v[me], 2, lf);
+        v[me].ref[0] = leaf_ref(offset, kLeafMaxPrims);
+        int rest = leafRef(lf, offset + kLeafMaxPrims, cnt - kLeafMaxPrims);
+        v[me].ref[2] = rest;
+        return me;
+    };
+    std::vector<std::pair<int, int>> todo;  // (source interior node, Node4 index)
+    v.push_back(blank());
+    if (nodes[0].n_prims > 0) {
+        setBox(v[0], 0, nodes[0]);
+        int r = leafRef(nodes[0], nodes[0].offset, nodes[0].n_prims);
+        v[0].ref[0] = r;
+    } else todo.push_back({0, 0});
+    while (!todo.empty()) {
+        auto [x, me] = todo.back();
+        todo.pop_back();
+        const int c[2] = {x + 1, nodes[x].offset};
+        if (c[0] >= n || c[1] <= x || c[1] >= n) { *err = "malformed BVH node array"; return false; }
+        v[me].axTop = nodes[x].axis > 2 ? 0 : nodes[x].axis;
+        for (int k = 0; k < 2; ++k) {
+            const gnx_bvh_node &C = nodes[c[k]];
+            int &ax = k == 0 ? v[me].ax0 : v[me].ax1;
+            if (C.n_prims > 0) {
+                ax = 3;
+                setBox(v[me], 2 * k, C);
+                int r = leafRef(C, C.offset, C.n_prims);
+                v[me].ref[2 * k] = r;
+            } else {
+                ax = C.axis > 2 ? 0 : C.axis;
+                const int g[2] = {c[k] + 1, C.offset};
+                if (g[0] >= n || g[1] <= c[k] || g[1] >= n) { *err = "malformed BVH node array"; return false; }
+                for (int j = 0; j < 2; ++j) {
+                    const gnx_bvh_node &G = nodes[g[j]];
+                    setBox(v[me], 2 * k + j, G);
+                    if (G.n_prims > 0) { int r = leafRef(G, G.offset, G.n_prims); v[me].ref[2 * k + j] = r; }
+                    else {
+                        int idx = (int)v.size();
+                        v.push_back(blank());
+                        v[me].ref[2 * k + j] = idx;
+                        todo.push_back({g[j], idx});
+                    }
+                }
+            }
+        }
+    }
+    out.resize(v.size() * 8);
+    for (size_t i = 0; i < v.size(); ++i) {
+        const N4 &r = v[i];
+        for (int c = 0; c < 3; ++c) {
+            out[8 * i + c] = make_float4(r.lo[c][0], r.lo[c][1], r.lo[c][2], r.lo[c][3]);
+            out[8 * i + 3 + c] = make_float4(r.hi[c][0], r.hi[c][1], r.hi[c][2], r.hi[c][3]);
+        }
+        float f[4], a[3];
+        for (int k = 0; k < 4; ++k) memcpy(&f[k], &r.ref[k], 4);
+        memcpy(&a[0], &r.axTop, 4); memcpy(&a[1], &r.ax0, 4); memcpy(&a[2], &r.ax1, 4);
+        out[8 * i + 6] = make_float4(f[0], f[1], f[2], f[3]);
+        out[8 * i + 7] = make_float4(a[0], a[1], a[2], 0.f);
+    }
+    return true;
+}
+
+// Packs the node array in the layout the library was compiled for (GNX_BVH_WIDTH).
+inline bool build_nodes(const gnx_bvh_node *nodes, int n, std::vector<float4> &out, int *count, std::string *err) {
+#if GNX_BVH_WIDTH == 4
+    if (!build_node4(nodes, n, out, err)) return false;
+    *count = (int)(out.size() / 8);
+#else
+    if (!build_node2(nodes, n, out, err)) return false;
+    *count = (int)(out.size() / 4);
+#endif
     return true;
 }
 

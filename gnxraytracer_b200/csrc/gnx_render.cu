@@ -191,14 +191,15 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
     {
         std::vector<float4> n2, tris;
         std::string perr;
-        if (!build_node2(g.nodes, g.n_nodes, n2, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        int nNodes = 0;
+        if (!build_nodes(g.nodes, g.n_nodes, n2, &nNodes, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
         if (!pack_triangles(*d, tris, &typeMask, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
         std::vector<float4> both(n2);
         both.insert(both.end(), tris.begin(), tris.end());
         float4 *dn;
         if ((rc = dupload(ctx, pool, both.data(), both.size(), &dn))) return rc;
         sc.nodes2 = dn;
-        sc.n_nodes2 = (int)(n2.size() / 4);
+        sc.n_nodes2 = nNodes;
         sc.tris = dn + n2.size();
         ctx->geom_base = dn;
         ctx->geom_bytes = both.size() * sizeof(float4);

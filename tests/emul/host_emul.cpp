@@ -36,9 +36,8 @@ struct EmulScene {
 bool build(const gnx_scene_desc *d, EmulScene &e) {
     DeviceScene &sc = e.sc;
     const gnx_geometry &g = d->geom;
-    if (!build_node2(g.nodes, g.n_nodes, e.nodes2, &e.err)) return false;
+    if (!build_nodes(g.nodes, g.n_nodes, e.nodes2, &sc.n_nodes2, &e.err)) return false;
     sc.nodes2 = e.nodes2.data();
-    sc.n_nodes2 = (int)(e.nodes2.size() / 4);
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
     if (!pack_triangles(*d, e.tris, &e.typeMask, &e.err)) return false;

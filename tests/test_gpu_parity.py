@@ -174,10 +174,9 @@ def test_gpu_counters_match_the_restated_reference_traversal(ref, ctx):
     # reference runs a closest-hit query, so they test slightly FEWER nodes / triangles on this scene; with
     # area lights only (tests/test_restate.py, Cornell) the triangle counts are identical.
     assert 0 <= c["tris_tested"] - int(st.tris_tested) <= 0.03 * c["tris_tested"]
-    # slab tests: the two-child layout tests a node's box at its parent, so a ray that enters the root costs
-    # one test less than in the reference and a ray that misses the root one more (two children instead of
-    # the root itself); on this scene (91 % of camera rays miss) the totals agree to < 1 %
-    assert abs(c["nodes_visited"] - int(st.nodes_visited)) <= 0.02 * c["nodes_visited"]
+    # slab tests: the 4-wide layout never tests a child's own box, only its grandchildren's (see
+    # tests/test_restate.py): fewer tests than the reference order, never more
+    assert 0.6 * c["nodes_visited"] <= int(st.nodes_visited) <= 1.02 * c["nodes_visited"]
     rs.close(); ro.close()
 
 

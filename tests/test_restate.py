@@ -70,8 +70,8 @@ def test_restate_and_emulated_kernels_agree_on_counters(ref, restate, emul):
     assert rel_mse(b, a) <= 1e-6
     assert ca["rays_extend"] == sb.rays_extend and ca["rays_shadow"] == sb.rays_shadow
     assert ca["tris_tested"] == sb.tris_tested
-    # the two-child layout tests a node's box at its parent, so every box test of the reference order has
-    # its counterpart except the root's own (one per ray)
-    rays = int(sb.rays_extend + sb.rays_shadow + sb.rays_mis)
-    assert abs(ca["nodes_visited"] - (int(sb.nodes_visited) + rays)) <= 0.01 * ca["nodes_visited"]
+    # Slab tests: the 4-wide layout tests the boxes of a node's grandchildren directly, so it never tests a
+    # child's own box: fewer tests than the reference order (which tests every popped node), never more, and
+    # the very same leaves in the very same order (triangle counts above are identical).
+    assert 0.6 * ca["nodes_visited"] <= int(sb.nodes_visited) <= ca["nodes_visited"]
     r.close()
