@@ -92,7 +92,7 @@ GNX_D V3 cosine_sample_hemisphere(float u0, float u1) {
 }
 
 // ---- Fresnel, core/Reflection.cpp:16-64 -------------------------------------------------------------
-GNX_D float fr_dielectric(float cosThetaI, float etaI, float etaT) {
+GNX_LOBE_FN float fr_dielectric(float cosThetaI, float etaI, float etaT) {
     cosThetaI = clampf(cosThetaI, -1, 1);
     bool entering = cosThetaI > 0.f;
     if (!entering) { float t = etaI; etaI = etaT; etaT = t; cosThetaI = fabsf(cosThetaI); }
@@ -104,7 +104,7 @@ GNX_D float fr_dielectric(float cosThetaI, float etaI, float etaT) {
     float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
     return (Rparl * Rparl + Rperp * Rperp) / 2;
 }
-GNX_D V3 fr_conductor(float cosThetaI, V3 etai, V3 etat, V3 k) {
+GNX_LOBE_FN V3 fr_conductor(float cosThetaI, V3 etai, V3 etat, V3 k) {
     cosThetaI = clampf(cosThetaI, -1, 1);
     V3 eta = etat / etai, etak = k / etai;
     float cosThetaI2 = cosThetaI * cosThetaI;
@@ -145,14 +145,14 @@ GNX_D V3 lobe_fresnel(const Lobe &l, float cosI) {
 }
 
 // ---- TrowbridgeReitzDistribution, core/MicroFacet.cpp:129-136,150-159,215-316 ----------------------
-GNX_D float tr_D(V3 wh, float ax, float ay) {
+GNX_LOBE_FN float tr_D(V3 wh, float ax, float ay) {
     float tan2Theta = tan2_theta(wh);
     if (finf(tan2Theta)) return 0.f;
     const float cos4Theta = cos2_theta(wh) * cos2_theta(wh);
     float e = (cos2_phi(wh) / (ax * ax) + sin2_phi(wh) / (ay * ay)) * tan2Theta;
     return 1 / (kPi * ax * ay * cos4Theta * (1 + e) * (1 + e));
 }
-GNX_D float tr_lambda(V3 w, float ax, float ay) {
+GNX_LOBE_FN float tr_lambda(V3 w, float ax, float ay) {
     float absTanTheta = fabsf(tan_theta(w));
     if (finf(absTanTheta)) return 0.f;
     float alpha = sqrtf(cos2_phi(w) * ax * ax + sin2_phi(w) * ay * ay);
@@ -191,7 +191,7 @@ GNX_D void tr_sample11(float cosTheta, float U1, float U2, float *slope_x, float
               (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
     *slope_y = S * z * sqrtf(1.f + *slope_x * *slope_x);
 }
-GNX_D V3 tr_sample(V3 wi, float ax, float ay, float U1, float U2) {
+GNX_LOBE_FN V3 tr_sample(V3 wi, float ax, float ay, float U1, float U2) {
     V3 wiS = normalize(V3(ax * wi.x, ay * wi.y, wi.z));
     float sx, sy;
     tr_sample11(cos_theta(wiS), U1, U2, &sx, &sy);
@@ -229,7 +229,7 @@ GNX_D float smith_g_ggx(float cosTheta, float alpha) {
 }
 
 // ---- per-lobe f / pdf / sample ----------------------------------------------------------------------------
-GNX_D V3 lobe_f(const Lobe &l, V3 wo, V3 wi) {
+GNX_LOBE_FN V3 lobe_f(const Lobe &l, V3 wo, V3 wi) {
     switch (l.kind) {
     case LK_LAMBERT_R:
     case LK_LAMBERT_T:
@@ -317,7 +317,7 @@ GNX_D V3 lobe_f(const Lobe &l, V3 wo, V3 wi) {
     }
 }
 
-GNX_D float lobe_pdf(const Lobe &l, V3 wo, V3 wi) {
+GNX_LOBE_FN float lobe_pdf(const Lobe &l, V3 wo, V3 wi) {
     switch (l.kind) {
     case LK_LAMBERT_R:
     case LK_OREN_NAYAR:
@@ -355,8 +355,11 @@ GNX_D float lobe_pdf(const Lobe &l, V3 wo, V3 wi) {
     }
 }
 
-// Returns f; *pdf == 0 means "no sample".  *sampledType is preset to l.type by the caller.
-GNX_D V3 lobe_sample(const Lobe &l, V3 wo, float u0, float u1, V3 *wi, float *pdf, int *sampledType) {
+// *pdf == 0 means "no sample".  *sampledType is preset to l.type by the caller.  The return value is f for the
+// SPECULAR lobes only: for every other lobe BSDF::Sample_f discards the sampled lobe's f and re-evaluates the
+// sum over all matching lobes (core/Reflection.cpp:545-556), so it is not computed here (it was 10 % of the
+// shade kernel, at half-empty warps).
+GNX_LOBE_FN V3 lobe_sample(const Lobe &l, V3 wo, float u0, float u1, V3 *wi, float *pdf, int *sampledType) {
     switch (l.kind) {
     case LK_SPEC_R: {  // core/Reflection.cpp:89-97
         *wi = V3(-wo.x, -wo.y, wo.z);
@@ -397,7 +400,7 @@ GNX_D V3 lobe_sample(const Lobe &l, V3 wo, float u0, float u1, V3 *wi, float *pd
         *wi = reflect(wo, wh);
         if (!same_hemisphere(wo, *wi)) return V3(0.f);
         *pdf = tr_pdf(wo, wh, l.p0, l.p1) / (4 * dot(wo, wh));
-        return lobe_f(l, wo, *wi);
+        return V3(0.f);
     }
     case LK_MICRO_T: {  // core/Reflection.cpp:249-258
         if (wo.z == 0) return V3(0.f);
@@ -406,13 +409,13 @@ GNX_D V3 lobe_sample(const Lobe &l, V3 wo, float u0, float u1, V3 *wi, float *pd
         float eta = cos_theta(wo) > 0 ? (l.e0 / l.e1) : (l.e1 / l.e0);
         if (!refract(wo, wh, eta, wi)) return V3(0.f);
         *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        return V3(0.f);
     }
     case LK_LAMBERT_T: {  // core/Reflection.cpp:146-154
         *wi = cosine_sample_hemisphere(u0, u1);
         if (wo.z > 0) wi->z *= -1;
         *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        return V3(0.f);
     }
     case LK_DISNEY_CLEARCOAT: {  // DisneyMaterial.cpp:260-283
         if (wo.z == 0) return V3(0.f);
@@ -425,15 +428,43 @@ GNX_D V3 lobe_sample(const Lobe &l, V3 wo, float u0, float u1, V3 *wi, float *pd
         *wi = reflect(wo, wh);
         if (!same_hemisphere(wo, *wi)) return V3(0.f);
         *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        return V3(0.f);
     }
     default: {  // BxDF::Sample_f, core/Reflection.cpp:394-402
         *wi = cosine_sample_hemisphere(u0, u1);
         if (wo.z < 0) wi->z *= -1;
         *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        return V3(0.f);
     }
     }
+}
+
+// f and pdf of one lobe for the same pair of directions.  The microfacet reflection lobe shares the half vector,
+// D(wh) and Lambda(wo) between the two (identical inputs, hence identical bits); every other lobe is the two
+// separate evaluations.
+GNX_D void lobe_eval(const Lobe &l, V3 wo, V3 wi, bool needF, bool needPdf, V3 *f, float *pdf) {
+    *f = V3(0.f);
+    *pdf = 0.f;
+    if (l.kind == LK_MICRO_R) {
+        const float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
+        const V3 whs = wi + wo;
+        const bool fOk = needF && !(cosThetaI == 0 || cosThetaO == 0) && !(whs.x == 0 && whs.y == 0 && whs.z == 0);
+        const bool pdfOk = needPdf && same_hemisphere(wo, wi);
+        if (!(fOk || pdfOk)) return;
+        const V3 wh = normalize(whs);
+        const float D = tr_D(wh, l.p0, l.p1);
+        const float lambdaO = tr_lambda(wo, l.p0, l.p1);
+        if (pdfOk) *pdf = (D * (1 / (1 + lambdaO)) * absdot(wo, wh) / abs_cos_theta(wo)) / (4 * dot(wo, wh));
+        if (fOk) {
+            const V3 F = lobe_fresnel(l, dot(wi, faceforward(wh, V3(0, 0, 1))));
+            const float lambdaI = tr_lambda(wi, l.p0, l.p1);
+            const float G = l.distrib == DK_DISNEY ? (1 / (1 + lambdaO)) * (1 / (1 + lambdaI)) : 1 / (1 + lambdaO + lambdaI);
+            *f = div_each(l.R * D * G * F, 4 * cosThetaI * cosThetaO);
+        }
+        return;
+    }
+    if (needF) *f = lobe_f(l, wo, wi);
+    if (needPdf) *pdf = lobe_pdf(l, wo, wi);
 }
 
 // ---- BSDF::f / Pdf / Sample_f, core/Reflection.cpp:440-563 -----------------------------------------------------
@@ -464,6 +495,32 @@ GNX_D float bsdf_pdf(const Bsdf<MAXL> &b, V3 woW, V3 wiW, int flags) {
     return matching > 0 ? pdf / matching : 0.f;
 }
 
+// BSDF::f and BSDF::Pdf for the same directions (EstimateDirect's light-sampling half calls both)
+template <int MAXL>
+GNX_D void bsdf_f_pdf(const Bsdf<MAXL> &b, V3 woW, V3 wiW, int flags, V3 *fOut, float *pdfOut) {
+    *fOut = V3(0.f);
+    *pdfOut = 0.f;
+    V3 wi = b.to_local(wiW), wo = b.to_local(woW);
+    if (wo.z == 0 || b.n == 0) return;
+    bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    V3 f(0.f);
+    float pdf = 0.f;
+    int matching = 0;
+    for (int i = 0; i < b.n; ++i) {
+        const Lobe &l = b.lobes[i];
+        if ((l.type & flags) != l.type) continue;
+        ++matching;
+        const bool needF = (refl && (l.type & BSDF_REFLECTION)) || (!refl && (l.type & BSDF_TRANSMISSION));
+        V3 fi;
+        float pi;
+        lobe_eval(l, wo, wi, needF, true, &fi, &pi);
+        if (needF) f += fi;
+        pdf += pi;
+    }
+    *fOut = f;
+    *pdfOut = matching > 0 ? pdf / matching : 0.f;
+}
+
 template <int MAXL>
 GNX_D V3 bsdf_sample(const Bsdf<MAXL> &b, V3 woW, V3 *wiW, float u0, float u1, float *pdf, int flags, int *sampledType) {
     int matching = b.num_components(flags);
@@ -483,20 +540,25 @@ GNX_D V3 bsdf_sample(const Bsdf<MAXL> &b, V3 woW, V3 *wiW, float u0, float u1, f
     V3 f = lobe_sample(l, wo, ur0, u1, &wi, pdf, sampledType);
     if (*pdf == 0) { *sampledType = 0; return V3(0.f); }
     *wiW = b.to_world(wi);
-    if (!(l.type & BSDF_SPECULAR) && matching > 1)
-        for (int i = 0; i < b.n; ++i)
-            if (i != chosen && (b.lobes[i].type & flags) == b.lobes[i].type) *pdf += lobe_pdf(b.lobes[i], wo, wi);
-    if (matching > 1) *pdf /= matching;
     if (!(l.type & BSDF_SPECULAR)) {
-        bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        // pdf: the other matching lobes are added in lobe order; f: the sum over the lobes on the right side
+        // of the geometric normal, in lobe order (core/Reflection.cpp:536-556) — one pass serves both
+        const bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
         f = V3(0.f);
         for (int i = 0; i < b.n; ++i) {
             const Lobe &li = b.lobes[i];
-            if ((li.type & flags) == li.type &&
-                ((refl && (li.type & BSDF_REFLECTION)) || (!refl && (li.type & BSDF_TRANSMISSION))))
-                f += lobe_f(li, wo, wi);
+            if ((li.type & flags) != li.type) continue;
+            const bool needF = (refl && (li.type & BSDF_REFLECTION)) || (!refl && (li.type & BSDF_TRANSMISSION));
+            const bool needPdf = i != chosen && matching > 1;
+            if (!(needF || needPdf)) continue;
+            V3 fi;
+            float pi;
+            lobe_eval(li, wo, wi, needF, needPdf, &fi, &pi);
+            if (needF) f += fi;
+            if (needPdf) *pdf += pi;
         }
     }
+    if (matching > 1) *pdf /= matching;
     return f;
 }
 

@@ -126,6 +126,7 @@ struct TraversalCounters { unsigned nodes, tris; };
 // oversized leaves).  The order in which leaves are intersected is the reference's order, so the
 // closest hit is the same hit (not merely an equally close one).
 constexpr int kRefNone = 0x7fffffff;
+constexpr int kRefPop = 0x7ffffffe;   // traversal state: "take the next entry from the stack" (see trav_pop)
 constexpr int kLeafMaxPrims = 16;
 GNX_HD int leaf_ref(int offset, int count) { return ~(offset | ((count - 1) << 27)); }
 
@@ -137,7 +138,13 @@ struct Trav {
     bool hit;
     TriHit h;
     int prim;
-    int2 spill[kSpillStack];
+    int2 *spill;  // kSpillStack entries of the caller's local memory (kept out of the struct so that cur / sp /
+                  // tMax stay in registers: with the array inside, every step stored them to the local frame)
+};
+// Trav with its own spill storage, for the sequential callers.
+struct TravLocal : Trav {
+    int2 store[kSpillStack];
+    GNX_D TravLocal() { spill = store; }
 };
 
 GNX_D void trav_init(const DeviceScene &sc, Trav &t, V3 o, V3 d, float tMax) {
@@ -155,22 +162,25 @@ GNX_D void trav_init(const DeviceScene &sc, Trav &t, V3 o, V3 d, float tMax) {
 // Bounds3::IntersectP(ray, invDir, dirIsNeg), core/Geometry.h:1380-1406; *tminOut is the entry distance
 // the reference compares with ray.tMax.
 GNX_D bool slab_test(const Trav &t, float lox, float loy, float loz, float hix, float hiy, float hiz, float *tminOut) {
+    // Same operations and comparisons as the reference, without its early returns: a warp gathers 32
+    // unrelated nodes, so some lane always needs the z slab, and the branches only added divergence
+    // bookkeeping.  (Selects, not fminf/fmaxf: a NaN from 0 * inf must propagate as it does in the reference.)
     const float widen = 1 + 2 * gamma_n(3);
     const bool n0 = t.neg & 1, n1 = t.neg & 2, n2 = t.neg & 4;
     float tmin = ((n0 ? hix : lox) - t.o.x) * t.invDir.x, tmax = ((n0 ? lox : hix) - t.o.x) * t.invDir.x;
     float tymin = ((n1 ? hiy : loy) - t.o.y) * t.invDir.y, tymax = ((n1 ? loy : hiy) - t.o.y) * t.invDir.y;
     tmax *= widen;
     tymax *= widen;
-    if (tmin > tymax || tymin > tmax) return false;
-    if (tymin > tmin) tmin = tymin;
-    if (tymax < tmax) tmax = tymax;
+    const bool missXY = (tmin > tymax) | (tymin > tmax);
+    tmin = tymin > tmin ? tymin : tmin;
+    tmax = tymax < tmax ? tymax : tmax;
     float tzmin = ((n2 ? hiz : loz) - t.o.z) * t.invDir.z, tzmax = ((n2 ? loz : hiz) - t.o.z) * t.invDir.z;
     tzmax *= widen;
-    if (tmin > tzmax || tzmin > tmax) return false;
-    if (tzmin > tmin) tmin = tzmin;
-    if (tzmax < tmax) tmax = tzmax;
+    const bool missZ = (tmin > tzmax) | (tzmin > tmax);
+    tmin = tzmin > tmin ? tzmin : tmin;
+    tmax = tzmax < tmax ? tzmax : tmax;
     *tminOut = tmin;
-    return (tmin < t.tMax) && (tmax > 0);
+    return !missXY & !missZ & (tmin < t.tMax) & (tmax > 0);
 }
 
 // The traversal is split the "while-while" way so that the lanes of a warp do the same kind of work at
@@ -178,17 +188,21 @@ GNX_D bool slab_test(const Trav &t, float lox, float loy, float loz, float hix, 
 // trav_leaf intersects one leaf and pops.  t.cur is an interior index (0 <= cur < kRefNone), a leaf
 // reference (negative) or kRefNone when the traversal is over.  `stack` is the calling thread's column
 // of a shared-memory stack (entry k at stack[k * stride]); deeper levels spill into t.spill.
-GNX_D bool trav_is_interior(const Trav &t) { return (unsigned)t.cur < (unsigned)kRefNone; }
+GNX_D bool trav_is_interior(const Trav &t) { return (unsigned)t.cur < (unsigned)kRefPop; }
+GNX_D bool trav_needs_pop(const Trav &t) { return t.cur == kRefPop; }
 GNX_D bool trav_is_leaf(const Trav &t) { return t.cur < 0; }
 GNX_D bool trav_done(const Trav &t) { return t.cur == kRefNone; }
 
-// pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax)
+// pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax).  An any-hit
+// ray's tMax never shrinks, so its entries stay valid.  trav_interior / trav_leaf only request the pop
+// (cur = kRefPop): the caller runs it for all requesting lanes of the warp together.
+template <bool ANY>
 GNX_D void trav_pop(Trav &t, const int2 *stack, int stride) {
     while (true) {
         if (t.sp == 0) { t.cur = kRefNone; return; }
         --t.sp;
         const int2 e = t.sp < kSmemStack ? stack[t.sp * stride] : t.spill[t.sp - kSmemStack];
-        if (i2f(e.y) < t.tMax) { t.cur = e.x; return; }
+        if (ANY || i2f(e.y) < t.tMax) { t.cur = e.x; return; }
     }
 }
 
@@ -235,8 +249,7 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
             first = sl;
         }
     }
-    if (first >= 0) t.cur = ref[first];
-    else trav_pop(t, stack, stride);
+    t.cur = first >= 0 ? ref[first] : kRefPop;
 }
 #else
 GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
@@ -245,25 +258,20 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
     ldg256(np, &n0, &n1);
     ldg256(np + 2, &n2, &n3);
     const int ref0 = f2i(n3.x), ref1 = f2i(n3.y), axis = f2i(n3.z);
-    float tmin0 = 0, tmin1 = 0;
-    bool hit0 = false, hit1 = false;
-    if (ref0 != kRefNone) { ++cnt.nodes; hit0 = slab_test(t, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, &tmin0); }
-    if (ref1 != kRefNone) { ++cnt.nodes; hit1 = slab_test(t, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, &tmin1); }
-    const bool nearIs1 = axis < 3 && ((t.neg >> axis) & 1);
+    float tmin0, tmin1;
+    const bool hit0 = slab_test(t, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, &tmin0) & (ref0 != kRefNone);
+    const bool hit1 = slab_test(t, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, &tmin1) & (ref1 != kRefNone);
+    cnt.nodes += 2;
+    if (ref1 == kRefNone) --cnt.nodes;  // single-child link of a chained oversized leaf (ref0 is never empty)
+    const bool nearIs1 = (axis < 3) & ((t.neg >> axis) & 1);
     const int refN = nearIs1 ? ref1 : ref0, refF = nearIs1 ? ref0 : ref1;
     const bool hitN = nearIs1 ? hit1 : hit0, hitF = nearIs1 ? hit0 : hit1;
-    if (hitN) {
-        t.cur = refN;
-        if (hitF) {
-            const int2 e = make_int2(refF, f2i(nearIs1 ? tmin0 : tmin1));
-            if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
-            ++t.sp;
-        }
-    } else if (hitF) {
-        t.cur = refF;
-    } else {
-        trav_pop(t, stack, stride);
+    if (hitN & hitF) {
+        const int2 e = make_int2(refF, f2i(nearIs1 ? tmin0 : tmin1));
+        if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
+        ++t.sp;
     }
+    t.cur = hitN ? refN : (hitF ? refF : kRefPop);
 }
 
 #endif
@@ -284,7 +292,7 @@ GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stri
             if (ANY) { t.cur = kRefNone; return; }
         }
     }
-    trav_pop(t, stack, stride);
+    t.cur = kRefPop;
 }
 
 // One step for sequential callers: an interior node and whatever leaves follow it.  Returns true when
@@ -292,7 +300,11 @@ GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stri
 template <bool ANY>
 GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
     if (trav_is_interior(t)) trav_interior(sc, t, stack, stride, cnt);
-    while (trav_is_leaf(t)) trav_leaf<ANY>(sc, t, stack, stride, cnt);
+    if (trav_needs_pop(t)) trav_pop<ANY>(t, stack, stride);
+    while (trav_is_leaf(t)) {
+        trav_leaf<ANY>(sc, t, stack, stride, cnt);
+        if (trav_needs_pop(t)) trav_pop<ANY>(t, stack, stride);
+    }
     return trav_done(t);
 }
 
@@ -300,7 +312,7 @@ GNX_D bool trav_step(const DeviceScene &sc, Trav &t, int2 *stack, int stride, Tr
 template <bool ANY>
 GNX_D bool traverse(const DeviceScene &sc, V3 o, V3 d, float tMax, int2 *stack, int stride, int *primOut, TriHit *hitOut,
                     TraversalCounters &cnt) {
-    Trav t;
+    TravLocal t;
     trav_init(sc, t, o, d, tMax);
     while (!trav_step<ANY>(sc, t, stack, stride, cnt)) {}
     if (t.hit) { *primOut = t.prim; *hitOut = t.h; }

@@ -59,7 +59,17 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
 //   KIND 2: probe_q (closest hit must be the light's triangle)   -> L += contrib
 //   KIND 3: camera rays of the batch, generated in registers (ray-gen fused with the first extension;
 //           path state is written only for rays that hit)      -> L = Le or hit record + shade queues
-constexpr int kRefetchBelow = 24;
+#ifndef GNX_REFETCH
+#define GNX_REFETCH 24
+#endif
+constexpr int kRefetchBelow = GNX_REFETCH;
+#ifndef GNX_REFETCH_PRIMARY
+#define GNX_REFETCH_PRIMARY 1
+#endif
+// Camera rays refill only when the whole warp has drained: generating a camera ray (Halton digits, lens,
+// ray transform) costs about as much as tracing it, so ray-gen must run with all 32 lanes (measured on C2:
+// threshold 24 -> 39.4 ms, 12 -> 36.2, 4 -> 35.1, 1 -> 34.5).
+constexpr int kRefetchBelowPrimary = GNX_REFETCH_PRIMARY;
 #ifndef GNX_LEAF_BATCH
 #define GNX_LEAF_BATCH 8
 #endif
@@ -83,15 +93,27 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     TraversalCounters cnt{0, 0};
     unsigned rays = 0;
     Trav t;
+    int2 spill[kSpillStack];
+    t.spill = spill;
     t.cur = kRefNone;
     bool active = false, exhausted = false;
     int item = 0;            // path slot (KIND 0, 3) or queue index (KIND 1, 2) of the lane's ray
     int pendType = -1, pendSlot = 0;
     uint32_t hidx = 0;       // KIND 3 only
     V3 camD;                 // KIND 3 only
+    bool needFinish = false;  // KIND 0 / 3: traversal over, result not consumed yet
     while (true) {
         if (kExtend) {
-            // shade-queue pushes of the rays that finished since the last visit, one atomic per warp and queue
+            // The rays that finished since the last visit are consumed here, together: the environment lookup
+            // of escaped rays (atan2f / acosf / bilinear fetch) and the path-state writes of hits run with as
+            // many lanes as were idle instead of one lane at a time inside the traversal loop.
+            if (needFinish) {
+                if (KIND == 3) pendType = primary_finish(sc, ps, rc, item, hidx, camD, t);
+                else pendType = extend_finish(sc, ps, rc, item, t);
+                pendSlot = item;
+                needFinish = false;
+            }
+            // shade-queue pushes, one atomic per warp and queue
             if (__any_sync(kFull, pendType >= 0)) {
 #pragma unroll
                 for (int ty = 0; ty < kNumShadeTypes; ++ty) {
@@ -140,15 +162,16 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
             if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
+            // pops requested by this round's interior steps (both children missed) and leaves, together
+            if (active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock);
             if (active && trav_done(t)) {
-                if (KIND == 3) { pendType = primary_finish(sc, ps, rc, item, hidx, camD, t); pendSlot = item; }
-                else if (KIND == 0) { pendType = extend_finish(sc, ps, rc, item, t); pendSlot = item; }
+                if (kExtend) needFinish = true;
                 else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
                 else probe_finish(ps, q.probe_q + item, t);
                 active = false;
             }
             const unsigned actMask = __ballot_sync(kFull, active);
-            if (actMask == 0 || (!exhausted && __popc(actMask) < kRefetchBelow)) break;
+            if (actMask == 0 || (!exhausted && __popc(actMask) < (KIND == 3 ? kRefetchBelowPrimary : kRefetchBelow))) break;
         }
     }
     flush_stats(st, kExtend ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);

@@ -32,6 +32,23 @@ inline void make_primes(std::vector<int> &primes, std::vector<int> &sums) {
     int s = 0;
     for (size_t i = 0; i < primes.size(); ++i) { sums[i] = s; s += primes[i]; }
 }
+// Per-dimension record of the scrambled radical inverse: the prime, the offset of its permutation in the
+// concatenated table (PrimeSums, samplers/LowDiscrepancy.cpp:86-) and the exact-division constant of
+// gnx_sampler.cuh.
+inline void make_dim_table(const std::vector<int> &primes, const std::vector<int> &sums, std::vector<uint4> &dims) {
+    dims.resize(primes.size());
+    for (size_t i = 0; i < primes.size(); ++i) {
+        uint64_t d = (uint64_t)primes[i];
+        uint64_t m = ((1ull << 38) + d - 1) / d;
+        dims[i] = make_uint4((uint32_t)primes[i], (uint32_t)sums[i], (uint32_t)(m & 0xffffffffu), (uint32_t)(m >> 32));
+    }
+}
+// Environment-map texels [h][w][3] -> one 16-byte record per texel (a bilinear lookup gathers four
+// unrelated texels: 4 x LDG.128 instead of 12 scalar loads).
+inline void pack_env_texels(const float *rgb, size_t n, std::vector<float4> &out) {
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f);
+}
 inline uint32_t pcg_bounded(Pcg32 &rng, uint32_t b) {
     uint32_t threshold = (~b + 1u) % b;
     while (true) {

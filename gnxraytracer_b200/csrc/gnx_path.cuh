@@ -121,7 +121,7 @@ GNX_D int extend_finish(const DeviceScene &sc, const PathState &ps, const Render
 }
 GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, int2 *stack, int stride,
                       TraversalCounters &cnt) {
-    Trav t;
+    TravLocal t;
     extend_begin(sc, ps, slot, t);
     while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
     return extend_finish(sc, ps, rc, slot, t);
@@ -194,8 +194,10 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
             LightSample ls;
             bool ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
             if (ok && ls.pdf > 0 && !is_black(ls.Li)) {
-                V3 f = bsdf_f(bsdf, s.wo, ls.wi, kNonSpec) * absdot(ls.wi, ns);
-                float scatteringPdf = bsdf_pdf(bsdf, s.wo, ls.wi, kNonSpec);
+                V3 f;
+                float scatteringPdf;
+                bsdf_f_pdf(bsdf, s.wo, ls.wi, kNonSpec, &f, &scatteringPdf);
+                f = f * absdot(ls.wi, ns);
                 if (!is_black(f)) {
                     V3 origin, dirv;
                     if (isEnv) {
@@ -303,7 +305,7 @@ GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav
 }
 GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int2 *stack, int stride,
                        TraversalCounters &cnt) {
-    Trav t;
+    TravLocal t;
     shadow_begin(sc, item, t);
     while (!trav_step<true>(sc, t, stack, stride, cnt)) {}
     shadow_finish(ps, item, t);
@@ -324,7 +326,7 @@ GNX_D void probe_finish(const PathState &ps, const ProbeItem *item, const Trav &
 }
 GNX_D void probe_item(const DeviceScene &sc, const PathState &ps, const ProbeItem *item, int2 *stack, int stride,
                       TraversalCounters &cnt) {
-    Trav t;
+    TravLocal t;
     probe_begin(sc, item, t);
     while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
     probe_finish(ps, item, t);

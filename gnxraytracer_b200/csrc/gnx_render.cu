@@ -280,7 +280,12 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         DevEnv &de = sc.env;
         de.present = 1; de.light_index = e.light_index;
         de.w = e.width; de.h = e.height; de.dw = e.dist_w; de.dh = e.dist_h;
-        if ((rc = dupload(ctx, pool, e.texels, (size_t)e.width * e.height * 3, &df))) return rc; de.texels = df;
+        {
+            std::vector<float4> tex;
+            pack_env_texels(e.texels, (size_t)e.width * e.height, tex);
+            float4 *d4;
+            if ((rc = dupload(ctx, pool, tex.data(), tex.size(), &d4))) return rc; de.texels = d4;
+        }
         if ((rc = dupload(ctx, pool, e.cond_func, (size_t)e.dist_w * e.dist_h, &df))) return rc; de.cond_func = df;
         if ((rc = dupload(ctx, pool, e.cond_cdf, (size_t)(e.dist_w + 1) * e.dist_h, &df))) return rc; de.cond_cdf = df;
         if ((rc = dupload(ctx, pool, e.cond_int, (size_t)e.dist_h, &df))) return rc; de.cond_int = df;
@@ -339,6 +344,8 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
     sc.smp.stride = s.sample_stride;
     sc.smp.mult_inv0 = s.mult_inverse[0]; sc.smp.mult_inv1 = s.mult_inverse[1];
     sc.smp.at_center = s.sample_at_pixel_center;
+    sc.smp.stride_over_scale0 = s.type == GNX_SAMPLER_HALTON ? s.sample_stride / s.base_scales[0] : 0;
+    sc.smp.stride_over_scale1 = s.type == GNX_SAMPLER_HALTON ? s.sample_stride / s.base_scales[1] : 0;
     {
         std::vector<int> primes, sums;
         make_primes(primes, sums);
@@ -348,10 +355,12 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         if (!hp) { make_permutations(primes, perms); hp = perms.data(); np = perms.size(); }
         size_t need = (size_t)sums.back() + primes.back();
         if (np < need) return fail(ctx, GNX_ERR_INVALID, "Halton permutation table too short");
-        uint16_t *dp; int *di;
+        std::vector<uint4> dims;
+        make_dim_table(primes, sums, dims);
+        uint16_t *dp; int *di; uint4 *dd;
         if ((rc = dupload(ctx, pool, hp, np, &dp))) return rc; sc.smp.perms = dp;
         if ((rc = dupload(ctx, pool, primes.data(), primes.size(), &di))) return rc; sc.smp.primes = di;
-        if ((rc = dupload(ctx, pool, sums.data(), sums.size(), &di))) return rc; sc.smp.prime_sums = di;
+        if ((rc = dupload(ctx, pool, dims.data(), dims.size(), &dd))) return rc; sc.smp.dims = dd;
         sc.smp.n_primes = (int)primes.size();
     }
     ctx->sc = sc;

@@ -23,18 +23,35 @@ GNX_HD uint64_t inverse_radical_inverse(uint64_t inverse, int base, int nDigits)
 }
 
 // HaltonSampler::GetIndexForSample(0) for pixel (px, py): the offset of the pixel's first sample.
+// With stride * 256 < 2^31 (always: stride = 128 * 243 at most) every intermediate fits 32 bits, the
+// base-2 digit reversal is one BREV and the base-3 one divides by a compile-time constant.
 GNX_HD uint64_t halton_pixel_offset(const DevSampler &s, int px, int py) {
-    uint64_t offset = 0;
-    if (s.stride > 1) {
-        int pmx = px % kMaxResolution, pmy = py % kMaxResolution;  // Mod() of non-negative ints
-        uint64_t d0 = inverse_radical_inverse((uint64_t)pmx, 2, s.base_exp0);
-        uint64_t d1 = inverse_radical_inverse((uint64_t)pmy, 3, s.base_exp1);
-        offset += d0 * (uint64_t)(s.stride / s.base_scale0) * (uint64_t)s.mult_inv0;
-        offset += d1 * (uint64_t)(s.stride / s.base_scale1) * (uint64_t)s.mult_inv1;
-        offset %= (uint64_t)s.stride;
+    if (s.stride <= 1) return 0;
+    int pmx = px % kMaxResolution, pmy = py % kMaxResolution;  // Mod() of non-negative ints
+    if ((uint64_t)s.stride * 256u < (1ull << 31)) {
+        uint32_t d0 = 0, x = (uint32_t)pmx;
+        for (int i = 0; i < s.base_exp0; ++i) { d0 = (d0 << 1) | (x & 1u); x >>= 1; }
+        uint32_t d1 = 0, y = (uint32_t)pmy;
+        for (int i = 0; i < s.base_exp1; ++i) { uint32_t q = y / 3u; d1 = d1 * 3u + (y - q * 3u); y = q; }
+        // d < scale, so d * (stride / scale) < stride; times multInverse (< scale <= 243) stays below 2^31
+        uint32_t a = d0 * (uint32_t)s.stride_over_scale0 * (uint32_t)s.mult_inv0;
+        uint32_t b = d1 * (uint32_t)s.stride_over_scale1 * (uint32_t)s.mult_inv1;
+        return (uint64_t)((a + b) % (uint32_t)s.stride);
     }
+    uint64_t offset = 0;
+    uint64_t d0 = inverse_radical_inverse((uint64_t)pmx, 2, s.base_exp0);
+    uint64_t d1 = inverse_radical_inverse((uint64_t)pmy, 3, s.base_exp1);
+    offset += d0 * (uint64_t)(s.stride / s.base_scale0) * (uint64_t)s.mult_inv0;
+    offset += d1 * (uint64_t)(s.stride / s.base_scale1) * (uint64_t)s.mult_inv1;
+    offset %= (uint64_t)s.stride;
     return offset;
 }
+
+// Exact division of a < 2^25 by a prime d < 2^13 through the precomputed m = ceil(2^38 / d):
+// floor(a * m / 2^38) == floor(a / d) because a * (m * d - 2^38) < 2^25 * 2^13 (Granlund-Montgomery).
+// One 64-bit multiply instead of the ~25-instruction 32-bit division sequence per digit.
+constexpr int kMagicShift = 38;
+constexpr uint32_t kMagicLimit = 1u << 25;
 
 // The digit loops run on 32-bit operands whenever the index fits (always, at the configs: the
 // largest index is 31 104 * 1024 + 31 103 < 2^25); the reversed-digit accumulator stays 64-bit.
@@ -63,14 +80,31 @@ GNX_D float radical_inverse_base(uint64_t a64, uint32_t base) {
     return fminf((float)reversed * invBaseN, kOneMinusEpsilon);
 }
 
-GNX_D float scrambled_radical_inverse_base(uint64_t a64, uint32_t base, const uint16_t *perm) {
+// RadicalInverseSpecialized<3>: the divisions are by a compile-time constant (multiply-high)
+GNX_D float radical_inverse_base3(uint64_t a64) {
+    if (a64 > 0xffffffffull) return radical_inverse_base(a64, 3u);
+    const float invBase = 1.0f / 3.0f;
+    uint64_t reversed = 0;
+    float invBaseN = 1;
+    uint32_t a = (uint32_t)a64;
+    while (a) {
+        uint32_t next = a / 3u;
+        uint32_t digit = a - next * 3u;
+        reversed = reversed * 3u + digit;
+        invBaseN *= invBase;
+        a = next;
+    }
+    return fminf((float)reversed * invBaseN, kOneMinusEpsilon);
+}
+
+GNX_D float scrambled_radical_inverse_base(uint64_t a64, uint32_t base, const uint16_t *perm, uint64_t magic) {
     const float invBase = 1.0f / (float)base;
     uint64_t reversed = 0;
     float invBaseN = 1;
-    if (a64 <= 0xffffffffull) {
+    if (a64 < kMagicLimit) {
         uint32_t a = (uint32_t)a64;
         while (a) {
-            uint32_t next = a / base;
+            uint32_t next = (uint32_t)(((uint64_t)a * magic) >> kMagicShift);
             uint32_t digit = a - next * base;
             reversed = reversed * base + ldg(perm + digit);
             invBaseN *= invBase;
@@ -106,12 +140,14 @@ GNX_D float radical_inverse(const DevSampler &s, int baseIndex, uint64_t a) {
 GNX_D float halton_sample_dimension(const DevSampler &s, uint64_t index, int dim) {
     if (s.at_center && (dim == 0 || dim == 1)) return 0.5f;
     if (dim == 0) return radical_inverse_base2(index >> s.base_exp0);
-    if (dim == 1) return radical_inverse_base(index / (uint64_t)s.base_scale1, 3u);
+    if (dim == 1)
+        return radical_inverse_base3(index <= 0xffffffffull ? (uint64_t)((uint32_t)index / (uint32_t)s.base_scale1)
+                                                           : index / (uint64_t)s.base_scale1);
     // ScrambledRadicalInverse returns 0 for base indices it has no case for (>= 1024); the
     // reference's PrimeSums read at dim >= 1000 is out of range, we return 0.
     if (dim >= s.n_primes) return 0.f;
-    uint32_t base = (uint32_t)ldg(s.primes + dim);
-    return scrambled_radical_inverse_base(index, base, s.perms + ldg(s.prime_sums + dim));
+    uint4 rec = ldg(s.dims + dim);  // {prime, offset of its permutation, magic lo, magic hi}
+    return scrambled_radical_inverse_base(index, rec.x, s.perms + rec.y, ((uint64_t)rec.w << 32) | rec.z);
 }
 
 // PCG32 (core/RNG.h:30-110), used as the per-pixel stream when the sampler is not Halton.

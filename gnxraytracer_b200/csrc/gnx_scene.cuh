@@ -15,7 +15,7 @@ struct DevTexture {
 struct DevEnv {
     int present, light_index;
     int w, h;                 // Lmap level 0
-    const float *texels;      // [h][w][3]
+    const float4 *texels;     // [h][w] rgb0
     int dw, dh;               // Distribution2D resolution
     const float *cond_func, *cond_cdf, *cond_int, *marg_func, *marg_cdf;
     float marg_int;
@@ -41,8 +41,10 @@ struct DevSampler {
     int type;
     int base_scale0, base_scale1, base_exp0, base_exp1;
     int stride, mult_inv0, mult_inv1, at_center;
+    int stride_over_scale0, stride_over_scale1;
     const uint16_t *perms;
-    const int *primes, *prime_sums;
+    const int *primes;
+    const uint4 *dims;        // per dimension {prime, PrimeSums, ceil(2^38 / prime) lo, hi}
     int n_primes;
 };
 

@@ -359,11 +359,16 @@ GNX_D V3 env_lookup(const DevEnv &e, float su, float sv) {
     float s = su * e.w - 0.5f, t = sv * e.h - 0.5f;
     int s0 = (int)floorf(s), t0 = (int)floorf(t);
     float ds = s - s0, dt = t - t0;
+    // Repeat wrap; the MIPMap resamples to powers of two, where Mod() is a mask (also for negatives)
+    const bool pow2 = ((e.w & (e.w - 1)) | (e.h & (e.h - 1))) == 0;
     auto tx = [&](int x, int y) {
-        x = x % e.w; if (x < 0) x += e.w;
-        y = y % e.h; if (y < 0) y += e.h;
-        const float *q = e.texels + ((size_t)y * e.w + x) * 3;
-        return V3(ldg(q), ldg(q + 1), ldg(q + 2));
+        if (pow2) { x &= e.w - 1; y &= e.h - 1; }
+        else {
+            x = x % e.w; if (x < 0) x += e.w;
+            y = y % e.h; if (y < 0) y += e.h;
+        }
+        const float4 q = ldg(e.texels + (size_t)y * e.w + x);
+        return V3(q.x, q.y, q.z);
     };
     return (1 - ds) * (1 - dt) * tx(s0, t0) + (1 - ds) * dt * tx(s0, t0 + 1) + ds * (1 - dt) * tx(s0 + 1, t0) +
            ds * dt * tx(s0 + 1, t0 + 1);

@@ -255,8 +255,8 @@ GNX_D V3 vol_sample_one_light(const DeviceScene &sc, const VPoint &it, const Bsd
         V3 f;
         float scatteringPdf;
         if (bsdf) {
-            f = bsdf_f(*bsdf, woSurf, ls.wi, kNonSpec) * absdot(ls.wi, bsdf->ns);
-            scatteringPdf = bsdf_pdf(*bsdf, woSurf, ls.wi, kNonSpec);
+            bsdf_f_pdf(*bsdf, woSurf, ls.wi, kNonSpec, &f, &scatteringPdf);
+            f = f * absdot(ls.wi, bsdf->ns);
         } else {
             float p = phase_hg(dot(woMedium, ls.wi), g);
             f = V3(p);

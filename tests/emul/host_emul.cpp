@@ -21,12 +21,13 @@ namespace {
 
 struct EmulScene {
     DeviceScene sc{};
-    std::vector<float4> tris, nodes2;
+    std::vector<float4> tris, nodes2, env_texels;
     std::vector<int2> media;
     std::vector<DevMedium> dev_media;
     std::vector<DevTexture> textures;
     std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int;
     std::vector<int> primes, sums;
+    std::vector<uint4> dims;
     std::vector<uint16_t> perms;
     unsigned typeMask = 0;
     float wb[6];
@@ -72,7 +73,8 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
         DevEnv &de = sc.env;
         de.present = 1; de.light_index = v.light_index;
         de.w = v.width; de.h = v.height; de.dw = v.dist_w; de.dh = v.dist_h;
-        de.texels = v.texels; de.cond_func = v.cond_func; de.cond_cdf = v.cond_cdf; de.cond_int = v.cond_int;
+        pack_env_texels(v.texels, (size_t)v.width * v.height, e.env_texels);
+        de.texels = e.env_texels.data(); de.cond_func = v.cond_func; de.cond_cdf = v.cond_cdf; de.cond_int = v.cond_int;
         de.marg_func = v.marg_func; de.marg_cdf = v.marg_cdf; de.marg_int = v.marg_int;
         memcpy(de.l2w.m, v.light_to_world, 64);
         memcpy(de.w2l.m, v.world_to_light, 64);
@@ -96,12 +98,15 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.smp.stride = s.sample_stride;
     sc.smp.mult_inv0 = s.mult_inverse[0]; sc.smp.mult_inv1 = s.mult_inverse[1];
     sc.smp.at_center = s.sample_at_pixel_center;
+    sc.smp.stride_over_scale0 = s.base_scales[0] > 0 ? s.sample_stride / s.base_scales[0] : 0;
+    sc.smp.stride_over_scale1 = s.base_scales[1] > 0 ? s.sample_stride / s.base_scales[1] : 0;
     make_primes(e.primes, e.sums);
+    make_dim_table(e.primes, e.sums, e.dims);
     if (s.perms) e.perms.assign(s.perms, s.perms + s.n_perm_entries);
     else make_permutations(e.primes, e.perms);
     sc.smp.perms = e.perms.data();
     sc.smp.primes = e.primes.data();
-    sc.smp.prime_sums = e.sums.data();
+    sc.smp.dims = e.dims.data();
     sc.smp.n_primes = (int)e.primes.size();
     return true;
 }
@@ -144,7 +149,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
     rc.batch_spp = 1;
     int2 stack[kSmemStack];
     // camera ray: generated and traversed in registers, like the fused primary kernel
-    Trav t;
+    TravLocal t;
     V3 d;
     primary_begin(sc, px, py, sample, &hidx, &d, t);
     ++rays[0];
