@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                     if (i < n) {
                         if (KIND == 3) {
                             item = i;
-                            const int pixel = i % rc.npix;
-                            primary_begin(sc, pixel % rc.width, pixel / rc.width, rc.first_sample + i / rc.npix, &hidx, &camD, t);
+                            int pixel, sample;
+                            slot_to_sample(rc, i, &pixel, &sample);
+                            primary_begin(sc, pixel % rc.width, pixel / rc.width, sample, &hidx, &camD, t);
                         } else if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
                         else if (KIND == 1) { item = i; shadow_begin(sc, shadowItems + i, t); }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
@@ -239,8 +240,9 @@ __global__ void __launch_bounds__(kBlock) k_volpath(const DeviceScene sc, PathSt
         if (base >= n) break;
         const int slot = base + lane;
         if (slot < n) {
-            const int pixel = slot % rc.npix;
-            V3 L = volpath_li(sc, rc, pixel % rc.width, pixel / rc.width, rc.first_sample + slot / rc.npix, stack, kBlock, cnt, vc);
+            int pixel, sample;
+            slot_to_sample(rc, slot, &pixel, &sample);
+            V3 L = volpath_li(sc, rc, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, vc);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();
@@ -258,7 +260,7 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
         float4 a = accum[pixel];
         for (int s = 0; s < rc.batch_spp; ++s) {
-            const float4 L = ps.L[(size_t)s * rc.npix + pixel];
+            const float4 L = ps.L[(size_t)pixel * rc.batch_spp + s];
             a.x += L.x; a.y += L.y; a.z += L.z;
         }
         accum[pixel] = a;

@@ -59,6 +59,16 @@ GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *
     camera_ray_uv(sc, px, py, u0, u1, l0, l1, o, d, tMax);
 }
 
+// Slot s of a batch holds sample (s % batch_spp) of pixel (s / batch_spp): the 32 lanes of a warp trace samples
+// of the same pixel (or of neighbouring pixels when the batch holds fewer than 32 samples per pixel).  Their rays
+// visit the same nodes and triangles, so the per-lane node gathers collapse into a few L1 wavefronts and the
+// lanes stay in step — the traversal kernels are bound by exactly those two things.
+// (Walking the pixels in 8x8 tiles instead of rows changed nothing measurable.)
+GNX_D void slot_to_sample(const RenderConsts &rc, int slot, int *pixel, int *sample) {
+    *pixel = slot / rc.batch_spp;
+    *sample = rc.first_sample + slot % rc.batch_spp;
+}
+
 GNX_D int shade_type_of(unsigned matWord) { return (int)((matWord >> 20) & 0xfu); }
 
 // Camera sample `sample` of pixel (px, py): the ray is generated in registers and traversed at once
