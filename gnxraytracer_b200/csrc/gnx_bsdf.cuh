@@ -495,38 +495,19 @@ GNX_D float bsdf_pdf(const Bsdf<MAXL> &b, V3 woW, V3 wiW, int flags) {
     return matching > 0 ? pdf / matching : 0.f;
 }
 
-// BSDF::f and BSDF::Pdf for the same directions (EstimateDirect's light-sampling half calls both)
+// The two halves of BSDF::Sample_f (core/Reflection.cpp:500-563), separately callable so that the shading kernel
+// can run one copy of each for its three uses (light-sample evaluation, MIS sample, continuation sample).
+//
+// bsdf_sample_dir: lobe choice and the chosen lobe's own Sample_f.  wo / *wi are in the shading frame.  Returns
+// false when there is no sample (*pdf == 0).  *fSpec is the sampled lobe's f, meaningful for SPECULAR lobes only.
 template <int MAXL>
-GNX_D void bsdf_f_pdf(const Bsdf<MAXL> &b, V3 woW, V3 wiW, int flags, V3 *fOut, float *pdfOut) {
-    *fOut = V3(0.f);
-    *pdfOut = 0.f;
-    V3 wi = b.to_local(wiW), wo = b.to_local(woW);
-    if (wo.z == 0 || b.n == 0) return;
-    bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
-    V3 f(0.f);
-    float pdf = 0.f;
-    int matching = 0;
-    for (int i = 0; i < b.n; ++i) {
-        const Lobe &l = b.lobes[i];
-        if ((l.type & flags) != l.type) continue;
-        ++matching;
-        const bool needF = (refl && (l.type & BSDF_REFLECTION)) || (!refl && (l.type & BSDF_TRANSMISSION));
-        V3 fi;
-        float pi;
-        lobe_eval(l, wo, wi, needF, true, &fi, &pi);
-        if (needF) f += fi;
-        pdf += pi;
-    }
-    *fOut = f;
-    *pdfOut = matching > 0 ? pdf / matching : 0.f;
-}
-
-template <int MAXL>
-GNX_D V3 bsdf_sample(const Bsdf<MAXL> &b, V3 woW, V3 *wiW, float u0, float u1, float *pdf, int flags, int *sampledType) {
-    int matching = b.num_components(flags);
+GNX_D bool bsdf_sample_dir(const Bsdf<MAXL> &b, V3 wo, float u0, float u1, int flags, int matching, int *chosenOut, V3 *wi,
+                           float *pdf, int *sampledType, V3 *fSpec) {
     *pdf = 0;
     *sampledType = 0;
-    if (matching == 0) return V3(0.f);
+    *chosenOut = -1;
+    *fSpec = V3(0.f);
+    if (matching == 0) return false;
     int comp = (int)floorf(u0 * matching);
     if (comp > matching - 1) comp = matching - 1;
     int chosen = -1, count = comp;
@@ -534,31 +515,62 @@ GNX_D V3 bsdf_sample(const Bsdf<MAXL> &b, V3 woW, V3 *wiW, float u0, float u1, f
         if ((b.lobes[i].type & flags) == b.lobes[i].type && count-- == 0) { chosen = i; break; }
     const Lobe &l = b.lobes[chosen];
     float ur0 = fminf(u0 * matching - comp, kOneMinusEpsilon);
-    V3 wi, wo = b.to_local(woW);
-    if (wo.z == 0) return V3(0.f);
+    if (wo.z == 0) return false;
     *sampledType = l.type;
-    V3 f = lobe_sample(l, wo, ur0, u1, &wi, pdf, sampledType);
-    if (*pdf == 0) { *sampledType = 0; return V3(0.f); }
-    *wiW = b.to_world(wi);
-    if (!(l.type & BSDF_SPECULAR)) {
-        // pdf: the other matching lobes are added in lobe order; f: the sum over the lobes on the right side
-        // of the geometric normal, in lobe order (core/Reflection.cpp:536-556) — one pass serves both
-        const bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
-        f = V3(0.f);
-        for (int i = 0; i < b.n; ++i) {
-            const Lobe &li = b.lobes[i];
-            if ((li.type & flags) != li.type) continue;
-            const bool needF = (refl && (li.type & BSDF_REFLECTION)) || (!refl && (li.type & BSDF_TRANSMISSION));
-            const bool needPdf = i != chosen && matching > 1;
-            if (!(needF || needPdf)) continue;
-            V3 fi;
-            float pi;
-            lobe_eval(li, wo, wi, needF, needPdf, &fi, &pi);
-            if (needF) f += fi;
-            if (needPdf) *pdf += pi;
-        }
+    *fSpec = lobe_sample(l, wo, ur0, u1, wi, pdf, sampledType);
+    if (*pdf == 0) { *sampledType = 0; return false; }
+    *chosenOut = chosen;
+    return true;
+}
+// bsdf_eval_sum: f summed over the matching lobes on the side of the geometric normal that (wo, wi) are on, and
+// the pdf of every matching lobe except `chosen` added to *pdfAcc — both in lobe order, as the reference adds them.
+template <int MAXL>
+GNX_D void bsdf_eval_sum(const Bsdf<MAXL> &b, V3 wo, V3 wi, bool refl, int flags, int chosen, V3 *fOut, float *pdfAcc) {
+    V3 f(0.f);
+    float pdf = *pdfAcc;
+    for (int i = 0; i < b.n; ++i) {
+        const Lobe &l = b.lobes[i];
+        if ((l.type & flags) != l.type) continue;
+        const bool needF = (refl && (l.type & BSDF_REFLECTION)) || (!refl && (l.type & BSDF_TRANSMISSION));
+        const bool needPdf = i != chosen;
+        if (!(needF || needPdf)) continue;
+        V3 fi;
+        float pi;
+        lobe_eval(l, wo, wi, needF, needPdf, &fi, &pi);
+        if (needF) f += fi;
+        if (needPdf) pdf += pi;
     }
-    if (matching > 1) *pdf /= matching;
+    *fOut = f;
+    *pdfAcc = pdf;
+}
+
+// BSDF::f and BSDF::Pdf for the same directions (EstimateDirect's light-sampling half calls both)
+template <int MAXL>
+GNX_D void bsdf_f_pdf(const Bsdf<MAXL> &b, V3 woW, V3 wiW, int flags, V3 *fOut, float *pdfOut) {
+    *fOut = V3(0.f);
+    *pdfOut = 0.f;
+    V3 wi = b.to_local(wiW), wo = b.to_local(woW);
+    if (wo.z == 0 || b.n == 0) return;
+    const int matching = b.num_components(flags);
+    const bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    float pdf = 0.f;
+    bsdf_eval_sum(b, wo, wi, refl, flags, -1, fOut, &pdf);
+    *pdfOut = matching > 0 ? pdf / matching : 0.f;
+}
+
+template <int MAXL>
+GNX_D V3 bsdf_sample(const Bsdf<MAXL> &b, V3 woW, V3 *wiW, float u0, float u1, float *pdf, int flags, int *sampledType) {
+    const int matching = b.num_components(flags);
+    const V3 wo = b.to_local(woW);
+    int chosen;
+    V3 wi, f;
+    if (!bsdf_sample_dir(b, wo, u0, u1, flags, matching, &chosen, &wi, pdf, sampledType, &f)) { *pdf = 0; return V3(0.f); }
+    *wiW = b.to_world(wi);
+    if (!(b.lobes[chosen].type & BSDF_SPECULAR)) {
+        const bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        bsdf_eval_sum(b, wo, wi, refl, flags, chosen, &f, pdf);
+    }
+    *pdf /= matching;  // "if (matchingComps > 1) *pdf /= matchingComps": x / 1 == x
     return f;
 }
 

@@ -46,15 +46,15 @@ GNX_D float permute_get(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z
 
 // Ray-space constants that the reference recomputes per triangle (shape/Triangle.cpp:88-101).
 struct RayShear {
-    int kx, ky, kz;
+    int kz;  // kx = (kz + 1) % 3, ky = (kx + 1) % 3 are re-derived where needed (one register instead of three)
     float Sx, Sy, Sz;
+    GNX_D int kx() const { return kz == 2 ? 0 : kz + 1; }
+    GNX_D int ky() const { return kz == 0 ? 2 : kz - 1; }
 };
 GNX_D RayShear make_shear(V3 d) {
     RayShear r;
     r.kz = max_dimension(vabs(d));
-    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
-    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
-    float dx = permute_get(d, r.kx), dy = permute_get(d, r.ky), dz = permute_get(d, r.kz);
+    float dx = permute_get(d, r.kx()), dy = permute_get(d, r.ky()), dz = permute_get(d, r.kz);
     r.Sx = -dx / dz;
     r.Sy = -dy / dz;
     r.Sz = 1.f / dz;
@@ -64,9 +64,10 @@ GNX_D RayShear make_shear(V3 d) {
 // shape/Triangle.cpp:82-168.  Returns true and fills `h` when the triangle is hit inside (0, tMax).
 GNX_D bool intersect_tri(const TriVerts &tv, V3 o, const RayShear &rs, float tMax, TriHit *h) {
     V3 q0 = tv.p0 - o, q1 = tv.p1 - o, q2 = tv.p2 - o;
-    float p0x = permute_get(q0, rs.kx), p0y = permute_get(q0, rs.ky), p0z = permute_get(q0, rs.kz);
-    float p1x = permute_get(q1, rs.kx), p1y = permute_get(q1, rs.ky), p1z = permute_get(q1, rs.kz);
-    float p2x = permute_get(q2, rs.kx), p2y = permute_get(q2, rs.ky), p2z = permute_get(q2, rs.kz);
+    const int kx = rs.kx(), ky = rs.ky();
+    float p0x = permute_get(q0, kx), p0y = permute_get(q0, ky), p0z = permute_get(q0, rs.kz);
+    float p1x = permute_get(q1, kx), p1y = permute_get(q1, ky), p1z = permute_get(q1, rs.kz);
+    float p2x = permute_get(q2, kx), p2y = permute_get(q2, ky), p2z = permute_get(q2, rs.kz);
     p0x += rs.Sx * p0z; p0y += rs.Sy * p0z;
     p1x += rs.Sx * p1z; p1y += rs.Sy * p1z;
     p2x += rs.Sx * p2z; p2y += rs.Sy * p2z;
@@ -193,15 +194,55 @@ GNX_D bool trav_needs_pop(const Trav &t) { return t.cur == kRefPop; }
 GNX_D bool trav_is_leaf(const Trav &t) { return t.cur < 0; }
 GNX_D bool trav_done(const Trav &t) { return t.cur == kRefNone; }
 
+// Stack entry k of the calling thread lives at stack[k * stride] for the first kSmemStack levels and in t.spill
+// beyond.  `sb`, when non-zero, is the shared-state-space address of stack[0], computed once by the kernel: through
+// the generic pointer every access re-derived the shared window base (S2R CgaCtaId, S2R TID, two LEAs).
+GNX_D void stack_store(Trav &t, int2 *stack, int stride, int level, int2 e, uint32_t sb = 0) {
+    if (level < kSmemStack) {
+#ifdef __CUDA_ARCH__
+        if (sb) {
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sb + (uint32_t)(level * stride) * 8u), "r"(e.x), "r"(e.y) : "memory");
+            return;
+        }
+#endif
+        stack[level * stride] = e;
+    } else {
+        t.spill[level - kSmemStack] = e;
+    }
+}
+GNX_D int2 stack_load(const Trav &t, const int2 *stack, int stride, int level, uint32_t sb = 0) {
+    if (level < kSmemStack) {
+#ifdef __CUDA_ARCH__
+        if (sb) {
+            int2 e;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(sb + (uint32_t)(level * stride) * 8u) : "memory");
+            return e;
+        }
+#endif
+        return stack[level * stride];
+    }
+    return t.spill[level - kSmemStack];
+}
+// shared-state-space address of p, pinned in a register (the compiler would otherwise rematerialize it)
+GNX_D uint32_t stack_shared_base(const int2 *p) {
+#ifdef __CUDA_ARCH__
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), b;
+    asm volatile("mov.u32 %0, %1;" : "=r"(b) : "r"(a));
+    return b;
+#else
+    return 0;
+#endif
+}
+
 // pop; the reference re-tests a popped node's box against the current tMax (tMin < ray.tMax).  An any-hit
 // ray's tMax never shrinks, so its entries stay valid.  trav_interior / trav_leaf only request the pop
 // (cur = kRefPop): the caller runs it for all requesting lanes of the warp together.
 template <bool ANY>
-GNX_D void trav_pop(Trav &t, const int2 *stack, int stride) {
+GNX_D void trav_pop(Trav &t, const int2 *stack, int stride, uint32_t sb = 0) {
     while (true) {
         if (t.sp == 0) { t.cur = kRefNone; return; }
         --t.sp;
-        const int2 e = t.sp < kSmemStack ? stack[t.sp * stride] : t.spill[t.sp - kSmemStack];
+        const int2 e = stack_load(t, stack, stride, t.sp, sb);
         if (ANY || i2f(e.y) < t.tMax) { t.cur = e.x; return; }
     }
 }
@@ -211,7 +252,7 @@ GNX_D void trav_pop(Trav &t, const int2 *stack, int stride) {
 // Slots 0-1 are the children of the source node's first child, slots 2-3 of its second child (a child
 // that is a leaf occupies the first slot of its pair).  Visiting order = the reference's depth-first order:
 // near pair first by the sign on axTop, near slot first inside a pair by ax0 / ax1 (axis 3: slot order).
-GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
+GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt, uint32_t sb = 0) {
     const float4 *np = sc.nodes2 + 8 * (size_t)t.cur;
     const float4 lx = ldg(np), ly = ldg(np + 1), lz = ldg(np + 2), hx = ldg(np + 3), hy = ldg(np + 4), hz = ldg(np + 5);
     const float4 rf = ldg(np + 6), ax = ldg(np + 7);
@@ -243,7 +284,7 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
         if (hit[sl]) {
             if (first >= 0) {
                 const int2 e = make_int2(ref[first], f2i(tmin[first]));
-                if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
+                stack_store(t, stack, stride, t.sp, e, sb);
                 ++t.sp;
             }
             first = sl;
@@ -252,7 +293,7 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
     t.cur = first >= 0 ? ref[first] : kRefPop;
 }
 #else
-GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt) {
+GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride, TraversalCounters &cnt, uint32_t sb = 0) {
     const float4 *np = sc.nodes2 + 4 * (size_t)t.cur;
     float4 n0, n1, n2, n3;
     ldg256(np, &n0, &n1);
@@ -268,7 +309,7 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
     const bool hitN = nearIs1 ? hit1 : hit0, hitF = nearIs1 ? hit0 : hit1;
     if (hitN & hitF) {
         const int2 e = make_int2(refF, f2i(nearIs1 ? tmin0 : tmin1));
-        if (t.sp < kSmemStack) stack[t.sp * stride] = e; else t.spill[t.sp - kSmemStack] = e;
+        stack_store(t, stack, stride, t.sp, e, sb);
         ++t.sp;
     }
     t.cur = hitN ? refN : (hitF ? refF : kRefPop);
@@ -276,9 +317,10 @@ GNX_D void trav_interior(const DeviceScene &sc, Trav &t, int2 *stack, int stride
 
 #endif
 
+// Intersects the triangles of leaf `ref` in order.  Returns true when an ANY-hit query is over.
 template <bool ANY>
-GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stride, TraversalCounters &cnt) {
-    const int x = ~t.cur, offset = x & 0x7ffffff, count = (x >> 27) + 1;
+GNX_D bool trav_leaf_ref(const DeviceScene &sc, Trav &t, int ref, TraversalCounters &cnt) {
+    const int x = ~ref, offset = x & 0x7ffffff, count = (x >> 27) + 1;
     for (int i = 0; i < count; ++i) {
         const int prim = offset + i;
         const TriVerts tv = load_tri(sc.tris, prim);
@@ -289,10 +331,14 @@ GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stri
             t.tMax = h.t;
             t.h = h;
             t.prim = prim;
-            if (ANY) { t.cur = kRefNone; return; }
+            if (ANY) return true;
         }
     }
-    t.cur = kRefPop;
+    return false;
+}
+template <bool ANY>
+GNX_D void trav_leaf(const DeviceScene &sc, Trav &t, const int2 *stack, int stride, TraversalCounters &cnt) {
+    t.cur = trav_leaf_ref<ANY>(sc, t, t.cur, cnt) ? kRefNone : kRefPop;
 }
 
 // One step for sequential callers: an interior node and whatever leaves follow it.  Returns true when

@@ -71,9 +71,9 @@ constexpr int kRefetchBelow = GNX_REFETCH;
 // threshold 24 -> 39.4 ms, 12 -> 36.2, 4 -> 35.1, 1 -> 34.5).
 constexpr int kRefetchBelowPrimary = GNX_REFETCH_PRIMARY;
 #ifndef GNX_LEAF_BATCH
-#define GNX_LEAF_BATCH 8
+#define GNX_LEAF_BATCH 4
 #endif
-constexpr int kLeafBatch = GNX_LEAF_BATCH;  // parked lanes that trigger a joint triangle-test round
+constexpr int kLeafBatch = GNX_LEAF_BATCH;  // parked lanes that trigger a joint triangle-test round (1..8 measure the same)
 
 #ifndef GNX_TRACE_BLOCKS
 #define GNX_TRACE_BLOCKS 8
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                                                       DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
+    const uint32_t sb = stack_shared_base(stack);
     const int lane = threadIdx.x & 31;
     const bool kExtend = KIND == 0 || KIND == 3;
     const int n = KIND == 3 ? rc.npix * rc.batch_spp
@@ -153,18 +154,17 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
         // force reconvergence every round), lanes without work are predicated off.
         while (true) {
             // A lane that reaches a leaf parks until kLeafBatch lanes of the warp hold one (or nobody can
-            // advance any more); then the warp runs the triangle test for all of them at once.  The
-            // kernel is issue-bound, leaves come up once per ~25 slab tests per lane, and the triangle
-            // test is ~3x an interior step: run on arrival it took 61 % of the issue slots at <= 3 active
-            // lanes (profiles/r01_trace_persistent.txt).  No speculation: node and triangle visits are
-            // exactly those of the reference order.
+            // advance any more); then the warp runs the triangle test for all of them at once.  No speculation:
+            // node and triangle visits are exactly those of the reference order.  (Measured alternatives, all
+            // slower: deferring the leaf while the lane goes on with its next stack entry, +4..30 % with the batch
+            // size; larger batches; see profiles/README.md.)
             bool parked = active && trav_is_leaf(t);
-            if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt); parked = trav_is_leaf(t); }
+            if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
             if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
             // pops requested by this round's interior steps (both children missed) and leaves, together
-            if (active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock);
+            if (active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
             if (active && trav_done(t)) {
                 if (kExtend) needFinish = true;
                 else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
@@ -197,9 +197,16 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, Pat
     }
 }
 
+#ifndef GNX_SHADE_BLOCK
+#define GNX_SHADE_BLOCK 128
+#endif
+#ifndef GNX_SHADE_SYNC
+#define GNX_SHADE_SYNC 0  // measured: block barriers between stages help C1 (-10 %), cost C2 / C3 (+5 %)
+#endif
+constexpr int kShadeBlock = GNX_SHADE_BLOCK;
 template <int MAXL>
-__global__ void __launch_bounds__(kBlock) k_shade(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
-                                                   int type, int outQ) {
+__global__ void __launch_bounds__(kShadeBlock) k_shade(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
+                                                        int type, int outQ) {
     const int n = q.counts[kCntShade0 + type];
     const int *list = q.shade_q + (size_t)type * q.capacity;
     const int stride = gridDim.x * blockDim.x;
@@ -207,11 +214,9 @@ __global__ void __launch_bounds__(kBlock) k_shade(const DeviceScene sc, PathStat
         const int i = base + threadIdx.x;
         int slot = 0;
         ShadeOut out;
-        out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
-        if (i < n) {
-            slot = list[i];
-            shade_slot<MAXL>(sc, ps, rc, slot, out);
-        }
+        if (i < n) slot = list[i];
+        // every thread of the block walks through the stages (barriers inside), with or without an item
+        shade_slot<MAXL, GNX_SHADE_SYNC != 0>(sc, ps, rc, slot, out, i < n);
         int idx = warp_push(&q.counts[kCntShadow], out.haveShadowA);
         if (idx >= 0) q.shadow_q[idx] = out.shA;
         idx = warp_push(&q.counts[kCntShadow + 1], out.haveShadowB);

@@ -165,10 +165,21 @@ struct ShadeOut {
     ProbeItem pr;
 };
 
-template <int MAXL>
-GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, ShadeOut &out) {
+// The function has no early exit and a fixed sequence of stages: with SYNC the thread block meets at a barrier
+// between stages (every thread of the block must call it, `valid` false for threads without an item).  The
+// shading code is ~50 KB of straight-line instructions per item against a 32 KB instruction cache; warps drifting
+// through it independently made the kernel instruction-fetch bound (ncu: stall_no_instruction first, 26-30 % issue
+// utilisation).  Marching in step, the warps of a block share each fetched line.
+#if defined(__CUDA_ARCH__)
+#define GNX_STAGE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
+#else
+#define GNX_STAGE_SYNC() do { } while (0)
+#endif
+template <int MAXL, bool SYNC = false>
+GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, ShadeOut &out, bool valid = true) {
     const int kNonSpec = BSDF_ALL & ~BSDF_SPECULAR;
     out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
+    if (!valid) slot = 0;
     const float4 rd4 = ps.ray_d[slot], hit = ps.hit[slot], b4 = ps.beta[slot];
     const V3 rayD(rd4.x, rd4.y, rd4.z);
     V3 beta(b4.x, b4.y, b4.z);
@@ -177,64 +188,115 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
     const int bounces = (meta >> 16) & 0xff;
     const bool specularBounce = ((meta >> 24) & kFlagSpecular) != 0;
     PathSampler smp(sc.smp, (uint64_t)ps.hidx[slot], (int)(meta & 0xffff));
-    Surface s = make_surface(sc, f2i(hit.w), hit.x, hit.y, hit.z, rayD);
-    // ---- emitted light at the vertex (PathIntegrator.cpp:101-111)
-    if ((bounces == 0 || specularBounce) && s.light >= 0) {
-        float4 L4 = ps.L[slot];
-        V3 add = beta * area_light_L(sc.lights[s.light], s.n, -rayD);
-        L4.x += add.x; L4.y += add.y; L4.z += add.z;
-        ps.L[slot] = L4;
-    }
-    if (bounces >= rc.max_depth) return;
-    const gnx_material &mat = sc.materials[s.material];
+    Surface s;
     Bsdf<MAXL> bsdf;
-    build_bsdf<MAXL>(sc, mat, s, bsdf);
+    bsdf.n = 0;
+    bool live = valid;
+    if (live) {
+        s = make_surface(sc, f2i(hit.w), hit.x, hit.y, hit.z, rayD);
+        // ---- emitted light at the vertex (PathIntegrator.cpp:101-111)
+        if ((bounces == 0 || specularBounce) && s.light >= 0) {
+            float4 L4 = ps.L[slot];
+            V3 add = beta * area_light_L(sc.lights[s.light], s.n, -rayD);
+            L4.x += add.x; L4.y += add.y; L4.z += add.z;
+            ps.L[slot] = L4;
+        }
+        live = bounces < rc.max_depth;
+    }
+    GNX_STAGE_SYNC();
+    if (live) build_bsdf<MAXL>(sc, sc.materials[s.material], s, bsdf);
     const V3 ns = bsdf.ns;
-    // ---- UniformSampleOneLight (core/Integrator.cpp:57-79)
-    if (bsdf.num_components(kNonSpec) > 0 && sc.n_lights > 0) {
-        float selPdf;
-        const int lightNum = choose_light(sc, s.p, smp.get1d(), &selPdf);
+    GNX_STAGE_SYNC();
+    // ---- UniformSampleOneLight (core/Integrator.cpp:57-79), EstimateDirect (core/Integrator.cpp:107-208) and the
+    // continuation sample (PathIntegrator.cpp:143-163) as three passes over ONE copy of the BSDF code:
+    //   P_LIGHT  direction from the light sample     -> f, pdf for it                -> shadow ray A
+    //   P_MIS    direction from BSDF::Sample_f(kNonSpec) -> f, pdf                   -> shadow ray B / probe
+    //   P_CONT   direction from BSDF::Sample_f(BSDF_ALL) -> f, pdf                   -> next path segment
+    // Inlined three times the lobe code made the kernel 54 K instructions, with a hot footprint of ~107 KB against
+    // a 32 KB instruction cache (46 % hit rate, stall_no_instruction on top).
+    enum { P_LIGHT = 0, P_MIS = 1, P_CONT = 2 };
+    const int nNonSpec = bsdf.num_components(kNonSpec);
+    float selPdf = 0, ul0 = 0, ul1 = 0, us0 = 0, us1 = 0;
+    int lightNum = 0;
+    if (live && nNonSpec > 0 && sc.n_lights > 0) {
+        lightNum = choose_light(sc, s.p, smp.get1d(), &selPdf);
         if (selPdf != 0) {
-            float ul0, ul1, us0, us1;
             smp.get2d(&ul0, &ul1);
             smp.get2d(&us0, &us1);
-            const gnx_light &light = sc.lights[lightNum];
-            const bool isEnv = light.type == GNX_LIGHT_INFINITE;
-            // ---- EstimateDirect, light-sampling half (core/Integrator.cpp:107-160)
-            LightSample ls;
-            bool ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
-            if (ok && ls.pdf > 0 && !is_black(ls.Li)) {
-                V3 f;
-                float scatteringPdf;
-                bsdf_f_pdf(bsdf, s.wo, ls.wi, kNonSpec, &f, &scatteringPdf);
-                f = f * absdot(ls.wi, ns);
-                if (!is_black(f)) {
-                    V3 origin, dirv;
-                    if (isEnv) {
-                        // VisibilityTester(ref, Interaction(ref.p + wi * (2 * worldRadius), ...)): the far
-                        // point has neither normal nor error bound, so SpawnRayTo's target is the point itself
-                        V3 p1 = s.p + ls.wi * (2 * sc.env.world_radius);
-                        origin = offset_ray_origin(s.p, s.pError, s.n, p1 - s.p);
-                        dirv = p1 - origin;
-                    } else {
-                        origin = offset_ray_origin(s.p, s.pError, s.n, ls.pl - s.p);
-                        V3 target = offset_ray_origin(ls.pl, ls.plError, ls.nl, origin - ls.pl);
-                        dirv = target - origin;
-                    }
-                    float weight = (ls.pdf * ls.pdf) / (ls.pdf * ls.pdf + scatteringPdf * scatteringPdf);
-                    V3 Ld = div_each(f * ls.Li * weight, ls.pdf);
-                    V3 c = beta * div_each(Ld, selPdf);
-                    out.shA.o_tmax = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
-                    out.shA.d_path = make_float4(dirv.x, dirv.y, dirv.z, i2f(slot));
-                    out.shA.contrib = make_float4(c.x, c.y, c.z, 0.f);
-                    out.haveShadowA = true;
-                }
+        }
+    }
+    const gnx_light &light = sc.lights[lightNum];
+    const bool isEnv = sc.n_lights > 0 && light.type == GNX_LIGHT_INFINITE;
+    V3 wi(0.f), f(0.f);
+    float pdf = 0;
+    int flags = 0;
+#pragma unroll 1
+    for (int pass = P_LIGHT; pass <= P_CONT; ++pass) {
+        GNX_STAGE_SYNC();
+        const bool run = live && (pass == P_CONT || selPdf != 0);
+        const int lobeFlags = pass == P_CONT ? BSDF_ALL : kNonSpec;
+        const int matching = pass == P_CONT ? bsdf.num_components(BSDF_ALL) : nNonSpec;
+        const V3 woW = pass == P_CONT ? -rayD : s.wo;  // isect.wo is normalized, PathIntegrator's wo = -ray.d is not
+        const V3 wo = bsdf.to_local(woW);
+        V3 wiL;
+        int chosen = -1;
+        bool have = false;
+        LightSample ls;
+        pdf = 0;
+        f = V3(0.f);
+        flags = 0;
+        if (!run) {
+        } else if (pass == P_LIGHT) {
+            const bool ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
+            have = ok && ls.pdf > 0 && !is_black(ls.Li) && wo.z != 0;
+            wi = ls.wi;
+            wiL = bsdf.to_local(wi);
+        } else {
+            float ua = us0, ub = us1;
+            if (pass == P_CONT) smp.get2d(&ua, &ub);
+            have = bsdf_sample_dir(bsdf, wo, ua, ub, lobeFlags, matching, &chosen, &wiL, &pdf, &flags, &f);
+            if (have) wi = bsdf.to_world(wiL);
+        }
+        GNX_STAGE_SYNC();
+        if (have) {
+            if (chosen < 0 || !(bsdf.lobes[chosen].type & BSDF_SPECULAR)) {
+                const bool refl = dot(wi, bsdf.ng) * dot(woW, bsdf.ng) > 0;
+                bsdf_eval_sum(bsdf, wo, wiL, refl, lobeFlags, chosen, &f, &pdf);
             }
-            // ---- EstimateDirect, BSDF-sampling half (core/Integrator.cpp:163-208)
-            V3 wi;
-            float scatteringPdf;
-            int sampledType;
-            V3 f = bsdf_sample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, kNonSpec, &sampledType);
+            pdf /= matching;
+        }
+        GNX_STAGE_SYNC();
+        if (!run) {
+        } else if (pass == P_LIGHT) {
+            if (!have) continue;
+            // ---- EstimateDirect, light-sampling half
+            f = f * absdot(ls.wi, ns);
+            const float scatteringPdf = pdf;
+            if (!is_black(f)) {
+                V3 origin, dirv;
+                if (isEnv) {
+                    // VisibilityTester(ref, Interaction(ref.p + wi * (2 * worldRadius), ...)): the far
+                    // point has neither normal nor error bound, so SpawnRayTo's target is the point itself
+                    V3 p1 = s.p + ls.wi * (2 * sc.env.world_radius);
+                    origin = offset_ray_origin(s.p, s.pError, s.n, p1 - s.p);
+                    dirv = p1 - origin;
+                } else {
+                    origin = offset_ray_origin(s.p, s.pError, s.n, ls.pl - s.p);
+                    V3 target = offset_ray_origin(ls.pl, ls.plError, ls.nl, origin - ls.pl);
+                    dirv = target - origin;
+                }
+                float weight = (ls.pdf * ls.pdf) / (ls.pdf * ls.pdf + scatteringPdf * scatteringPdf);
+                V3 Ld = div_each(f * ls.Li * weight, ls.pdf);
+                V3 c = beta * div_each(Ld, selPdf);
+                out.shA.o_tmax = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
+                out.shA.d_path = make_float4(dirv.x, dirv.y, dirv.z, i2f(slot));
+                out.shA.contrib = make_float4(c.x, c.y, c.z, 0.f);
+                out.haveShadowA = true;
+            }
+        } else if (pass == P_MIS) {
+            if (!have) continue;
+            // ---- EstimateDirect, BSDF-sampling half
+            const float scatteringPdf = pdf;
             f = f * absdot(wi, ns);
             if (!is_black(f) && scatteringPdf > 0) {
                 V3 o = offset_ray_origin(s.p, s.pError, s.n, wi);
@@ -268,16 +330,14 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
                     }
                 }
             }
+        } else if (!have) {
+            live = false;
         }
     }
-    // ---- sample the BSDF for the next direction (PathIntegrator.cpp:143-163)
+    GNX_STAGE_SYNC();
+    // ---- the next direction (PathIntegrator.cpp:143-163): wi, f, pdf, flags are the P_CONT pass's
     const V3 wo = -rayD;
-    V3 wi;
-    float pdf, u0, u1;
-    int flags;
-    smp.get2d(&u0, &u1);
-    V3 f = bsdf_sample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
-    if (is_black(f) || pdf == 0.f) return;
+    if (!live || is_black(f) || pdf == 0.f) return;
     beta *= div_each(f * absdot(wi, ns), pdf);
     const bool spec = (flags & BSDF_SPECULAR) != 0;
     if (spec && (flags & BSDF_TRANSMISSION)) {

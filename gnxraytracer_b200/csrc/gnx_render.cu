@@ -139,7 +139,7 @@ int gnx_create(gnx_ctx **out, int device) {
     {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
@@ -550,8 +550,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
-                if (t == GNX_MAT_DISNEY) k_shade<8><<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
-                else k_shade<2><<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                if (t == GNX_MAT_DISNEY) k_shade<8><<<gridShade, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
                 ++launches;
             }
             if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, out); ++launches; }
