@@ -487,7 +487,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     if (batch_spp <= 0) {
         size_t freeB = 0, totalB = 0;
         long long slots = 64ll << 20;
-        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+        // (cudaMemGetInfo costs ~0.5 ms: only asked when the buffers of an earlier call do not already cover the batch)
+        const long long want = std::min(slots, (long long)npix * p->spp);
+        if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
             const long long bytesPerSlot = 288;  // PathState 92 B + queues 180 B, rounded up
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
