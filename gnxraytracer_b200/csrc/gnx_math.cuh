@@ -83,6 +83,15 @@ GNX_HD void ldg256(const float4 *p, float4 *a, float4 *b) {
     *a = p[0]; *b = p[1];
 #endif
 }
+GNX_HD uint32_t brev32(uint32_t n) {
+#ifdef __CUDA_ARCH__
+    return __brev(n);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) { r = (r << 1) | (n & 1); n >>= 1; }
+    return r;
+#endif
+}
 GNX_HD uint64_t brev64(uint64_t n) {
 #ifdef __CUDA_ARCH__
     return __brevll(n);

@@ -29,8 +29,8 @@ GNX_HD uint64_t halton_pixel_offset(const DevSampler &s, int px, int py) {
     if (s.stride <= 1) return 0;
     int pmx = px % kMaxResolution, pmy = py % kMaxResolution;  // Mod() of non-negative ints
     if ((uint64_t)s.stride * 256u < (1ull << 31)) {
-        uint32_t d0 = 0, x = (uint32_t)pmx;
-        for (int i = 0; i < s.base_exp0; ++i) { d0 = (d0 << 1) | (x & 1u); x >>= 1; }
+        // InverseRadicalInverse<2>: the low base_exp0 bits of pmx, reversed (pmx < 128 = 2^7 >= scale)
+        uint32_t d0 = s.base_exp0 > 0 ? brev32((uint32_t)pmx) >> (32 - s.base_exp0) : 0u;
         uint32_t d1 = 0, y = (uint32_t)pmy;
         for (int i = 0; i < s.base_exp1; ++i) { uint32_t q = y / 3u; d1 = d1 * 3u + (y - q * 3u); y = q; }
         // d < scale, so d * (stride / scale) < stride; times multInverse (< scale <= 243) stays below 2^31
@@ -125,6 +125,9 @@ GNX_D float scrambled_radical_inverse_base(uint64_t a64, uint32_t base, const ui
 
 // RadicalInverse(0, a): ReverseBits64(a) * 2^-64 in double, narrowed (LowDiscrepancy.cpp:396-405)
 GNX_D float radical_inverse_base2(uint64_t a) {
+    // a < 2^32: the reversed bits fill the top word only, so the double holds them exactly and the one rounding
+    // that matters is the narrowing to float — the same rounding as uint32 -> float (no fp64 on the fast path)
+    if (a <= 0xffffffffull) return (float)brev32((uint32_t)a) * 2.3283064365386963e-10f;
     uint64_t r = brev64(a);
     return (float)((double)r * 5.4210108624275222e-20);
 }
