@@ -204,8 +204,14 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, Pat
 #define GNX_SHADE_SYNC 0  // measured: block barriers between stages help C1 (-10 %), cost C2 / C3 (+5 %)
 #endif
 constexpr int kShadeBlock = GNX_SHADE_BLOCK;
+// Resident blocks per SM asked of the compiler (it caps the registers accordingly).  The kernel is bound by the
+// latency of its dependent table loads, so more warps pay although the code then spills: measured on C2 / C3 shade
+// stage, 4 blocks (128 regs) 4.85 / 27.9 ms, 6: 4.59 / 26.2, 7: 4.52 / 24.0, 8 (64 regs): 4.59 / 22.9 (Disney).
+#ifndef GNX_SHADE_MINBLOCKS
+#define GNX_SHADE_MINBLOCKS(MAXL) ((MAXL) > 2 ? 8 : 7)
+#endif
 template <int MAXL>
-__global__ void __launch_bounds__(kShadeBlock) k_shade(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
+__global__ void __launch_bounds__(kShadeBlock, GNX_SHADE_MINBLOCKS(MAXL)) k_shade(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
                                                         int type, int outQ) {
     const int n = q.counts[kCntShade0 + type];
     const int *list = q.shade_q + (size_t)type * q.capacity;

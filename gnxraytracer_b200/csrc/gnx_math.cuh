@@ -230,4 +230,19 @@ GNX_HD int find_interval_cdf(const float *cdf, int size, float u) {
     return r < 0 ? 0 : (r > size - 2 ? size - 2 : r);
 }
 
+// The same answer through a guide table: guide[b] = find_interval_cdf(cdf, size, b / G) for b = 0..G (G a power of
+// two, so b = floor(u * G) is exact and b / G <= u < (b + 1) / G).  The answer is monotone in u, hence it lies in
+// [guide[b], guide[b + 1]]: a 12-step chain of dependent loads becomes one guide load and ~log2(size / G) steps.
+GNX_HD int find_interval_guided(const float *cdf, int size, float u, const uint16_t *guide, int G) {
+    if (!guide) return find_interval_cdf(cdf, size, u);
+    int b = (int)(u * (float)G);
+    b = b < 0 ? 0 : (b > G - 1 ? G - 1 : b);
+    int lo = guide[b], hi = guide[b + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cdf[mid] <= u) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 }  // namespace gnx

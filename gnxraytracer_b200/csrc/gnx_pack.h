@@ -49,6 +49,15 @@ inline void pack_env_texels(const float *rgb, size_t n, std::vector<float4> &out
     out.resize(n);
     for (size_t i = 0; i < n; ++i) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f);
 }
+// Guide table of find_interval_guided for one cdf of `size` entries (size - 1 <= 65535).
+inline void make_cdf_guide(const float *cdf, int size, int G, uint16_t *guide) {
+    for (int b = 0; b <= G; ++b) guide[b] = (uint16_t)find_interval_cdf(cdf, size, (float)b / (float)G);
+}
+inline int guide_buckets(int n) {  // power of two, about n / 8 buckets
+    int g = 1;
+    while (g * 8 < n) g <<= 1;
+    return g;
+}
 inline uint32_t pcg_bounded(Pcg32 &rng, uint32_t b) {
     uint32_t threshold = (~b + 1u) % b;
     while (true) {

@@ -26,7 +26,7 @@ struct gnx_ctx {
     void *geom_base = nullptr;
     size_t geom_bytes = 0;
     int l2_persist = 0;  // measured on B200/C2: 52.1 ms with the window vs 46.1 ms without (set-aside starves the rest)
-    int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_volpath = 148 * 2;  // SM count x resident blocks (occupancy query at create)
+    int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_shade8 = 148 * 4, grid_volpath = 148 * 2;  // SM count x resident blocks (occupancy query at create)
     // scene
     bool has_scene = false;
     DeviceScene sc{};
@@ -140,6 +140,7 @@ int gnx_create(gnx_ctx **out, int device) {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
@@ -292,6 +293,21 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         if ((rc = dupload(ctx, pool, e.marg_func, (size_t)e.dist_h, &df))) return rc; de.marg_func = df;
         if ((rc = dupload(ctx, pool, e.marg_cdf, (size_t)e.dist_h + 1, &df))) return rc; de.marg_cdf = df;
         de.marg_int = e.marg_int;
+        de.cond_guide = de.marg_guide = nullptr;
+        de.cond_g = de.marg_g = 0;
+        if (e.dist_w < 65536 && e.dist_h < 65536 && !getenv("GNX_NO_CDF_GUIDE")) {
+            // guide tables for the two inverse-cdf searches of InfiniteAreaLight::Sample_Li (same results, ~half the
+            // dependent loads)
+            de.cond_g = guide_buckets(e.dist_w);
+            de.marg_g = guide_buckets(e.dist_h);
+            std::vector<uint16_t> cg((size_t)e.dist_h * (de.cond_g + 1)), mg((size_t)de.marg_g + 1);
+            for (int v = 0; v < e.dist_h; ++v)
+                make_cdf_guide(e.cond_cdf + (size_t)v * (e.dist_w + 1), e.dist_w + 1, de.cond_g, cg.data() + (size_t)v * (de.cond_g + 1));
+            make_cdf_guide(e.marg_cdf, e.dist_h + 1, de.marg_g, mg.data());
+            uint16_t *du;
+            if ((rc = dupload(ctx, pool, cg.data(), cg.size(), &du))) return rc; de.cond_guide = du;
+            if ((rc = dupload(ctx, pool, mg.data(), mg.size(), &du))) return rc; de.marg_guide = du;
+        }
         memcpy(de.l2w.m, e.light_to_world, 64);
         memcpy(de.w2l.m, e.world_to_light, 64);
         de.world_radius = e.world_radius;
@@ -552,7 +568,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
-                if (t == GNX_MAT_DISNEY) k_shade<8><<<gridShade, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
                 else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
                 ++launches;
             }

@@ -18,6 +18,8 @@ struct DevEnv {
     const float4 *texels;     // [h][w] rgb0
     int dw, dh;               // Distribution2D resolution
     const float *cond_func, *cond_cdf, *cond_int, *marg_func, *marg_cdf;
+    const uint16_t *cond_guide, *marg_guide;  // find_interval_guided tables: [dh][cond_g + 1], [marg_g + 1] (null: plain search)
+    int cond_g, marg_g;
     float marg_int;
     M44 l2w, w2l;
     float world_radius;

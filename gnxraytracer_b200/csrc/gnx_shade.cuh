@@ -381,8 +381,9 @@ GNX_D V3 env_Le(const DevEnv &e, V3 rayD) {
     return env_lookup(e, spherical_phi(w) * kInv2Pi, spherical_theta(w) * kInvPi);
 }
 // Distribution1D::SampleContinuous, core/Sampling.h:40-59
-GNX_D float dist1d_sample_continuous(const float *func, const float *cdf, float funcInt, int n, float u, float *pdf, int *off) {
-    int offset = find_interval_cdf(cdf, n + 1, u);
+GNX_D float dist1d_sample_continuous(const float *func, const float *cdf, float funcInt, int n, float u, float *pdf, int *off,
+                                     const uint16_t *guide = nullptr, int G = 0) {
+    int offset = find_interval_guided(cdf, n + 1, u, guide, G);
     *off = offset;
     float du = u - cdf[offset];
     if ((cdf[offset + 1] - cdf[offset]) > 0) du /= (cdf[offset + 1] - cdf[offset]);
@@ -392,9 +393,10 @@ GNX_D float dist1d_sample_continuous(const float *func, const float *cdf, float 
 GNX_D bool env_sample_li(const DevEnv &e, float u0, float u1, LightSample *ls) {
     float pdf1, pdf0;
     int v, dummy;
-    float d1 = dist1d_sample_continuous(e.marg_func, e.marg_cdf, e.marg_int, e.dh, u1, &pdf1, &v);
+    float d1 = dist1d_sample_continuous(e.marg_func, e.marg_cdf, e.marg_int, e.dh, u1, &pdf1, &v, e.marg_guide, e.marg_g);
     float d0 = dist1d_sample_continuous(e.cond_func + (size_t)v * e.dw, e.cond_cdf + (size_t)v * (e.dw + 1),
-                                        e.cond_int[v], e.dw, u0, &pdf0, &dummy);
+                                        e.cond_int[v], e.dw, u0, &pdf0, &dummy,
+                                        e.cond_guide ? e.cond_guide + (size_t)v * (e.cond_g + 1) : nullptr, e.cond_g);
     float mapPdf = pdf0 * pdf1;
     ls->pdf = 0;
     ls->Li = V3(0.f);

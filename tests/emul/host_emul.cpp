@@ -76,6 +76,7 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
         pack_env_texels(v.texels, (size_t)v.width * v.height, e.env_texels);
         de.texels = e.env_texels.data(); de.cond_func = v.cond_func; de.cond_cdf = v.cond_cdf; de.cond_int = v.cond_int;
         de.marg_func = v.marg_func; de.marg_cdf = v.marg_cdf; de.marg_int = v.marg_int;
+        de.cond_guide = de.marg_guide = nullptr; de.cond_g = de.marg_g = 0;
         memcpy(de.l2w.m, v.light_to_world, 64);
         memcpy(de.w2l.m, v.world_to_light, 64);
         de.world_radius = v.world_radius;
