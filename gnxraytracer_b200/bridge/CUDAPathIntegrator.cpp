@@ -57,7 +57,11 @@
 #include "core/Scene.h"
 #include "core/Texture.h"
 #include "lights/DiffuseAreaLight.h"
+#include "lights/DistantLight.h"
 #include "lights/InfiniteAreaLight.h"
+#include "lights/PointLight.h"
+#include "lights/SkyBoxLight.h"
+#include "lights/SpotLight.h"
 #include "materials/DisneyMaterial.h"
 #include "materials/GlassMaterial.h"
 #include "materials/MatteMaterial.h"
@@ -359,11 +363,15 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
 
     // ---- lights ---------------------------------------------------------------------------
     d.env.present = 0;
+    d.skybox.present = 0;
     for (size_t i = 0; i < scene.lights.size(); ++i) {
         const Light *l = scene.lights[i].get();
         gnx_light gl{};
         gl.prim = -1;
-        gl.medium = fl.MediumIndex(l->mediumInterface.inside);
+        // SkyBoxLight hands its own, not yet constructed, mediumInterface member to the Light base class
+        // (lights/SkyBoxLight.h:17): the base copy holds indeterminate pointers and must not be looked at.
+        const bool skybox = dynamic_cast<const SkyBoxLight *>(l) != nullptr;
+        gl.medium = skybox ? -1 : fl.MediumIndex(l->mediumInterface.inside);
         if (gl.medium == -2) return false;
         if (auto *al = dynamic_cast<const DiffuseAreaLight *>(l)) {
             gl.type = GNX_LIGHT_AREA_TRI;
@@ -409,8 +417,32 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
             CopyMatrix(il->WorldToLight.m, e.world_to_light);
             for (int c = 0; c < 3; ++c) e.world_center[c] = il->worldCenter[c];
             e.world_radius = il->worldRadius;
+        } else if (auto *sl = dynamic_cast<const SpotLight *>(l)) {
+            gl.type = GNX_LIGHT_SPOT;
+            for (int c = 0; c < 3; ++c) { gl.L[c] = sl->I[c]; gl.p[c] = sl->pLight[c]; }
+            gl.cos_total = sl->cosTotalWidth;
+            gl.cos_falloff = sl->cosFalloffStart;
+            CopyMatrix(sl->WorldToLight.m, gl.world_to_light);
+        } else if (auto *pl = dynamic_cast<const PointLight *>(l)) {
+            gl.type = GNX_LIGHT_POINT;
+            for (int c = 0; c < 3; ++c) { gl.L[c] = pl->I[c]; gl.p[c] = pl->pLight[c]; }
+        } else if (auto *dl = dynamic_cast<const DistantLight *>(l)) {
+            gl.type = GNX_LIGHT_DISTANT;
+            for (int c = 0; c < 3; ++c) { gl.L[c] = dl->L[c]; gl.p[c] = dl->wLight[c]; }
+            gl.area = dl->worldRadius;  // set by DistantLight::Preprocess (Scene constructor)
+        } else if (auto *sb = dynamic_cast<const SkyBoxLight *>(l)) {
+            if (d.skybox.present) return fl.Fail("more than one SkyBoxLight");
+            gl.type = GNX_LIGHT_SKYBOX;
+            CopyMatrix(sb->LightToWorld.m, gl.world_to_light);
+            gnx_skybox &k = d.skybox;
+            k.present = 1;
+            k.light_index = (int32_t)i;
+            k.width = sb->imageWidth; k.height = sb->imageHeight; k.channels = sb->nrComponents;
+            k.data = sb->data;  // owned by the light, alive as long as the scene
+            for (int c = 0; c < 3; ++c) k.center[c] = sb->worldCenter[c];
+            k.radius = sb->worldRadius;
         } else {
-            return fl.Fail("unsupported Light subclass (hot path: DiffuseAreaLight, InfiniteAreaLight)");
+            return fl.Fail("unsupported Light subclass");
         }
         out->lights.push_back(gl);
     }
@@ -478,7 +510,7 @@ CUDAPathIntegrator::CUDAPathIntegrator(int maxDepth, std::shared_ptr<const Camer
       fb_(pFrameBuffer),
       rrThreshold_(rrThreshold),
       lightSampleStrategy_(lightSampleStrategy),
-      volumetric_(volumetric) {
+      integrator_(volumetric ? GNX_INTEGRATOR_VOLPATH : GNX_INTEGRATOR_PATH) {
     int rc = gnx_create(&ctx_, device);
     if (rc != GNX_OK) {
         error_ = std::string("gnx_create failed: ") + gnx_last_error(nullptr);
@@ -499,7 +531,7 @@ gnx_render_params CUDAPathIntegrator::MakeParams() const {
     p.spp_normalize = 0;
     p.max_depth = maxDepth_;
     p.rr_threshold = rrThreshold_;
-    p.integrator = volumetric_ ? GNX_INTEGRATOR_VOLPATH : GNX_INTEGRATOR_PATH;
+    p.integrator = integrator_;
     // CreateLightSampleDistribution (core/LightDistribution.cpp:15-33); the single-light override
     // is applied inside the library, which knows the light count.
     p.light_strategy = lightSampleStrategy_ == "uniform" ? GNX_LIGHTS_UNIFORM

@@ -67,6 +67,9 @@ class CUDAPathIntegrator : public pbr::Integrator {
     bool PrimaryHits(const pbr::Scene &scene, int sample, std::vector<int32_t> *orderedPrimIndex);
     const FlatScene *flat() const { return flat_.get(); }
     gnx_render_params MakeParams() const;
+    // GNX_INTEGRATOR_WHITTED / GNX_INTEGRATOR_DIRECT: stand in for pbr::WhittedIntegrator /
+    // pbr::DirectLightingIntegrator(LightStrategy::UniformSampleOne) instead of PathIntegrator / VolPathIntegrator
+    void SetIntegrator(int gnxIntegrator) { integrator_ = gnxIntegrator; }
 
   private:
     bool EnsureUploaded(const pbr::Scene &scene);
@@ -78,7 +81,7 @@ class CUDAPathIntegrator : public pbr::Integrator {
     FrameBuffer *fb_;
     const pbr::Float rrThreshold_;
     const std::string lightSampleStrategy_;
-    const bool volumetric_;
+    int integrator_;  // gnx_integrator
     gnx_ctx *ctx_ = nullptr;
     const pbr::Scene *uploaded_ = nullptr;
     std::unique_ptr<FlatScene> flat_;

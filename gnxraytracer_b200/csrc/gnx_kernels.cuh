@@ -8,7 +8,7 @@
 // persistent kernel never has a partial second wave.  The traversal kernel keeps its stacks in shared
 // memory (24 KB per 128-thread block).
 #pragma once
-#include "gnx_volpath.cuh"
+#include "gnx_whitted.cuh"
 
 namespace gnx {
 
@@ -263,6 +263,38 @@ __global__ void __launch_bounds__(kBlock) k_volpath(const DeviceScene sc, PathSt
     flush_stats(st, 0, nodes, tris, vc.extend);
     flush_stats(st, 1, 0, 0, vc.shadow);
     flush_stats(st, 2, 0, 0, vc.mis);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+}
+
+// WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
+// stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
+__global__ void __launch_bounds__(kBlock) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int direct,
+                                                     DevStats *st) {
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
+    const int n = rc.npix * rc.batch_spp;
+    const int lane = threadIdx.x & 31;
+    int *cursor = &q.counts[kCntFetch];
+    TraversalCounters cnt{0, 0};
+    RecCounters rcnt{0, 0, 0};
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        const int slot = base + lane;
+        if (slot < n) {
+            int pixel, sample;
+            slot_to_sample(rc, slot, &pixel, &sample);
+            V3 L = recursive_li<8>(sc, rc, direct != 0, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
+            ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+        __syncwarp();
+    }
+    unsigned nodes = cnt.nodes, tris = cnt.tris;
+    flush_stats(st, 0, nodes, tris, rcnt.extend);
+    flush_stats(st, 1, 0, 0, rcnt.shadow);
+    flush_stats(st, 2, 0, 0, rcnt.mis);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
 

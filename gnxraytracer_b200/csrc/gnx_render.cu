@@ -26,9 +26,10 @@ struct gnx_ctx {
     void *geom_base = nullptr;
     size_t geom_bytes = 0;
     int l2_persist = 0;  // measured on B200/C2: 52.1 ms with the window vs 46.1 ms without (set-aside starves the rest)
-    int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_shade8 = 148 * 4, grid_volpath = 148 * 2;  // SM count x resident blocks (occupancy query at create)
+    int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_shade8 = 148 * 4, grid_volpath = 148 * 2, grid_recursive = 148 * 2;  // SM count x resident blocks (occupancy query at create)
     // scene
     bool has_scene = false;
+    bool has_next_lights = false;  // point / spot / distant / skybox lights present
     DeviceScene sc{};
     std::vector<void *> scene_allocs;
     unsigned shade_type_mask = 0;  // which k_shade variants the scene needs
@@ -142,6 +143,7 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
@@ -172,6 +174,7 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
     free_pool(ctx->scene_allocs);
     ctx->has_scene = false;
     ctx->spatial_built = false;
+    ctx->has_next_lights = false;
     DeviceScene sc{};
     std::vector<void *> &pool = ctx->scene_allocs;
     const gnx_geometry &g = d->geom;
@@ -265,8 +268,30 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
             if (l.prim < 0 || l.prim >= g.n_prims) return fail(ctx, GNX_ERR_INVALID, "area light primitive out of range");
         } else if (l.type == GNX_LIGHT_INFINITE) {
             if (!d->env.present || d->env.light_index != i) return fail(ctx, GNX_ERR_INVALID, "infinite light without envmap record");
+        } else if (l.type == GNX_LIGHT_POINT || l.type == GNX_LIGHT_SPOT || l.type == GNX_LIGHT_DISTANT) {
+            ctx->has_next_lights = true;  // rendered by the Whitted / DirectLighting integrators only
+        } else if (l.type == GNX_LIGHT_SKYBOX) {
+            if (!d->skybox.present || d->skybox.light_index != i) return fail(ctx, GNX_ERR_INVALID, "skybox light without skybox record");
+            ctx->has_next_lights = true;
         } else {
-            return fail(ctx, GNX_ERR_UNSUPPORTED, "light type outside the hot path (area, infinite)");
+            return fail(ctx, GNX_ERR_INVALID, "unknown light type");
+        }
+    }
+    sc.skybox.present = 0;
+    if (d->skybox.present) {
+        const gnx_skybox &sb = d->skybox;
+        sc.skybox.present = 1; sc.skybox.light_index = sb.light_index;
+        sc.skybox.w = sb.width; sc.skybox.h = sb.height; sc.skybox.nc = sb.channels;
+        sc.skybox.center = V3(sb.center[0], sb.center[1], sb.center[2]);
+        sc.skybox.radius = sb.radius;
+        sc.skybox.data = nullptr;
+        if (sb.data && sb.width > 0 && sb.height > 0 && sb.channels >= 3) {
+            // getLightValue indexes (w + h * W) * C + 0..2 with w = u * W, h = v * H, u and v up to 1: one padding row
+            std::vector<float> img((size_t)sb.width * (sb.height + 1) * sb.channels + 4, 0.f);
+            memcpy(img.data(), sb.data, sizeof(float) * (size_t)sb.width * sb.height * sb.channels);
+            float *dimg;
+            if ((rc = dupload(ctx, pool, img.data(), img.size(), &dimg))) return rc;
+            sc.skybox.data = dimg;
         }
     }
     gnx_light *dl;
@@ -455,7 +480,14 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
         return fail(ctx, GNX_ERR_INVALID, "bad render parameters");
     if ((long long)p->width * p->height > (1ll << 28)) return fail(ctx, GNX_ERR_INVALID, "image too large");
-    if (p->integrator != GNX_INTEGRATOR_PATH && p->integrator != GNX_INTEGRATOR_VOLPATH) return fail(ctx, GNX_ERR_INVALID, "unknown integrator");
+    if (p->integrator < GNX_INTEGRATOR_PATH || p->integrator > GNX_INTEGRATOR_DIRECT) return fail(ctx, GNX_ERR_INVALID, "unknown integrator");
+    const bool recursive = p->integrator == GNX_INTEGRATOR_WHITTED || p->integrator == GNX_INTEGRATOR_DIRECT;
+    if (!recursive && ctx->has_next_lights)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "point / spot / distant / skybox lights are rendered by GNX_INTEGRATOR_WHITTED and GNX_INTEGRATOR_DIRECT");
+    if (recursive && ctx->sc.smp.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use the Halton sampler");
+    if (recursive && ctx->sc.n_media > 0) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting ignore participating media");
+    if (recursive && ctx->n_textures_host > 0)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting filter image textures with ray differentials (EWA), which is not implemented");
     if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.smp.type != GNX_SAMPLER_HALTON)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "the wavefront PathIntegrator keeps a Halton (index, dimension) per path; the PCG32 stream sampler is for VolPath");
     if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.n_media > 0)
@@ -494,7 +526,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     int rc = validate_params(ctx, p);
     if (rc) return rc;
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
-    if ((rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
+    const bool recursiveInteg = p->integrator == GNX_INTEGRATOR_WHITTED || p->integrator == GNX_INTEGRATOR_DIRECT;
+    if (!recursiveInteg && (rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
     const int npix = p->width * p->height;
     // Paths in flight per wavefront batch.  Late bounces carry few rays and every launch has a tail, so
     // the batch is made as large as memory comfortably allows (profiles/README.md: 4 M -> 64 M slots took
@@ -541,10 +574,11 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         rcn.batch_spp = std::min(batch_spp, p->spp - done);
         rcn.first_sample = p->first_sample + done;
         rcn.capacity = ctx->capacity;
-        if (p->integrator == GNX_INTEGRATOR_VOLPATH) {
+        if (p->integrator != GNX_INTEGRATOR_PATH) {
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
             tm.begin(ST_EXTEND);
-            k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
+            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
+            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, p->integrator == GNX_INTEGRATOR_DIRECT, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
             k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);

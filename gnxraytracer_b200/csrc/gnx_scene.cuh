@@ -25,6 +25,14 @@ struct DevEnv {
     float world_radius;
 };
 
+struct DevSkybox {
+    int present, light_index;
+    int w, h, nc;
+    const float *data;
+    V3 center;
+    float radius;
+};
+
 struct DevLightDistrib {
     int mode;                 // gnx_light_strategy actually in force
     const float *uni_func, *uni_cdf;   // [nL], [nL+1]  (uniform / power: one table for the whole scene)
@@ -79,6 +87,7 @@ struct DeviceScene {
     const gnx_light *lights;
     int n_lights;
     DevEnv env;
+    DevSkybox skybox;
     DevLightDistrib ld;
     const DevMedium *media;
     int n_media;

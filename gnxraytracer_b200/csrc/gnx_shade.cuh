@@ -126,8 +126,10 @@ GNX_D float clamp_alpha(float a) { return fmaxf(0.001f, a); }  // TrowbridgeReit
 // <Material>::ComputeScatteringFunctions (materials/*.cpp), allowMultipleLobes == true,
 // TransportMode::Radiance.  Also applies Material::Bump's re-derivation of shading.n when a
 // (constant) bump map is attached, and fills the BSDF frame (core/Reflection.h:106-111).
+// multiLobes: the allowMultipleLobes argument (true for Path / VolPath, false for Whitted / DirectLighting; only
+// GlassMaterial looks at it, materials/GlassMaterial.cpp:31).
 template <int MAXL>
-GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, Bsdf<MAXL> &b) {
+GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, Bsdf<MAXL> &b, bool multiLobes = true) {
     if (m.flags & GNX_MATF_BUMP_IDENTITY) {
         // SetShadingGeometry(dpdu, dpdv, ..., false) with unchanged dpdu/dpdv (core/Material.cpp:45-51)
         s.ns = normalize(cross(s.dpdu_s, s.dpdv_s));
@@ -193,10 +195,21 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
         b.eta = eta;
         if (is_black(R) && is_black(T)) break;
         bool isSpecular = ur == 0 && vr == 0;
-        if (isSpecular) {
+        if (isSpecular && multiLobes) {
             Lobe l = make_lobe(LK_FRESNEL_SPEC, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, R);
             l.a = T; l.e0 = 1.f; l.e1 = eta;
             b.add(l);
+        } else if (isSpecular) {
+            if (!is_black(R)) {
+                Lobe l = make_lobe(LK_SPEC_R, BSDF_REFLECTION | BSDF_SPECULAR, R);
+                l.fresnel = FR_DIELECTRIC; l.e0 = 1.f; l.e1 = eta;
+                b.add(l);
+            }
+            if (!is_black(T)) {
+                Lobe l = make_lobe(LK_SPEC_T, BSDF_TRANSMISSION | BSDF_SPECULAR, T);
+                l.e0 = 1.f; l.e1 = eta;
+                b.add(l);
+            }
         } else {
             if (m.flags & GNX_MATF_REMAP_ROUGHNESS) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
             if (!is_black(R)) {

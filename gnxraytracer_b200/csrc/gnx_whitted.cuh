@@ -1,0 +1,338 @@
+// gnx_whitted.cuh — WhittedIntegrator and DirectLightingIntegrator, with the lights the
+// reference's UI uses with them: PointLight, SpotLight, DistantLight, SkyBoxLight (next to DiffuseAreaLight and
+// InfiniteAreaLight).
+//
+// Both integrators are recursive (SpecularReflect / SpecularTransmit, core/Integrator.cpp:321-420) and draw their
+// Halton dimensions in depth-first order: the reflection subtree of a vertex consumes its dimensions before the
+// transmission sample of that vertex is drawn.  A breadth-first wavefront would have to know the size of every
+// subtree in advance, so — like VolPath — the recursion runs per lane, as an explicit depth-first stack of frames;
+// a pending transmission frame keeps only the hit record and is re-shaded when it is popped.
+//
+// Ray differentials are carried by the reference only to filter textures; these integrators are therefore
+// refused for scenes with image textures (gnx_render.cu), everything else is independent of them.
+#pragma once
+#include "gnx_volpath.cuh"
+
+namespace gnx {
+
+struct WLightSample {
+    V3 wi, Li;
+    float pdf;
+    V3 target, targetN, targetErr;  // VisibilityTester p1 (normal and error zero for points in space)
+    bool delta;                     // IsDeltaLight(flags)
+};
+
+// SpotLight::Falloff, lights/SpotLight.cpp:33-43
+GNX_D float spot_falloff(const gnx_light &l, V3 w) {
+    M44 w2l;
+    for (int i = 0; i < 16; ++i) w2l.m[i] = l.world_to_light[i];
+    V3 wl = normalize(xform_vector(w2l, w));
+    float cosTheta = wl.z;
+    if (cosTheta < l.cos_total) return 0;
+    if (cosTheta >= l.cos_falloff) return 1;
+    float delta = (cosTheta - l.cos_total) / (l.cos_falloff - l.cos_total);
+    return (delta * delta) * (delta * delta);
+}
+
+// SkyBoxLight::getLightValue, lights/SkyBoxLight.cpp:27-43
+GNX_D V3 skybox_value(const DevSkybox &sb, float u, float v) {
+    V3 Lv(0.f);
+    if (sb.data) {
+        int w = (int)(u * sb.w), h = (int)(v * sb.h);
+        int offset = (w + h * sb.w) * sb.nc;
+        const float scale = 1.0f / 10.0f;
+        Lv = V3(ldg(sb.data + offset) * scale, ldg(sb.data + offset + 1) * scale, ldg(sb.data + offset + 2) * scale);
+    }
+    return Lv;
+}
+// SkyBoxLight::Le, lights/SkyBoxLight.cpp:57-86 (the reference mixes float and double here: b, t)
+GNX_D V3 skybox_le(const DevSkybox &sb, V3 o, V3 d) {
+    V3 oc = o - sb.center;
+    float a = dot(d, d);
+    float b = (float)(2.0 * (double)dot(oc, d));
+    float c = dot(oc, oc) - sb.radius * sb.radius;
+    float discriminant = b * b - 4 * a * c;
+    if (discriminant < 0) return V3(0.f);
+    float t = (float)(((double)(-b) + sqrt((double)discriminant)) / (2.0 * (double)a));
+    V3 hitPos = o + t * d;
+    V3 hp = hitPos - sb.center;
+    V3 q = div_each(hp, sb.radius);
+    // get_sphere_uv: atan2 / asin are the double overloads in the reference (float arguments promoted)
+    float phi = (float)atan2((double)q.z, (double)q.x);
+    float theta = (float)asin((double)q.y);
+    float u = 1 - (phi + kPi) * kInv2Pi;
+    float v = (theta + kPiOver2) * kInvPi;
+    if (sb.data) return skybox_value(sb, u, v);
+    return V3((hp.x + sb.radius) / (2.f * sb.radius), (hp.y + sb.radius) / (2.f * sb.radius), (hp.z + sb.radius) / (2.f * sb.radius));
+}
+
+// Light::Le summed over the scene's lights for a ray that escapes (only the two infinite kinds return non-zero)
+GNX_D V3 scene_le(const DeviceScene &sc, V3 o, V3 d) {
+    V3 L(0.f);
+    // scene.lights order: whichever infinite light comes first is added first
+    const bool envFirst = !sc.skybox.present || (sc.env.present && sc.env.light_index < sc.skybox.light_index);
+    if (envFirst) {
+        if (sc.env.present) L += env_Le(sc.env, d);
+        if (sc.skybox.present) L += skybox_le(sc.skybox, o, d);
+    } else {
+        L += skybox_le(sc.skybox, o, d);
+        if (sc.env.present) L += env_Le(sc.env, d);
+    }
+    return L;
+}
+
+// Light::Sample_Li for every light type (lights/*.cpp)
+GNX_D bool w_sample_li(const DeviceScene &sc, const gnx_light &l, V3 refP, float u0, float u1, WLightSample *o) {
+    o->delta = false;
+    o->targetN = V3(0.f);
+    o->targetErr = V3(0.f);
+    switch (l.type) {
+    case GNX_LIGHT_AREA_TRI: {
+        LightSample ls;
+        bool ok = area_sample_li(sc, l, refP, u0, u1, &ls);
+        o->wi = ls.wi; o->Li = ls.Li; o->pdf = ls.pdf;
+        o->target = ls.pl; o->targetN = ls.nl; o->targetErr = ls.plError;
+        return ok;
+    }
+    case GNX_LIGHT_INFINITE: {
+        LightSample ls;
+        bool ok = env_sample_li(sc.env, u0, u1, &ls);
+        o->wi = ls.wi; o->Li = ls.Li; o->pdf = ls.pdf;
+        o->target = refP + ls.wi * (2 * sc.env.world_radius);
+        return ok;
+    }
+    case GNX_LIGHT_POINT:
+    case GNX_LIGHT_SPOT: {
+        const V3 pLight(l.p[0], l.p[1], l.p[2]);
+        o->wi = normalize(pLight - refP);
+        o->pdf = 1.f;
+        o->target = pLight;
+        o->delta = true;
+        V3 I(l.L[0], l.L[1], l.L[2]);
+        if (l.type == GNX_LIGHT_SPOT) I = I * spot_falloff(l, -o->wi);
+        o->Li = div_each(I, length_sq(pLight - refP));
+        return true;
+    }
+    case GNX_LIGHT_DISTANT: {
+        const V3 wLight(l.p[0], l.p[1], l.p[2]);
+        o->wi = wLight;
+        o->pdf = 1;
+        o->target = refP + wLight * (2 * l.area);  // area: the scene's bounding-sphere radius (Preprocess)
+        o->delta = true;
+        o->Li = V3(l.L[0], l.L[1], l.L[2]);
+        return true;
+    }
+    case GNX_LIGHT_SKYBOX: {
+        float theta = u1 * kPi, phi = u0 * 2 * kPi;
+        float cosTheta = cosf(theta), sinTheta = sinf(theta);
+        float sinPhi = sinf(phi), cosPhi = cosf(phi);
+        M44 l2w;
+        for (int i = 0; i < 16; ++i) l2w.m[i] = l.world_to_light[i];  // SKYBOX: LightToWorld
+        o->wi = xform_vector(l2w, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));
+        o->pdf = 1.f / (4 * kPi);
+        o->target = refP + o->wi * (2 * sc.skybox.radius);
+        o->Li = 16 * skybox_value(sc.skybox, u0, u1);
+        return true;
+    }
+    default:
+        o->pdf = 0; o->Li = V3(0.f);
+        return false;
+    }
+}
+
+// Light::Pdf_Li for the BSDF-sampling half of EstimateDirect (0 for SkyBoxLight and the delta lights)
+GNX_D float w_pdf_li(const DeviceScene &sc, const gnx_light &l, V3 refP, V3 rayO, V3 wi) {
+    if (l.type == GNX_LIGHT_AREA_TRI) return area_pdf_li(sc, l, refP, rayO, wi);
+    if (l.type == GNX_LIGHT_INFINITE) return env_pdf_li(sc.env, wi);
+    return 0.f;
+}
+
+struct RecCounters { unsigned extend, shadow, mis; };
+
+// VisibilityTester::Unoccluded (core/Light.cpp:22-25): !scene.IntersectP(p0.SpawnRayTo(p1))
+GNX_D bool w_unoccluded(const DeviceScene &sc, const Surface &s, const WLightSample &ls, int2 *stack, int stride,
+                        TraversalCounters &cnt, RecCounters &rcnt) {
+    V3 origin = offset_ray_origin(s.p, s.pError, s.n, ls.target - s.p);
+    V3 target = ls.target;
+    if (ls.targetN.x != 0 || ls.targetN.y != 0 || ls.targetN.z != 0 || ls.targetErr.x != 0 || ls.targetErr.y != 0 || ls.targetErr.z != 0)
+        target = offset_ray_origin(ls.target, ls.targetErr, ls.targetN, origin - ls.target);
+    V3 d = target - origin;
+    int prim;
+    TriHit h;
+    ++rcnt.shadow;
+    return !traverse<true>(sc, origin, d, 1 - kShadowEpsilon, stack, stride, &prim, &h, cnt);
+}
+
+// EstimateDirect (core/Integrator.cpp:99-215) for a surface, handleMedia = false, specular = false
+template <int MAXL>
+GNX_D V3 w_estimate_direct(const DeviceScene &sc, const Surface &s, const Bsdf<MAXL> &bsdf, const gnx_light &light, float ul0, float ul1,
+                           float us0, float us1, int2 *stack, int stride, TraversalCounters &cnt, RecCounters &rcnt) {
+    const int kNonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+    V3 Ld(0.f);
+    WLightSample ls;
+    w_sample_li(sc, light, s.p, ul0, ul1, &ls);
+    if (ls.pdf > 0 && !is_black(ls.Li)) {
+        V3 f;
+        float scatteringPdf;
+        bsdf_f_pdf(bsdf, s.wo, ls.wi, kNonSpec, &f, &scatteringPdf);
+        f = f * absdot(ls.wi, bsdf.ns);
+        if (!is_black(f)) {
+            V3 Li = ls.Li;
+            if (!w_unoccluded(sc, s, ls, stack, stride, cnt, rcnt)) Li = V3(0.f);
+            if (!is_black(Li)) {
+                if (ls.delta) Ld += div_each(f * Li, ls.pdf);
+                else {
+                    float weight = (ls.pdf * ls.pdf) / (ls.pdf * ls.pdf + scatteringPdf * scatteringPdf);
+                    Ld += div_each(f * Li * weight, ls.pdf);
+                }
+            }
+        }
+    }
+    if (!ls.delta) {
+        V3 wi;
+        float scatteringPdf;
+        int sampledType;
+        V3 f = bsdf_sample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, kNonSpec, &sampledType);
+        f = f * absdot(wi, bsdf.ns);
+        const bool sampledSpecular = (sampledType & BSDF_SPECULAR) != 0;
+        if (!is_black(f) && scatteringPdf > 0) {
+            float weight = 1;
+            V3 o = offset_ray_origin(s.p, s.pError, s.n, wi);
+            if (!sampledSpecular) {
+                float lightPdf = w_pdf_li(sc, light, s.p, o, wi);
+                if (lightPdf == 0) return Ld;
+                weight = (scatteringPdf * scatteringPdf) / (scatteringPdf * scatteringPdf + lightPdf * lightPdf);
+            }
+            int prim;
+            TriHit h;
+            ++rcnt.mis;
+            bool found = traverse<false>(sc, o, wi, GNX_INF, stack, stride, &prim, &h, cnt);
+            V3 Li(0.f);
+            if (found) {
+                if (light.type == GNX_LIGHT_AREA_TRI && prim == light.prim) {
+                    Surface ls2 = make_surface(sc, prim, h.b0, h.b1, h.b2, wi);
+                    Li = area_light_L(light, ls2.n, -wi);
+                }
+            } else if (light.type == GNX_LIGHT_INFINITE) Li = env_Le(sc.env, wi);
+            else if (light.type == GNX_LIGHT_SKYBOX) Li = skybox_le(sc.skybox, o, wi);
+            if (!is_black(Li)) Ld += div_each(f * Li * weight, scatteringPdf);
+        }
+    }
+    return Ld;
+}
+
+// One pending piece of the recursion.
+struct RecFrame {
+    V3 o, d;          // kind 0: the ray to trace.  kind 1: d = direction of the ray that produced the hit
+    V3 weight;        // product of f * |cos| / pdf down to here
+    float hb0, hb1, hb2;
+    int prim;         // kind 1: the hit to re-shade
+    int depth;
+    int kind;         // 0 = Li(ray, depth), 1 = SpecularTransmit of an already lit vertex
+};
+constexpr int kMaxRecDepth = 16;
+
+// WhittedIntegrator::Li / DirectLightingIntegrator::Li (UniformSampleOne) for camera sample `sample` of pixel (px, py).
+//   direct = false: integrators/WhittedIntegrator.cpp:14-67      direct = true: integrators/DirectLightingIntegrator.cpp:28-63
+template <int MAXL>
+GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, bool direct, int px, int py, int sample, int2 *stack, int stride,
+                      TraversalCounters &cnt, RecCounters &rcnt) {
+    const uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    PathSampler smp(sc.smp, hidx, 5);  // dimensions 0-4 belong to the camera sample
+    RecFrame frames[kMaxRecDepth + 2];
+    int nf = 0;
+    {
+        V3 o, d;
+        float tMax;
+        camera_ray(sc, px, py, hidx, &o, &d, &tMax);
+        RecFrame &f = frames[nf++];
+        f.o = o; f.d = d; f.weight = V3(1.f); f.depth = 0; f.kind = 0; f.prim = -1;
+        f.hb0 = f.hb1 = f.hb2 = 0;
+    }
+    V3 L(0.f);
+    const int maxDepth = rc.max_depth < kMaxRecDepth ? rc.max_depth : kMaxRecDepth;
+    while (nf > 0) {
+        RecFrame fr = frames[--nf];
+        Surface s;
+        Bsdf<MAXL> bsdf;
+        bool lit = false;  // true: a freshly hit vertex (lights + reflection), false: the postponed transmission
+        if (fr.kind == 0) {
+            // ---- Li(ray, depth): closest hit, skipping surfaces without a material at the same depth
+            bool escaped = false;
+            for (int guard = 0; guard < 4096; ++guard) {
+                int prim;
+                TriHit h;
+                ++rcnt.extend;
+                if (!traverse<false>(sc, fr.o, fr.d, GNX_INF, stack, stride, &prim, &h, cnt)) { escaped = true; break; }
+                s = make_surface(sc, prim, h.b0, h.b1, h.b2, fr.d);
+                fr.prim = prim; fr.hb0 = h.b0; fr.hb1 = h.b1; fr.hb2 = h.b2;
+                if (s.material >= 0) break;
+                fr.o = offset_ray_origin(s.p, s.pError, s.n, fr.d);  // isect.SpawnRay(ray.d)
+            }
+            if (escaped) { L += fr.weight * scene_le(sc, fr.o, fr.d); continue; }
+            if (s.material < 0) continue;
+            lit = true;
+        } else {
+            s = make_surface(sc, fr.prim, fr.hb0, fr.hb1, fr.hb2, fr.d);
+        }
+        build_bsdf<MAXL>(sc, sc.materials[s.material], s, bsdf, false);
+        const V3 ns = bsdf.ns;
+        if (lit) {
+            // ---- emitted light, then the direct illumination of the integrator
+            if (s.light >= 0) L += fr.weight * area_light_L(sc.lights[s.light], s.n, s.wo);
+            V3 lightL(0.f);
+            if (!direct) {
+                for (int j = 0; j < sc.n_lights; ++j) {
+                    float u0, u1;
+                    smp.get2d(&u0, &u1);
+                    WLightSample ls;
+                    w_sample_li(sc, sc.lights[j], s.p, u0, u1, &ls);
+                    if (is_black(ls.Li) || ls.pdf == 0) continue;
+                    V3 f;
+                    float pdfUnused;
+                    bsdf_f_pdf(bsdf, s.wo, ls.wi, BSDF_ALL, &f, &pdfUnused);
+                    if (!is_black(f) && w_unoccluded(sc, s, ls, stack, stride, cnt, rcnt))
+                        lightL += div_each(f * ls.Li * absdot(ls.wi, ns), ls.pdf);
+                }
+            } else if (sc.n_lights > 0) {
+                // UniformSampleOneLight without a light distribution (core/Integrator.cpp:70-79)
+                int lightNum = (int)(smp.get1d() * sc.n_lights);
+                if (lightNum > sc.n_lights - 1) lightNum = sc.n_lights - 1;
+                const float lightPdf = 1.f / sc.n_lights;
+                float ul0, ul1, us0, us1;
+                smp.get2d(&ul0, &ul1);
+                smp.get2d(&us0, &us1);
+                lightL = div_each(w_estimate_direct<MAXL>(sc, s, bsdf, sc.lights[lightNum], ul0, ul1, us0, us1, stack, stride, cnt, rcnt), lightPdf);
+            }
+            L += fr.weight * lightL;
+            if (!(fr.depth + 1 < maxDepth)) continue;
+        }
+        // ---- SpecularReflect (lit vertex) or SpecularTransmit (postponed frame): BSDF::Sample_f restricted to the
+        // specular lobes of one hemisphere
+        float u0, u1, pdf;
+        smp.get2d(&u0, &u1);
+        V3 wi;
+        int sampledType;
+        const int lobeFlags = (lit ? BSDF_REFLECTION : BSDF_TRANSMISSION) | BSDF_SPECULAR;
+        V3 f = bsdf_sample(bsdf, s.wo, &wi, u0, u1, &pdf, lobeFlags, &sampledType);
+        if (lit && nf < kMaxRecDepth + 1) {
+            // the transmission sample of this vertex is drawn after the whole reflection subtree
+            RecFrame &t = frames[nf++];
+            t = fr;
+            t.kind = 1;
+        }
+        if (pdf > 0.f && !is_black(f) && absdot(wi, ns) != 0.f && nf < kMaxRecDepth + 2) {
+            RecFrame &c = frames[nf++];
+            c.o = offset_ray_origin(s.p, s.pError, s.n, wi);
+            c.d = wi;
+            c.weight = fr.weight * div_each(f * absdot(wi, ns), pdf);
+            c.depth = fr.depth + 1;
+            c.kind = 0;
+            c.prim = -1;
+            c.hb0 = c.hb1 = c.hb2 = 0;
+        }
+    }
+    return L;
+}
+
+}  // namespace gnx

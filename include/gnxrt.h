@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GNX_ABI_VERSION 1
+#define GNX_ABI_VERSION 2
 
 typedef enum gnx_status {
     GNX_OK = 0,
@@ -135,9 +135,10 @@ typedef struct gnx_texture {
 typedef enum gnx_light_type {
     GNX_LIGHT_AREA_TRI = 0, /* DiffuseAreaLight on one Triangle   lights/DiffuseAreaLight.cpp:37-58 */
     GNX_LIGHT_INFINITE = 1, /* InfiniteAreaLight                  lights/InfiniteAreaLight.cpp:12-132 */
-    GNX_LIGHT_POINT = 2,
-    GNX_LIGHT_SPOT = 3,
-    GNX_LIGHT_DISTANT = 4
+    GNX_LIGHT_POINT = 2,    /* PointLight    lights/PointLight.cpp:13-22      (WHITTED / DIRECT integrators) */
+    GNX_LIGHT_SPOT = 3,     /* SpotLight     lights/SpotLight.cpp:22-43                                       */
+    GNX_LIGHT_DISTANT = 4,  /* DistantLight  lights/DistantLight.cpp:16-27                                    */
+    GNX_LIGHT_SKYBOX = 5    /* SkyBoxLight   lights/SkyBoxLight.cpp:45-86, image in gnx_scene_desc.skybox     */
 } gnx_light_type;
 
 typedef struct gnx_light {
@@ -146,11 +147,21 @@ typedef struct gnx_light {
     int32_t two_sided;   /* AREA_TRI: DiffuseAreaLight::twoSided                     */
     int32_t medium;      /* medium index the light sits in, -1 = none                */
     float L[3];          /* AREA_TRI: Lemit; POINT/SPOT: I; DISTANT: L               */
-    float area;          /* AREA_TRI: Shape::Area()                                  */
-    float p[3];          /* POINT/SPOT position; DISTANT direction (world)           */
+    float area;          /* AREA_TRI: Shape::Area(); DISTANT: worldRadius (Preprocess) */
+    float p[3];          /* POINT/SPOT position; DISTANT direction wLight (world)    */
     float cos_total, cos_falloff; /* SPOT */
-    float world_to_light[16];     /* SPOT */
+    float world_to_light[16];     /* SPOT: WorldToLight; SKYBOX: LightToWorld (row-major)   */
 } gnx_light;
+
+/* SkyBoxLight private state (lights/SkyBoxLight.h:44-48). */
+typedef struct gnx_skybox {
+    int32_t present;
+    int32_t light_index;       /* its position in lights[]                                  */
+    int32_t width, height, channels; /* stbi_loadf image, rows flipped as loaded; 0 = none  */
+    const float *data;         /* [height][width][channels] or NULL (procedural colours)    */
+    float center[3];           /* worldCenter                                               */
+    float radius;              /* worldRadius                                               */
+} gnx_skybox;
 
 /* InfiniteAreaLight private state (lights/InfiniteAreaLight.h:39-42) flattened by value. */
 typedef struct gnx_envmap {
@@ -242,9 +253,15 @@ typedef struct gnx_scene_desc {
     const gnx_medium *media;
     gnx_camera camera;
     gnx_sampler sampler;
+    gnx_skybox skybox;
 } gnx_scene_desc;
 
-typedef enum gnx_integrator { GNX_INTEGRATOR_PATH = 0, GNX_INTEGRATOR_VOLPATH = 1 } gnx_integrator;
+typedef enum gnx_integrator {
+    GNX_INTEGRATOR_PATH = 0,     /* integrators/PathIntegrator.cpp                                          */
+    GNX_INTEGRATOR_VOLPATH = 1,  /* integrators/VolPathIntegrator.cpp                                       */
+    GNX_INTEGRATOR_WHITTED = 2,  /* integrators/WhittedIntegrator.cpp (the UI's default, ui/RenderThread.cpp:163) */
+    GNX_INTEGRATOR_DIRECT = 3    /* integrators/DirectLightingIntegrator.cpp, LightStrategy::UniformSampleOne */
+} gnx_integrator;
 typedef enum gnx_film { GNX_FILM_BOX = 0, GNX_FILM_GAUSSIAN = 1 } gnx_film;
 
 typedef struct gnx_render_params {

@@ -27,8 +27,14 @@
 #include "core/Transform.h"
 #include "integrators/PathIntegrator.h"
 #include "integrators/VolPathIntegrator.h"
+#include "integrators/DirectLightingIntegrator.h"
+#include "integrators/WhittedIntegrator.h"
 #include "lights/DiffuseAreaLight.h"
+#include "lights/DistantLight.h"
 #include "lights/InfiniteAreaLight.h"
+#include "lights/PointLight.h"
+#include "lights/SkyBoxLight.h"
+#include "lights/SpotLight.h"
 #include "materials/DisneyMaterial.h"
 #include "materials/GlassMaterial.h"
 #include "materials/MatteMaterial.h"
@@ -46,6 +52,11 @@
 #include "gnxraytracer_b200/host/scenekit_mesh.h"
 
 using namespace pbr;
+
+// lights/SkyBoxLight.cpp:21 switches stb_image's process-wide "flip vertically" flag on and never off again; every
+// image the reference loads afterwards (environment maps, textures) would come out upside down.  The harness builds
+// many scenes per process, so it puts the flag back once a SkyBoxLight has been constructed.
+extern "C" void stbi_set_flip_vertically_on_load(int flag_true_if_should_flip);
 
 namespace {
 
@@ -71,7 +82,7 @@ struct HarnessScene {
     std::unique_ptr<AnimatedTransform> animated;
     std::shared_ptr<const Camera> camera;
     std::shared_ptr<Sampler> sampler;
-    int integrator = 0;  // 0 = PathIntegrator, 1 = VolPathIntegrator
+    int integrator = 0;  // gnx_integrator: 0 Path, 1 VolPath, 2 Whitted, 3 DirectLighting (UniformSampleOne)
     std::unique_ptr<Scene> scene;
     std::unique_ptr<FrameBuffer> fb;
     std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
@@ -203,6 +214,62 @@ void BuildCornell(HarnessScene &hs, int variant, int subdiv) {
     Finish(hs);
 }
 
+// the Cornell room (open towards the camera) with a Mirror and a Glass sphere and a plastic
+// box, lit by a PointLight, a SpotLight, a DistantLight, the area light and a SkyBoxLight (visible through the
+// opening and in the mirror).  lightMask selects the lights (bit 0 area, 1 point, 2 spot, 3 distant, 4 skybox,
+// 5 = skybox with the awesomeface.jpg image instead of the procedural colours).
+void BuildLightsRoom(HarnessScene &hs, int lightMask, int subdiv) {
+    auto white = Matte(0.91f, 0.91f, 0.91f, 0.f);
+    auto red = Matte(0.9f, 0.1f, 0.17f, 0.f);
+    auto blue = Matte(0.14f, 0.21f, 0.87f, 30.f);
+    auto mirror = std::make_shared<MirrorMaterial>(ConstSpec(0.9f, 0.9f, 0.9f), ConstF(0.0f));
+    auto glass = std::make_shared<GlassMaterial>(ConstSpec(0.98f, 0.98f, 0.98f), ConstSpec(0.98f, 0.98f, 0.98f), ConstF(0.0f),
+                                                 ConstF(0.0f), ConstF(1.5f), ConstF(0.0f), false);
+    auto plastic = std::make_shared<PlasticMaterial>(ConstSpec(0.35f, 0.12f, 0.48f), ConstSpec(0.65f, 0.88f, 0.52f), ConstF(0.1f),
+                                                     ConstF(0.0f), true);
+    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, -1.0f, -1.7f, -0.5f), Transform(), mirror, nullptr);
+    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, 1.0f, -1.7f, 0.8f), Transform(), glass, nullptr);
+    AddMesh(hs, gnxsk::icosphere(subdiv > 1 ? subdiv - 1 : subdiv, 0.5f, 0.0f, -2.0f, 1.6f), Transform(), plastic, nullptr);
+    gnxsk::Mesh walls = gnxsk::cornell_walls(5.0f);
+    Transform box2world = Translate(Vector3f(-2.5f, -2.5f, -2.5f));
+    for (int i = 0; i < 10; ++i) {
+        gnxsk::Mesh one;
+        for (int v = 0; v < 3; ++v) {
+            one.P.insert(one.P.end(), {walls.P[9 * i + 3 * v], walls.P[9 * i + 3 * v + 1], walls.P[9 * i + 3 * v + 2]});
+            one.idx.push_back(v);
+        }
+        AddMesh(hs, one, box2world, (i == 6 || i == 7) ? red : (i == 8 || i == 9) ? blue : white, nullptr);
+    }
+    if (lightMask & 1) {
+        Spectrum Le(3.0f);
+        AddMesh(hs, gnxsk::area_light_quad(1.4f), Translate(Vector3f(0.0f, 2.45f, 0.0f)), white, &Le);
+    }
+    if (lightMask & 2) {
+        Spectrum I;
+        I[0] = 6.f; I[1] = 5.f; I[2] = 4.f;
+        hs.lights.push_back(std::make_shared<PointLight>(Translate(Vector3f(1.5f, 1.8f, 1.0f)), MediumInterface(), I));
+    }
+    if (lightMask & 4) {
+        Spectrum I;
+        I[0] = 9.f; I[1] = 14.f; I[2] = 18.f;
+        Transform l2w = Inverse(LookAt(Point3f(-1.8f, 2.0f, 1.8f), Point3f(0.2f, -2.0f, 0.0f), Vector3f(0.f, 1.f, 0.f)));
+        hs.lights.push_back(std::make_shared<SpotLight>(l2w, MediumInterface(), I, 32.f, 22.f));
+    }
+    if (lightMask & 8) {
+        Spectrum L;
+        L[0] = 0.5f; L[1] = 0.45f; L[2] = 0.35f;
+        hs.lights.push_back(std::make_shared<DistantLight>(RotateY(15), L, Vector3f(0.3f, 0.4f, 1.0f)));
+    }
+    if (lightMask & (16 | 32)) {
+        std::string img = (lightMask & 32) ? ResourceDir() + "awesomeface.jpg" : std::string("/nonexistent");
+        // ui/RenderThread.cpp:145: SkyBoxLight(transform, worldCenter, worldRadius, file, nSamples)
+        hs.lights.push_back(std::make_shared<SkyBoxLight>(RotateX(10), Point3f(0.f, 0.f, 0.f), 50.f, img.c_str(), 1));
+        stbi_set_flip_vertically_on_load(0);
+    }
+    SetupCamera(hs, Point3f(0.f, 0.f, 6.5f), Point3f(0.f, -0.4f, 0.0f));
+    Finish(hs);
+}
+
 std::shared_ptr<Material> PurplePlastic() {  // ui/MaterialList.cpp:48-56
     return std::make_shared<PlasticMaterial>(ConstSpec(0.35f, 0.12f, 0.48f), ConstSpec(1.f - 0.35f, 1.f - 0.12f, 1.f - 0.48f),
                                              ConstF(0.1f), ConstF(0.0f), true);
@@ -321,6 +388,7 @@ extern "C" {
 //       "dragon"  (p0 = variant, p1 = nu, p2 = nv)
 //       "nano"    (p0 = variant, p1 = nu, p2 = nv)
 //       "smoke"   (p0 = variant)   -> VolPathIntegrator
+//       "whitted" / "direct" (p0 = light mask, p1 = sphere subdivision) -> WhittedIntegrator / DirectLightingIntegrator
 void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0, int p1, int p2) {
     auto *hs = new HarnessScene;
     hs->name = name;
@@ -329,6 +397,10 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else if (hs->name == "smoke") BuildSmoke(*hs, p0);
+    else if (hs->name == "whitted" || hs->name == "direct") {
+        BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);
+        hs->integrator = hs->name == "whitted" ? 2 : 3;
+    }
     else hs->error = "unknown scene";
     return hs;
 }
@@ -336,6 +408,16 @@ const char *gnxh_scene_error(void *h) { return ((HarnessScene *)h)->error.c_str(
 void gnxh_scene_destroy(void *h) { delete (HarnessScene *)h; }
 int gnxh_scene_num_prims(void *h) { return (int)((HarnessScene *)h)->prims.size(); }
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
+
+static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth) {
+    Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+    switch (hs->integrator) {
+    case 1: return new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get());
+    case 2: return new WhittedIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
+    case 3: return new DirectLightingIntegrator(LightStrategy::UniformSampleOne, maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
+    default: return new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    }
+}
 
 // The reference's own render: PathIntegrator::Render with `threads` OpenMP threads (0 = default).
 // rgba_out receives FrameBuffer's float buffer; *seconds the reference's own timeConsume.
@@ -346,9 +428,7 @@ int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, d
     hs->fb->InitBuffer(hs->width, hs->height, 4);
     hs->fb->renderCountClear();
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-    std::unique_ptr<SamplerIntegrator> integ;
-    if (hs->integrator == 1) integ.reset(new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get()));
-    else integ.reset(new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
+    std::unique_ptr<SamplerIntegrator> integ(MakeReferenceIntegrator(hs, maxDepth));
     double t = 0;
     integ->Render(*hs->scene, t);
     if (seconds) *seconds = t;
@@ -363,9 +443,7 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
     auto *hs = (HarnessScene *)h;
     if (!hs->scene) return -1;
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-    std::unique_ptr<SamplerIntegrator> integp;
-    if (hs->integrator == 1) integp.reset(new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get()));
-    else integp.reset(new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial"));
+    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth));
     SamplerIntegrator &integ = *integp;
     integ.Preprocess(*hs->scene, *hs->sampler);
 #pragma omp parallel for schedule(dynamic, 64)
@@ -421,6 +499,7 @@ static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
         Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
         hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial",
                                                    hs->integrator == 1));
+        hs->cuda->SetIntegrator(hs->integrator);
         hs->cudaMaxDepth = maxDepth;
     }
     return hs->cuda.get();

@@ -25,7 +25,14 @@ SCENES = {
     "nano_full": ("nano", 0, 320, 64),      # ~ 90 k triangles
     "smoke": ("smoke", 0, 0, 0),            # config 4: VolPath, grid density medium in homogeneous fog, PCG stream sampler
     "fog": ("smoke", 1, 0, 0),              # VolPath, homogeneous fog only, Halton sampler
+    # Whitted / DirectLighting with area + point + spot + distant + skybox lights (p0 = light mask)
+    "whitted": ("whitted", 31, 2, 0),
+    "whitted_img": ("whitted", 1 | 2 | 32, 2, 0),   # skybox with the awesomeface.jpg image
+    "direct": ("direct", 31, 2, 0),
+    "direct_area": ("direct", 1, 2, 0),             # area light only: both MIS halves of EstimateDirect
 }
+INTEGRATOR_OF = {"whitted": 2, "direct": 3, "smoke": 1}
+
 
 
 def grid(width, height):

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "gnx_pack.h"
-#include "gnx_volpath.cuh"
+#include "gnx_whitted.cuh"
 
 using namespace gnx;
 
@@ -25,7 +25,7 @@ struct EmulScene {
     std::vector<int2> media;
     std::vector<DevMedium> dev_media;
     std::vector<DevTexture> textures;
-    std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int;
+    std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int, skybox_img;
     std::vector<int> primes, sums;
     std::vector<uint4> dims;
     std::vector<uint16_t> perms;
@@ -80,6 +80,20 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
         memcpy(de.l2w.m, v.light_to_world, 64);
         memcpy(de.w2l.m, v.world_to_light, 64);
         de.world_radius = v.world_radius;
+    }
+    sc.skybox.present = 0;
+    if (d->skybox.present) {
+        const gnx_skybox &sb = d->skybox;
+        sc.skybox.present = 1; sc.skybox.light_index = sb.light_index;
+        sc.skybox.w = sb.width; sc.skybox.h = sb.height; sc.skybox.nc = sb.channels;
+        sc.skybox.center = V3(sb.center[0], sb.center[1], sb.center[2]);
+        sc.skybox.radius = sb.radius;
+        sc.skybox.data = nullptr;
+        if (sb.data && sb.width > 0 && sb.height > 0 && sb.channels >= 3) {
+            e.skybox_img.assign((size_t)sb.width * (sb.height + 1) * sb.channels + 4, 0.f);
+            memcpy(e.skybox_img.data(), sb.data, sizeof(float) * (size_t)sb.width * sb.height * sb.channels);
+            sc.skybox.data = e.skybox_img.data();
+        }
     }
     if (d->n_lights > 0) {
         sc.ld.uni_int = uniform_light_distribution(d->n_lights, e.uni_func, e.uni_cdf);
@@ -138,6 +152,15 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         rays[0] += vc.extend; rays[1] += vc.shadow; rays[2] += vc.mis;
         return Lv;
     }
+    if (p.integrator == GNX_INTEGRATOR_WHITTED || p.integrator == GNX_INTEGRATOR_DIRECT) {
+        RenderConsts rcw{};
+        rcw.width = p.width; rcw.height = p.height; rcw.max_depth = p.max_depth; rcw.rr_threshold = p.rr_threshold;
+        int2 wstack[kSmemStack];
+        RecCounters rcnt{0, 0, 0};
+        V3 Lw = recursive_li<8>(sc, rcw, p.integrator == GNX_INTEGRATOR_DIRECT, px, py, sample, wstack, 1, cnt, rcnt);
+        rays[0] += rcnt.extend; rays[1] += rcnt.shadow; rays[2] += rcnt.mis;
+        return Lw;
+    }
     float4 ray_o, ray_d, beta, L, hit;
     uint32_t hidx, meta;
     int32_t medium = -1;
@@ -185,7 +208,7 @@ void gnxe_destroy(void *h) { delete (EmulScene *)h; }
 
 int gnxe_render(void *h, const gnx_render_params *p, float *rgba_out, gnx_stats *stats) {
     auto *e = (EmulScene *)h;
-    ensure_spatial(*e, p->light_strategy);
+    if (p->integrator < GNX_INTEGRATOR_WHITTED) ensure_spatial(*e, p->light_strategy);
     unsigned long long nodes = 0, tris = 0, r0 = 0, r1 = 0, r2 = 0;
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : nodes, tris, r0, r1, r2)
     for (int pixel = 0; pixel < p->width * p->height; ++pixel) {
@@ -212,7 +235,7 @@ int gnxe_render(void *h, const gnx_render_params *p, float *rgba_out, gnx_stats 
 
 int gnxe_samples(void *h, const gnx_render_params *p, int n, const int *px, const int *py, const int *sample, float *rgb_out) {
     auto *e = (EmulScene *)h;
-    ensure_spatial(*e, p->light_strategy);
+    if (p->integrator < GNX_INTEGRATOR_WHITTED) ensure_spatial(*e, p->light_strategy);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < n; ++i) {
         TraversalCounters cnt{0, 0};

@@ -78,3 +78,45 @@ def test_volpath_matches_reference(ref, emul, preset):
     assert rel_mse(img, img_ref) <= 1e-6
     assert st.rays_shadow > 0 and st.rays_mis > 0
     rs.close(); es.close()
+
+
+@pytest.mark.parametrize("preset", ["whitted", "whitted_img", "direct", "direct_area"])
+def test_whitted_and_direct_lighting_match_reference(ref, emul, preset):
+    """WhittedIntegrator / DirectLightingIntegrator(UniformSampleOne) with Point, Spot, Distant and
+    SkyBox lights next to the area light; mirror and glass spheres exercise SpecularReflect / SpecularTransmit and the
+    depth-first order of the Halton dimensions.  Per-sample radiance against the reference's Li."""
+    from _harness import INTEGRATOR_OF, SCENES
+    res = 48
+    integ = INTEGRATOR_OF[SCENES[preset][0]]
+    rs = ref.scene(preset, res, res, 4)
+    es = emul.scene(rs.desc)
+    px, py = grid(res, res)
+    p = RenderParams.make(res, res, 4, max_depth=5, integrator=integ)
+    for s in (0, 3):
+        sm = np.full(px.size, s, np.int32)
+        rgb, prim = rs.reference_samples(px, py, sm, max_depth=5)
+        hits = rs.to_original(es.primary_hits(res, res, s))
+        assert np.mean(hits == prim) >= 0.9999
+        mine = es.samples(p, px, py, sm)
+        scale = np.maximum(np.abs(rgb).max(axis=1), 1e-3)
+        rel = np.abs(mine - rgb).max(axis=1) / scale
+        assert np.mean(rel < 1e-4) >= 0.999, f"per-sample radiance parity {np.mean(rel < 1e-4)}"
+        assert abs(mine.mean() - rgb.mean()) <= 1e-3 * abs(rgb.mean())
+        assert rgb.mean() > 0.01
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, st = es.render(p)
+    assert rel_mse(img, img_ref) <= 1e-6
+    assert st.rays_shadow > 0
+    rs.close(); es.close()
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_whitted_depth_limits(ref, emul, depth):
+    rs = ref.scene("whitted", 32, 32, 2)
+    es = emul.scene(rs.desc)
+    px, py = grid(32, 32)
+    sm = np.zeros(px.size, np.int32)
+    rgb, _ = rs.reference_samples(px, py, sm, max_depth=depth, want_prim=False)
+    mine = es.samples(RenderParams.make(32, 32, 2, max_depth=depth, integrator=2), px, py, sm)
+    assert np.allclose(mine, rgb, rtol=1e-4, atol=1e-6)
+    rs.close(); es.close()

@@ -210,6 +210,44 @@ def test_volpath_bridge_render_matches_reference(ref, preset, res, spp):
     rs.close()
 
 
+@pytest.mark.parametrize("preset,res,spp", [("whitted", 160, 8), ("whitted_img", 128, 8), ("direct", 160, 8), ("direct_area", 128, 8)])
+def test_whitted_and_direct_bridge_render_matches_reference(ref, emul, preset, res, spp):
+    """WhittedIntegrator / DirectLightingIntegrator through the drop-in class (SetIntegrator) against
+    the reference's own Render on a pbr::Scene with Point, Spot, Distant, SkyBox and area lights."""
+    from _harness import INTEGRATOR_OF, SCENES
+    rs = ref.scene(preset, res, res, spp)
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, seconds, st = rs.render_cuda(max_depth=5)
+    assert st.paths == res * res * spp and st.rays_shadow > 0
+    r = rel_mse(img, img_ref)
+    assert r <= 1e-3, f"rel-MSE {r}"
+    px, py = grid(res, res)
+    _, prim = rs.reference_samples(px, py, np.zeros(px.size, np.int32), want_rgb=False)
+    hits = rs.to_original(rs.cuda_primary_hits(0))
+    assert float(np.mean(hits == prim)) >= 0.9999
+    sel = np.random.default_rng(9).choice(px.size, 512, replace=False)
+    samples = np.stack([rs.reference_samples(px[sel], py[sel], np.full(sel.size, s, np.int32), want_prim=False)[0] for s in range(spp)])
+    sigma = samples.std(axis=0, ddof=1) / np.sqrt(spp) + 1e-4
+    assert np.mean(np.abs(img.reshape(-1, 4)[sel, :3] - img_ref.reshape(-1, 4)[sel, :3]) <= 3 * sigma) >= 0.999
+    # and the GPU equals the CPU emulation of the same device code
+    p = RenderParams.make(res, res, spp, max_depth=5, integrator=INTEGRATOR_OF[SCENES[preset][0]])
+    emu, _ = emul.scene(rs.desc).render(p)
+    assert rel_mse(img, emu) <= 1e-6
+    rs.close()
+
+
+def test_new_lights_are_refused_by_the_path_integrator(ref, ctx):
+    from gnxraytracer_b200.api import GnxError
+    rs = ref.scene("whitted", 32, 32, 2)
+    ctx.upload(rs.desc)
+    with pytest.raises(GnxError) as e:
+        ctx.render(RenderParams.make(32, 32, 2, integrator=0))
+    assert e.value.code == -4
+    img, st = ctx.render(RenderParams.make(32, 32, 2, integrator=2))
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0.01
+    rs.close()
+
+
 def test_volpath_scene_kit_and_integrator_rules(ctx, emul):
     from gnxraytracer_b200.api import GnxError
     res = 64
