@@ -40,6 +40,11 @@ WORKLOADS = {
            "C4: VolPathIntegrator, GridDensityMedium density_render.70.volume inside HomogeneousMedium fog, Matte ground, MonValley env, 1024x1024, 64 spp, maxDepth 5, PCG32 stream sampler"),
     "c1": ("cornell", 0, 3, 0, 512, 512, 16, 5,
            "C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
+    # SURVEY 8f rank 1 (the UI's default integrator): not a BASELINE config, measured to the same bar
+    "w1": ("lights", 31, 4, 2, 1024, 1024, 16, 5,
+           "W1: WhittedIntegrator, Cornell room + Mirror / Glass / Plastic spheres (11 532 tris), area + Point + Spot + Distant + SkyBox lights, 1024x1024, 16 spp, maxDepth 5"),
+    "d1": ("lights", 31, 4, 3, 1024, 1024, 16, 5,
+           "D1: DirectLightingIntegrator (UniformSampleOne), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
 }
 
 
@@ -194,7 +199,8 @@ def run_ours(args, wl):
     t_upload = time.time() - t0
 
     first, count = weak_sample_range(spp, rank)
-    integ = 1 if scene == "smoke" else 0  # VolPathIntegrator for the participating-media config
+    # VolPathIntegrator for the participating-media config; "lights" carries its gnx_integrator in p2
+    integ = 1 if scene == "smoke" else (p2 if scene == "lights" else 0)
     params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world, integrator=integ)
     fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
@@ -263,8 +269,8 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "paths_per_step_per_gpu": paths_step, "l2_policy": "inputs larger than L2: per-step path state + queues ~1.1 GB, scene 125 MB",
-                       "sample_range": "rank r renders Halton samples [64r, 64r+64) of every pixel; NCCL sum-reduce to rank 0 inside the timed region" if world > 1 else "samples [0, 64)",
+            "config": {"workload": desc, "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2: every step rewrites its path state and queues ({paths_step * 288 / 1e9:.1f} GB for the wavefront integrators, {paths_step * 16 / 1e9:.2f} GB of per-sample radiance for the per-lane ones) between launches",
+                       "sample_range": f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region" if world > 1 else f"samples [0, {spp})",
                        "scene_build_s": round(t_build, 3), "bvh_build_s": round(sk.build_seconds, 3), "scene_upload_s": round(t_upload, 3),
                        "num_prims": sk.num_prims},
             "mrays_per_s": st.rays * world / ms_step / 1e3,

@@ -397,9 +397,10 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else if (hs->name == "smoke") BuildSmoke(*hs, p0);
-    else if (hs->name == "whitted" || hs->name == "direct") {
+    else if (hs->name == "whitted" || hs->name == "direct" || hs->name == "lights") {
+        // "lights": the scene kit's name for the same room, p2 = gnx_integrator (2 Whitted, 3 DirectLighting)
         BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);
-        hs->integrator = hs->name == "whitted" ? 2 : 3;
+        hs->integrator = hs->name == "whitted" ? 2 : hs->name == "direct" ? 3 : (p2 == 3 ? 3 : 2);
     }
     else hs->error = "unknown scene";
     return hs;

@@ -26,7 +26,7 @@ if a.res:
 ctx = Context(0)
 sk = SceneKit(scene, W, H, spp, p0, p1, p2)
 ctx.upload(sk.desc)
-p = RenderParams.make(W, H, spp, max_depth=depth, batch_spp=a.batch_spp, integrator=1 if scene == 'smoke' else 0)
+p = RenderParams.make(W, H, spp, max_depth=depth, batch_spp=a.batch_spp, integrator=1 if scene == 'smoke' else (p2 if scene == 'lights' else 0))
 for i in range(a.steps):
     img, st = ctx.render(p)
 d = st.as_dict()
