@@ -269,7 +269,7 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2: every step rewrites its path state and queues ({paths_step * 288 / 1e9:.1f} GB for the wavefront integrators, {paths_step * 16 / 1e9:.2f} GB of per-sample radiance for the per-lane ones) between launches",
+            "config": {"workload": desc, "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_step * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_step * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
                        "sample_range": f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region" if world > 1 else f"samples [0, {spp})",
                        "scene_build_s": round(t_build, 3), "bvh_build_s": round(sk.build_seconds, 3), "scene_upload_s": round(t_upload, 3),
                        "num_prims": sk.num_prims},
