@@ -4,6 +4,8 @@
   halton_values.npz        HaltonSampler::SampleDimension for a table of (index, dim)      [bit-exact]
   cornell_96x96_4spp.npz   reference Render() image + per-pixel primary-hit primitive ids
   dragon_96x96_4spp.npz    same for the (256 x 32)-quad dragon-class mesh under MonValley
+  whitted_96x96_4spp.npz   WhittedIntegrator::Render on the lights room (area + point + spot + distant + skybox)
+  direct_96x96_4spp.npz    DirectLightingIntegrator(UniformSampleOne)::Render on the same room
 """
 import os
 import sys
@@ -25,7 +27,8 @@ def main():
     dim[:512] = rng.integers(0, 6, 512)
     np.savez_compressed(os.path.join(HERE, "halton_values.npz"), index=idx, dim=dim, value=rs.sample_dims(idx, dim),
                         pixel_index=np.array([[x, y, s, rs.sample_index(x, y, s)] for x, y, s in rng.integers(0, 96, (256, 3))], np.int64))
-    for preset, name in (("cornell", "cornell_96x96_4spp"), ("dragon", "dragon_96x96_4spp")):
+    for preset, name in (("cornell", "cornell_96x96_4spp"), ("dragon", "dragon_96x96_4spp"), ("whitted", "whitted_96x96_4spp"),
+                         ("direct", "direct_96x96_4spp")):
         rs = ref.scene(preset, 96, 96, 4)
         img, _ = rs.render_reference(max_depth=5)
         px, py = _harness.grid(96, 96)

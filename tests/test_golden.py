@@ -42,3 +42,18 @@ def test_dragon_golden_image_and_hits(emul):
     img, _ = es.render(RenderParams.make(96, 96, 4, max_depth=5))
     assert rel_mse(img, g["image"]) <= 1e-3
     es.close(); sk.close()
+
+
+def test_whitted_and_direct_golden_images(emul):
+    """the committed reference renders of WhittedIntegrator / DirectLightingIntegrator on the lights
+    room against the product's device code on the scene kit's own build of that room."""
+    import pytest
+    for name, integ in (("whitted", 2), ("direct", 3)):
+        g = np.load(os.path.join(G, f"{name}_96x96_4spp.npz"))
+        sk = SceneKit("lights", 96, 96, 4, 31, 2, 0)
+        es = emul.scene(sk.desc)
+        hits = es.primary_hits(96, 96, 0)
+        assert np.mean(hits == g["primary_hit"]) >= 0.999
+        img, _ = es.render(RenderParams.make(96, 96, 4, max_depth=int(g["max_depth"]), integrator=integ))
+        assert rel_mse(img, g["image"]) <= 1e-3
+        es.close(); sk.close()
