@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(kShadeBlock, GNX_SHADE_MINBLOCKS(MAXL)) k_shad
 
 // VolPathIntegrator: one path per lane from camera to termination (gnx_volpath.cuh explains why this
 // integrator is not cut into wavefront stages).  Lanes pull camera samples through a warp-aggregated cursor.
-__global__ void __launch_bounds__(kBlock) k_volpath(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
+// Resident blocks per SM for the two per-lane kernels (latency-bound: more warps pay despite the spills).  Measured:
+// k_volpath C4 4 blocks 2.1 s, 6: 1.97 s, 8: 1.85 s; k_recursive W1 / D1 4: 25.5 / 34.0 ms, 6: 23.9 / 32.0, 8: 25.0 / 30.2.
+__global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
     const int n = rc.npix * rc.batch_spp;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kBlock) k_volpath(const DeviceScene sc, PathSt
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
 // stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
-__global__ void __launch_bounds__(kBlock) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int direct,
+__global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int direct,
                                                      DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
