@@ -120,3 +120,18 @@ def test_whitted_depth_limits(ref, emul, depth):
     mine = es.samples(RenderParams.make(32, 32, 2, max_depth=depth, integrator=2), px, py, sm)
     assert np.allclose(mine, rgb, rtol=1e-4, atol=1e-6)
     rs.close(); es.close()
+
+
+@pytest.mark.parametrize("preset,w,h,spp", [("cornell", 70, 37, 3), ("dragon", 33, 90, 1), ("whitted", 61, 40, 2)])
+def test_non_square_odd_sizes(ref, emul, preset, w, h, spp):
+    """Ragged shapes: widths and heights that are not multiples of anything (Halton base scales that do not divide the
+    resolution, a sample count below the warp width) through Render() of both sides."""
+    from _harness import INTEGRATOR_OF, SCENES
+    integ = INTEGRATOR_OF.get(SCENES[preset][0], 0)
+    rs = ref.scene(preset, w, h, spp)
+    es = emul.scene(rs.desc)
+    img_ref, _ = rs.render_reference(max_depth=4)
+    img, st = es.render(RenderParams.make(w, h, spp, max_depth=4, integrator=integ))
+    assert img.shape == (h, w, 4) and st.paths == w * h * spp
+    assert rel_mse(img, img_ref) <= 1e-6
+    rs.close(); es.close()

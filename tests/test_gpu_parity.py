@@ -236,6 +236,21 @@ def test_whitted_and_direct_bridge_render_matches_reference(ref, emul, preset, r
     rs.close()
 
 
+@pytest.mark.parametrize("preset,w,h,spp", [("cornell", 70, 37, 3), ("dragon", 33, 90, 1), ("whitted", 61, 40, 2), ("cornell", 200, 120, 33)])
+def test_non_square_odd_sizes_on_gpu(ref, preset, w, h, spp):
+    """Ragged shapes through the drop-in class: resolutions that no tile or Halton base scale divides, sample counts
+    below and just above the warp width (a warp then spans pixel boundaries)."""
+    rs = ref.scene(preset, w, h, spp)
+    img_ref, _ = rs.render_reference(max_depth=4)
+    img, _, st = rs.render_cuda(max_depth=4)
+    assert img.shape == (h, w, 4) and st.paths == w * h * spp
+    assert rel_mse(img, img_ref) <= 1e-3
+    px, py = grid(w, h)
+    _, prim = rs.reference_samples(px, py, np.zeros(px.size, np.int32), want_rgb=False)
+    assert float(np.mean(rs.to_original(rs.cuda_primary_hits(0)) == prim)) >= 0.9999
+    rs.close()
+
+
 def test_new_lights_are_refused_by_the_path_integrator(ref, ctx):
     from gnxraytracer_b200.api import GnxError
     rs = ref.scene("whitted", 32, 32, 2)
