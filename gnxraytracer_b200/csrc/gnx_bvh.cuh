@@ -247,6 +247,30 @@ GNX_D void trav_pop(Trav &t, const int2 *stack, int stride, uint32_t sb = 0) {
     }
 }
 
+// One pop attempt without divergence, for the warp-synchronous kernel: every lane reads the entry under its stack
+// top (a shared-memory load whether it needs it or not) and lanes with cur == kRefPop take it.  An entry that the
+// current tMax culls leaves the lane in the kRefPop state: it pops again in the next round.  Levels beyond the shared
+// part of the stack take the (rare) branch.
+template <bool ANY>
+GNX_D void trav_pop_round(Trav &t, const int2 *stack, int stride, uint32_t sb, bool active) {
+    const bool need = active && t.cur == kRefPop;
+    const int top = t.sp - 1;
+    if (need && top >= kSmemStack) {
+        const int2 e = t.spill[top - kSmemStack];
+        t.sp = top;
+        if (ANY || i2f(e.y) < t.tMax) t.cur = e.x;
+        return;
+    }
+    const int2 e = stack_load(t, stack, stride, top < 0 ? 0 : (top >= kSmemStack ? kSmemStack - 1 : top), sb);
+    if (need) {
+        if (top < 0) t.cur = kRefNone;
+        else {
+            t.sp = top;
+            if (ANY || i2f(e.y) < t.tMax) t.cur = e.x;
+        }
+    }
+}
+
 #if GNX_BVH_WIDTH == 4
 // Node4 (128 B = eight float4): lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] refs[4] (axTop, ax0, ax1, -).
 // Slots 0-1 are the children of the source node's first child, slots 2-3 of its second child (a child

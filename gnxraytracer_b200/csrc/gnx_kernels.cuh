@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     const uint32_t sb = stack_shared_base(stack);
     const int lane = threadIdx.x & 31;
     const bool kExtend = KIND == 0 || KIND == 3;
+    constexpr bool kPopRound = KIND == 1;
     const int n = KIND == 3 ? rc.npix * rc.batch_spp
                             : (KIND == 0 ? q.counts[arg] : (KIND == 1 ? q.counts[kCntShadow + arg] : q.counts[kCntProbe]));
     int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? 1 + arg : 3))];
@@ -158,13 +159,16 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             // node and triangle visits are exactly those of the reference order.  (Measured alternatives, all
             // slower: deferring the leaf while the lane goes on with its next stack entry, +4..30 % with the batch
             // size; larger batches; see profiles/README.md.)
+            // Pops requested by the previous round's interior steps and leaves.  Any-hit rays (entries never go stale):
+            // predicated at the top of the round, no divergent block (shadow stage -3 %); closest-hit rays measure
+            // 1-2 % better with the divergent pop below, whose re-validation loop skips culled entries at once.
+            if (kPopRound) trav_pop_round<KIND == 1>(t, stack, kBlock, sb, active);
             bool parked = active && trav_is_leaf(t);
             if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
             if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
-            // pops requested by this round's interior steps (both children missed) and leaves, together
-            if (active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
+            if (!kPopRound && active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
             if (active && trav_done(t)) {
                 if (kExtend) needFinish = true;
                 else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
