@@ -61,7 +61,7 @@ class Stats(ctypes.Structure):
         return d
 
 
-EXPORTS = ["gnx_abi_version", "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_upload_scene",
+EXPORTS = ["gnx_abi_version", "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_upload_scene", "gnx_bvh_build_ms",
            "gnx_render", "gnx_render_device", "gnx_primary_hits", "gnx_sample_dimensions", "gnx_tonemap_rgba8"]
 
 _lib = None
@@ -87,6 +87,8 @@ def load_library():
     lib.gnx_last_error.argtypes = [c_void_p]
     lib.gnx_last_error.restype = ctypes.c_char_p
     lib.gnx_upload_scene.argtypes = [c_void_p, c_void_p]
+    lib.gnx_bvh_build_ms.argtypes = [c_void_p]
+    lib.gnx_bvh_build_ms.restype = c_double
     lib.gnx_render.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_void_p, ctypes.POINTER(Stats)]
     lib.gnx_render_device.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_void_p, c_void_p, ctypes.POINTER(Stats)]
     lib.gnx_primary_hits.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_int32, c_void_p]
@@ -114,6 +116,11 @@ class Context:
     def upload(self, desc_ptr):
         """desc_ptr: address of a gnx_scene_desc (from SceneKit or from the bridge's FlattenScene)."""
         self._check(self.lib.gnx_upload_scene(self.h, c_void_p(int(desc_ptr))))
+
+    @property
+    def bvh_build_ms(self):
+        """Device time of the BVH build done by the last upload (0 when the description carried its own nodes)."""
+        return self.lib.gnx_bvh_build_ms(self.h)
 
     def render(self, params, out=None, want_stats=True):
         if out is None:
@@ -166,7 +173,7 @@ class Context:
 
 
 # ---- host-side scene kit (include/gnx_scenekit.h): builds gnx_scene_desc for the BASELINE configs ----
-SCENEKIT_EXPORTS = ["gnxsk_create", "gnxsk_destroy", "gnxsk_desc", "gnxsk_error", "gnxsk_num_prims", "gnxsk_build_seconds"]
+SCENEKIT_EXPORTS = ["gnxsk_create", "gnxsk_destroy", "gnxsk_desc", "gnxsk_error", "gnxsk_num_prims", "gnxsk_build_seconds", "gnxsk_strip_bvh"]
 _sk = None
 
 
@@ -194,6 +201,8 @@ def load_scenekit():
     sk.gnxsk_num_prims.argtypes = [c_void_p]
     sk.gnxsk_build_seconds.argtypes = [c_void_p]
     sk.gnxsk_build_seconds.restype = c_double
+    sk.gnxsk_strip_bvh.argtypes = [c_void_p]
+    sk.gnxsk_strip_bvh.restype = None
     _sk = sk
     return sk
 
@@ -230,6 +239,10 @@ class SceneKit:
     @property
     def build_seconds(self):
         return self.sk.gnxsk_build_seconds(self.h)
+
+    def strip_bvh(self):
+        """Drop the host-built BVH: the library then builds one on the GPU at upload."""
+        self.sk.gnxsk_strip_bvh(self.h)
 
     def close(self):
         if self.h:

@@ -1,0 +1,237 @@
+// gnx_lbvh.cuh — BVH construction on the GPU, used by gnx_upload_scene when the caller
+// passes triangles without a node array.
+//
+// The reference builds its BVH on one host thread (accelerator/BVHAccel.cpp:147-189, ~2.3 s per million triangles);
+// this builder is the classic linear BVH: 30-bit Morton codes of the triangle centroids, a radix sort of
+// (code, index) keys, the Karras 2012 radix tree built with one thread per internal node, a bottom-up bounds pass,
+// and an emit pass that writes the 64-byte two-child nodes the traversal kernels read (gnx_bvh.cuh) directly in
+// device memory.  Subtrees of at most kLbvhLeafPrims triangles become one leaf (their triangles are contiguous in
+// the sorted order).  The near child of a node is the one whose centroid is lower on the axis where the two
+// children are furthest apart, so the traversal's "near child by ray sign" rule applies unchanged.
+//
+// The tree differs from the reference's SAH tree, hence so does the order in which equally distant triangles are
+// met; results agree with the reference-order build on >= 99.99 % of primary hits and to rel-MSE ~1e-9 on images
+// (tests/test_gpu_parity.py::test_device_built_bvh).
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gnx_bvh.cuh"
+
+namespace gnx {
+
+constexpr int kLbvhLeafPrims = 4;
+
+struct LbvhNode {       // internal node of the radix tree
+    int left, right;    // child: >= 0 internal index, < 0 leaf ~position
+    int first, last;    // sorted-position range covered
+    int parent;
+};
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+// key = Morton code of the centroid (30 bits) in the high word, primitive index in the low word: unique keys
+__global__ void k_lbvh_keys(const float *prim_p, int n, float3 cmin, float3 cinv, unsigned long long *keys) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *p = prim_p + 9 * (size_t)i;
+        float lo[3], hi[3];
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = fminf(p[c], fminf(p[3 + c], p[6 + c]));
+            hi[c] = fmaxf(p[c], fmaxf(p[3 + c], p[6 + c]));
+        }
+        const float cx = (.5f * lo[0] + .5f * hi[0] - cmin.x) * cinv.x, cy = (.5f * lo[1] + .5f * hi[1] - cmin.y) * cinv.y,
+                    cz = (.5f * lo[2] + .5f * hi[2] - cmin.z) * cinv.z;
+        const uint32_t x = (uint32_t)fminf(fmaxf(cx * 1024.f, 0.f), 1023.f), y = (uint32_t)fminf(fmaxf(cy * 1024.f, 0.f), 1023.f),
+                       z = (uint32_t)fminf(fmaxf(cz * 1024.f, 0.f), 1023.f);
+        const uint32_t code = (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+        keys[i] = ((unsigned long long)code << 32) | (unsigned)i;
+    }
+}
+
+__device__ __forceinline__ int lbvh_delta(const unsigned long long *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll(keys[i] ^ keys[j]);  // keys are unique
+}
+
+// Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees" (2012), one thread per
+// internal node i in [0, n - 1)
+__global__ void k_lbvh_tree(const unsigned long long *keys, int n, LbvhNode *nodes, int *leafParent) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+        const int d = lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+        const int dmin = lbvh_delta(keys, n, i, i - d);
+        int lmax = 2;
+        while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+        int l = 0;
+        for (int t = lmax / 2; t >= 1; t /= 2)
+            if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+        const int j = i + l * d;
+        const int dnode = lbvh_delta(keys, n, i, j);
+        int s = 0;
+        for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+            if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+            if (t == 1) break;
+        }
+        const int gamma = i + s * d + min(d, 0);
+        const int first = min(i, j), last = max(i, j);
+        const int left = first == gamma ? ~gamma : gamma, right = last == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+        // (.parent of node i is written by the thread that owns its parent; the array starts out as all -1)
+        nodes[i].left = left; nodes[i].right = right; nodes[i].first = first; nodes[i].last = last;
+        if (left >= 0) nodes[left].parent = i; else leafParent[~left] = i;
+        if (right >= 0) nodes[right].parent = i; else leafParent[~right] = i;
+    }
+}
+
+// Bounds: each leaf walks up; the second arrival at a node (atomic counter) merges the children's boxes.
+__global__ void k_lbvh_fit(const float *prim_p, const unsigned long long *keys, int n, const LbvhNode *nodes, const int *leafParent,
+                           float *leafBox, float *nodeBox, int *visits) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int prim = (int)(keys[k] & 0xffffffffu);
+        const float *p = prim_p + 9 * (size_t)prim;
+        float b[6];
+        for (int c = 0; c < 3; ++c) {
+            b[c] = fminf(p[c], fminf(p[3 + c], p[6 + c]));
+            b[3 + c] = fmaxf(p[c], fmaxf(p[3 + c], p[6 + c]));
+        }
+        for (int c = 0; c < 6; ++c) leafBox[6 * (size_t)k + c] = b[c];
+        if (n == 1) return;
+        int node = leafParent[k];
+        while (node >= 0) {
+            __threadfence();
+            if (atomicAdd(&visits[node], 1) == 0) break;  // the sibling subtree is not done yet
+            const LbvhNode nd = nodes[node];
+            const float *bl = nd.left >= 0 ? nodeBox + 6 * (size_t)nd.left : leafBox + 6 * (size_t)(~nd.left);
+            const float *br = nd.right >= 0 ? nodeBox + 6 * (size_t)nd.right : leafBox + 6 * (size_t)(~nd.right);
+            float m[6];
+            for (int c = 0; c < 3; ++c) {
+                m[c] = fminf(((volatile const float *)bl)[c], ((volatile const float *)br)[c]);
+                m[3 + c] = fmaxf(((volatile const float *)bl)[3 + c], ((volatile const float *)br)[3 + c]);
+            }
+            for (int c = 0; c < 6; ++c) nodeBox[6 * (size_t)node + c] = m[c];
+            node = nd.parent;
+        }
+    }
+}
+
+// Node2 records (layout in gnx_bvh.cuh) + the primitive order
+__global__ void k_lbvh_emit(const unsigned long long *keys, int n, const LbvhNode *nodes, const float *leafBox, const float *nodeBox,
+                            float4 *nodes2, int *order) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) order[k] = (int)(keys[k] & 0xffffffffu);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(n - 1, 1); i += gridDim.x * blockDim.x) {
+        int ref[2];
+        float box[2][6];
+        if (n == 1) {
+            ref[0] = leaf_ref(0, 1); ref[1] = kRefNone;
+            for (int c = 0; c < 6; ++c) { box[0][c] = leafBox[c]; box[1][c] = 0.f; }
+        } else {
+            const LbvhNode nd = nodes[i];
+            const int ch[2] = {nd.left, nd.right};
+            for (int s = 0; s < 2; ++s) {
+                if (ch[s] < 0) {
+                    ref[s] = leaf_ref(~ch[s], 1);
+                    for (int c = 0; c < 6; ++c) box[s][c] = leafBox[6 * (size_t)(~ch[s]) + c];
+                } else {
+                    const LbvhNode cn = nodes[ch[s]];
+                    const int size = cn.last - cn.first + 1;
+                    ref[s] = size <= kLbvhLeafPrims ? leaf_ref(cn.first, size) : ch[s];
+                    for (int c = 0; c < 6; ++c) box[s][c] = nodeBox[6 * (size_t)ch[s] + c];
+                }
+            }
+        }
+        int axis = 3;
+        if (ref[1] != kRefNone) {
+            float best = -1.f;
+            for (int c = 0; c < 3; ++c) {
+                const float d = fabsf((box[1][c] + box[1][3 + c]) - (box[0][c] + box[0][3 + c]));
+                if (d > best) { best = d; axis = c; }
+            }
+            if ((box[1][axis] + box[1][3 + axis]) < (box[0][axis] + box[0][3 + axis])) {  // child 0 = the lower one
+                const int r = ref[0]; ref[0] = ref[1]; ref[1] = r;
+                for (int c = 0; c < 6; ++c) { const float t = box[0][c]; box[0][c] = box[1][c]; box[1][c] = t; }
+            }
+        }
+        float4 *o = nodes2 + 4 * (size_t)i;
+        o[0] = make_float4(box[0][0], box[0][1], box[0][2], box[0][3]);
+        o[1] = make_float4(box[0][4], box[0][5], box[1][0], box[1][1]);
+        o[2] = make_float4(box[1][2], box[1][3], box[1][4], box[1][5]);
+        o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(axis), 0.f);
+    }
+}
+
+// Host driver.  prim_p: host, 9 floats per triangle.  On success *d_nodes2 is a device array of *nNodes2 64-byte
+// records (the caller owns it, cudaFree) and order[k] is the caller's index of the k-th triangle of the new order.
+inline cudaError_t lbvh_build(const float *prim_p, int n, cudaStream_t st, float4 **d_nodes2, int *nNodes2, std::vector<int> &order,
+                              float *buildMs) {
+    *d_nodes2 = nullptr;
+    *nNodes2 = 0;
+    order.clear();
+    if (n <= 0) return cudaSuccess;
+    // centroid bounds on the host (the triangles are host memory anyway)
+    float cmin[3] = {GNX_INF, GNX_INF, GNX_INF}, cmax[3] = {-GNX_INF, -GNX_INF, -GNX_INF};
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const float *p = prim_p + 9 * (size_t)i;
+            const float lo = std::min(p[c], std::min(p[3 + c], p[6 + c])), hi = std::max(p[c], std::max(p[3 + c], p[6 + c]));
+            const float ce = .5f * lo + .5f * hi;
+            cmin[c] = std::min(cmin[c], ce); cmax[c] = std::max(cmax[c], ce);
+        }
+    float3 cm = make_float3(cmin[0], cmin[1], cmin[2]);
+    float3 ci = make_float3(cmax[0] > cmin[0] ? 1.f / (cmax[0] - cmin[0]) : 0.f, cmax[1] > cmin[1] ? 1.f / (cmax[1] - cmin[1]) : 0.f,
+                            cmax[2] > cmin[2] ? 1.f / (cmax[2] - cmin[2]) : 0.f);
+    float *dP = nullptr, *leafBox = nullptr, *nodeBox = nullptr;
+    unsigned long long *keysA = nullptr, *keysB = nullptr;
+    LbvhNode *nodes = nullptr;
+    int *leafParent = nullptr, *visits = nullptr, *dOrder = nullptr;
+    void *tmp = nullptr;
+    size_t tmpBytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaSuccess;
+    const int nInt = std::max(n - 1, 1);
+    auto freeAll = [&]() {
+        cudaFree(dP); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(keysA); cudaFree(keysB); cudaFree(nodes); cudaFree(leafParent);
+        cudaFree(visits); cudaFree(dOrder); cudaFree(tmp);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define GNX_LB(call) do { err = (call); if (err != cudaSuccess) { freeAll(); if (*d_nodes2) { cudaFree(*d_nodes2); *d_nodes2 = nullptr; } return err; } } while (0)
+    GNX_LB(cudaMalloc((void **)&dP, sizeof(float) * 9 * (size_t)n));
+    GNX_LB(cudaMalloc((void **)&keysA, sizeof(unsigned long long) * (size_t)n));
+    GNX_LB(cudaMalloc((void **)&keysB, sizeof(unsigned long long) * (size_t)n));
+    GNX_LB(cudaMalloc((void **)&nodes, sizeof(LbvhNode) * (size_t)nInt));
+    GNX_LB(cudaMalloc((void **)&leafParent, sizeof(int) * (size_t)n));
+    GNX_LB(cudaMalloc((void **)&visits, sizeof(int) * (size_t)nInt));
+    GNX_LB(cudaMalloc((void **)&leafBox, sizeof(float) * 6 * (size_t)n));
+    GNX_LB(cudaMalloc((void **)&nodeBox, sizeof(float) * 6 * (size_t)nInt));
+    GNX_LB(cudaMalloc((void **)&dOrder, sizeof(int) * (size_t)n));
+    GNX_LB(cudaMalloc((void **)d_nodes2, sizeof(float4) * 4 * (size_t)nInt));
+    GNX_LB(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keysA, keysB, n, 0, 62, st));
+    GNX_LB(cudaMalloc(&tmp, tmpBytes));
+    GNX_LB(cudaMemcpyAsync(dP, prim_p, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice, st));
+    GNX_LB(cudaEventCreate(&e0));
+    GNX_LB(cudaEventCreate(&e1));
+    GNX_LB(cudaEventRecord(e0, st));
+    const int blocks = std::min((n + 255) / 256, 148 * 8);
+    k_lbvh_keys<<<blocks, 256, 0, st>>>(dP, n, cm, ci, keysA);
+    GNX_LB(cub::DeviceRadixSort::SortKeys(tmp, tmpBytes, keysA, keysB, n, 0, 62, st));
+    GNX_LB(cudaMemsetAsync(visits, 0, sizeof(int) * (size_t)nInt, st));
+    GNX_LB(cudaMemsetAsync(nodes, 0xff, sizeof(LbvhNode) * (size_t)nInt, st));
+    if (n > 1) k_lbvh_tree<<<blocks, 256, 0, st>>>(keysB, n, nodes, leafParent);
+    k_lbvh_fit<<<blocks, 256, 0, st>>>(dP, keysB, n, nodes, leafParent, leafBox, nodeBox, visits);
+    k_lbvh_emit<<<blocks, 256, 0, st>>>(keysB, n, nodes, leafBox, nodeBox, *d_nodes2, dOrder);
+    GNX_LB(cudaEventRecord(e1, st));
+    order.resize(n);
+    GNX_LB(cudaMemcpyAsync(order.data(), dOrder, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    GNX_LB(cudaStreamSynchronize(st));
+    GNX_LB(cudaGetLastError());
+    if (buildMs) cudaEventElapsedTime(buildMs, e0, e1);
+#undef GNX_LB
+    *nNodes2 = nInt;
+    freeAll();
+    return cudaSuccess;
+}
+
+}  // namespace gnx

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "gnx_kernels.cuh"
+#include "gnx_lbvh.cuh"
 #include "gnx_pack.h"
 
 using namespace gnx;
@@ -30,6 +31,7 @@ struct gnx_ctx {
     // scene
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
+    float bvh_build_ms = 0;        // device time of the last device-side BVH build (0: the caller supplied the nodes)
     DeviceScene sc{};
     std::vector<void *> scene_allocs;
     unsigned shade_type_mask = 0;  // which k_shade variants the scene needs
@@ -167,19 +169,82 @@ void gnx_destroy(gnx_ctx *ctx) {
     delete ctx;
 }
 
-int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
-    if (!ctx || !d) return GNX_ERR_INVALID;
-    if (d->abi_version != GNX_ABI_VERSION) return fail(ctx, GNX_ERR_INVALID, "abi_version mismatch");
+// A copy of the per-primitive arrays of a scene description in another primitive order (device-built BVH).
+struct ReorderedGeometry {
+    gnx_scene_desc desc;
+    std::vector<float> p, uv, n;
+    std::vector<uint8_t> has_n, flags, transition;
+    std::vector<int32_t> material, light, id, med_in, med_out;
+    std::vector<gnx_light> lights;
+    void build(const gnx_scene_desc &src, const std::vector<int> &order) {
+        desc = src;
+        const gnx_geometry &g = src.geom;
+        const int np = g.n_prims;
+        std::vector<int> newIndex(np);
+        for (int k = 0; k < np; ++k) newIndex[order[k]] = k;
+        auto gather = [&](auto &dst, const auto *srcArr, int stride) {
+            if (!srcArr) return;
+            dst.resize((size_t)np * stride);
+            for (int k = 0; k < np; ++k)
+                for (int c = 0; c < stride; ++c) dst[(size_t)k * stride + c] = srcArr[(size_t)order[k] * stride + c];
+        };
+        gather(p, g.prim_p, 9); gather(uv, g.prim_uv, 6); gather(n, g.prim_n, 9); gather(has_n, g.prim_has_n, 1);
+        gather(flags, g.prim_flags, 1); gather(transition, g.prim_is_transition, 1); gather(material, g.prim_material, 1);
+        gather(light, g.prim_light, 1); gather(med_in, g.prim_medium_in, 1); gather(med_out, g.prim_medium_out, 1);
+        id.resize(np);
+        for (int k = 0; k < np; ++k) id[k] = g.prim_id ? g.prim_id[order[k]] : order[k];
+        gnx_geometry &o = desc.geom;
+        o.prim_p = p.data(); o.prim_id = id.data();
+        if (g.prim_uv) o.prim_uv = uv.data();
+        if (g.prim_n) o.prim_n = n.data();
+        if (g.prim_has_n) o.prim_has_n = has_n.data();
+        if (g.prim_flags) o.prim_flags = flags.data();
+        if (g.prim_is_transition) o.prim_is_transition = transition.data();
+        if (g.prim_material) o.prim_material = material.data();
+        if (g.prim_light) o.prim_light = light.data();
+        if (g.prim_medium_in) o.prim_medium_in = med_in.data();
+        if (g.prim_medium_out) o.prim_medium_out = med_out.data();
+        lights.assign(src.lights, src.lights + src.n_lights);
+        for (gnx_light &l : lights)
+            if (l.type == GNX_LIGHT_AREA_TRI && l.prim >= 0 && l.prim < np) l.prim = newIndex[l.prim];
+        desc.lights = lights.data();
+    }
+};
+
+int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
+    if (!ctx || !d_in) return GNX_ERR_INVALID;
+    if (d_in->abi_version != GNX_ABI_VERSION) return fail(ctx, GNX_ERR_INVALID, "abi_version mismatch");
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
     free_pool(ctx->scene_allocs);
     ctx->has_scene = false;
     ctx->spatial_built = false;
     ctx->has_next_lights = false;
+    ctx->bvh_build_ms = 0;
     DeviceScene sc{};
     std::vector<void *> &pool = ctx->scene_allocs;
-    const gnx_geometry &g = d->geom;
-    if (g.n_prims < 0 || g.n_nodes < 0 || (g.n_prims > 0 && (!g.nodes || !g.prim_p || !g.prim_material)))
+    if (d_in->geom.n_prims < 0 || d_in->geom.n_nodes < 0 || (d_in->geom.n_prims > 0 && (!d_in->geom.prim_p || !d_in->geom.prim_material)) ||
+        (d_in->geom.n_nodes > 0 && !d_in->geom.nodes))
         return fail(ctx, GNX_ERR_INVALID, "geometry arrays missing");
+    // No node array: the BVH is built here, on the device (gnx_lbvh.cuh), and the per-primitive arrays are
+    // re-ordered to match it.  prim_id keeps pointing at the caller's order.
+    const bool deviceBuilt = d_in->geom.n_prims > 0 && d_in->geom.n_nodes == 0;
+    float4 *lbvhNodes = nullptr;
+    int lbvhCount = 0;
+    ReorderedGeometry reordered;
+    const gnx_scene_desc *d = d_in;
+    if (deviceBuilt) {
+        std::vector<int> order;
+        cudaError_t be = lbvh_build(d_in->geom.prim_p, d_in->geom.n_prims, ctx->stream, &lbvhNodes, &lbvhCount, order, &ctx->bvh_build_ms);
+        if (be != cudaSuccess) { ctx->err = std::string("device BVH build: ") + cudaGetErrorString(be); return GNX_ERR_CUDA; }
+        for (int i = 0; i < d_in->n_lights; ++i)
+            if (d_in->lights[i].type == GNX_LIGHT_AREA_TRI && (d_in->lights[i].prim < 0 || d_in->lights[i].prim >= d_in->geom.n_prims)) {
+                cudaFree(lbvhNodes);
+                return fail(ctx, GNX_ERR_INVALID, "area light primitive out of range");
+            }
+        reordered.build(*d_in, order);
+        d = &reordered.desc;
+    }
+    const gnx_geometry &g = d->geom;
     if (d->n_materials > (1 << 20) - 2) return fail(ctx, GNX_ERR_UNSUPPORTED, "too many materials");
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type < 0 || d->materials[i].type > GNX_MAT_DISNEY)
@@ -196,17 +261,27 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d) {
         std::vector<float4> n2, tris;
         std::string perr;
         int nNodes = 0;
-        if (!build_nodes(g.nodes, g.n_nodes, n2, &nNodes, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
-        if (!pack_triangles(*d, tris, &typeMask, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
-        std::vector<float4> both(n2);
-        both.insert(both.end(), tris.begin(), tris.end());
+        float4 *devNodes = nullptr;  // nodes built on the device (no node array supplied)
+        if (deviceBuilt) {
+            devNodes = lbvhNodes;
+            nNodes = lbvhCount;
+        } else if (!build_nodes(g.nodes, g.n_nodes, n2, &nNodes, &perr)) return fail(ctx, GNX_ERR_INVALID, perr);
+        if (!pack_triangles(*d, tris, &typeMask, &perr)) { if (devNodes) cudaFree(devNodes); return fail(ctx, GNX_ERR_INVALID, perr); }
+        const size_t nodeF4 = deviceBuilt ? (size_t)nNodes * 4 : n2.size();
         float4 *dn;
-        if ((rc = dupload(ctx, pool, both.data(), both.size(), &dn))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, nodeF4 + tris.size(), &dn))) { if (devNodes) cudaFree(devNodes); return rc; }
+        cudaError_t ce;
+        if (deviceBuilt) {
+            ce = cudaMemcpy(dn, devNodes, nodeF4 * sizeof(float4), cudaMemcpyDeviceToDevice);
+            cudaFree(devNodes);
+        } else ce = cudaMemcpy(dn, n2.data(), nodeF4 * sizeof(float4), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(dn + nodeF4, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        GNX_CUDA(ctx, ce);
         sc.nodes2 = dn;
         sc.n_nodes2 = nNodes;
-        sc.tris = dn + n2.size();
+        sc.tris = dn + nodeF4;
         ctx->geom_base = dn;
-        ctx->geom_bytes = both.size() * sizeof(float4);
+        ctx->geom_bytes = (nodeF4 + tris.size()) * sizeof(float4);
     }
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
@@ -673,6 +748,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
 }
 
 extern "C" {
+
+double gnx_bvh_build_ms(const gnx_ctx *ctx) { return ctx ? (double)ctx->bvh_build_ms : 0.0; }
 
 int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, gnx_stats *stats) {
     if (!ctx || !rgba_out) return GNX_ERR_INVALID;

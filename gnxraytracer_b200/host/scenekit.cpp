@@ -796,5 +796,10 @@ const char *gnxsk_error(const gnxsk_scene *s) { return s ? s->error.c_str() : "n
 const gnx_scene_desc *gnxsk_desc(const gnxsk_scene *s) { return (s && s->error.empty()) ? &s->desc : nullptr; }
 int gnxsk_num_prims(const gnxsk_scene *s) { return s ? s->desc.geom.n_prims : 0; }
 double gnxsk_build_seconds(const gnxsk_scene *s) { return s ? s->build_seconds : 0; }
+void gnxsk_strip_bvh(gnxsk_scene *s) {
+    if (!s) return;
+    s->desc.geom.n_nodes = 0;
+    s->desc.geom.nodes = nullptr;
+}
 
 }  // extern "C"

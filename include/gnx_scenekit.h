@@ -27,6 +27,8 @@ typedef struct gnxsk_scene gnxsk_scene;
  *       "nano"    (p0: 0 = Disney, 1 = thin Disney; p1 x p2: knot quads, 0 = 320 x 64; textured, smooth-shaded)
  *       "smoke"   (p0: 0 = grid density medium in fog, PCG32 stream sampler; 1 = fog only, Halton) -> render with
  *                 GNX_INTEGRATOR_VOLPATH
+ *       "lights"  (p0: light mask, bit 0 area, 1 point, 2 spot, 3 distant, 4 skybox, 0 = all; p1: sphere subdivision)
+ *                 -> render with GNX_INTEGRATOR_WHITTED or GNX_INTEGRATOR_DIRECT
  * resources: directory holding MonValley1000.hdr (only read by "dragon").
  * Never returns NULL; check gnxsk_error(). */
 gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int p0, int p1, int p2,
@@ -36,6 +38,9 @@ const char *gnxsk_error(const gnxsk_scene *s);         /* "" when the scene is u
 const gnx_scene_desc *gnxsk_desc(const gnxsk_scene *s); /* valid until gnxsk_destroy   */
 int gnxsk_num_prims(const gnxsk_scene *s);
 double gnxsk_build_seconds(const gnxsk_scene *s);      /* BVH build wall time          */
+/* Drops the kit's host-built BVH from the description (geom.n_nodes = 0): gnx_upload_scene then builds the
+ * hierarchy on the GPU.  The primitive arrays stay as they are (any order is valid without nodes). */
+void gnxsk_strip_bvh(gnxsk_scene *s);
 
 #ifdef __cplusplus
 }

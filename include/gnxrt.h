@@ -306,7 +306,12 @@ void gnx_destroy(gnx_ctx *ctx);
 const char *gnx_last_error(const gnx_ctx *ctx);          /* ctx may be NULL: last create error */
 
 /* Scene ------------------------------------------------------------------------------------ */
+/* scene->geom.n_nodes == 0 (nodes NULL): the library builds the BVH itself, on the GPU (linear BVH, SURVEY 8f
+ * rank 2; replaces BVHAccel's host build, accelerator/BVHAccel.cpp:147-189), and re-orders the per-primitive
+ * arrays to match; prim_id keeps the caller's numbering.  Otherwise the node array is the reference's own
+ * LinearBVHNode layout and the reference's traversal order is reproduced exactly. */
 int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *scene);
+double gnx_bvh_build_ms(const gnx_ctx *ctx); /* device time of that build; 0 when the caller supplied nodes */
 
 /* Render: replaces SamplerIntegrator::Render.  rgba_out is a HOST buffer of width*height*4
  * floats receiving the per-pixel mean radiance in (x + y*width)*4 + c order with alpha 1, i.e.
