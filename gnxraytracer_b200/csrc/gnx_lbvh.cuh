@@ -6,7 +6,7 @@
 // (code, index) keys, the Karras 2012 radix tree built with one thread per internal node, a bottom-up bounds pass,
 // and an emit pass that writes the 64-byte two-child nodes the traversal kernels read (gnx_bvh.cuh) directly in
 // device memory.  Subtrees of at most kLbvhLeafPrims triangles become one leaf (their triangles are contiguous in
-// the sorted order).  The near child of a node is the one whose centroid is lower on the axis where the two
+// the sorted order; 1 by default, like the reference UI's BVHAccel(prims, 1)).  The near child of a node is the one whose centroid is lower on the axis where the two
 // children are furthest apart, so the traversal's "near child by ray sign" rule applies unchanged.
 //
 // The tree differs from the reference's SAH tree, hence so does the order in which equally distant triangles are
@@ -19,7 +19,12 @@
 
 namespace gnx {
 
-constexpr int kLbvhLeafPrims = 4;
+// Triangles per leaf.  The traversal kernels run the triangle test at few active lanes, so big leaves cost more than
+// they save: C2 renders in 25.5 ms with 1, 25.9 with 2, 28.0 with 4 (the caller-supplied SAH tree: 25.2 ms).
+#ifndef GNX_LBVH_LEAF
+#define GNX_LBVH_LEAF 1
+#endif
+constexpr int kLbvhLeafPrims = GNX_LBVH_LEAF;
 
 struct LbvhNode {       // internal node of the radix tree
     int left, right;    // child: >= 0 internal index, < 0 leaf ~position

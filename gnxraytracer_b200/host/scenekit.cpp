@@ -128,9 +128,13 @@ struct BvhBuilder {
     std::vector<int> order;
     static constexpr int kBins = 16;
     static constexpr int kTaskCutoff = 4096;
+    // maxPrimsInNode of the SAH termination rule (accelerator/BVHAccel.cpp:297-318).  The reference's UI passes 1
+    // (ui/RenderThread.cpp:155); GNXSK_MAX_LEAF overrides it for experiments (profiles/README.md).
+    int maxLeaf = 1;
 
     BvhBuilder(const std::vector<Box> &b, const std::vector<float> &c) : pb(b), cen(c), order(b.size()) {
         for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        if (const char *e = getenv("GNXSK_MAX_LEAF")) maxLeaf = std::max(1, std::min(16, atoi(e)));
     }
 
     void leaf(std::vector<gnx_bvh_node> &out, int self, const Box &b, int lo, int hi) {
@@ -178,6 +182,8 @@ struct BvhBuilder {
                 float cost = 0.125f + (c * area(acc) + rightCnt[k + 1] * rightArea[k + 1]) * invA;
                 if (cost < best) { best = cost; bestK = k; }
             }
+            // leaf instead of a split when it is no more expensive (cost of a leaf: one unit per primitive)
+            if (n <= maxLeaf && !(best < (float)n)) { leaf(out, self, b, lo, hi); return; }
             if (bestK >= 0) {
                 auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](int prim) { return binOf(prim) <= bestK; });
                 mid = (int)(it - order.begin());
