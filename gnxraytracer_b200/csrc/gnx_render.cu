@@ -597,7 +597,8 @@ static void set_l2_window(gnx_ctx *ctx, cudaStream_t st) {
     cudaGetLastError();
 }
 
-static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats) {
+static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats,
+                       bool callerSyncs = false) {
     int rc = validate_params(ctx, p);
     if (rc) return rc;
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -711,7 +712,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     ++launches;
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     GNX_CUDA(ctx, cudaGetLastError());
-    if (stats || !rgba_dev_out) {
+    if (stats || (!rgba_dev_out && !callerSyncs)) {
         GNX_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
         GNX_CUDA(ctx, cudaGetLastError());
     }
@@ -753,7 +754,8 @@ double gnx_bvh_build_ms(const gnx_ctx *ctx) { return ctx ? (double)ctx->bvh_buil
 
 int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, gnx_stats *stats) {
     if (!ctx || !rgba_out) return GNX_ERR_INVALID;
-    int rc = render_impl(ctx, params, nullptr, nullptr, stats);
+    // the device-to-host copy is queued right behind the film kernel; one synchronisation at the end
+    int rc = render_impl(ctx, params, nullptr, nullptr, stats, true);
     if (rc) return rc;
     const size_t bytes = (size_t)params->width * params->height * sizeof(float4);
     GNX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->rgba, bytes, cudaMemcpyDeviceToHost, ctx->stream));
