@@ -33,7 +33,7 @@ __device__ __forceinline__ void flush_stats(DevStats *st, int kind, unsigned nod
         tris += __shfl_down_sync(kFull, tris, o);
         rays += __shfl_down_sync(kFull, rays, o);
     }
-    if ((threadIdx.x & 31) == 0 && rays) {
+    if ((threadIdx.x & 31) == 0 && (rays | nodes | tris)) {
         atomicAdd(&st->nodes[kind], (unsigned long long)nodes);
         atomicAdd(&st->tris[kind], (unsigned long long)tris);
         atomicAdd(&st->rays[kind], (unsigned long long)rays);
@@ -87,11 +87,15 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     const int lane = threadIdx.x & 31;
     const bool kExtend = KIND == 0 || KIND == 3;
     constexpr bool kPopRound = KIND == 1;
+    // KIND 1: arg 0 = shadow A items, 1 = shadow B items, 2 = both halves in one launch (A first)
+    const int nShA = KIND == 1 ? q.counts[kCntShadow] : 0, nShB = KIND == 1 ? q.counts[kCntShadow + 1] : 0;
     const int n = KIND == 3 ? rc.npix * rc.batch_spp
-                            : (KIND == 0 ? q.counts[arg] : (KIND == 1 ? q.counts[kCntShadow + arg] : q.counts[kCntProbe]));
-    int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? 1 + arg : 3))];
+                            : (KIND == 0 ? q.counts[arg] : (KIND == 1 ? (arg == 0 ? nShA : (arg == 1 ? nShB : nShA + nShB)) : q.counts[kCntProbe]));
+    int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? (arg == 1 ? 2 : 1) : 3))];
     const int *inList = KIND == 0 ? q.extend_q[arg] : nullptr;
-    const ShadowItem *shadowItems = q.shadow_q + (size_t)(KIND == 1 ? arg : 0) * q.capacity;
+    const int firstB = KIND == 1 ? (arg == 0 ? 0x7fffffff : (arg == 1 ? 0 : nShA)) : 0;  // items from here on are B items
+    auto shadowItem = [&](int i) { return i >= firstB ? q.shadow_q + (size_t)q.capacity + (i - firstB) : q.shadow_q + i; };
+    unsigned raysB = 0;
     TraversalCounters cnt{0, 0};
     unsigned rays = 0;
     Trav t;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                             slot_to_sample(rc, i, &pixel, &sample);
                             primary_begin(sc, pixel % rc.width, pixel / rc.width, sample, &hidx, &camD, t);
                         } else if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
-                        else if (KIND == 1) { item = i; shadow_begin(sc, shadowItems + i, t); }
+                        else if (KIND == 1) { item = i; shadow_begin(sc, shadowItem(i), t); if (i >= firstB) ++raysB; }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
                         active = true;
                         ++rays;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             if (!kPopRound && active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
             if (active && trav_done(t)) {
                 if (kExtend) needFinish = true;
-                else if (KIND == 1) shadow_finish(ps, shadowItems + item, t);
+                else if (KIND == 1) shadow_finish(ps, shadowItem(item), t, item >= firstB);
                 else probe_finish(ps, q.probe_q + item, t);
                 active = false;
             }
@@ -179,7 +183,11 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             if (actMask == 0 || (!exhausted && __popc(actMask) < (KIND == 3 ? kRefetchBelowPrimary : kRefetchBelow))) break;
         }
     }
-    flush_stats(st, kExtend ? 0 : (KIND == 1 ? (arg == 0 ? 1 : 2) : 2), cnt.nodes, cnt.tris, rays);
+    if (KIND == 1) {
+        // any-hit rays: shadow rays (A) are booked as kind 1, environment-MIS rays (B) as kind 2
+        flush_stats(st, 1, cnt.nodes, cnt.tris, rays - raysB);
+        flush_stats(st, 2, 0, 0, raysB);
+    } else flush_stats(st, kExtend ? 0 : 2, cnt.nodes, cnt.tris, rays);
     if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
 
@@ -309,7 +317,11 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
         float4 a = accum[pixel];
         for (int s = 0; s < rc.batch_spp; ++s) {
-            const float4 L = ps.L[(size_t)pixel * rc.batch_spp + s];
+            float4 L = ps.L[(size_t)pixel * rc.batch_spp + s];
+            if (L.w != 0.f) {  // the path has a second accumulator (environment-MIS contributions)
+                const float4 Lb = ps.Lb[(size_t)pixel * rc.batch_spp + s];
+                L.x += Lb.x; L.y += Lb.y; L.z += Lb.z;
+            }
             a.x += L.x; a.y += L.y; a.z += L.z;
         }
         accum[pixel] = a;

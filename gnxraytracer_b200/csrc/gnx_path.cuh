@@ -92,7 +92,8 @@ GNX_D int primary_finish(const DeviceScene &sc, const PathState &ps, const Rende
         ps.L[slot] = make_float4(Le.x, Le.y, Le.z, 0.f);
         return -1;
     }
-    ps.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ps.L[slot] = make_float4(0.f, 0.f, 0.f, ps.Lb ? 1.f : 0.f);
+    if (ps.Lb) ps.Lb[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 1.f);  // w: etaScale = 1
     ps.beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
     ps.hidx[slot] = hidx;
@@ -365,13 +366,14 @@ GNX_D void shadow_begin(const DeviceScene &sc, const ShadowItem *item, Trav &t) 
     const float4 o4 = ldg(&item->o_tmax), d4 = ldg(&item->d_path);
     trav_init(sc, t, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), o4.w);
 }
-GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav &t) {
+GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav &t, bool toLb = false) {
     if (t.hit) return;
     const float4 c = ldg(&item->contrib);
     const int slot = f2i(ldg(&item->d_path).w);
-    float4 L = ps.L[slot];
+    float4 *acc = (toLb && ps.Lb) ? ps.Lb : ps.L;
+    float4 L = acc[slot];
     L.x += c.x; L.y += c.y; L.z += c.z;
-    ps.L[slot] = L;
+    acc[slot] = L;
 }
 GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int2 *stack, int stride,
                        TraversalCounters &cnt) {

@@ -31,6 +31,7 @@ struct gnx_ctx {
     // scene
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
+    bool merge_shadow = true;      // GNX_MERGE_SHADOW=0: shadow A and B rays in two launches
     float bvh_build_ms = 0;        // device time of the last device-side BVH build (0: the caller supplied the nodes)
     DeviceScene sc{};
     std::vector<void *> scene_allocs;
@@ -148,6 +149,7 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
+    if (const char *ms = getenv("GNX_MERGE_SHADOW")) ctx->merge_shadow = ms[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
@@ -528,6 +530,7 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix) {
         if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.hidx))) return rc;
         if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.meta))) return rc;
         if ((rc = dupload<int32_t>(ctx, pool, nullptr, n, &ctx->ps.medium))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.Lb))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[0]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[1]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n * kNumShadeTypes, &ctx->q.shade_q))) return rc;
@@ -615,7 +618,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         // (cudaMemGetInfo costs ~0.5 ms: only asked when the buffers of an earlier call do not already cover the batch)
         const long long want = std::min(slots, (long long)npix * p->spp);
         if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            const long long bytesPerSlot = 288;  // PathState 92 B + queues 180 B, rounded up
+            const long long bytesPerSlot = 304;  // PathState 108 B + queues 180 B, rounded up
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
         }
@@ -628,6 +631,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     cudaStream_t st = userStream ? userStream : ctx->stream;
     set_l2_window(ctx, st);
     const DeviceScene &sc = ctx->sc;
+    // the second accumulator is only needed when shadow A and B rays share a launch
+    PathState psv = ctx->ps;
+    if (!(sc.env.present && ctx->merge_shadow)) psv.Lb = nullptr;
     const int gridTrace = ctx->grid_trace, gridShade = ctx->grid_shade, gridWide = ctx->sm_count * 16;
     const bool hasNull = (ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u;
     unsigned long long launches = 0;
@@ -653,11 +659,11 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         if (p->integrator != GNX_INTEGRATOR_PATH) {
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
             tm.begin(ST_EXTEND);
-            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, ctx->d_stats);
-            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, p->integrator == GNX_INTEGRATOR_DIRECT, ctx->d_stats);
+            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
+            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, p->integrator == GNX_INTEGRATOR_DIRECT, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
-            k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);
+            k_accumulate<<<gridWide, 256, 0, st>>>(psv, ctx->accum, rcn);
             tm.end();
             launches += 3;
             ++extendLaunches;
@@ -670,26 +676,28 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             const int out = 1 - in;
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
             tm.begin(ST_EXTEND);
-            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats);  // ray-gen fused in
-            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, in, ctx->d_stats);
+            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats);  // ray-gen fused in
+            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
             ++extendLaunches;
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
-                if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
-                else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, t, out);
+                if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
+                else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
                 ++launches;
             }
-            if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, out); ++launches; }
+            if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, out); ++launches; }
             tm.end();
             tm.begin(ST_SHADOW);
             if (sc.n_lights > 0) {
-                k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats);
+                // shadow rays (A) and, with an environment light, its MIS rays (B) in one launch: they add to separate
+                // accumulators (ps.L / ps.Lb), so the two rays of a path do not race
+                k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, (sc.env.present && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
                 ++launches;
-                if (sc.env.present) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
-                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, ctx->ps, ctx->q, rcn, 0, ctx->d_stats); ++launches; }
+                if (sc.env.present && !ctx->merge_shadow) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
+                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats); ++launches; }
             }
             tm.end();
             in = out;
@@ -702,7 +710,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             }
         }
         tm.begin(ST_FILM);
-        k_accumulate<<<gridWide, 256, 0, st>>>(ctx->ps, ctx->accum, rcn);
+        k_accumulate<<<gridWide, 256, 0, st>>>(psv, ctx->accum, rcn);
         tm.end();
         ++launches;
     }

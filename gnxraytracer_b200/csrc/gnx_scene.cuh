@@ -100,11 +100,14 @@ struct PathState {
     float4 *ray_o;     // xyz origin, w = tMax
     float4 *ray_d;     // xyz direction, w = etaScale
     float4 *beta;      // xyz throughput, w unused
-    float4 *L;         // xyz radiance accumulated by this path
+    float4 *L;         // xyz radiance accumulated by this path; w != 0: Lb[slot] is live as well
     float4 *hit;       // b0 b1 b2 bits(prim) written by extend
     uint32_t *hidx;    // Halton sample index (low 32 bits; the reference's int64 never exceeds 2^32 at the configs)
     uint32_t *meta;    // dimension (16 bits) | bounces (8) | flags (8)
     int32_t *medium;   // current ray medium (VolPath), -1 none
+    float4 *Lb;        // contributions of the environment-MIS (shadow B) rays, kept apart from L so that the shadow A
+                       // and shadow B rays of a path can be traced in the same launch without racing on one float4
+                       // (null: they go to L, sequential callers)
 };
 constexpr uint32_t kFlagSpecular = 1u;
 
