@@ -279,8 +279,9 @@ def run_ours(args, wl):
             "mrays_per_s": st.rays * world / ms_step / 1e3,
             "rays_per_path": st.rays / st.paths,
             "stage_ms": {"raygen": st.ms_raygen, "extend": st.ms_extend, "shade": st.ms_shade, "shadow": st.ms_shadow, "film": st.ms_film,
-                         "device_total": st.device_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "device_total": st.device_ms,
+                         "note": "extend = the k_trace<3|4|0> launches: camera rays, then per bounce the extension rays TOGETHER WITH the previous bounce's shadow / environment-MIS rays (one mixed launch); shadow = the any-hit launch after the last bounce and the area-light MIS probes"},
+            "roofline": {"bound": "hbm", "kernel": "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
                          "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_dram_trace.csv)", "peak_source": peak_src,
                          "launches_per_step": st.extend_launches, "avg_launch_ms": ext_ms,

@@ -46,6 +46,18 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
     if (i < kNumCounters && i != (1 - outExtend)) counts[i] = 0;
 }
 
+// Zeroes the shadow / probe counters and the fetch cursors (between a mixed trace launch and the shade stage).
+__global__ void k_reset_ray_counts(int *counts) {
+    int i = threadIdx.x;
+    if (i >= kCntShadow && i < kNumCounters) counts[i] = 0;
+}
+// Zeroes the counters of the queues the coming stages will fill, keeping the extend queue `in` AND the shadow queues
+// (both are consumed by the mixed trace launch that follows); fetch cursors are zeroed.
+__global__ void k_reset_counts_keep_rays(int *counts, int outExtend) {
+    int i = threadIdx.x;
+    if (i < kNumCounters && i != (1 - outExtend) && !(i >= kCntShadow && i < kCntShadow + 2)) counts[i] = 0;
+}
+
 // ---- the traversal kernel --------------------------------------------------------------------------------
 // Persistent threads with dynamic ray fetch (Aila & Laine's while-while scheme): the grid is exactly the
 // number of resident blocks; every lane owns at most one ray; lanes whose ray has finished pull the next
@@ -57,6 +69,8 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
 //   KIND 0: extension rays of the path slots in extend_q[arg]   -> hit record, env radiance, shade queues
 //   KIND 1: shadow_q half `arg` (any-hit)                        -> L += contrib when unoccluded
 //   KIND 2: probe_q (closest hit must be the light's triangle)   -> L += contrib
+//   KIND 4: KIND 0 and KIND 1 (both halves) in one launch: the extension rays of bounce d+1 and the any-hit rays of
+//           bounce d are independent work, and every launch of this persistent kernel ends in a tail of a few long rays
 //   KIND 3: camera rays of the batch, generated in registers (ray-gen fused with the first extension;
 //           path state is written only for rays that hit)      -> L = Le or hit record + shade queues
 #ifndef GNX_REFETCH
@@ -85,15 +99,21 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     int2 *stack = s_stack + threadIdx.x;
     const uint32_t sb = stack_shared_base(stack);
     const int lane = threadIdx.x & 31;
-    const bool kExtend = KIND == 0 || KIND == 3;
+    const bool kExtend = KIND == 0 || KIND == 3 || KIND == 4;
+    constexpr bool kMixed = KIND == 4;
     constexpr bool kPopRound = KIND == 1;
     // KIND 1: arg 0 = shadow A items, 1 = shadow B items, 2 = both halves in one launch (A first)
-    const int nShA = KIND == 1 ? q.counts[kCntShadow] : 0, nShB = KIND == 1 ? q.counts[kCntShadow + 1] : 0;
+    // KIND 4: arg = extend queue; shadow items (A then B) follow the nE extension rays in the index space
+    const int nShA = (KIND == 1 || kMixed) ? q.counts[kCntShadow] : 0, nShB = (KIND == 1 || kMixed) ? q.counts[kCntShadow + 1] : 0;
+    const int nE = (KIND == 0 || kMixed) ? q.counts[arg] : 0;
     const int n = KIND == 3 ? rc.npix * rc.batch_spp
-                            : (KIND == 0 ? q.counts[arg] : (KIND == 1 ? (arg == 0 ? nShA : (arg == 1 ? nShB : nShA + nShB)) : q.counts[kCntProbe]));
+                            : (KIND == 0 ? nE : (kMixed ? nE + nShA + nShB
+                                                        : (KIND == 1 ? (arg == 0 ? nShA : (arg == 1 ? nShB : nShA + nShB)) : q.counts[kCntProbe])));
     int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? (arg == 1 ? 2 : 1) : 3))];
-    const int *inList = KIND == 0 ? q.extend_q[arg] : nullptr;
-    const int firstB = KIND == 1 ? (arg == 0 ? 0x7fffffff : (arg == 1 ? 0 : nShA)) : 0;  // items from here on are B items
+    const int *inList = (KIND == 0 || kMixed) ? q.extend_q[arg] : nullptr;
+    const int firstB = kMixed ? nShA : (KIND == 1 ? (arg == 0 ? 0x7fffffff : (arg == 1 ? 0 : nShA)) : 0);  // shadow items from here on are B items
+    bool shLane = false;  // KIND 4: the lane's ray is an any-hit ray
+    unsigned raysSh = 0;
     auto shadowItem = [&](int i) { return i >= firstB ? q.shadow_q + (size_t)q.capacity + (i - firstB) : q.shadow_q + i; };
     unsigned raysB = 0;
     TraversalCounters cnt{0, 0};
@@ -144,6 +164,10 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                             int pixel, sample;
                             slot_to_sample(rc, i, &pixel, &sample);
                             primary_begin(sc, pixel % rc.width, pixel / rc.width, sample, &hidx, &camD, t);
+                        } else if (kMixed) {
+                            shLane = i >= nE;
+                            if (shLane) { item = i - nE; shadow_begin(sc, shadowItem(item), t); ++raysSh; if (item >= firstB) ++raysB; }
+                            else { item = inList[i]; extend_begin(sc, ps, item, t); }
                         } else if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
                         else if (KIND == 1) { item = i; shadow_begin(sc, shadowItem(i), t); if (i >= firstB) ++raysB; }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
@@ -171,11 +195,14 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
-            if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
+            if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) {
+                trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
+                if (kMixed && shLane && t.hit) t.cur = kRefNone;  // any-hit ray in a mixed launch
+            }
             if (!kPopRound && active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
             if (active && trav_done(t)) {
-                if (kExtend) needFinish = true;
-                else if (KIND == 1) shadow_finish(ps, shadowItem(item), t, item >= firstB);
+                if (kExtend && !(kMixed && shLane)) needFinish = true;
+                else if (KIND == 1 || kMixed) shadow_finish(ps, shadowItem(item), t, item >= firstB);
                 else probe_finish(ps, q.probe_q + item, t);
                 active = false;
             }
@@ -187,6 +214,13 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
         // any-hit rays: shadow rays (A) are booked as kind 1, environment-MIS rays (B) as kind 2
         flush_stats(st, 1, cnt.nodes, cnt.tris, rays - raysB);
         flush_stats(st, 2, 0, 0, raysB);
+    } else if (kMixed) {
+        // nodes / triangles of both ray kinds are booked under the extension rays; the ray counts stay per kind
+        flush_stats(st, 0, cnt.nodes, cnt.tris, rays - raysSh);
+        flush_stats(st, 1, 0, 0, raysSh - raysB);
+        flush_stats(st, 2, 0, 0, raysB);
+        for (int o = 16; o > 0; o >>= 1) raysSh += __shfl_down_sync(kFull, raysSh, o);
+        if ((threadIdx.x & 31) == 0 && raysSh) atomicAdd(&st->shadow_rays_in_extend_launches, (unsigned long long)raysSh);
     } else flush_stats(st, kExtend ? 0 : 2, cnt.nodes, cnt.tris, rays);
     if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
@@ -318,9 +352,9 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
         float4 a = accum[pixel];
         for (int s = 0; s < rc.batch_spp; ++s) {
             float4 L = ps.L[(size_t)pixel * rc.batch_spp + s];
-            if (L.w != 0.f) {  // the path has a second accumulator (environment-MIS contributions)
-                const float4 Lb = ps.Lb[(size_t)pixel * rc.batch_spp + s];
-                L.x += Lb.x; L.y += Lb.y; L.z += Lb.z;
+            if (L.w != 0.f) {  // the path has separate accumulators for its shadow / environment-MIS contributions
+                if (ps.La) { const float4 La = ps.La[(size_t)pixel * rc.batch_spp + s]; L.x += La.x; L.y += La.y; L.z += La.z; }
+                if (ps.Lb) { const float4 Lb = ps.Lb[(size_t)pixel * rc.batch_spp + s]; L.x += Lb.x; L.y += Lb.y; L.z += Lb.z; }
             }
             a.x += L.x; a.y += L.y; a.z += L.z;
         }

@@ -92,8 +92,9 @@ GNX_D int primary_finish(const DeviceScene &sc, const PathState &ps, const Rende
         ps.L[slot] = make_float4(Le.x, Le.y, Le.z, 0.f);
         return -1;
     }
-    ps.L[slot] = make_float4(0.f, 0.f, 0.f, ps.Lb ? 1.f : 0.f);
+    ps.L[slot] = make_float4(0.f, 0.f, 0.f, (ps.Lb || ps.La) ? 1.f : 0.f);
     if (ps.Lb) ps.Lb[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ps.La) ps.La[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 1.f);  // w: etaScale = 1
     ps.beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
     ps.hidx[slot] = hidx;
@@ -370,7 +371,7 @@ GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav
     if (t.hit) return;
     const float4 c = ldg(&item->contrib);
     const int slot = f2i(ldg(&item->d_path).w);
-    float4 *acc = (toLb && ps.Lb) ? ps.Lb : ps.L;
+    float4 *acc = toLb ? (ps.Lb ? ps.Lb : ps.L) : (ps.La ? ps.La : ps.L);
     float4 L = acc[slot];
     L.x += c.x; L.y += c.y; L.z += c.z;
     acc[slot] = L;

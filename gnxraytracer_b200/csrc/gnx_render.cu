@@ -31,6 +31,7 @@ struct gnx_ctx {
     // scene
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
+    bool merge_extend = true;      // GNX_MERGE_EXTEND=0: the any-hit rays of a bounce get their own launch(es)
     bool merge_shadow = true;      // GNX_MERGE_SHADOW=0: shadow A and B rays in two launches
     float bvh_build_ms = 0;        // device time of the last device-side BVH build (0: the caller supplied the nodes)
     DeviceScene sc{};
@@ -150,6 +151,7 @@ int gnx_create(gnx_ctx **out, int device) {
     }
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     if (const char *ms = getenv("GNX_MERGE_SHADOW")) ctx->merge_shadow = ms[0] != '0';
+    if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
@@ -531,6 +533,7 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix) {
         if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.meta))) return rc;
         if ((rc = dupload<int32_t>(ctx, pool, nullptr, n, &ctx->ps.medium))) return rc;
         if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.Lb))) return rc;
+        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.La))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[0]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[1]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n * kNumShadeTypes, &ctx->q.shade_q))) return rc;
@@ -618,7 +621,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         // (cudaMemGetInfo costs ~0.5 ms: only asked when the buffers of an earlier call do not already cover the batch)
         const long long want = std::min(slots, (long long)npix * p->spp);
         if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            const long long bytesPerSlot = 304;  // PathState 108 B + queues 180 B, rounded up
+            const long long bytesPerSlot = 320;  // PathState 124 B + queues 180 B, rounded up
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
         }
@@ -633,7 +636,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     const DeviceScene &sc = ctx->sc;
     // the second accumulator is only needed when shadow A and B rays share a launch
     PathState psv = ctx->ps;
-    if (!(sc.env.present && ctx->merge_shadow)) psv.Lb = nullptr;
+    const bool wantMixed = ctx->merge_extend && ctx->merge_shadow && p->integrator == GNX_INTEGRATOR_PATH && sc.n_lights > 0 &&
+                           !((ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u);
+    if (!wantMixed) psv.La = nullptr;
+    if (!wantMixed && !(sc.env.present && ctx->merge_shadow)) psv.Lb = nullptr;
     const int gridTrace = ctx->grid_trace, gridShade = ctx->grid_shade, gridWide = ctx->sm_count * 16;
     const bool hasNull = (ctx->shade_type_mask >> (kNumShadeTypes - 1)) & 1u;
     unsigned long long launches = 0;
@@ -670,17 +676,25 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             continue;
         }
         int in = 0;
+        // Mixed launches: from the second bounce on, the extension rays of bounce d+1 and the shadow / environment-MIS
+        // rays of bounce d go through ONE traversal launch (k_trace<4>): every launch of the persistent kernel ends in
+        // a tail of a few long rays, and the late bounces are mostly tail.  Not with material-less surfaces (the loop
+        // below polls the queue from the host) and not when the caller turned it off.
+        const bool mixed = ctx->merge_extend && psv.La && psv.Lb && !hasNull && sc.n_lights > 0;
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.
         for (int iter = 0;; ++iter) {
             const int out = 1 - in;
-            k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
+            if (mixed && iter > 0) k_reset_counts_keep_rays<<<1, 32, 0, st>>>(ctx->q.counts, out);
+            else k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
             tm.begin(ST_EXTEND);
             if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats);  // ray-gen fused in
+            else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, in, ctx->d_stats);
             else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
             ++extendLaunches;
+            if (mixed && iter > 0) { k_reset_ray_counts<<<1, 32, 0, st>>>(ctx->q.counts); ++launches; }
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
@@ -691,12 +705,16 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, out); ++launches; }
             tm.end();
             tm.begin(ST_SHADOW);
+            const bool last = iter >= p->max_depth && !hasNull;
             if (sc.n_lights > 0) {
                 // shadow rays (A) and, with an environment light, its MIS rays (B) in one launch: they add to separate
-                // accumulators (ps.L / ps.Lb), so the two rays of a path do not race
-                k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, (sc.env.present && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
-                ++launches;
-                if (sc.env.present && !ctx->merge_shadow) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
+                // accumulators (ps.L / ps.Lb), so the two rays of a path do not race.  In mixed mode they wait for the
+                // next bounce's extension launch, except after the last bounce.
+                if (!mixed || last) {
+                    k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, (psv.Lb && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
+                    ++launches;
+                    if (sc.env.present && !(psv.Lb && ctx->merge_shadow)) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
+                }
                 if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats); ++launches; }
             }
             tm.end();
@@ -744,7 +762,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         stats->extend_nodes = hs.nodes[0];
         stats->extend_tris = hs.tris[0];
         stats->extend_launches = extendLaunches;
-        stats->extend_bytes = 32ull * hs.nodes[0] + 48ull * hs.tris[0] + 48ull * hs.rays[0];
+        // (mixed launches trace the previous bounce's any-hit rays as well: their nodes / triangles are in nodes[0] / tris[0])
+        stats->extend_bytes = 32ull * hs.nodes[0] + 48ull * hs.tris[0] + 48ull * (hs.rays[0] + hs.shadow_rays_in_extend_launches);
         double acc[ST_COUNT] = {0, 0, 0, 0, 0};
         for (size_t i = 0; i * 2 + 1 < ctx->ev_used + 0 && i < ctx->ev_stage.size(); ++i) {
             float t = 0;

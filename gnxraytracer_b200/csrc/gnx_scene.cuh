@@ -108,6 +108,8 @@ struct PathState {
     float4 *Lb;        // contributions of the environment-MIS (shadow B) rays, kept apart from L so that the shadow A
                        // and shadow B rays of a path can be traced in the same launch without racing on one float4
                        // (null: they go to L, sequential callers)
+    float4 *La;        // likewise for the shadow (A) rays, needed when they share a launch with the next bounce's
+                       // extension rays, whose escape adds the environment radiance to L (null: they go to L)
 };
 constexpr uint32_t kFlagSpecular = 1u;
 
@@ -139,6 +141,7 @@ constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCn
 
 struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
     unsigned long long rays[3], nodes[3], tris[3], paths;
+    unsigned long long shadow_rays_in_extend_launches;  // any-hit rays traced by the mixed launches (booked under nodes[0] / tris[0])
 };
 
 }  // namespace gnx
