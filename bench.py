@@ -30,9 +30,9 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "Mpaths/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the six k_trace<3|0> launches of one
-# C2 step: 1462 + 535 + 448 + 275 + 138 + 9 MB), from the ncu pass of this command kept in profiles/r01_dram_trace.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c2": 2867e6 / 6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the six k_trace<3|4> launches of one
+# C2 step: 1676 + 1491 + 941 + 519 + 251 + 82 MB), from the ncu pass of this command kept in profiles/r01_dram_trace.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c2": 4959e6 / 6}
 WORKLOADS = {
     # name: (scene, p0, p1, p2, width, height, spp, max_depth, description)
     "c2": ("dragon", 0, 0, 0, 1024, 1024, 64, 5,
@@ -286,7 +286,7 @@ def run_ours(args, wl):
                          "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_dram_trace.csv)", "peak_source": peak_src,
                          "launches_per_step": st.extend_launches, "avg_launch_ms": ext_ms,
                          "algorithmic_bytes_per_launch": ext_bytes,
-                         "note": "algorithmic bytes = 32 B x BVH nodes popped + 48 B x triangles tested + 48 B x rays (ray read + hit write), counted by the kernel itself; the scene (97 MB of nodes+triangles) is L2-resident, so DRAM traffic is ~18x below the algorithmic bytes (no re-reads from HBM) and the kernel is bound by instruction issue and L1 wavefronts (profiles/README.md), not by HBM"},
+                         "note": "algorithmic bytes = 32 B x BVH nodes popped + 48 B x triangles tested + 48 B x rays (ray read + hit write), counted by the kernel itself; the scene (97 MB of nodes+triangles) is L2-resident, so DRAM traffic is ~17x below the algorithmic bytes (no re-reads from HBM) and the kernel is bound by instruction issue and L1 wavefronts (profiles/README.md), not by HBM"},
             "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": ctypes.sizeof(params), "d2h_bytes_per_step": W * H * 16,
                     "ms_per_step": e2e_ms, "note": "gnx_render(): params in, float RGBA framebuffer out to pinned host memory; scene uploaded once (like the reference, which excludes scene build from timeConsume)"},
             "gpu_launches": int(st.kernel_launches) * args.steps,
