@@ -25,9 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL writes its "NCCL version ..." banner (any NCCL_DEBUG level from VERSION up,
+# WARN included) and its warnings to stdout unless told otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "Mpaths/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the six k_trace<3|4> launches of one
@@ -119,7 +119,8 @@ def run_reference(args, wl):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgnxref.so was not built (no /root/reference at build time)"}))
         return 0
     ref = _harness.Ref()
-    cores = ref.max_threads()
+    # all the host threads the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sample_spp = args.ref_spp
     lib = ref.lib
     h = lib.gnxh_scene_create(scene.encode(), W, H, sample_spp, p0, p1 or (2048 if scene == "dragon" else 0), p2 or (213 if scene == "dragon" else 0))
@@ -130,7 +131,7 @@ def run_reference(args, wl):
     rs = _harness.RefScene(lib, h, W, H, sample_spp)
     times = []
     for i in range(args.warmup + args.steps):
-        _, sec = rs.render_reference(max_depth=depth, threads=0)
+        _, sec = rs.render_reference(max_depth=depth, threads=cores)
         if i >= args.warmup:
             times.append(sec)
     t = sum(times) / len(times)
@@ -163,14 +164,15 @@ def cpu_baseline(wl, budget_s=15.0):
     if lib.gnxh_scene_error(h):
         return None, None
     rs = _harness.RefScene(lib, h, W, H, 1)
-    _, sec1 = rs.render_reference(max_depth=depth)           # 1 spp probe (also warms the light tables)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _, sec1 = rs.render_reference(max_depth=depth, threads=cores)           # 1 spp probe (also warms the light tables)
     n = int(max(1, min(spp, budget_s / max(sec1, 1e-3))))
     rs.close()
     h = lib.gnxh_scene_create(scene.encode(), W, H, n, p0, p1 or full[0], p2 or full[1])
     rs = _harness.RefScene(lib, h, W, H, n)
-    img, sec = rs.render_reference(max_depth=depth)
+    img, sec = rs.render_reference(max_depth=depth, threads=cores)
     val = W * H * n / sec / 1e6
-    info = {"value": val, "unit": "Mpaths/s", "cores": ref.max_threads(), "kind": "reference",
+    info = {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "reference",
             "sample": f"{W}x{H} x {n} spp of the {spp}-spp workload, one render, reference timeConsume {sec:.2f} s, "
                       f"-O2 -fopenmp, printf interposed, scene+BVH build {time.time() - t0 - sec - sec1:.1f} s untimed"}
     return info, (rs, img, n)
