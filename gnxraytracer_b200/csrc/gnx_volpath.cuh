@@ -331,39 +331,45 @@ GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int p
         V3 pMi;
         if (ray.medium >= 0) beta *= medium_sample(sc.media[ray.medium], ray, smp, &miValid, &pMi);
         if (is_black(beta)) break;
+        // The medium-vertex and surface-vertex cases share ONE call of the direct-lighting code: it is most of the
+        // work of an iteration (shadow rays with their transmittance walks, the MIS ray) and lanes of both kinds are
+        // present in a warp; called from two places, the warp ran it twice with the lanes split between the calls.
+        VPoint it;
+        Surface s;
+        Bsdf<8> bsdf;
+        bsdf.n = 0;
+        const V3 wo = -ray.d;
+        float g = 0;
         if (miValid) {
             if (bounces >= rc.max_depth) break;
-            const DevMedium &m = sc.media[ray.medium];
-            VPoint it;
+            g = sc.media[ray.medium].g;
             it.p = pMi; it.pError = V3(0.f); it.n = V3(0.f);
             it.mIn = it.mOut = ray.medium;
-            const V3 wo = -ray.d;
-            L += beta * vol_sample_one_light<2>(sc, it, nullptr, V3(0.f), wo, m.g, smp, stack, stride, cnt, vc.shadow, vc.mis);
-            float s0, s1;
-            smp.get2d(&s0, &s1);
-            V3 wi;
-            hg_sample_p(wo, &wi, s0, s1, m.g);
-            ray = spawn_ray(it, wi);
-            specularBounce = false;
         } else {
-            Surface s;
             if (found) s = make_surface(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
             if (bounces == 0 || specularBounce) {
                 if (found) { if (s.light >= 0) L += beta * area_light_L(sc.lights[s.light], s.n, -ray.d); }
                 else if (sc.env.present) L += beta * env_Le(sc.env, ray.d);
             }
             if (!found || bounces >= rc.max_depth) break;
-            const VPoint it = surface_point(sc, s, ray.medium);
+            it = surface_point(sc, s, ray.medium);
             if (s.material < 0) {
                 ray = spawn_ray(it, ray.d);
                 bounces--;
                 continue;
             }
-            const gnx_material &mat = sc.materials[s.material];
-            Bsdf<8> bsdf;
-            build_bsdf<8>(sc, mat, s, bsdf);
-            L += beta * vol_sample_one_light<8>(sc, it, &bsdf, s.wo, V3(0.f), 0.f, smp, stack, stride, cnt, vc.shadow, vc.mis);
-            const V3 wo = -ray.d;
+            build_bsdf<8>(sc, sc.materials[s.material], s, bsdf);
+        }
+        L += beta * vol_sample_one_light<8>(sc, it, miValid ? nullptr : &bsdf, miValid ? V3(0.f) : s.wo, miValid ? wo : V3(0.f), g, smp,
+                                            stack, stride, cnt, vc.shadow, vc.mis);
+        if (miValid) {
+            float s0, s1;
+            smp.get2d(&s0, &s1);
+            V3 wi;
+            hg_sample_p(wo, &wi, s0, s1, g);
+            ray = spawn_ray(it, wi);
+            specularBounce = false;
+        } else {
             V3 wi;
             float pdf, b0, b1;
             int flags;
