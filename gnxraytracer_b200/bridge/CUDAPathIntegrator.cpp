@@ -445,9 +445,12 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
             return fl.Fail("unsupported Light subclass");
         }
         out->lights.push_back(gl);
+        // the input of ComputeLightPowerDistribution (core/Integrator.cpp:216-217), from the light itself
+        out->light_power.push_back(l->Power().y());
     }
     d.n_lights = (int32_t)out->lights.size();
     d.lights = out->lights.data();
+    d.light_power = out->light_power.data();
 
     d.n_materials = (int32_t)out->materials.size();
     d.materials = out->materials.data();

@@ -35,6 +35,7 @@ struct FlatScene {
     std::vector<gnx_texture> textures;
     std::vector<std::vector<float>> texture_texels;
     std::vector<gnx_light> lights;
+    std::vector<float> light_power;
     std::vector<float> env_texels, env_cond_func, env_cond_cdf, env_cond_int, env_marg_func, env_marg_cdf;
     std::vector<gnx_medium> media;
     std::vector<std::vector<float>> media_density;

@@ -290,6 +290,39 @@ inline float uniform_light_distribution(int n, std::vector<float> &func, std::ve
     return funcInt;
 }
 
+// PowerLightDistribution: Distribution1D over Light::Power().y() (core/Integrator.cpp:212-220,
+// core/Sampling.h:22-35; an all-zero table falls back to a linear cdf like the reference's).
+inline float power_light_distribution(int n, const float *power, std::vector<float> &func, std::vector<float> &cdf) {
+    func.assign(power, power + n);
+    cdf.assign((size_t)n + 1, 0.f);
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+    float funcInt = cdf[n];
+    if (funcInt == 0) for (int i = 1; i < n + 1; ++i) cdf[i] = float(i) / float(n);
+    else for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    return funcInt;
+}
+
+// Light::Power().y() from the flattened records, for callers that pass no light_power table:
+// DiffuseAreaLight (lights/DiffuseAreaLight.cpp:32-35), PointLight (lights/PointLight.cpp:24),
+// SpotLight (lights/SpotLight.cpp:42-45), DistantLight (lights/DistantLight.cpp:28-31).
+// Returns false for light types whose power depends on private state the record does not hold.
+inline bool derive_light_power(const gnx_light &l, float *out) {
+    const float kPiF = 3.14159265358979323846f;
+    // Spectrum::y(), core/Spectrum.h (RGBSpectrum): YWeight = {0.212671, 0.715160, 0.072169}
+    auto lum = [](float r, float g, float b) { return 0.212671f * r + 0.715160f * g + 0.072169f * b; };
+    // each product in the reference's association order (left to right)
+    float c[3];
+    switch (l.type) {
+    case GNX_LIGHT_AREA_TRI: for (int i = 0; i < 3; ++i) c[i] = ((l.two_sided ? 2.f : 1.f) * l.L[i]) * l.area * kPiF; break;
+    case GNX_LIGHT_POINT: for (int i = 0; i < 3; ++i) c[i] = (4 * kPiF) * l.L[i]; break;
+    case GNX_LIGHT_SPOT: for (int i = 0; i < 3; ++i) c[i] = l.L[i] * 2 * kPiF * (1 - .5f * (l.cos_falloff + l.cos_total)); break;
+    case GNX_LIGHT_DISTANT: for (int i = 0; i < 3; ++i) c[i] = l.L[i] * kPiF * l.area * l.area; break;
+    default: return false;
+    }
+    *out = lum(c[0], c[1], c[2]);
+    return true;
+}
+
 // SpatialLightDistribution ctor (core/LightDistribution.cpp:70-87): 64 voxels on the widest axis.
 inline size_t spatial_voxel_resolution(const float wb[6], int nvox[3]) {
     float diag[3] = {wb[3] - wb[0], wb[4] - wb[1], wb[5] - wb[2]};

@@ -38,6 +38,10 @@ struct gnx_ctx {
     std::vector<void *> scene_allocs;
     unsigned shade_type_mask = 0;  // which k_shade variants the scene needs
     bool spatial_built = false;
+    // the two scene-wide light tables (uniform / power); choose_light reads whichever sc.ld.uni_* points at
+    const float *one_func = nullptr, *one_cdf = nullptr, *pow_func = nullptr, *pow_cdf = nullptr;
+    float one_int = 0, pow_int = 0;
+    std::string pow_error;         // why there is no power table
     int n_lights_host = 0, n_textures_host = 0;
     float wb[6]{};
     // wavefront buffers
@@ -423,6 +427,23 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
         if ((rc = dupload(ctx, pool, func.data(), func.size(), &df))) return rc; sc.ld.uni_func = df;
         if ((rc = dupload(ctx, pool, cdf.data(), cdf.size(), &df))) return rc; sc.ld.uni_cdf = df;
         sc.ld.uni_int = funcInt;
+        ctx->one_func = sc.ld.uni_func; ctx->one_cdf = sc.ld.uni_cdf; ctx->one_int = funcInt;
+        // power light distribution (PowerLightDistribution, core/LightDistribution.cpp:44-50)
+        std::vector<float> power((size_t)d->n_lights);
+        ctx->pow_func = ctx->pow_cdf = nullptr; ctx->pow_error.clear();
+        for (int i = 0; i < d->n_lights; ++i) {
+            if (d->light_power) power[i] = d->light_power[i];
+            else if (!derive_light_power(d->lights[i], &power[i])) {
+                ctx->pow_error = "power light distribution: the scene description has no light_power table and light " +
+                                 std::to_string(i) + " is an environment / skybox light";
+                break;
+            }
+        }
+        if (ctx->pow_error.empty()) {
+            ctx->pow_int = power_light_distribution(d->n_lights, power.data(), func, cdf);
+            if ((rc = dupload(ctx, pool, func.data(), func.size(), &df))) return rc; ctx->pow_func = df;
+            if ((rc = dupload(ctx, pool, cdf.data(), cdf.size(), &df))) return rc; ctx->pow_cdf = df;
+        }
     }
     sc.ld.mode = GNX_LIGHTS_UNIFORM;
 
@@ -494,8 +515,14 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
 static int ensure_light_distribution(gnx_ctx *ctx, int strategy) {
     DeviceScene &sc = ctx->sc;
     // CreateLightSampleDistribution: uniform when asked for or when exactly one light exists
-    if (strategy == GNX_LIGHTS_POWER) return fail(ctx, GNX_ERR_UNSUPPORTED, "power light distribution is not on the hot path");
+    sc.ld.uni_func = ctx->one_func; sc.ld.uni_cdf = ctx->one_cdf; sc.ld.uni_int = ctx->one_int;
     if (strategy == GNX_LIGHTS_UNIFORM || sc.n_lights <= 1) { sc.ld.mode = GNX_LIGHTS_UNIFORM; return GNX_OK; }
+    if (strategy == GNX_LIGHTS_POWER) {
+        if (!ctx->pow_func) return fail(ctx, GNX_ERR_UNSUPPORTED, ctx->pow_error.c_str());
+        sc.ld.uni_func = ctx->pow_func; sc.ld.uni_cdf = ctx->pow_cdf; sc.ld.uni_int = ctx->pow_int;
+        sc.ld.mode = GNX_LIGHTS_POWER;
+        return GNX_OK;
+    }
     if (!ctx->spatial_built) {
         size_t nv = spatial_voxel_resolution(ctx->wb, sc.ld.nvox);
         if (nv * (size_t)sc.n_lights > ((size_t)1 << 28))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GNX_ABI_VERSION 2
+#define GNX_ABI_VERSION 3
 
 typedef enum gnx_status {
     GNX_OK = 0,
@@ -186,7 +186,8 @@ typedef enum gnx_light_strategy {
     GNX_LIGHTS_UNIFORM = 0, /* UniformLightDistribution, also used when exactly one light exists
                                (core/LightDistribution.cpp:15-33)                               */
     GNX_LIGHTS_SPATIAL = 1, /* SpatialLightDistribution: voxel grid, 128 Halton points per voxel */
-    GNX_LIGHTS_POWER = 2
+    GNX_LIGHTS_POWER = 2    /* PowerLightDistribution: one Distribution1D over Light::Power().y()
+                               (core/LightDistribution.cpp:44-50)                                */
 } gnx_light_strategy;
 
 /* ------------------------------------------------------------------------------------------
@@ -254,6 +255,10 @@ typedef struct gnx_scene_desc {
     gnx_camera camera;
     gnx_sampler sampler;
     gnx_skybox skybox;
+    const float *light_power; /* [n_lights] Light::Power().y() of every light, the input of
+                                 ComputeLightPowerDistribution (core/Integrator.cpp:212-220).  Only read for
+                                 GNX_LIGHTS_POWER; NULL = the library derives it for area / point / spot /
+                                 distant lights and refuses power sampling of an environment / skybox light */
 } gnx_scene_desc;
 
 typedef enum gnx_integrator {

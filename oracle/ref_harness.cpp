@@ -87,6 +87,7 @@ struct HarnessScene {
     std::unique_ptr<FrameBuffer> fb;
     std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
     int cudaMaxDepth = -1;
+    std::string strategy = "spatial";  // lightSampleStrategy handed to both integrators
     std::unordered_map<const Primitive *, int> orderedIndex;  // BVH-ordered index of each primitive
     std::unordered_map<const Primitive *, int> originalIndex; // position in `prims` (the caller's order)
     std::string error;
@@ -184,7 +185,7 @@ std::shared_ptr<Material> Matte(float r, float g, float b, float sigma) {
 }
 
 // Config 1: Cornell box, two icospheres (Mirror, Glass), two-triangle area light.
-// variant: 0 = Lambert walls (sigma 0), 1 = the UI's Oren-Nayar sigma 60; sphere subdivision in p1.
+// variant: 0 = Lambert walls (sigma 0), 1 = the UI's Oren-Nayar sigma 60, 2 = Lambert + a second emitter; sphere subdivision in p1.
 void BuildCornell(HarnessScene &hs, int variant, int subdiv) {
     float sigma = variant == 1 ? 60.0f : 0.0f;
     auto white = Matte(0.91f, 0.91f, 0.91f, sigma);
@@ -210,6 +211,10 @@ void BuildCornell(HarnessScene &hs, int variant, int subdiv) {
     }
     Spectrum Le(5.0f);
     AddMesh(hs, gnxsk::area_light_quad(1.4f), Translate(Vector3f(0.0f, 2.45f, 0.0f)), white, &Le);
+    if (variant == 2) {  // a second, smaller and differently coloured emitter: unequal Light::Power() for "power" sampling
+        Spectrum Le2; Le2[0] = 9.0f; Le2[1] = 3.0f; Le2[2] = 1.0f;
+        AddMesh(hs, gnxsk::area_light_quad(0.6f), Translate(Vector3f(-1.5f, 2.45f, 1.2f)), white, &Le2);
+    }
     SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
     Finish(hs);
 }
@@ -408,15 +413,21 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
 const char *gnxh_scene_error(void *h) { return ((HarnessScene *)h)->error.c_str(); }
 void gnxh_scene_destroy(void *h) { delete (HarnessScene *)h; }
 int gnxh_scene_num_prims(void *h) { return (int)((HarnessScene *)h)->prims.size(); }
+// lightSampleStrategy of both integrators: 0 "uniform", 1 "spatial" (default), 2 "power"
+void gnxh_scene_set_light_strategy(void *h, int strategy) {
+    auto *hs = (HarnessScene *)h;
+    hs->strategy = strategy == 0 ? "uniform" : strategy == 2 ? "power" : "spatial";
+    hs->cuda.reset();
+}
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
 
 static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth) {
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
     switch (hs->integrator) {
-    case 1: return new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, "spatial", hs->fb.get());
+    case 1: return new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, hs->strategy, hs->fb.get());
     case 2: return new WhittedIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
     case 3: return new DirectLightingIntegrator(LightStrategy::UniformSampleOne, maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
-    default: return new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial");
+    default: return new PathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, hs->strategy);
     }
 }
 
@@ -498,7 +509,7 @@ int64_t gnxh_reference_sample_index(void *h, int px, int py, int sample) {
 static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
     if (!hs->cuda || hs->cudaMaxDepth != maxDepth) {
         Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, "spatial",
+        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, hs->strategy,
                                                    hs->integrator == 1));
         hs->cuda->SetIntegrator(hs->integrator);
         hs->cudaMaxDepth = maxDepth;

@@ -211,7 +211,7 @@ struct Scene {
     std::mutex voxMutex;
     std::unordered_map<uint64_t, std::vector<Float>> voxels;  // packed voxel -> [func(n) | cdf(n+1) | funcInt]
     int nVoxels[3];
-    std::vector<Float> uniformTab;
+    std::vector<Float> uniformTab, powerTab;  // func[n] | cdf[n+1] | funcInt
 
     Vec P(int prim, int v) const { const float *p = d->geom.prim_p + (size_t)prim * 9 + 3 * v; return Vec(p[0], p[1], p[2]); }
 
@@ -718,6 +718,8 @@ bool SampleLi(const Scene &sc, const gnx_light &l, const Vec &refP, const Float 
 void LookupDistribution(Scene &sc, const Vec &p, int strategy, const Float **func, const Float **cdf, Float *funcInt) {
     const int n = sc.d->n_lights;
     if (strategy == GNX_LIGHTS_UNIFORM || n == 1) { *func = sc.uniformTab.data(); *cdf = sc.uniformTab.data() + n; *funcInt = sc.uniformTab[2 * n + 1]; return; }
+    // PowerLightDistribution::Lookup (core/LightDistribution.cpp:44-50)
+    if (strategy == GNX_LIGHTS_POWER) { *func = sc.powerTab.data(); *cdf = sc.powerTab.data() + n; *funcInt = sc.powerTab[2 * n + 1]; return; }
     const float *wb = sc.d->geom.world_bound;
     int pi[3];
     for (int i = 0; i < 3; ++i) {
@@ -929,6 +931,18 @@ void *gnxr_create(const gnx_scene_desc *d) {
     Float fi = n ? c[n] : 0;
     for (int i = 1; i < n + 1; ++i) c[i] /= fi;
     if (n) sc.uniformTab[2 * n + 1] = fi;
+    // ComputeLightPowerDistribution (core/Integrator.cpp:212-220): Distribution1D over Light::Power().y(),
+    // taken from the description's light_power table (the restatement does not re-derive Light::Power)
+    sc.powerTab.assign(2 * n + 2, 0.f);
+    if (n && d->light_power) {
+        Float *pc = sc.powerTab.data() + n;
+        for (int i = 0; i < n; ++i) sc.powerTab[i] = d->light_power[i];
+        for (int i = 1; i < n + 1; ++i) pc[i] = pc[i - 1] + sc.powerTab[i - 1] / n;
+        Float pfi = pc[n];
+        if (pfi == 0) for (int i = 1; i < n + 1; ++i) pc[i] = Float(i) / Float(n);
+        else for (int i = 1; i < n + 1; ++i) pc[i] /= pfi;
+        sc.powerTab[2 * n + 1] = pfi;
+    }
     const float *wb = d->geom.world_bound;  // SpatialLightDistribution ctor, LightDistribution.cpp:70-87
     Float diag[3] = {wb[3] - wb[0], wb[4] - wb[1], wb[5] - wb[2]};
     int mx = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);

@@ -16,6 +16,7 @@ vp, ci = ctypes.c_void_p, ctypes.c_int
 SCENES = {
     "cornell": ("cornell", 0, 2, 0),        # Lambert walls, mirror + glass icospheres (320 tris each)
     "cornell_on": ("cornell", 1, 2, 0),     # the UI's Oren-Nayar sigma = 60 walls
+    "cornell_2l": ("cornell", 2, 2, 0),     # + a second, smaller emitter of another colour (unequal light powers)
     "cornell_full": ("cornell", 0, 3, 0),   # BASELINE config 1 geometry (2 x 1280-triangle spheres)
     "dragon": ("dragon", 0, 256, 32),       # Plastic knot, MonValley environment
     "dragon_metal": ("dragon", 1, 256, 32),
@@ -53,6 +54,10 @@ class RefScene:
             if not self._desc:
                 raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
         return self._desc
+
+    def set_light_strategy(self, strategy):
+        """lightSampleStrategy of the reference integrators and of the drop-in class: LIGHTS_UNIFORM / SPATIAL / POWER."""
+        self.lib.gnxh_scene_set_light_strategy(self.h, int(strategy))
 
     def render_reference(self, max_depth=5, threads=0):
         out = np.zeros((self.height, self.width, 4), np.float32)
@@ -119,6 +124,7 @@ class Ref:
         l.gnxh_scene_destroy.argtypes = [vp]
         l.gnxh_scene_num_prims.argtypes = [vp]
         l.gnxh_scene_bvh_seconds.argtypes = [vp]
+        l.gnxh_scene_set_light_strategy.argtypes = [vp, ci]
         l.gnxh_scene_bvh_seconds.restype = ctypes.c_double
         l.gnxh_flatten.restype = vp
         l.gnxh_flatten.argtypes = [vp]

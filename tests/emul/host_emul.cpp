@@ -25,7 +25,7 @@ struct EmulScene {
     std::vector<int2> media;
     std::vector<DevMedium> dev_media;
     std::vector<DevTexture> textures;
-    std::vector<float> uni_func, uni_cdf, sp_func, sp_cdf, sp_int, skybox_img;
+    std::vector<float> uni_func, uni_cdf, pow_func, pow_cdf, power, sp_func, sp_cdf, sp_int, skybox_img;
     std::vector<int> primes, sums;
     std::vector<uint4> dims;
     std::vector<uint16_t> perms;
@@ -99,6 +99,11 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
         sc.ld.uni_int = uniform_light_distribution(d->n_lights, e.uni_func, e.uni_cdf);
         sc.ld.uni_func = e.uni_func.data();
         sc.ld.uni_cdf = e.uni_cdf.data();
+        e.power.assign((size_t)d->n_lights, 0.f);
+        for (int i = 0; i < d->n_lights; ++i) {
+            if (d->light_power) e.power[i] = d->light_power[i];
+            else derive_light_power(d->lights[i], &e.power[i]);
+        }
     }
     sc.ld.mode = GNX_LIGHTS_UNIFORM;
     memcpy(sc.cam.r2c.m, d->camera.raster_to_camera, 64);
@@ -128,7 +133,17 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
 
 void ensure_spatial(EmulScene &e, int strategy) {
     DeviceScene &sc = e.sc;
+    if (sc.n_lights > 0) {
+        sc.ld.uni_int = uniform_light_distribution(sc.n_lights, e.uni_func, e.uni_cdf);
+        sc.ld.uni_func = e.uni_func.data(); sc.ld.uni_cdf = e.uni_cdf.data();
+    }
     if (strategy == GNX_LIGHTS_UNIFORM || sc.n_lights <= 1) { sc.ld.mode = GNX_LIGHTS_UNIFORM; return; }
+    if (strategy == GNX_LIGHTS_POWER) {  // the test scenes always carry light_power or derivable lights
+        sc.ld.uni_int = power_light_distribution(sc.n_lights, e.power.data(), e.pow_func, e.pow_cdf);
+        sc.ld.uni_func = e.pow_func.data(); sc.ld.uni_cdf = e.pow_cdf.data();
+        sc.ld.mode = GNX_LIGHTS_POWER;
+        return;
+    }
     size_t nv = spatial_voxel_resolution(e.wb, sc.ld.nvox);
     e.sp_func.assign(nv * sc.n_lights, 0.f);
     e.sp_cdf.assign(nv * (sc.n_lights + 1), 0.f);

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from _harness import grid, rel_mse
-from gnxraytracer_b200.api import Context, RenderParams, SceneKit, LIGHTS_UNIFORM
+from gnxraytracer_b200.api import Context, RenderParams, SceneKit, LIGHTS_UNIFORM, LIGHTS_POWER
 
 pytestmark = pytest.mark.gpu
 
@@ -152,6 +152,34 @@ def test_uniform_light_strategy_and_depth_zero(ref, ctx):
     imgu, _ = ctx.render(RenderParams.make(res, res, 2, light_strategy=LIGHTS_UNIFORM))
     assert np.isfinite(imgu).all() and imgu[..., :3].mean() > 0
     rs.close()
+
+
+@pytest.mark.parametrize("strategy", [LIGHTS_UNIFORM, LIGHTS_POWER])
+def test_uniform_and_power_light_distributions(ref, ctx, strategy):
+    """lightSampleStrategy "uniform" / "power" (core/LightDistribution.cpp:15-50) on two emitters of unequal
+    Light::Power(): the image against the reference's Render() with that strategy, and per-sample radiance."""
+    res, spp = 96, 8
+    rs = ref.scene("cornell_2l", res, res, spp)
+    rs.set_light_strategy(strategy)
+    img_ref, _ = rs.render_reference(max_depth=5)
+    ctx.upload(rs.desc)
+    img, st = ctx.render(RenderParams.make(res, res, spp, max_depth=5, light_strategy=strategy))
+    assert rel_mse(img, img_ref) <= 1e-6
+    other, _ = ctx.render(RenderParams.make(res, res, spp, max_depth=5, light_strategy=2 - strategy))
+    assert rel_mse(other, img_ref) > 1e-4, "the strategies should sample differently"
+    # and through the drop-in class, which takes the strategy as the reference's constructor string
+    img2, _, _ = rs.render_cuda(max_depth=5)
+    assert np.array_equal(img2, img)
+    rs.close()
+
+
+def test_power_sampling_needs_light_powers(ctx):
+    """A description without a light_power table (the scene kit's): powers are derived from the area-light records."""
+    sk = SceneKit("cornell", 64, 64, 2, 0, 2, 0)
+    ctx.upload(sk.desc)
+    img, _ = ctx.render(RenderParams.make(64, 64, 2, light_strategy=LIGHTS_POWER))
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0
+    sk.close()
 
 
 def test_gpu_counters_match_the_restated_reference_traversal(ref, ctx):

@@ -60,6 +60,22 @@ def test_restate_matches_live_reference(ref, restate, preset, res):
     r.close(); rs.close()
 
 
+@pytest.mark.parametrize("strategy", [0, 2])
+def test_restate_uniform_and_power_light_distributions(ref, restate, strategy):
+    """lightSampleStrategy "uniform" / "power" on two emitters of unequal power, restatement against PathIntegrator::Li."""
+    res = 40
+    r = ref.scene("cornell_2l", res, res, 4)
+    r.set_light_strategy(strategy)
+    rs = restate.scene(r.desc)
+    px, py = grid(res, res)
+    sm = np.full(px.size, 2, np.int32)
+    rgb, _ = r.reference_samples(px, py, sm, want_prim=False)
+    mine = rs.samples(RenderParams.make(res, res, 4, max_depth=5, light_strategy=strategy), px, py, sm)
+    scale = np.maximum(np.abs(rgb).max(axis=1), 1e-3)
+    assert np.mean(np.abs(mine - rgb).max(axis=1) / scale < 1e-5) >= 0.999
+    r.close(); rs.close()
+
+
 def test_restate_and_emulated_kernels_agree_on_counters(ref, restate, emul):
     """BVH nodes visited / triangles tested by the kernels' traversal must agree with the
     reference-order traversal to < 1 %."""
