@@ -14,6 +14,7 @@ c_int32, c_float, c_u64, c_double, c_void_p = ctypes.c_int32, ctypes.c_float, ct
 
 LIGHTS_UNIFORM, LIGHTS_SPATIAL, LIGHTS_POWER = 0, 1, 2
 INTEGRATOR_PATH, INTEGRATOR_VOLPATH = 0, 1
+FILM_BOX, FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS = 0, 1, 2
 
 STATUS = {0: "GNX_OK", -1: "GNX_ERR_INVALID", -2: "GNX_ERR_NO_DEVICE", -3: "GNX_ERR_CUDA", -4: "GNX_ERR_UNSUPPORTED",
           -5: "GNX_ERR_NO_SCENE"}
@@ -36,9 +37,10 @@ class RenderParams(ctypes.Structure):
 
     @classmethod
     def make(cls, width, height, spp, max_depth=5, first_sample=0, spp_normalize=0, rr_threshold=1.0,
-             light_strategy=LIGHTS_SPATIAL, integrator=INTEGRATOR_PATH, batch_spp=0):
+             light_strategy=LIGHTS_SPATIAL, integrator=INTEGRATOR_PATH, batch_spp=0, film=FILM_BOX, filter_radius=0.0,
+             filter_alpha=0.0):
         return cls(width, height, spp, first_sample, spp_normalize, max_depth, rr_threshold, integrator,
-                   light_strategy, 0, 0.0, 0.0, batch_spp)
+                   light_strategy, film, filter_radius, filter_alpha, batch_spp)
 
 
 class Stats(ctypes.Structure):

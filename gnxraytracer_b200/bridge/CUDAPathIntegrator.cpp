@@ -539,7 +539,8 @@ gnx_render_params CUDAPathIntegrator::MakeParams() const {
     // is applied inside the library, which knows the light count.
     p.light_strategy = lightSampleStrategy_ == "uniform" ? GNX_LIGHTS_UNIFORM
                        : lightSampleStrategy_ == "power" ? GNX_LIGHTS_POWER : GNX_LIGHTS_SPATIAL;
-    p.film = GNX_FILM_BOX;
+    p.film = filterRadius_ > 0 ? GNX_FILM_GAUSSIAN : GNX_FILM_BOX;
+    p.filter_radius = filterRadius_; p.filter_alpha = filterAlpha_;
     return p;
 }
 

@@ -71,6 +71,9 @@ class CUDAPathIntegrator : public pbr::Integrator {
     // GNX_INTEGRATOR_WHITTED / GNX_INTEGRATOR_DIRECT: stand in for pbr::WhittedIntegrator /
     // pbr::DirectLightingIntegrator(LightStrategy::UniformSampleOne) instead of PathIntegrator / VolPathIntegrator
     void SetIntegrator(int gnxIntegrator) { integrator_ = gnxIntegrator; }
+    // Reconstruct the image with the reference's GaussianFilter(Vector2f(radius, radius), alpha)
+    // (filters/GaussianFilter.h:12-33) instead of Render()'s box average; radius <= 0 switches back to the box.
+    void SetGaussianFilter(pbr::Float radius, pbr::Float alpha) { filterRadius_ = radius; filterAlpha_ = alpha; }
 
   private:
     bool EnsureUploaded(const pbr::Scene &scene);
@@ -83,6 +86,7 @@ class CUDAPathIntegrator : public pbr::Integrator {
     const pbr::Float rrThreshold_;
     const std::string lightSampleStrategy_;
     int integrator_;  // gnx_integrator
+    pbr::Float filterRadius_ = 0, filterAlpha_ = 0;
     gnx_ctx *ctx_ = nullptr;
     const pbr::Scene *uploaded_ = nullptr;
     std::unique_ptr<FlatScene> flat_;

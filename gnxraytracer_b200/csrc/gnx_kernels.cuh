@@ -9,6 +9,7 @@
 // memory (24 KB per 128-thread block).
 #pragma once
 #include "gnx_whitted.cuh"
+#include "gnx_film.cuh"
 
 namespace gnx {
 
@@ -360,6 +361,41 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
         }
         accum[pixel] = a;
     }
+}
+
+// Gaussian film, step 1 (per path slot): the sample's radiance summed into L.xyz and its film offset written into the
+// slot's ray-origin record, which is dead once the bounce loop has ended.
+__global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts rc) {
+    const int n = rc.npix * rc.batch_spp;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        int pixel, sample;
+        slot_to_sample(rc, slot, &pixel, &sample);
+        float u0, u1;
+        film_sample_offset(sc, rc.width, pixel % rc.width, pixel / rc.width, sample, &u0, &u1);
+        ps.ray_o[slot] = make_float4(u0, u1, 0.f, 0.f);
+        float4 L = ps.L[slot];
+        if (L.w != 0.f) {
+            if (ps.La) { const float4 La = ps.La[slot]; L.x += La.x; L.y += La.y; L.z += La.z; }
+            if (ps.Lb) { const float4 Lb = ps.Lb[slot]; L.x += Lb.x; L.y += Lb.y; L.z += Lb.z; }
+            ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+    }
+}
+
+// Gaussian film, step 2 (per pixel): gather the batch's samples within the filter's reach; accum = (sum L f, sum f).
+__global__ void k_accumulate_gauss(PathState ps, float4 *accum, RenderConsts rc, FilmFilter f) {
+    for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
+        const float4 g = gaussian_gather(ps.L, ps.ray_o, rc, f, pixel % rc.width, pixel / rc.width);
+        float4 a = accum[pixel];
+        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        accum[pixel] = a;
+    }
+}
+
+// resolve = 1: sum(L f) / sum(f); 0: the raw sums (N-GPU jobs reduce them across ranks before dividing)
+__global__ void k_film_gauss(const float4 *accum, float4 *rgba, int npix, int resolve) {
+    for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)
+        rgba[pixel] = resolve ? gaussian_resolve(accum[pixel]) : accum[pixel];
 }
 
 // colObj / samplesPerPixel, alpha 1 (core/Integrator.cpp:293,307-310)

@@ -602,7 +602,10 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
         return fail(ctx, GNX_ERR_UNSUPPORTED, "scene has participating media: use GNX_INTEGRATOR_VOLPATH (PathIntegrator ignores media)");
     if (p->integrator == GNX_INTEGRATOR_VOLPATH && ctx->n_textures_host > 0)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "VolPath with image textures needs ray-differential (EWA) filtering at the camera vertex, which is not implemented");
-    if (p->film != GNX_FILM_BOX) return fail(ctx, GNX_ERR_UNSUPPORTED, "only the box film of the reference is implemented");
+    if (p->film != GNX_FILM_BOX && p->film != GNX_FILM_GAUSSIAN && p->film != GNX_FILM_GAUSSIAN_SUMS)
+        return fail(ctx, GNX_ERR_INVALID, "unknown film");
+    if (p->film != GNX_FILM_BOX && !(p->filter_radius > 0.f && p->filter_radius <= 16.f && p->filter_alpha >= 0.f))
+        return fail(ctx, GNX_ERR_INVALID, "Gaussian film: filter_radius must be in (0, 16] and filter_alpha >= 0");
     // the Halton index must fit the 32-bit path state
     unsigned long long maxIdx = (unsigned long long)(p->first_sample + p->spp) * (unsigned long long)ctx->sc.smp.stride;
     if (ctx->sc.smp.type == GNX_SAMPLER_HALTON && maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
@@ -681,6 +684,21 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     GNX_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)npix * sizeof(float4), st));
 
+    // film: the reference's box average, or the Gaussian reconstruction filter (gnx_film.cuh)
+    const bool gaussian = p->film != GNX_FILM_BOX;
+    FilmFilter filt{};
+    if (gaussian) {
+        filt.radius = p->filter_radius; filt.alpha = p->filter_alpha;
+        filt.expv = std::exp(-filt.alpha * filt.radius * filt.radius);
+        filt.reach = (int)std::floor(filt.radius + 0.5f);
+    }
+    auto accumulate = [&](const PathState &psb, const RenderConsts &rcb) -> int {
+        if (!gaussian) { k_accumulate<<<gridWide, 256, 0, st>>>(psb, ctx->accum, rcb); return 1; }
+        k_film_prepare<<<gridWide, 256, 0, st>>>(sc, psb, rcb);
+        k_accumulate_gauss<<<gridWide, 128, 0, st>>>(psb, ctx->accum, rcb, filt);
+        return 2;
+    };
+
     for (int done = 0; done < p->spp; done += batch_spp) {
         RenderConsts rcn{};
         rcn.width = p->width; rcn.height = p->height; rcn.npix = npix;
@@ -696,9 +714,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, p->integrator == GNX_INTEGRATOR_DIRECT, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
-            k_accumulate<<<gridWide, 256, 0, st>>>(psv, ctx->accum, rcn);
+            launches += accumulate(psv, rcn);
             tm.end();
-            launches += 3;
+            launches += 2;
             ++extendLaunches;
             continue;
         }
@@ -755,13 +773,13 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             }
         }
         tm.begin(ST_FILM);
-        k_accumulate<<<gridWide, 256, 0, st>>>(psv, ctx->accum, rcn);
+        launches += accumulate(psv, rcn);
         tm.end();
-        ++launches;
     }
     const float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
     float4 *out = rgba_dev_out ? (float4 *)rgba_dev_out : ctx->rgba;
-    k_film<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, norm);
+    if (gaussian) k_film_gauss<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, p->film == GNX_FILM_GAUSSIAN);
+    else k_film<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, norm);
     ++launches;
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     GNX_CUDA(ctx, cudaGetLastError());

@@ -267,7 +267,13 @@ typedef enum gnx_integrator {
     GNX_INTEGRATOR_WHITTED = 2,  /* integrators/WhittedIntegrator.cpp (the UI's default, ui/RenderThread.cpp:163) */
     GNX_INTEGRATOR_DIRECT = 3    /* integrators/DirectLightingIntegrator.cpp, LightStrategy::UniformSampleOne */
 } gnx_integrator;
-typedef enum gnx_film { GNX_FILM_BOX = 0, GNX_FILM_GAUSSIAN = 1 } gnx_film;
+typedef enum gnx_film {
+    GNX_FILM_BOX = 0,           /* the reference: mean of the pixel's own samples (core/Integrator.cpp:274-293)      */
+    GNX_FILM_GAUSSIAN = 1,      /* GaussianFilter (filters/GaussianFilter.h:12-33) with Film::AddSample semantics:
+                                   rgb = max(0, sum(L f) / sum(f)) over the samples within the filter radius, alpha 1 */
+    GNX_FILM_GAUSSIAN_SUMS = 2  /* the same sums unresolved: rgba = (sum(L f), sum(f)); an N-GPU job adds the ranks'
+                                   buffers and divides afterwards (spp_normalize is not used by either Gaussian film) */
+} gnx_film;
 
 typedef struct gnx_render_params {
     int32_t width, height;      /* pixelBounds.pMax (core/Integrator.cpp:257-259)                */
@@ -280,7 +286,7 @@ typedef struct gnx_render_params {
     int32_t integrator;         /* gnx_integrator                                                 */
     int32_t light_strategy;     /* gnx_light_strategy                                             */
     int32_t film;               /* gnx_film; BOX == the reference (core/Integrator.cpp:293)       */
-    float filter_radius, filter_alpha; /* GAUSSIAN only (filters/GaussianFilter.h:12-33)          */
+    float filter_radius, filter_alpha; /* GAUSSIAN films: radius in pixels (both axes), falloff alpha  */
     int32_t batch_spp;          /* samples per pixel in flight per wavefront batch; 0 = auto      */
 } gnx_render_params;
 

@@ -25,6 +25,7 @@
 #include "core/Integrator.h"
 #include "core/Scene.h"
 #include "core/Transform.h"
+#include "filters/GaussianFilter.h"
 #include "integrators/PathIntegrator.h"
 #include "integrators/VolPathIntegrator.h"
 #include "integrators/DirectLightingIntegrator.h"
@@ -87,6 +88,7 @@ struct HarnessScene {
     std::unique_ptr<FrameBuffer> fb;
     std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
     int cudaMaxDepth = -1;
+    float filterRadius = 0, filterAlpha = 0;  // CUDAPathIntegrator::SetGaussianFilter
     std::string strategy = "spatial";  // lightSampleStrategy handed to both integrators
     std::unordered_map<const Primitive *, int> orderedIndex;  // BVH-ordered index of each primitive
     std::unordered_map<const Primitive *, int> originalIndex; // position in `prims` (the caller's order)
@@ -419,6 +421,12 @@ void gnxh_scene_set_light_strategy(void *h, int strategy) {
     hs->strategy = strategy == 0 ? "uniform" : strategy == 2 ? "power" : "spatial";
     hs->cuda.reset();
 }
+// Image reconstruction of the drop-in class: GaussianFilter(radius, alpha); radius <= 0 = the reference's box average.
+void gnxh_scene_set_gaussian_filter(void *h, float radius, float alpha) {
+    auto *hs = (HarnessScene *)h;
+    hs->filterRadius = radius; hs->filterAlpha = alpha;
+    hs->cuda.reset();
+}
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
 
 static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth) {
@@ -488,6 +496,68 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
     return 0;
 }
 
+// The reference's GaussianFilter::Evaluate (filters/GaussianFilter.cpp:9-12) at n points.
+int gnxh_reference_gaussian_eval(float radius, float alpha, int n, const float *x, const float *y, float *out) {
+    GaussianFilter filt(Vector2f(radius, radius), alpha);
+    for (int i = 0; i < n; ++i) out[i] = filt.Evaluate(Point2f(x[i], y[i]));
+    return 0;
+}
+
+// Gaussian-filtered image.  The reference has the filter class but no Film that uses it (its Render() box-averages,
+// core/Integrator.cpp:274-293), so this is the splat of the renderer it descends from (pbrt-v3 Film::AddSample /
+// WriteImage) around the reference's OWN pieces: Sampler::GetCameraSample for pFilm, the integrator's Li for the
+// radiance, GaussianFilter::Evaluate for the weight (evaluated exactly, no 16 x 16 table).  sums_out (optional)
+// receives (sum L f, sum f) per pixel.
+int gnxh_reference_gaussian_film(void *h, int maxDepth, float radius, float alpha, float *rgba_out, float *sums_out) {
+    auto *hs = (HarnessScene *)h;
+    if (!hs->scene) return -1;
+    const int W = hs->width, H = hs->height, spp = hs->spp;
+    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth));
+    SamplerIntegrator &integ = *integp;
+    integ.Preprocess(*hs->scene, *hs->sampler);
+    std::vector<float> L((size_t)W * H * spp * 3), pf((size_t)W * H * spp * 2);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int pix = 0; pix < W * H; ++pix) {
+        MemoryArena arena;
+        Point2i pixel(pix % W, pix / W);
+        std::unique_ptr<Sampler> s = hs->sampler->Clone(pix);
+        s->StartPixel(pixel);
+        for (int k = 0; k < spp; ++k) {
+            s->SetSampleNumber(k);
+            CameraSample cs = s->GetCameraSample(pixel);
+            RayDifferential ray;
+            hs->camera->GenerateRayDifferential(cs, &ray);
+            ray.ScaleDifferentials(1 / std::sqrt((Float)s->samplesPerPixel));
+            Spectrum Li = integ.Li(ray, *hs->scene, *s, arena, 0);
+            size_t i = (size_t)pix * spp + k;
+            L[3 * i] = Li[0]; L[3 * i + 1] = Li[1]; L[3 * i + 2] = Li[2];
+            pf[2 * i] = cs.pFilm.x; pf[2 * i + 1] = cs.pFilm.y;
+            arena.Reset();
+        }
+    }
+    GaussianFilter filt(Vector2f(radius, radius), alpha);
+    std::vector<float> sums((size_t)W * H * 4, 0.f);
+    for (size_t i = 0; i < (size_t)W * H * spp; ++i) {  // Film::AddSample
+        Point2f pFilmDiscrete(pf[2 * i] - 0.5f, pf[2 * i + 1] - 0.5f);
+        int x0 = std::max((int)std::ceil(pFilmDiscrete.x - radius), 0), x1 = std::min((int)std::floor(pFilmDiscrete.x + radius) + 1, W);
+        int y0 = std::max((int)std::ceil(pFilmDiscrete.y - radius), 0), y1 = std::min((int)std::floor(pFilmDiscrete.y + radius) + 1, H);
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) {
+                Float w = filt.Evaluate(Point2f(x - pFilmDiscrete.x, y - pFilmDiscrete.y));
+                float *px = &sums[4 * ((size_t)y * W + x)];
+                px[0] += L[3 * i] * w; px[1] += L[3 * i + 1] * w; px[2] += L[3 * i + 2] * w; px[3] += w;
+            }
+    }
+    for (size_t q = 0; q < (size_t)W * H; ++q) {  // Film::WriteImage
+        const float *px = &sums[4 * q];
+        float inv = px[3] != 0 ? 1 / px[3] : 0.f;
+        for (int c = 0; c < 3; ++c) rgba_out[4 * q + c] = std::max(0.f, px[c] * inv);
+        rgba_out[4 * q + 3] = 1.f;
+    }
+    if (sums_out) memcpy(sums_out, sums.data(), sums.size() * sizeof(float));
+    return 0;
+}
+
 int gnxh_reference_sample_dims(void *h, int n, const int64_t *index, const int *dim, float *out) {
     auto *hs = (HarnessScene *)h;
     auto *hal = dynamic_cast<HaltonSampler *>(hs->sampler.get());
@@ -512,6 +582,7 @@ static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
         hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, hs->strategy,
                                                    hs->integrator == 1));
         hs->cuda->SetIntegrator(hs->integrator);
+        hs->cuda->SetGaussianFilter(hs->filterRadius, hs->filterAlpha);
         hs->cudaMaxDepth = maxDepth;
     }
     return hs->cuda.get();

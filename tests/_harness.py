@@ -59,6 +59,18 @@ class RefScene:
         """lightSampleStrategy of the reference integrators and of the drop-in class: LIGHTS_UNIFORM / SPATIAL / POWER."""
         self.lib.gnxh_scene_set_light_strategy(self.h, int(strategy))
 
+    def set_gaussian_filter(self, radius, alpha):
+        """Film of the drop-in class: GaussianFilter(radius, alpha); radius <= 0 = the reference's box average."""
+        self.lib.gnxh_scene_set_gaussian_filter(self.h, float(radius), float(alpha))
+
+    def reference_gaussian_film(self, radius, alpha, max_depth=5):
+        """Film::AddSample splat of the reference's own samples / Li / GaussianFilter::Evaluate: (image, sums)."""
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        sums = np.zeros((self.height, self.width, 4), np.float32)
+        rc = self.lib.gnxh_reference_gaussian_film(self.h, max_depth, float(radius), float(alpha), out.ctypes.data, sums.ctypes.data)
+        assert rc == 0
+        return out, sums
+
     def render_reference(self, max_depth=5, threads=0):
         out = np.zeros((self.height, self.width, 4), np.float32)
         sec = ctypes.c_double()
@@ -125,6 +137,9 @@ class Ref:
         l.gnxh_scene_num_prims.argtypes = [vp]
         l.gnxh_scene_bvh_seconds.argtypes = [vp]
         l.gnxh_scene_set_light_strategy.argtypes = [vp, ci]
+        l.gnxh_scene_set_gaussian_filter.argtypes = [vp, ctypes.c_float, ctypes.c_float]
+        l.gnxh_reference_gaussian_film.argtypes = [vp, ci, ctypes.c_float, ctypes.c_float, vp, vp]
+        l.gnxh_reference_gaussian_eval.argtypes = [ctypes.c_float, ctypes.c_float, ci, vp, vp, vp]
         l.gnxh_scene_bvh_seconds.restype = ctypes.c_double
         l.gnxh_flatten.restype = vp
         l.gnxh_flatten.argtypes = [vp]
@@ -194,6 +209,7 @@ class Emul:
         l.gnxe_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, ctypes.POINTER(Stats)]
         l.gnxe_samples.argtypes = [vp, ctypes.POINTER(RenderParams), ci, vp, vp, vp, vp]
         l.gnxe_primary_hits.argtypes = [vp, ci, ci, ci, vp]
+        l.gnxe_gaussian_eval.argtypes = [ctypes.c_float, ctypes.c_float, ci, vp, vp, vp]
         l.gnxe_sample_dims.argtypes = [vp, ci, vp, vp, vp]
         l.gnxe_sample_index.restype = ctypes.c_int64
         l.gnxe_sample_index.argtypes = [vp, ci, ci, ci]

@@ -14,6 +14,7 @@
 
 #include "gnx_pack.h"
 #include "gnx_whitted.cuh"
+#include "gnx_film.cuh"
 
 using namespace gnx;
 
@@ -225,19 +226,45 @@ int gnxe_render(void *h, const gnx_render_params *p, float *rgba_out, gnx_stats 
     auto *e = (EmulScene *)h;
     if (p->integrator < GNX_INTEGRATOR_WHITTED) ensure_spatial(*e, p->light_strategy);
     unsigned long long nodes = 0, tris = 0, r0 = 0, r1 = 0, r2 = 0;
+    // Gaussian film (gnx_film.cuh): per-sample radiance and film offsets of the whole image as ONE batch, then the same
+    // gather the kernels run
+    const bool gaussian = p->film != GNX_FILM_BOX;
+    std::vector<float4> Ls, offs;
+    if (gaussian) { Ls.resize((size_t)p->width * p->height * p->spp); offs.resize(Ls.size()); }
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : nodes, tris, r0, r1, r2)
     for (int pixel = 0; pixel < p->width * p->height; ++pixel) {
         int px = pixel % p->width, py = pixel / p->width;
         V3 sum(0.f);
         TraversalCounters cnt{0, 0};
         unsigned long long rays[3] = {0, 0, 0};
-        for (int s = 0; s < p->spp; ++s) sum += trace_sample(*e, *p, px, py, p->first_sample + s, cnt, rays);
+        for (int s = 0; s < p->spp; ++s) {
+            V3 L = trace_sample(*e, *p, px, py, p->first_sample + s, cnt, rays);
+            sum += L;
+            if (gaussian) {
+                float u0, u1;
+                film_sample_offset(e->sc, p->width, px, py, p->first_sample + s, &u0, &u1);
+                Ls[(size_t)pixel * p->spp + s] = make_float4(L.x, L.y, L.z, 0.f);
+                offs[(size_t)pixel * p->spp + s] = make_float4(u0, u1, 0.f, 0.f);
+            }
+        }
         float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
         rgba_out[4 * pixel + 0] = sum.x / norm;
         rgba_out[4 * pixel + 1] = sum.y / norm;
         rgba_out[4 * pixel + 2] = sum.z / norm;
         rgba_out[4 * pixel + 3] = 1.f;
         nodes += cnt.nodes; tris += cnt.tris; r0 += rays[0]; r1 += rays[1]; r2 += rays[2];
+    }
+    if (gaussian) {
+        RenderConsts rc{};
+        rc.width = p->width; rc.height = p->height; rc.npix = p->width * p->height; rc.batch_spp = p->spp;
+        FilmFilter f{p->filter_radius, p->filter_alpha, std::exp(-p->filter_alpha * p->filter_radius * p->filter_radius),
+                     (int)std::floor(p->filter_radius + 0.5f)};
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int pixel = 0; pixel < rc.npix; ++pixel) {
+            float4 a = gaussian_gather(Ls.data(), offs.data(), rc, f, pixel % rc.width, pixel / rc.width);
+            if (p->film == GNX_FILM_GAUSSIAN) a = gaussian_resolve(a);
+            memcpy(rgba_out + 4 * (size_t)pixel, &a, 16);
+        }
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -258,6 +285,13 @@ int gnxe_samples(void *h, const gnx_render_params *p, int n, const int *px, cons
         V3 L = trace_sample(*e, *p, px[i], py[i], sample[i], cnt, rays);
         rgb_out[3 * i] = L.x; rgb_out[3 * i + 1] = L.y; rgb_out[3 * i + 2] = L.z;
     }
+    return 0;
+}
+
+// gaussian_1d(x) * gaussian_1d(y) of the film code (gnx_film.cuh) at n points
+int gnxe_gaussian_eval(float radius, float alpha, int n, const float *x, const float *y, float *out) {
+    FilmFilter f{radius, alpha, std::exp(-alpha * radius * radius), (int)std::floor(radius + 0.5f)};
+    for (int i = 0; i < n; ++i) out[i] = gaussian_1d(f, x[i]) * gaussian_1d(f, y[i]);
     return 0;
 }
 
