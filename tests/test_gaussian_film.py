@@ -83,7 +83,7 @@ def test_gpu_gaussian_film_matches_reference_splat(ref, preset, w, h, spp, radiu
     # the drop-in class with SetGaussianFilter
     rs.set_gaussian_filter(radius, alpha)
     img2, _, _ = rs.render_cuda(max_depth=4)
-    assert np.array_equal(img2, img)
+    assert np.array_equal(img2[..., :3], img[..., :3])  # (the FrameBuffer sink only receives r, g, b)
     rs.close()
 
 
