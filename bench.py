@@ -182,8 +182,8 @@ def run_ours(args, wl):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from gnxraytracer_b200.api import Context, RenderParams, SceneKit
-    from gnxraytracer_b200.dist import reduce_framebuffer, weak_sample_range
+    from gnxraytracer_b200.api import FILM_BOX, FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS, Context, RenderParams, SceneKit
+    from gnxraytracer_b200.dist import reduce_filtered_sums, reduce_framebuffer, weak_sample_range
 
     scene, p0, p1, p2, W, H, spp, depth, desc = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +206,12 @@ def run_ours(args, wl):
     first, count = weak_sample_range(spp, rank)
     # VolPathIntegrator for the participating-media config; "lights" carries its gnx_integrator in p2
     integ = 1 if scene == "smoke" else (p2 if scene == "lights" else 0)
-    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world, integrator=integ)
+    # --film gaussian: GaussianFilter(radius 2, alpha 2) reconstruction instead of the reference's box average; N > 1 ranks
+    # exchange the unresolved sums (gnxraytracer_b200.dist.reduce_filtered_sums)
+    gauss = args.film == "gaussian"
+    film = (FILM_GAUSSIAN_SUMS if world > 1 else FILM_GAUSSIAN) if gauss else FILM_BOX
+    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world, integrator=integ,
+                               film=film, filter_radius=2.0 if gauss else 0.0, filter_alpha=2.0 if gauss else 0.0)
     fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
@@ -214,7 +219,7 @@ def run_ours(args, wl):
     def step_device(want_stats=False):
         st = ctx.render_device(params, fb.data_ptr(), stream, want_stats=want_stats)
         if world > 1:
-            reduce_framebuffer(fb, 0)
+            (reduce_filtered_sums if gauss else reduce_framebuffer)(fb, 0)
         return st
 
     def barrier():
@@ -255,7 +260,7 @@ def run_ours(args, wl):
         ctx.render_host_ptr(params, host.data_ptr(), want_stats=False)
         if world > 1:
             hb = host.cuda(non_blocking=True)
-            reduce_framebuffer(hb, 0)
+            (reduce_filtered_sums if gauss else reduce_framebuffer)(hb, 0)
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
     t = torch.tensor([e2e_ms], device="cuda")
@@ -274,7 +279,7 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_step * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_step * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
+            "config": {"workload": desc + (", Gaussian film (radius 2, alpha 2)" if gauss else ""), "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_step * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_step * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
                        "sample_range": f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region" if world > 1 else f"samples [0, {spp})",
                        "scene_build_s": round(t_build, 3), "bvh_build_s": round(sk.build_seconds, 3), "scene_upload_s": round(t_upload, 3),
                        "num_prims": sk.num_prims},
@@ -322,6 +327,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one reference-arm step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--film", default="box", choices=["box", "gaussian"], help="box = the reference's film (the headline); gaussian = GaussianFilter(2, 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]

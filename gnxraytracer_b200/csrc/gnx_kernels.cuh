@@ -392,6 +392,75 @@ __global__ void k_accumulate_gauss(PathState ps, float4 *accum, RenderConsts rc,
     }
 }
 
+// Gaussian film, step 2 as a shared-memory tiled gather: a block owns a 32 x 8 tile of output pixels and stages, for
+// `chunk` samples per pixel at a time, the radiance of the (32 + 2 reach) x (8 + 2 reach) source pixels around it
+// together with each sample's 1-D filter weights toward the 2 reach + 1 output columns and rows it can touch
+// (2 (2 reach + 1) exponentials per staged sample instead of two per (output pixel, sample) pair, and coalesced loads
+// instead of one sample stream per lane).  The weights vanish outside the radius (max(0, exp(-a d^2) - exp(-a r^2))), so
+// Film::AddSample's pixel bounds need no test of their own.  A warp is one row of 32 pixels and the per-pixel sample
+// stride is odd: the shared-memory reads are conflict-free.  Threads sum in a fixed order: deterministic.
+// RT / CT > 0: reach and chunk known at compile time (the index divisions become multiplications).
+constexpr int kFilmTW = 32, kFilmTH = 8;
+template <int RT, int CT>
+__global__ void __launch_bounds__(kFilmTW * kFilmTH) k_accumulate_gauss_tiled(PathState ps, float4 *accum, RenderConsts rc, FilmFilter f,
+                                                                              int chunkArg, int tilesX, int tilesY) {
+    extern __shared__ float film_sm[];
+    const int r = RT > 0 ? RT : f.reach, chunk = CT > 0 ? CT : chunkArg;
+    const int nw = 2 * r + 1, SW = kFilmTW + 2 * r, SH = kFilmTH + 2 * r, npx = SW * SH, stride = chunk | 1;
+    const int plane = npx * stride;
+    float *sLx = film_sm, *sLy = film_sm + plane, *sLz = film_sm + 2 * plane, *sWX = film_sm + 3 * plane, *sWY = sWX + nw * plane;
+    const int lx = threadIdx.x % kFilmTW, ly = threadIdx.x / kFilmTW;
+    for (int tile = blockIdx.x; tile < tilesX * tilesY; tile += gridDim.x) {
+        const int tx0 = (tile % tilesX) * kFilmTW, ty0 = (tile / tilesX) * kFilmTH;
+        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        for (int s0 = 0; s0 < rc.batch_spp; s0 += chunk) {
+            const int n = rc.batch_spp - s0 < chunk ? rc.batch_spp - s0 : chunk;
+            __syncthreads();
+            for (int i = threadIdx.x; i < npx * chunk; i += blockDim.x) {
+                const int spx = i / chunk, s = i - spx * chunk;
+                const int row = spx / SW;
+                const int sx = tx0 - r + (spx - row * SW), sy = ty0 - r + row;
+                const int idx = spx * stride + s;
+                const bool in = s < n && sx >= 0 && sx < rc.width && sy >= 0 && sy < rc.height;
+                float4 l = make_float4(0.f, 0.f, 0.f, 0.f), o = l;
+                if (in) {
+                    const size_t slot = ((size_t)sy * rc.width + sx) * rc.batch_spp + s0 + s;
+                    l = ps.L[slot];
+                    o = ps.ray_o[slot];
+                }
+                sLx[idx] = l.x; sLy[idx] = l.y; sLz[idx] = l.z;
+                const float pdx = ((float)sx + o.x) - 0.5f, pdy = ((float)sy + o.y) - 0.5f;
+#pragma unroll
+                for (int k = 0; k < nw; ++k) {
+                    sWX[k * plane + idx] = in ? gaussian_1d(f, (float)(sx + k - r) - pdx) : 0.f;
+                    sWY[k * plane + idx] = in ? gaussian_1d(f, (float)(sy + k - r) - pdy) : 0.f;
+                }
+            }
+            __syncthreads();
+            // source pixel (x + dx - r, y + dy - r) reaches output column x through its weight number 2r - dx
+#pragma unroll
+            for (int dy = 0; dy < nw; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < nw; ++dx) {
+                    const int base = ((ly + dy) * SW + lx + dx) * stride;
+                    const float *wx = sWX + (2 * r - dx) * plane + base, *wy = sWY + (2 * r - dy) * plane + base;
+#pragma unroll
+                    for (int s = 0; s < chunk; ++s) {
+                        const float w = wx[s] * wy[s];
+                        ax = __fmaf_rn(sLx[base + s], w, ax); ay = __fmaf_rn(sLy[base + s], w, ay); az = __fmaf_rn(sLz[base + s], w, az);
+                        aw += w;
+                    }
+                }
+        }
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x < rc.width && y < rc.height) {
+            float4 a = accum[(size_t)y * rc.width + x];
+            a.x += ax; a.y += ay; a.z += az; a.w += aw;
+            accum[(size_t)y * rc.width + x] = a;
+        }
+    }
+}
+
 // resolve = 1: sum(L f) / sum(f); 0: the raw sums (N-GPU jobs reduce them across ranks before dividing)
 __global__ void k_film_gauss(const float4 *accum, float4 *rgba, int npix, int resolve) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)

@@ -29,3 +29,18 @@ def reduce_framebuffer(fb: torch.Tensor, dst: int = 0):
         if dist.get_rank() == dst:
             fb.view(-1, 4)[:, 3] = 1.0
     return fb
+
+
+def reduce_filtered_sums(sums: torch.Tensor, dst: int = 0):
+    """Gaussian film across ranks: every rank renders its sample range with GNX_FILM_GAUSSIAN_SUMS, the
+    (sum L f, sum f) buffers are summed onto rank `dst`, which then resolves rgb = max(0, sum(L f) / sum(f)), alpha 1
+    (the division the single-GPU GNX_FILM_GAUSSIAN film does on the device)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM)
+        if dist.get_rank() != dst:
+            return sums
+    v = sums.view(-1, 4)
+    w = v[:, 3:4]
+    v[:, :3] = torch.where(w != 0, (v[:, :3] * (1.0 / torch.where(w != 0, w, torch.ones_like(w)))).clamp_min(0.0), torch.zeros_like(v[:, :3]))
+    v[:, 3] = 1.0
+    return sums

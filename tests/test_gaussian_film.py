@@ -48,7 +48,8 @@ def test_gaussian_film_matches_reference_splat(ref, emul, preset, w, h, spp, rad
 # ---- on the B200, through the C ABI and through the drop-in class ------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("preset,w,h,spp,radius,alpha,integ", [("cornell", 96, 80, 8, 2.0, 2.0, 0), ("dragon", 101, 67, 5, 1.5, 0.5, 0),
-                                                              ("fog", 48, 48, 4, 2.0, 2.0, 1), ("whitted", 64, 48, 4, 2.5, 1.0, 2)])
+                                                              ("fog", 48, 48, 4, 2.0, 2.0, 1), ("whitted", 64, 48, 4, 2.5, 1.0, 2),
+                                                              ("cornell", 50, 30, 2, 6.0, 0.1, 0), ("cornell", 33, 20, 9, 1.0, 3.0, 0)])
 def test_gpu_gaussian_film_matches_reference_splat(ref, preset, w, h, spp, radius, alpha, integ):
     from gnxraytracer_b200.api import Context
     rs = ref.scene(preset, w, h, spp)

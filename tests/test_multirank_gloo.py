@@ -29,9 +29,16 @@ def _worker(rank, world, port, out_path):
     img, _ = es.render(RenderParams.make(res, res, count, first_sample=first, spp_normalize=spp))
     fb = torch.from_numpy(img)
     reduce_framebuffer(fb, dst=0)
+    # the Gaussian film: ranks exchange the unresolved (sum L f, sum f) buffers
+    from gnxraytracer_b200.api import FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS
+    from gnxraytracer_b200.dist import reduce_filtered_sums
+    sums, _ = es.render(RenderParams.make(res, res, count, first_sample=first, film=FILM_GAUSSIAN_SUMS, filter_radius=2.0, filter_alpha=2.0))
+    gs = torch.from_numpy(sums)
+    reduce_filtered_sums(gs, dst=0)
     if rank == 0:
         full, _ = es.render(RenderParams.make(res, res, spp))
-        np.savez(out_path, reduced=fb.numpy(), full=full)
+        gfull, _ = es.render(RenderParams.make(res, res, spp, film=FILM_GAUSSIAN, filter_radius=2.0, filter_alpha=2.0))
+        np.savez(out_path, reduced=fb.numpy(), full=full, greduced=gs.numpy(), gfull=gfull)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -43,6 +50,8 @@ def test_two_ranks_reduce_to_the_single_rank_image(tmp_path, emul):
     d = np.load(out)
     assert np.allclose(d["reduced"][..., :3], d["full"][..., :3], rtol=1e-5, atol=1e-6)
     assert np.all(d["reduced"][..., 3] == 1.0)
+    assert np.allclose(d["greduced"][..., :3], d["gfull"][..., :3], rtol=1e-4, atol=1e-6)
+    assert np.all(d["greduced"][..., 3] == 1.0)
 
 
 def test_sample_ranges_partition():
