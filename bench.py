@@ -327,10 +327,17 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one reference-arm step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mesh", default=None, help="a .3d mesh file (the reference's format) to render in place of C2's stand-in mesh")
     ap.add_argument("--film", default="box", choices=["box", "gaussian"], help="box = the reference's film (the headline); gaussian = GaussianFilter(2, 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
+    if args.mesh:
+        # the real asset when the user has it: C2 with the mesh read from a .3d file (shape/plyRead.h layout) by the scene kit's
+        # reader (our arm) and by the reference's plyInfo (reference arm), placed as ui/ModelList.cpp:49-69 places dragon.3d
+        if args.workload != "c2":
+            ap.error("--mesh replaces the mesh of workload c2")
+        wl = ("dragon3d:" + os.path.abspath(args.mesh),) + wl[1:8] + (wl[8].replace("872448 tris (torus-knot stand-in for dragon.3d)", "from " + os.path.basename(args.mesh)),)
     if args.impl == "reference":
         return run_reference(args, wl)
     return run_ours(args, wl)

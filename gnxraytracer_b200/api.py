@@ -205,6 +205,9 @@ def load_scenekit():
     sk.gnxsk_build_seconds.restype = c_double
     sk.gnxsk_strip_bvh.argtypes = [c_void_p]
     sk.gnxsk_strip_bvh.restype = None
+    ip = ctypes.POINTER(ctypes.c_int)
+    sk.gnxsk_mesh_info.argtypes = [ctypes.c_char_p, ip, ip, ip, ip, ctypes.c_char_p, ctypes.c_int]
+    sk.gnxsk_write_knot_3d.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
     _sk = sk
     return sk
 
@@ -216,6 +219,25 @@ def resources_dir():
     if env:
         return env
     return os.path.join(repo_root(), "oracle", "_ref", "Resources")
+
+
+def mesh_info(path):
+    """Parses a .3d file (the reference's mesh format, shape/plyRead.h) or a Wavefront .obj with the scene kit's readers:
+    {"vertices", "triangles", "has_uv", "has_normals"}; raises RuntimeError with the reader's message."""
+    sk = load_scenekit()
+    v = [ctypes.c_int() for _ in range(4)]
+    err = ctypes.create_string_buffer(512)
+    if sk.gnxsk_mesh_info(str(path).encode(), *[ctypes.byref(x) for x in v], err, 512) != 0:
+        raise RuntimeError(err.value.decode())
+    return {"vertices": v[0].value, "triangles": v[1].value, "has_uv": bool(v[2].value), "has_normals": bool(v[3].value)}
+
+
+def write_knot_3d(path, nu, nv):
+    """Writes the kit's nu x nv torus knot as a .3d file (tests, tools)."""
+    sk = load_scenekit()
+    err = ctypes.create_string_buffer(512)
+    if sk.gnxsk_write_knot_3d(str(path).encode(), int(nu), int(nv), err, 512) != 0:
+        raise RuntimeError(err.value.decode())
 
 
 class SceneKit:

@@ -16,6 +16,7 @@
 
 #include "gnx_scenekit.h"
 #include "scenekit_mesh.h"
+#include "scenekit_io.h"
 
 namespace {
 
@@ -684,7 +685,9 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
         }
         sc->cam_eye[2] = 6.5; sc->cam_look[1] = -0.4f;
         sc->finalize(soup, width, height, spp, false, Mat4::identity());
-    } else if (nm == "dragon") {
+    } else if (nm == "dragon" || nm.rfind("dragon3d:", 0) == 0 || nm.rfind("obj:", 0) == 0) {
+        // "dragon3d:<path>": the mesh comes from a .3d file, placed like ui/ModelList.cpp:49-69 (plyInfo's x20, then
+        // Translate(0, -2.9, 0)); "obj:<path>": a Wavefront OBJ fitted into a sphere of radius 2.5 around (0, -0.4, 0)
         // oracle/ref_harness.cpp::BuildDragon (ui/MaterialList.cpp:48-69, ui/ModelList.cpp:49-69,172-178)
         if (p0 == 1) {
             gnx_material m = make_material(GNX_MAT_METAL, GNX_MATF_BUMP_IDENTITY);
@@ -696,7 +699,18 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
             sc->materials.push_back(m);
         }
         const float T[3] = {0.f, -2.9f, 0.f};
-        add_mesh(soup, gnxsk::torus_knot(p1 > 0 ? p1 : 2048, p2 > 0 ? p2 : 213), 20.f, T, 0);
+        if (nm == "dragon") add_mesh(soup, gnxsk::torus_knot(p1 > 0 ? p1 : 2048, p2 > 0 ? p2 : 213), 20.f, T, 0);
+        else {
+            gnxsk::Mesh file;
+            const bool obj = nm[0] == 'o';
+            if (!(obj ? gnxsk::load_obj(nm.substr(4), &file, &sc->error) : gnxsk::load_3d(nm.substr(9), &file, &sc->error))) return sc;
+            if (file.nTris() == 0) { sc->error = "mesh file without triangles"; return sc; }
+            if (obj) {
+                const float centre[3] = {0.f, -0.4f, 0.f}, zero[3] = {0.f, 0.f, 0.f};
+                gnxsk::fit_to_sphere(&file, 2.5f, centre);
+                add_mesh(soup, file, 1.f, zero, 0);
+            } else add_mesh(soup, file, 20.f, T, 0);
+        }
         int w0, h0;
         std::vector<float> rgb;
         std::string path = std::string(resources ? resources : ".") + "/MonValley1000.hdr";
@@ -802,6 +816,28 @@ const char *gnxsk_error(const gnxsk_scene *s) { return s ? s->error.c_str() : "n
 const gnx_scene_desc *gnxsk_desc(const gnxsk_scene *s) { return (s && s->error.empty()) ? &s->desc : nullptr; }
 int gnxsk_num_prims(const gnxsk_scene *s) { return s ? s->desc.geom.n_prims : 0; }
 double gnxsk_build_seconds(const gnxsk_scene *s) { return s ? s->build_seconds : 0; }
+// Mesh files without a scene: 0 on success, else -1 with the reason in err (when err_len > 0).
+static int io_result(bool ok, const std::string &e, char *err, int err_len) {
+    if (!ok && err && err_len > 0) { strncpy(err, e.c_str(), (size_t)err_len - 1); err[err_len - 1] = 0; }
+    return ok ? 0 : -1;
+}
+int gnxsk_write_knot_3d(const char *path, int nu, int nv, char *err, int err_len) {
+    std::string e;
+    return io_result(gnxsk::save_3d(path, gnxsk::torus_knot(nu, nv), &e), e, err, err_len);
+}
+int gnxsk_mesh_info(const char *path, int *n_vertices, int *n_triangles, int *has_uv, int *has_normals, char *err, int err_len) {
+    std::string e, p(path);
+    gnxsk::Mesh m;
+    const bool obj = p.size() > 4 && p.compare(p.size() - 4, 4, ".obj") == 0;
+    bool ok = obj ? gnxsk::load_obj(p, &m, &e) : gnxsk::load_3d(p, &m, &e);
+    if (ok) {
+        if (n_vertices) *n_vertices = m.nVerts();
+        if (n_triangles) *n_triangles = m.nTris();
+        if (has_uv) *has_uv = !m.UV.empty();
+        if (has_normals) *has_normals = !m.N.empty();
+    }
+    return io_result(ok, e, err, err_len);
+}
 void gnxsk_strip_bvh(gnxsk_scene *s) {
     if (!s) return;
     s->desc.geom.n_nodes = 0;

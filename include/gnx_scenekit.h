@@ -24,6 +24,10 @@ typedef struct gnxsk_scene gnxsk_scene;
 
 /* name: "cornell" (p0: 0 = Lambert walls, 1 = Oren-Nayar sigma 60; p1: icosphere subdivision, -1 = none)
  *       "dragon"  (p0: 0 = Plastic, 1 = Metal; p1 x p2: torus-knot quads, 0 = 2048 x 213)
+ *       "dragon3d:<path>"  the same scene with the mesh read from a .3d file — the reference's mesh format
+ *                 (shape/plyRead.h:19-48) — and placed as ui/ModelList.cpp:49-69 places dragon.3d (x20, y - 2.9)
+ *       "obj:<path>"       the same scene with a Wavefront OBJ mesh (uv / normals kept when every corner has them),
+ *                 fitted into a sphere of radius 2.5 around (0, -0.4, 0)
  *       "nano"    (p0: 0 = Disney, 1 = thin Disney; p1 x p2: knot quads, 0 = 320 x 64; textured, smooth-shaded)
  *       "smoke"   (p0: 0 = grid density medium in fog, PCG32 stream sampler; 1 = fog only, Halton) -> render with
  *                 GNX_INTEGRATOR_VOLPATH
@@ -41,6 +45,12 @@ double gnxsk_build_seconds(const gnxsk_scene *s);      /* BVH build wall time   
 /* Drops the kit's host-built BVH from the description (geom.n_nodes = 0): gnx_upload_scene then builds the
  * hierarchy on the GPU.  The primitive arrays stay as they are (any order is valid without nodes). */
 void gnxsk_strip_bvh(gnxsk_scene *s);
+
+/* Mesh files on their own.  Both return 0, or -1 with the reason copied into err (NUL-terminated, err_len bytes).
+ * gnxsk_mesh_info parses a .3d file (or a Wavefront OBJ when the path ends in ".obj") and reports its counts;
+ * gnxsk_write_knot_3d writes the kit's nu x nv torus knot in the .3d layout (tests, tools). */
+int gnxsk_mesh_info(const char *path, int *n_vertices, int *n_triangles, int *has_uv, int *has_normals, char *err, int err_len);
+int gnxsk_write_knot_3d(const char *path, int nu, int nv, char *err, int err_len);
 
 #ifdef __cplusplus
 }

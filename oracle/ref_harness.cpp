@@ -46,6 +46,7 @@
 #include "media/HomogeneousMedium.h"
 #include "samplers/HaltonSampler.h"
 #include "shape/Triangle.h"
+#include "shape/plyRead.h"
 #include "textures/ConstantTexture.h"
 #include "textures/ImageTexture.h"
 
@@ -288,10 +289,23 @@ std::shared_ptr<Material> YellowMetal() {  // ui/MaterialList.cpp:58-69
 
 // Config 2: dragon-class mesh (torus knot stand-in for the stripped dragon.3d) under the MonValley
 // environment light.  variant 0 = Plastic, 1 = Metal; nu x nv quads.
-bool BuildDragon(HarnessScene &hs, int variant, int nu, int nv, const std::string &hdr) {
-    gnxsk::Mesh knot = gnxsk::torus_knot(nu, nv);
-    for (float &x : knot.P) x *= 20;  // plyInfo scales every vertex by 20 (shape/plyRead.h:38)
-    AddMesh(hs, knot, Translate(Vector3f(0.f, -2.9f, 0.f)), variant == 1 ? YellowMetal() : PurplePlastic(), nullptr);
+// file3d non-empty: the mesh is read by the reference's OWN reader, plyInfo, exactly as ui/ModelList.cpp:49-69 does.
+bool BuildDragon(HarnessScene &hs, int variant, int nu, int nv, const std::string &hdr, const std::string &file3d = "") {
+    if (!file3d.empty()) {
+        FILE *fp = fopen(file3d.c_str(), "rb");
+        if (!fp) { hs.error = "missing mesh " + file3d; return false; }
+        fclose(fp);
+        plyInfo plyi(file3d);
+        gnxsk::Mesh m;
+        for (int i = 0; i < plyi.nVertices; ++i) for (int c = 0; c < 3; ++c) m.P.push_back(plyi.vertexArray[i][c]);
+        m.idx.assign(plyi.vertexIndices, plyi.vertexIndices + 3 * plyi.nTriangles);
+        plyi.Release();
+        AddMesh(hs, m, Translate(Vector3f(0.f, -2.9f, 0.f)), variant == 1 ? YellowMetal() : PurplePlastic(), nullptr);
+    } else {
+        gnxsk::Mesh knot = gnxsk::torus_knot(nu, nv);
+        for (float &x : knot.P) x *= 20;  // plyInfo scales every vertex by 20 (shape/plyRead.h:38)
+        AddMesh(hs, knot, Translate(Vector3f(0.f, -2.9f, 0.f)), variant == 1 ? YellowMetal() : PurplePlastic(), nullptr);
+    }
     std::string path = ResourceDir() + hdr;
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) { hs.error = "missing resource " + path; return false; }
@@ -402,6 +416,7 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     hs->width = width; hs->height = height; hs->spp = spp;
     if (hs->name == "cornell") BuildCornell(*hs, p0, p1);
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
+    else if (hs->name.rfind("dragon3d:", 0) == 0) BuildDragon(*hs, p0, 0, 0, "MonValley1000.hdr", hs->name.substr(9));
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else if (hs->name == "smoke") BuildSmoke(*hs, p0);
     else if (hs->name == "whitted" || hs->name == "direct" || hs->name == "lights") {

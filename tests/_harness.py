@@ -161,6 +161,14 @@ class Ref:
             raise RuntimeError(err)
         return RefScene(self.lib, h, width, height, spp)
 
+    def scene_named(self, name, width, height, spp, p0=0, p1=0, p2=0):
+        """A harness scene by its raw name, e.g. "dragon3d:<path>" (mesh read by the reference's plyInfo)."""
+        h = self.lib.gnxh_scene_create(name.encode(), width, height, spp, p0, p1, p2)
+        err = self.lib.gnxh_scene_error(h).decode()
+        if err:
+            raise RuntimeError(err)
+        return RefScene(self.lib, h, width, height, spp)
+
     def max_threads(self):
         return self.lib.gnxh_max_threads()
 
