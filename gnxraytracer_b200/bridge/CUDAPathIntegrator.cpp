@@ -447,10 +447,12 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
         out->lights.push_back(gl);
         // the input of ComputeLightPowerDistribution (core/Integrator.cpp:216-217), from the light itself
         out->light_power.push_back(l->Power().y());
+        out->light_n_samples.push_back(std::max(1, l->nSamples));  // Light::Light clamps the same way (core/Light.cpp)
     }
     d.n_lights = (int32_t)out->lights.size();
     d.lights = out->lights.data();
     d.light_power = out->light_power.data();
+    d.light_n_samples = out->light_n_samples.data();
 
     d.n_materials = (int32_t)out->materials.size();
     d.materials = out->materials.data();

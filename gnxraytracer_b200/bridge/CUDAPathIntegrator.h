@@ -36,6 +36,7 @@ struct FlatScene {
     std::vector<std::vector<float>> texture_texels;
     std::vector<gnx_light> lights;
     std::vector<float> light_power;
+    std::vector<int32_t> light_n_samples;
     std::vector<float> env_texels, env_cond_func, env_cond_cdf, env_cond_int, env_marg_func, env_marg_cdf;
     std::vector<gnx_medium> media;
     std::vector<std::vector<float>> media_density;
@@ -68,7 +69,7 @@ class CUDAPathIntegrator : public pbr::Integrator {
     bool PrimaryHits(const pbr::Scene &scene, int sample, std::vector<int32_t> *orderedPrimIndex);
     const FlatScene *flat() const { return flat_.get(); }
     gnx_render_params MakeParams() const;
-    // GNX_INTEGRATOR_WHITTED / GNX_INTEGRATOR_DIRECT: stand in for pbr::WhittedIntegrator /
+    // GNX_INTEGRATOR_WHITTED / GNX_INTEGRATOR_DIRECT / GNX_INTEGRATOR_DIRECT_ALL (LightStrategy::UniformSampleAll): stand in for pbr::WhittedIntegrator /
     // pbr::DirectLightingIntegrator(LightStrategy::UniformSampleOne) instead of PathIntegrator / VolPathIntegrator
     void SetIntegrator(int gnxIntegrator) { integrator_ = gnxIntegrator; }
     // Reconstruct the image with the reference's GaussianFilter(Vector2f(radius, radius), alpha)

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
         if (slot < n) {
             int pixel, sample;
             slot_to_sample(rc, slot, &pixel, &sample);
-            V3 L = recursive_li<8>(sc, rc, direct != 0, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
+            V3 L = recursive_li<8>(sc, rc, direct, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();

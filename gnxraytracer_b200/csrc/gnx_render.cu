@@ -384,6 +384,14 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     sc.lights = dl;
     sc.n_lights = d->n_lights;
     ctx->n_lights_host = d->n_lights;
+    sc.light_nsamples = nullptr;
+    if (d->light_n_samples && d->n_lights > 0) {
+        for (int i = 0; i < d->n_lights; ++i)
+            if (d->light_n_samples[i] < 1 || d->light_n_samples[i] > 4096) return fail(ctx, GNX_ERR_INVALID, "light_n_samples out of range");
+        int *dn;
+        if ((rc = dupload(ctx, pool, d->light_n_samples, (size_t)d->n_lights, &dn))) return rc;
+        sc.light_nsamples = dn;
+    }
     if (d->env.present) {
         const gnx_envmap &e = d->env;
         if (!e.texels || !e.cond_func || !e.cond_cdf || !e.cond_int || !e.marg_func || !e.marg_cdf)
@@ -590,8 +598,10 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
         return fail(ctx, GNX_ERR_INVALID, "bad render parameters");
     if ((long long)p->width * p->height > (1ll << 28)) return fail(ctx, GNX_ERR_INVALID, "image too large");
-    if (p->integrator < GNX_INTEGRATOR_PATH || p->integrator > GNX_INTEGRATOR_DIRECT) return fail(ctx, GNX_ERR_INVALID, "unknown integrator");
-    const bool recursive = p->integrator == GNX_INTEGRATOR_WHITTED || p->integrator == GNX_INTEGRATOR_DIRECT;
+    if (p->integrator < GNX_INTEGRATOR_PATH || p->integrator > GNX_INTEGRATOR_DIRECT_ALL) return fail(ctx, GNX_ERR_INVALID, "unknown integrator");
+    const bool recursive = p->integrator >= GNX_INTEGRATOR_WHITTED;
+    if (p->integrator == GNX_INTEGRATOR_DIRECT_ALL && 5 + 4 * (long long)p->max_depth * ctx->sc.n_lights + 64 > 1000)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "UniformSampleAll: the sample arrays of maxDepth x lights need more Halton dimensions than the sampler has (1000)");
     if (!recursive && ctx->has_next_lights)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "point / spot / distant / skybox lights are rendered by GNX_INTEGRATOR_WHITTED and GNX_INTEGRATOR_DIRECT");
     if (recursive && ctx->sc.smp.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use the Halton sampler");
@@ -640,7 +650,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     int rc = validate_params(ctx, p);
     if (rc) return rc;
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
-    const bool recursiveInteg = p->integrator == GNX_INTEGRATOR_WHITTED || p->integrator == GNX_INTEGRATOR_DIRECT;
+    const bool recursiveInteg = p->integrator >= GNX_INTEGRATOR_WHITTED;
     if (!recursiveInteg && (rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
     const int npix = p->width * p->height;
     // Paths in flight per wavefront batch.  Late bounces carry few rays and every launch has a tail, so
@@ -730,7 +740,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
             tm.begin(ST_EXTEND);
             if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
-            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, p->integrator == GNX_INTEGRATOR_DIRECT, ctx->d_stats);
+            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, p->integrator - GNX_INTEGRATOR_WHITTED, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
             launches += accumulate(psv, rcn);

@@ -86,6 +86,7 @@ struct DeviceScene {
     const DevTexture *textures;
     const gnx_light *lights;
     int n_lights;
+    const int *light_nsamples;    // [n_lights] Light::nSamples or null (= 1), UniformSampleAllLights
     DevEnv env;
     DevSkybox skybox;
     DevLightDistrib ld;

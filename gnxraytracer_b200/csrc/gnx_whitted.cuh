@@ -232,13 +232,25 @@ struct RecFrame {
 };
 constexpr int kMaxRecDepth = 16;
 
-// WhittedIntegrator::Li / DirectLightingIntegrator::Li (UniformSampleOne) for camera sample `sample` of pixel (px, py).
-//   direct = false: integrators/WhittedIntegrator.cpp:14-67      direct = true: integrators/DirectLightingIntegrator.cpp:28-63
+// WhittedIntegrator::Li / DirectLightingIntegrator::Li for camera sample `sample` of pixel (px, py).
+//   direct = 0: integrators/WhittedIntegrator.cpp:14-67      direct = 1 / 2: integrators/DirectLightingIntegrator.cpp:28-63
+//   with LightStrategy::UniformSampleOne / UniformSampleAll.
+//
+// UniformSampleAll draws from the sampler's 2-D sample ARRAYS (Preprocess requests, per depth and light, one array for the
+// light samples and one for the BSDF samples, DirectLightingIntegrator.cpp:13-27).  GlobalSampler::StartPixel fills element
+// k of pixel sample s of array a with dimensions (5 + 2a, 5 + 2a + 1) of Halton index GetIndexForSample(s n + k)
+// (core/Sampler.cpp:134-144), so the arrays need no storage here: an element is two radical inverses.  The arrays are
+// handed out in the order the vertices ask for them (depth first); a sample whose recursion visits more vertices than
+// maxDepth finds none left and falls back to one Get2D pair per light (core/Integrator.cpp:38-43).  Ordinary dimensions
+// start behind the arrays' (GlobalSampler::Get1D / Get2D skip [arrayStartDim, arrayEndDim), core/Sampler.cpp).
 template <int MAXL>
-GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, bool direct, int px, int py, int sample, int2 *stack, int stride,
+GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct, int px, int py, int sample, int2 *stack, int stride,
                       TraversalCounters &cnt, RecCounters &rcnt) {
-    const uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
-    PathSampler smp(sc.smp, hidx, 5);  // dimensions 0-4 belong to the camera sample
+    const uint64_t pixOffset = halton_pixel_offset(sc.smp, px, py);
+    const uint64_t hidx = pixOffset + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    const int nArrays = direct == 2 ? 2 * rc.max_depth * sc.n_lights : 0;
+    int arrayCursor = 0;               // Sampler::array2DOffset
+    PathSampler smp(sc.smp, hidx, 5 + 2 * nArrays);  // dimensions 0-4 belong to the camera sample, then the arrays'
     RecFrame frames[kMaxRecDepth + 2];
     int nf = 0;
     {
@@ -281,7 +293,7 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, bool direct
             // ---- emitted light, then the direct illumination of the integrator
             if (s.light >= 0) L += fr.weight * area_light_L(sc.lights[s.light], s.n, s.wo);
             V3 lightL(0.f);
-            if (!direct) {
+            if (direct == 0) {
                 for (int j = 0; j < sc.n_lights; ++j) {
                     float u0, u1;
                     smp.get2d(&u0, &u1);
@@ -293,6 +305,28 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, bool direct
                     bsdf_f_pdf(bsdf, s.wo, ls.wi, BSDF_ALL, &f, &pdfUnused);
                     if (!is_black(f) && w_unoccluded(sc, s, ls, stack, stride, cnt, rcnt))
                         lightL += div_each(f * ls.Li * absdot(ls.wi, ns), ls.pdf);
+                }
+            } else if (direct == 2) {
+                // UniformSampleAllLights (core/Integrator.cpp:25-55)
+                for (int j = 0; j < sc.n_lights; ++j) {
+                    const int n = sc.light_nsamples ? sc.light_nsamples[j] : 1;
+                    if (arrayCursor + 2 > nArrays) {
+                        float ul0, ul1, us0, us1;
+                        smp.get2d(&ul0, &ul1);
+                        smp.get2d(&us0, &us1);
+                        lightL += w_estimate_direct<MAXL>(sc, s, bsdf, sc.lights[j], ul0, ul1, us0, us1, stack, stride, cnt, rcnt);
+                    } else {
+                        const int dimL = 5 + 2 * arrayCursor, dimS = dimL + 2;
+                        arrayCursor += 2;
+                        V3 Ld(0.f);
+                        for (int k = 0; k < n; ++k) {
+                            const uint64_t idx = pixOffset + ((uint64_t)sample * (uint64_t)n + (uint64_t)k) * (uint64_t)sc.smp.stride;
+                            const float ul0 = halton_sample_dimension(sc.smp, idx, dimL), ul1 = halton_sample_dimension(sc.smp, idx, dimL + 1);
+                            const float us0 = halton_sample_dimension(sc.smp, idx, dimS), us1 = halton_sample_dimension(sc.smp, idx, dimS + 1);
+                            Ld += w_estimate_direct<MAXL>(sc, s, bsdf, sc.lights[j], ul0, ul1, us0, us1, stack, stride, cnt, rcnt);
+                        }
+                        lightL += div_each(Ld, (float)n);
+                    }
                 }
             } else if (sc.n_lights > 0) {
                 // UniformSampleOneLight without a light distribution (core/Integrator.cpp:70-79)

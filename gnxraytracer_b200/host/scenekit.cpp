@@ -401,6 +401,7 @@ struct gnxsk_scene {
     std::vector<gnx_texture> textures;
     std::vector<float> texels;
     std::vector<gnx_light> lights;
+    std::vector<int32_t> light_n_samples;  // Light::nSamples: 5 for the UI's area lights (ui/ModelList.cpp:140-146), else 1
     EnvTables env;
     double build_seconds = 0;
 
@@ -511,6 +512,9 @@ struct gnxsk_scene {
             for (gnx_light &l : lights) if (l.type == GNX_LIGHT_DISTANT) l.area = world_radius;
         }
         desc.n_lights = (int32_t)lights.size(); desc.lights = lights.data();
+        light_n_samples.clear();
+        for (const gnx_light &l : lights) light_n_samples.push_back(l.type == GNX_LIGHT_AREA_TRI ? 5 : 1);
+        desc.light_n_samples = light_n_samples.data();
         // ---- camera: LookAt((0,0,5) -> origin, up +y), fov 90, near 1e-2, far 1000, screen window by
         // aspect (ui/RenderThread.cpp:60-68, camera/Perspective.cpp:114-135, core/Camera.h:54-75)
         Mat4 c2w = look_at_c2w(cam_eye, cam_look);

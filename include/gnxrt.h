@@ -259,13 +259,18 @@ typedef struct gnx_scene_desc {
                                  ComputeLightPowerDistribution (core/Integrator.cpp:212-220).  Only read for
                                  GNX_LIGHTS_POWER; NULL = the library derives it for area / point / spot /
                                  distant lights and refuses power sampling of an environment / skybox light */
+    const int32_t *light_n_samples; /* [n_lights] Light::nSamples (core/Light.h), read by GNX_INTEGRATOR_DIRECT_ALL only;
+                                       NULL = 1 sample per light */
 } gnx_scene_desc;
 
 typedef enum gnx_integrator {
     GNX_INTEGRATOR_PATH = 0,     /* integrators/PathIntegrator.cpp                                          */
     GNX_INTEGRATOR_VOLPATH = 1,  /* integrators/VolPathIntegrator.cpp                                       */
     GNX_INTEGRATOR_WHITTED = 2,  /* integrators/WhittedIntegrator.cpp (the UI's default, ui/RenderThread.cpp:163) */
-    GNX_INTEGRATOR_DIRECT = 3    /* integrators/DirectLightingIntegrator.cpp, LightStrategy::UniformSampleOne */
+    GNX_INTEGRATOR_DIRECT = 3,   /* integrators/DirectLightingIntegrator.cpp, LightStrategy::UniformSampleOne */
+    GNX_INTEGRATOR_DIRECT_ALL = 4 /* the same with LightStrategy::UniformSampleAll: every light at every vertex, with
+                                    light_n_samples[j] samples each out of the sampler's 2-D sample arrays
+                                    (DirectLightingIntegrator.cpp:13-27, core/Integrator.cpp:25-55)              */
 } gnx_integrator;
 typedef enum gnx_film {
     GNX_FILM_BOX = 0,           /* the reference: mean of the pixel's own samples (core/Integrator.cpp:274-293)      */

@@ -422,7 +422,7 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     else if (hs->name == "whitted" || hs->name == "direct" || hs->name == "lights") {
         // "lights": the scene kit's name for the same room, p2 = gnx_integrator (2 Whitted, 3 DirectLighting)
         BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);
-        hs->integrator = hs->name == "whitted" ? 2 : hs->name == "direct" ? 3 : (p2 == 3 ? 3 : 2);
+        hs->integrator = hs->name == "whitted" ? 2 : hs->name == "direct" ? (p2 == 4 ? 4 : 3) : (p2 == 3 || p2 == 4 ? p2 : 2);
     }
     else hs->error = "unknown scene";
     return hs;
@@ -444,9 +444,15 @@ void gnxh_scene_set_gaussian_filter(void *h, float radius, float alpha) {
 }
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
 
-static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth) {
+// Every integrator gets a fresh copy of the scene's sampler: DirectLightingIntegrator::Preprocess(UniformSampleAll) appends
+// sample-array requests to the sampler it is given, and a second Preprocess on the same object would append them again.
+static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth, std::shared_ptr<Sampler> *samplerOut = nullptr) {
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+    std::shared_ptr<Sampler> fresh(hs->sampler->Clone(0).release());
+    if (samplerOut) *samplerOut = fresh;
+    struct Swap { std::shared_ptr<Sampler> &a, b; Swap(std::shared_ptr<Sampler> &x, std::shared_ptr<Sampler> y) : a(x), b(x) { a = y; } ~Swap() { a = b; } } swap(hs->sampler, fresh);
     switch (hs->integrator) {
+    case 4: return new DirectLightingIntegrator(LightStrategy::UniformSampleAll, maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
     case 1: return new VolPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, 1.f, hs->strategy, hs->fb.get());
     case 2: return new WhittedIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
     case 3: return new DirectLightingIntegrator(LightStrategy::UniformSampleOne, maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get());
@@ -478,13 +484,14 @@ int gnxh_reference_samples(void *h, int maxDepth, int n, const int *px, const in
     auto *hs = (HarnessScene *)h;
     if (!hs->scene) return -1;
     Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth));
+    std::shared_ptr<Sampler> smp;
+    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth, &smp));
     SamplerIntegrator &integ = *integp;
-    integ.Preprocess(*hs->scene, *hs->sampler);
+    integ.Preprocess(*hs->scene, *smp);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < n; ++i) {
         MemoryArena arena;
-        std::unique_ptr<Sampler> s = hs->sampler->Clone(hs->width * py[i] + px[i]);
+        std::unique_ptr<Sampler> s = smp->Clone(hs->width * py[i] + px[i]);
         Point2i pixel(px[i], py[i]);
         s->StartPixel(pixel);
         s->SetSampleNumber(sample[i]);
@@ -527,15 +534,16 @@ int gnxh_reference_gaussian_film(void *h, int maxDepth, float radius, float alph
     auto *hs = (HarnessScene *)h;
     if (!hs->scene) return -1;
     const int W = hs->width, H = hs->height, spp = hs->spp;
-    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth));
+    std::shared_ptr<Sampler> smp;
+    std::unique_ptr<SamplerIntegrator> integp(MakeReferenceIntegrator(hs, maxDepth, &smp));
     SamplerIntegrator &integ = *integp;
-    integ.Preprocess(*hs->scene, *hs->sampler);
+    integ.Preprocess(*hs->scene, *smp);
     std::vector<float> L((size_t)W * H * spp * 3), pf((size_t)W * H * spp * 2);
 #pragma omp parallel for schedule(dynamic, 16)
     for (int pix = 0; pix < W * H; ++pix) {
         MemoryArena arena;
         Point2i pixel(pix % W, pix / W);
-        std::unique_ptr<Sampler> s = hs->sampler->Clone(pix);
+        std::unique_ptr<Sampler> s = smp->Clone(pix);
         s->StartPixel(pixel);
         for (int k = 0; k < spp; ++k) {
             s->SetSampleNumber(k);

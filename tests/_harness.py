@@ -31,8 +31,17 @@ SCENES = {
     "whitted_img": ("whitted", 1 | 2 | 32, 2, 0),   # skybox with the awesomeface.jpg image
     "direct": ("direct", 31, 2, 0),
     "direct_area": ("direct", 1, 2, 0),             # area light only: both MIS halves of EstimateDirect
+    # LightStrategy::UniformSampleAll: every light at every vertex, samples out of the sampler's 2-D arrays
+    "direct_all": ("direct", 31, 2, 4),
+    "direct_all_area": ("direct", 1, 2, 4),         # two area-light triangles with nSamples = 5 each
 }
 INTEGRATOR_OF = {"whitted": 2, "direct": 3, "smoke": 1}
+
+
+def integrator_of(preset):
+    """gnx_integrator of a preset (p2 = 4 selects DirectLightingIntegrator with UniformSampleAll)."""
+    name, _, _, p2 = SCENES[preset]
+    return 4 if name == "direct" and p2 == 4 else INTEGRATOR_OF.get(name, 0)
 
 
 

@@ -59,6 +59,7 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.textures = e.textures.data();
     sc.lights = d->lights;
     sc.n_lights = d->n_lights;
+    sc.light_nsamples = d->light_n_samples;
     if (g.prim_medium_in && g.prim_medium_out) {
         e.media.resize(g.n_prims);
         for (int k = 0; k < g.n_prims; ++k) e.media[k] = make_int2(g.prim_medium_in[k], g.prim_medium_out[k]);
@@ -168,12 +169,12 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         rays[0] += vc.extend; rays[1] += vc.shadow; rays[2] += vc.mis;
         return Lv;
     }
-    if (p.integrator == GNX_INTEGRATOR_WHITTED || p.integrator == GNX_INTEGRATOR_DIRECT) {
+    if (p.integrator >= GNX_INTEGRATOR_WHITTED) {
         RenderConsts rcw{};
         rcw.width = p.width; rcw.height = p.height; rcw.max_depth = p.max_depth; rcw.rr_threshold = p.rr_threshold;
         int2 wstack[kSmemStack];
         RecCounters rcnt{0, 0, 0};
-        V3 Lw = recursive_li<8>(sc, rcw, p.integrator == GNX_INTEGRATOR_DIRECT, px, py, sample, wstack, 1, cnt, rcnt);
+        V3 Lw = recursive_li<8>(sc, rcw, p.integrator - GNX_INTEGRATOR_WHITTED, px, py, sample, wstack, 1, cnt, rcnt);
         rays[0] += rcnt.extend; rays[1] += rcnt.shadow; rays[2] += rcnt.mis;
         return Lw;
     }

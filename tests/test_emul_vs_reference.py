@@ -80,14 +80,14 @@ def test_volpath_matches_reference(ref, emul, preset):
     rs.close(); es.close()
 
 
-@pytest.mark.parametrize("preset", ["whitted", "whitted_img", "direct", "direct_area"])
+@pytest.mark.parametrize("preset", ["whitted", "whitted_img", "direct", "direct_area", "direct_all", "direct_all_area"])
 def test_whitted_and_direct_lighting_match_reference(ref, emul, preset):
     """WhittedIntegrator / DirectLightingIntegrator(UniformSampleOne) with Point, Spot, Distant and
     SkyBox lights next to the area light; mirror and glass spheres exercise SpecularReflect / SpecularTransmit and the
     depth-first order of the Halton dimensions.  Per-sample radiance against the reference's Li."""
-    from _harness import INTEGRATOR_OF, SCENES
+    from _harness import integrator_of
     res = 48
-    integ = INTEGRATOR_OF[SCENES[preset][0]]
+    integ = integrator_of(preset)
     rs = ref.scene(preset, res, res, 4)
     es = emul.scene(rs.desc)
     px, py = grid(res, res)

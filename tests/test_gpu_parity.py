@@ -239,11 +239,12 @@ def test_volpath_bridge_render_matches_reference(ref, preset, res, spp):
     rs.close()
 
 
-@pytest.mark.parametrize("preset,res,spp", [("whitted", 160, 8), ("whitted_img", 128, 8), ("direct", 160, 8), ("direct_area", 128, 8)])
+@pytest.mark.parametrize("preset,res,spp", [("whitted", 160, 8), ("whitted_img", 128, 8), ("direct", 160, 8), ("direct_area", 128, 8),
+                                            ("direct_all", 128, 4), ("direct_all_area", 96, 4)])
 def test_whitted_and_direct_bridge_render_matches_reference(ref, emul, preset, res, spp):
     """WhittedIntegrator / DirectLightingIntegrator through the drop-in class (SetIntegrator) against
     the reference's own Render on a pbr::Scene with Point, Spot, Distant, SkyBox and area lights."""
-    from _harness import INTEGRATOR_OF, SCENES
+    from _harness import integrator_of
     rs = ref.scene(preset, res, res, spp)
     img_ref, _ = rs.render_reference(max_depth=5)
     img, seconds, st = rs.render_cuda(max_depth=5)
@@ -259,7 +260,7 @@ def test_whitted_and_direct_bridge_render_matches_reference(ref, emul, preset, r
     sigma = samples.std(axis=0, ddof=1) / np.sqrt(spp) + 1e-4
     assert np.mean(np.abs(img.reshape(-1, 4)[sel, :3] - img_ref.reshape(-1, 4)[sel, :3]) <= 3 * sigma) >= 0.999
     # and the GPU equals the CPU emulation of the same device code
-    p = RenderParams.make(res, res, spp, max_depth=5, integrator=INTEGRATOR_OF[SCENES[preset][0]])
+    p = RenderParams.make(res, res, spp, max_depth=5, integrator=integrator_of(preset))
     emu, _ = emul.scene(rs.desc).render(p)
     assert rel_mse(img, emu) <= 1e-6
     rs.close()

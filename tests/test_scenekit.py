@@ -9,12 +9,12 @@ from gnxraytracer_b200.api import RenderParams, SceneKit
 
 @pytest.mark.parametrize("preset,args", [("cornell", (0, 2, 0)), ("dragon", (0, 256, 32)), ("dragon_metal", (1, 256, 32)),
                                          ("smoke", (0, 0, 0)), ("fog", (1, 0, 0)), ("whitted", (31, 2, 0)),
-                                         ("direct", (31, 2, 0))])
+                                         ("direct", (31, 2, 0)), ("direct_all", (31, 2, 0))])
 def test_scenekit_scene_renders_like_the_reference(ref, emul, preset, args):
     res, spp = 48, 4
     rs = ref.scene(preset, res, res, spp)
-    sk = SceneKit({"fog": "smoke", "whitted": "lights", "direct": "lights"}.get(preset, preset.split("_")[0]), res, res, spp, *args)
-    integ = {"smoke": 1, "fog": 1, "whitted": 2, "direct": 3}.get(preset, 0)
+    sk = SceneKit({"fog": "smoke", "whitted": "lights", "direct": "lights", "direct_all": "lights"}.get(preset, preset.split("_")[0]), res, res, spp, *args)
+    integ = {"smoke": 1, "fog": 1, "whitted": 2, "direct": 3, "direct_all": 4}.get(preset, 0)
     assert sk.num_prims == rs.lib.gnxh_scene_num_prims(rs.h)
     es = emul.scene(sk.desc)
     px, py = grid(res, res)
