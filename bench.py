@@ -43,6 +43,9 @@ WORKLOADS = {
            "C4: VolPathIntegrator, GridDensityMedium density_render.70.volume inside HomogeneousMedium fog, Matte ground, MonValley env, 1024x1024, 64 spp, maxDepth 5, PCG32 stream sampler"),
     "c1": ("cornell", 0, 3, 0, 512, 512, 16, 5,
            "C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
+    # BASELINE config 5: ONE fixed job split across the ranks by sample range (strong scaling, "scaling": "strong")
+    "c5": ("dragon", 0, 0, 0, 3840, 2160, 1024, 5,
+           "C5: dragon-class mesh 872448 tris, Plastic, MonValley env, 3840x2160, 1024 spp in total, sample ranges dealt to the ranks, maxDepth 5"),
     # SURVEY 8f rank 1 (the UI's default integrator): not a BASELINE config, measured to the same bar
     "w1": ("lights", 31, 4, 2, 1024, 1024, 16, 5,
            "W1: WhittedIntegrator, Cornell room + Mirror / Glass / Plastic spheres (11 532 tris), area + Point + Spot + Distant + SkyBox lights, 1024x1024, 16 spp, maxDepth 5"),
@@ -183,7 +186,7 @@ def run_ours(args, wl):
     import torch
     import torch.distributed as dist
     from gnxraytracer_b200.api import FILM_BOX, FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS, Context, RenderParams, SceneKit
-    from gnxraytracer_b200.dist import reduce_filtered_sums, reduce_framebuffer, weak_sample_range
+    from gnxraytracer_b200.dist import reduce_filtered_sums, reduce_framebuffer, sample_range, weak_sample_range
 
     scene, p0, p1, p2, W, H, spp, depth, desc = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -203,14 +206,15 @@ def run_ours(args, wl):
     ctx.upload(sk.desc)
     t_upload = time.time() - t0
 
-    first, count = weak_sample_range(spp, rank)
+    strong = args.workload == "c5"
+    first, count = sample_range(spp, rank, world) if strong else weak_sample_range(spp, rank)
     # VolPathIntegrator for the participating-media config; "lights" carries its gnx_integrator in p2
     integ = 1 if scene == "smoke" else (p2 if scene == "lights" else 0)
     # --film gaussian: GaussianFilter(radius 2, alpha 2) reconstruction instead of the reference's box average; N > 1 ranks
     # exchange the unresolved sums (gnxraytracer_b200.dist.reduce_filtered_sums)
     gauss = args.film == "gaussian"
     film = (FILM_GAUSSIAN_SUMS if world > 1 else FILM_GAUSSIAN) if gauss else FILM_BOX
-    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp * world, integrator=integ,
+    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp if strong else spp * world, integrator=integ,
                                film=film, filter_radius=2.0 if gauss else 0.0, filter_alpha=2.0 if gauss else 0.0)
     fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
@@ -270,20 +274,21 @@ def run_ours(args, wl):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        value = paths_step * world / ms_step / 1e3  # Mpaths/s
-        e2e_val = paths_step * world / e2e_ms / 1e3
+        total_paths = W * H * spp if strong else paths_step * world  # all ranks together
+        value = total_paths / ms_step / 1e3  # Mpaths/s
+        e2e_val = total_paths / e2e_ms / 1e3
         ext_ms = st.ms_extend / max(1, st.extend_launches)
         ext_bytes = st.extend_bytes / max(1, st.extend_launches)
         achieved = (ext_bytes / (ext_ms * 1e-3)) / 1e9 if ext_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc + (", Gaussian film (radius 2, alpha 2)" if gauss else ""), "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_step * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_step * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
-                       "sample_range": f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region" if world > 1 else f"samples [0, {spp})",
+                       "sample_range": (f"the {spp} samples of every pixel are dealt out as {world} contiguous ranges; NCCL sum-reduce to rank 0 inside the timed region" if strong else f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region") if world > 1 else f"samples [0, {spp})",
                        "scene_build_s": round(t_build, 3), "bvh_build_s": round(sk.build_seconds, 3), "scene_upload_s": round(t_upload, 3),
                        "num_prims": sk.num_prims},
-            "mrays_per_s": st.rays * world / ms_step / 1e3,
+            "mrays_per_s": st.rays * (total_paths / max(1, st.paths)) / ms_step / 1e3,
             "rays_per_path": st.rays / st.paths,
             "stage_ms": {"raygen": st.ms_raygen, "extend": st.ms_extend, "shade": st.ms_shade, "shadow": st.ms_shadow, "film": st.ms_film,
                          "device_total": st.device_ms,
