@@ -28,6 +28,16 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: NCCL writes its "NCCL version ..." banner (any NCCL_DEBUG level from VERSION up,
 # WARN included) and its warnings to stdout unless told otherwise
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# ... and NCCL 2.28 prints the banner with a plain printf whatever NCCL_DEBUG_FILE says, so file descriptor 1 itself is pointed at
+# stderr for the whole run and the one JSON line is written to a duplicate of the original stdout (emit()).
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 METRIC = "Mpaths/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the six k_trace<3|4> launches of one
@@ -119,7 +129,7 @@ def run_reference(args, wl):
     import _harness
     scene, p0, p1, p2, W, H, spp, depth, desc = wl
     if not os.path.exists(_harness.REF_LIB):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgnxref.so was not built (no /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libgnxref.so was not built (no /root/reference at build time)"})
         return 0
     ref = _harness.Ref()
     # all the host threads the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
@@ -129,7 +139,7 @@ def run_reference(args, wl):
     h = lib.gnxh_scene_create(scene.encode(), W, H, sample_spp, p0, p1 or (2048 if scene == "dragon" else 0), p2 or (213 if scene == "dragon" else 0))
     err = lib.gnxh_scene_error(h).decode()
     if err:
-        print(json.dumps({"impl": "reference", "unavailable": err}))
+        emit({"impl": "reference", "unavailable": err})
         return 0
     rs = _harness.RefScene(lib, h, W, H, sample_spp)
     times = []
@@ -147,7 +157,7 @@ def run_reference(args, wl):
             "config": {"workload": desc, "sample": sample, "bvh_build_s": lib.gnxh_scene_bvh_seconds(h)},
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -315,7 +325,7 @@ def run_ours(args, wl):
                 import _harness
                 line["rel_mse_vs_cpu_ref"] = _harness.rel_mse(img, img_ref)
                 line["rel_mse_spp"] = n
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
