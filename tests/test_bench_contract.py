@@ -43,3 +43,20 @@ def test_product_arm_prints_one_json_line():
     assert e["value"] > 0 and e["d2h_bytes_per_step"] == 512 * 512 * 16 and e["h2d_bytes_per_step"] > 0
     assert e["value"] <= d["value"] * 1.05
     assert d["clocks"] is None or "sm_mhz" in d["clocks"]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """N > 1: the driver launches the reference arm like the product arm; rank 0 alone runs and prints, the other ranks
+    exit 0 without work, and nothing else (launcher or library banners) reaches stdout."""
+    from _harness import REF_LIB
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref not built")
+    port = 29600 + (os.getpid() % 300)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c1",
+                        "--steps", "1", "--warmup", "0", "--ref-spp", "1"], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
