@@ -154,6 +154,12 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
     }
+    // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
+    cudaFuncSetAttribute(k_accumulate_gauss_tiled<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute(k_accumulate_gauss_tiled<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute(k_accumulate_gauss_tiled<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute(k_accumulate_gauss_tiled<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaGetLastError();
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     if (const char *ms = getenv("GNX_MERGE_SHADOW")) ctx->merge_shadow = ms[0] != '0';
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
@@ -717,7 +723,6 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             const int grid = std::min(tilesX * tilesY, ctx->sm_count * 8);
             const size_t smem = perSample * (size_t)(chunk | 1);
             auto launch = [&](auto kern) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
                 kern<<<grid, kFilmTW * kFilmTH, smem, st>>>(psb, ctx->accum, rcb, filt, chunk, tilesX, tilesY);
             };
             if (filt.reach == 2 && chunk == 3) launch(k_accumulate_gauss_tiled<2, 3>);
