@@ -32,6 +32,7 @@ struct gnx_ctx {
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
     bool merge_extend = true;      // GNX_MERGE_EXTEND=0: the any-hit rays of a bounce get their own launch(es)
+    int film_chunk = 0;            // GNX_FILM_CHUNK: samples per pixel staged at a time by the tiled Gaussian gather (0 = auto)
     bool film_simple = false;      // GNX_FILM_SIMPLE=1: Gaussian film with the per-pixel gather instead of the tiled one
     bool merge_shadow = true;      // GNX_MERGE_SHADOW=0: shadow A and B rays in two launches
     float bvh_build_ms = 0;        // device time of the last device-side BVH build (0: the caller supplied the nodes)
@@ -156,6 +157,7 @@ int gnx_create(gnx_ctx **out, int device) {
     }
     // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute(k_accumulate_gauss_tiled<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
@@ -163,6 +165,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
     if (const char *ms = getenv("GNX_MERGE_SHADOW")) ctx->merge_shadow = ms[0] != '0';
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
+    if (const char *fc = getenv("GNX_FILM_CHUNK")) ctx->film_chunk = atoi(fc);
     if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
@@ -718,6 +721,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         const size_t perSample = (size_t)(3 + 2 * nw) * srcPx * sizeof(float);
         int chunk = (int)std::min<size_t>((size_t)72 * 1024 / perSample, 5);
         if (chunk % 2 == 0 && chunk > 0) --chunk;  // the kernel's sample stride is chunk | 1: an odd chunk wastes no padding
+        if (ctx->film_chunk > 0 && ctx->film_chunk <= chunk) chunk = ctx->film_chunk;  // GNX_FILM_CHUNK (tuning)
         if (chunk >= 1 && !ctx->film_simple) {
             const int tilesX = (rcb.width + kFilmTW - 1) / kFilmTW, tilesY = (rcb.height + kFilmTH - 1) / kFilmTH;
             const int grid = std::min(tilesX * tilesY, ctx->sm_count * 8);
@@ -726,6 +730,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
                 kern<<<grid, kFilmTW * kFilmTH, smem, st>>>(psb, ctx->accum, rcb, filt, chunk, tilesX, tilesY);
             };
             if (filt.reach == 2 && chunk == 3) launch(k_accumulate_gauss_tiled<2, 3>);
+            else if (filt.reach == 2 && chunk == 1) launch(k_accumulate_gauss_tiled<2, 1>);
             else if (filt.reach == 1 && chunk == 5) launch(k_accumulate_gauss_tiled<1, 5>);
             else if (filt.reach == 3 && chunk == 1) launch(k_accumulate_gauss_tiled<3, 1>);
             else launch(k_accumulate_gauss_tiled<0, 0>);
