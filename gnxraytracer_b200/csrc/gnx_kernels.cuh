@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(kFilmTW * kFilmTH) k_accumulate_gauss_tiled(Pa
         for (int s0 = 0; s0 < rc.batch_spp; s0 += chunk) {
             const int n = rc.batch_spp - s0 < chunk ? rc.batch_spp - s0 : chunk;
             __syncthreads();
-            for (int i = threadIdx.x; i < npx * chunk; i += blockDim.x) {
+            // (compile-time trip count for the <RT, CT> variants: unrolled, so that the global loads of a thread's five or six
+            // items are in flight together instead of one dependent load -> exp -> store chain per item)
+#pragma unroll
+            for (int i = threadIdx.x; i < npx * chunk; i += kFilmTW * kFilmTH) {
                 const int spx = i / chunk, s = i - spx * chunk;
                 const int row = spx / SW;
                 const int sx = tx0 - r + (spx - row * SW), sy = ty0 - r + row;
