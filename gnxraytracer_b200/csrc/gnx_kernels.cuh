@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, Pat
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
 // stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
-__global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int direct,
-                                                     DevStats *st) {
+template <int DIRECT>  // 0 Whitted, 1 DirectLighting UniformSampleOne, 2 UniformSampleAll
+__global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
     const int n = rc.npix * rc.batch_spp;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
         if (slot < n) {
             int pixel, sample;
             slot_to_sample(rc, slot, &pixel, &sample);
-            V3 L = recursive_li<8>(sc, rc, direct, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
+            V3 L = recursive_li<8, DIRECT>(sc, rc, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();

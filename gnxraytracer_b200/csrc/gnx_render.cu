@@ -153,7 +153,7 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
     }
     // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
@@ -750,7 +750,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
             tm.begin(ST_EXTEND);
             if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
-            else k_recursive<<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, p->integrator - GNX_INTEGRATOR_WHITTED, ctx->d_stats);
+            else if (p->integrator == GNX_INTEGRATOR_WHITTED) k_recursive<0><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
+            else if (p->integrator == GNX_INTEGRATOR_DIRECT) k_recursive<1><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
+            else k_recursive<2><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
             launches += accumulate(psv, rcn);

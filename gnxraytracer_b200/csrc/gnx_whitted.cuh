@@ -243,8 +243,10 @@ constexpr int kMaxRecDepth = 16;
 // handed out in the order the vertices ask for them (depth first); a sample whose recursion visits more vertices than
 // maxDepth finds none left and falls back to one Get2D pair per light (core/Integrator.cpp:38-43).  Ordinary dimensions
 // start behind the arrays' (GlobalSampler::Get1D / Get2D skip [arrayStartDim, arrayEndDim), core/Sampler.cpp).
-template <int MAXL>
-GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct, int px, int py, int sample, int2 *stack, int stride,
+// (direct is a template parameter: with the three integrators in one body the Whitted render measured 12 % slower —
+// the UniformSampleAll code costs registers in the hot loop even when it never runs.)
+template <int MAXL, int direct>
+GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int py, int sample, int2 *stack, int stride,
                       TraversalCounters &cnt, RecCounters &rcnt) {
     const uint64_t pixOffset = halton_pixel_offset(sc.smp, px, py);
     const uint64_t hidx = pixOffset + (uint64_t)sample * (uint64_t)sc.smp.stride;
@@ -293,7 +295,7 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct,
             // ---- emitted light, then the direct illumination of the integrator
             if (s.light >= 0) L += fr.weight * area_light_L(sc.lights[s.light], s.n, s.wo);
             V3 lightL(0.f);
-            if (direct == 0) {
+            if constexpr (direct == 0) {
                 for (int j = 0; j < sc.n_lights; ++j) {
                     float u0, u1;
                     smp.get2d(&u0, &u1);
@@ -306,7 +308,7 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct,
                     if (!is_black(f) && w_unoccluded(sc, s, ls, stack, stride, cnt, rcnt))
                         lightL += div_each(f * ls.Li * absdot(ls.wi, ns), ls.pdf);
                 }
-            } else if (direct == 2) {
+            } else if constexpr (direct == 2) {
                 // UniformSampleAllLights (core/Integrator.cpp:25-55)
                 for (int j = 0; j < sc.n_lights; ++j) {
                     const int n = sc.light_nsamples ? sc.light_nsamples[j] : 1;
@@ -369,4 +371,15 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct,
     return L;
 }
 
+}  // namespace gnx
+
+namespace gnx {
+// run-time selection of the integrator (host emulation, tests)
+template <int MAXL>
+GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct, int px, int py, int sample, int2 *stack, int stride,
+                      TraversalCounters &cnt, RecCounters &rcnt) {
+    if (direct == 0) return recursive_li<MAXL, 0>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+    if (direct == 1) return recursive_li<MAXL, 1>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+    return recursive_li<MAXL, 2>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+}
 }  // namespace gnx
