@@ -61,6 +61,8 @@ WORKLOADS = {
            "W1: WhittedIntegrator, Cornell room + Mirror / Glass / Plastic spheres (11 532 tris), area + Point + Spot + Distant + SkyBox lights, 1024x1024, 16 spp, maxDepth 5"),
     "d1": ("lights", 31, 4, 3, 1024, 1024, 16, 5,
            "D1: DirectLightingIntegrator (UniformSampleOne), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
+    "da1": ("lights", 31, 4, 4, 1024, 1024, 16, 5,
+            "DA1: DirectLightingIntegrator (UniformSampleAll: every light at every vertex, 5 samples per area-light triangle), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
 }
 
 
