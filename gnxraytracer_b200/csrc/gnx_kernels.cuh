@@ -257,7 +257,7 @@ constexpr int kShadeBlock = GNX_SHADE_BLOCK;
 #ifndef GNX_SHADE_MINBLOCKS
 #define GNX_SHADE_MINBLOCKS(MAXL) ((MAXL) > 2 ? 8 : 7)
 #endif
-template <int MAXL>
+template <int MAXL, bool NEXT = false>
 __global__ void __launch_bounds__(kShadeBlock, GNX_SHADE_MINBLOCKS(MAXL)) k_shade(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
                                                         int type, int outQ) {
     const int n = q.counts[kCntShade0 + type];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kShadeBlock, GNX_SHADE_MINBLOCKS(MAXL)) k_shad
         ShadeOut out;
         if (i < n) slot = list[i];
         // every thread of the block walks through the stages (barriers inside), with or without an item
-        shade_slot<MAXL, GNX_SHADE_SYNC != 0>(sc, ps, rc, slot, out, i < n);
+        shade_slot<MAXL, GNX_SHADE_SYNC != 0, NEXT>(sc, ps, rc, slot, out, i < n);
         int idx = warp_push(&q.counts[kCntShadow], out.haveShadowA);
         if (idx >= 0) q.shadow_q[idx] = out.shA;
         idx = warp_push(&q.counts[kCntShadow + 1], out.haveShadowB);

@@ -250,6 +250,44 @@ inline bool build_node4(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
     return true;
 }
 
+// Index hygiene at the ABI boundary: every index the kernels will dereference is checked here, once, so that a bad
+// description is GNX_ERR_INVALID at upload instead of an out-of-range device read at render time.
+inline bool validate_scene_desc(const gnx_scene_desc &d, std::string *err) {
+    const gnx_geometry &g = d.geom;
+    if (d.n_materials < 0 || d.n_textures < 0 || d.n_lights < 0 || d.n_media < 0) { *err = "negative array count"; return false; }
+    if (d.n_materials > 0 && !d.materials) { *err = "materials is NULL with n_materials > 0"; return false; }
+    if (d.n_textures > 0 && !d.textures) { *err = "textures is NULL with n_textures > 0"; return false; }
+    if (d.n_lights > 0 && !d.lights) { *err = "lights is NULL with n_lights > 0"; return false; }
+    if (d.n_media > 0 && !d.media) { *err = "media is NULL with n_media > 0"; return false; }
+    for (int i = 0; i < g.n_nodes; ++i) {
+        const gnx_bvh_node &nd = g.nodes[i];
+        if (nd.n_prims == 0) continue;
+        if (nd.offset < 0 || (long long)nd.offset + nd.n_prims > (long long)g.n_prims) { *err = "BVH leaf primitive range out of bounds"; return false; }
+    }
+    for (int k = 0; k < g.n_prims; ++k) {
+        if (g.prim_material[k] < -1 || g.prim_material[k] >= d.n_materials) { *err = "prim_material out of range"; return false; }
+        if (g.prim_light) {
+            const int l = g.prim_light[k];
+            if (l < -1 || l >= d.n_lights) { *err = "prim_light out of range"; return false; }
+            if (l >= 0 && d.lights[l].type != GNX_LIGHT_AREA_TRI) { *err = "prim_light points at a light that is not an area light"; return false; }
+        }
+        if (g.prim_medium_in && g.prim_medium_out &&
+            (g.prim_medium_in[k] < -1 || g.prim_medium_in[k] >= d.n_media || g.prim_medium_out[k] < -1 || g.prim_medium_out[k] >= d.n_media)) {
+            *err = "prim_medium index out of range"; return false;
+        }
+    }
+    for (int i = 0; i < d.n_materials; ++i) {
+        for (int s = 0; s < GNX_MAT_MAX_RGB; ++s)
+            if (d.materials[i].rgb_tex[s] < -1 || d.materials[i].rgb_tex[s] >= d.n_textures) { *err = "texture index out of range"; return false; }
+        for (int s = 0; s < GNX_MAT_MAX_F; ++s)
+            if (d.materials[i].f_tex[s] < -1 || d.materials[i].f_tex[s] >= d.n_textures) { *err = "texture index out of range"; return false; }
+    }
+    for (int i = 0; i < d.n_lights; ++i)
+        if (d.lights[i].medium < -1 || d.lights[i].medium >= d.n_media) { *err = "light medium index out of range"; return false; }
+    if (d.camera.medium < -1 || d.camera.medium >= d.n_media) { *err = "camera medium index out of range"; return false; }
+    return true;
+}
+
 // Packs the node array in the layout the library was compiled for (GNX_BVH_WIDTH).
 inline bool build_nodes(const gnx_bvh_node *nodes, int n, std::vector<float4> &out, int *count, std::string *err) {
 #if GNX_BVH_WIDTH == 4
@@ -317,6 +355,7 @@ inline bool derive_light_power(const gnx_light &l, float *out) {
     case GNX_LIGHT_POINT: for (int i = 0; i < 3; ++i) c[i] = (4 * kPiF) * l.L[i]; break;
     case GNX_LIGHT_SPOT: for (int i = 0; i < 3; ++i) c[i] = l.L[i] * 2 * kPiF * (1 - .5f * (l.cos_falloff + l.cos_total)); break;
     case GNX_LIGHT_DISTANT: for (int i = 0; i < 3; ++i) c[i] = l.L[i] * kPiF * l.area * l.area; break;
+    case GNX_LIGHT_SKYBOX: *out = 0.f; return true;  // SkyBoxLight::Power() is Spectrum(0) (lights/SkyBoxLight.h)
     default: return false;
     }
     *out = lum(c[0], c[1], c[2]);

@@ -88,7 +88,7 @@ GNX_D void primary_begin(const DeviceScene &sc, int px, int py, int sample, uint
 GNX_D int primary_finish(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, uint32_t hidx, V3 d,
                          const Trav &t) {
     if (!t.hit) {
-        V3 Le = sc.env.present ? env_Le(sc.env, d) : V3(0.f);
+        V3 Le = sc.skybox.present ? scene_le_cold(sc, t.o, d) : (sc.env.present ? env_Le(sc.env, d) : V3(0.f));
         ps.L[slot] = make_float4(Le.x, Le.y, Le.z, 0.f);
         return -1;
     }
@@ -121,11 +121,12 @@ GNX_D int extend_finish(const DeviceScene &sc, const PathState &ps, const Render
         ps.hit[slot] = make_float4(t.h.b0, t.h.b1, t.h.b2, i2f(t.prim));
         return shade_type_of(matWord);
     }
-    if (emitOk && sc.env.present) {
+    if (emitOk && (sc.env.present || sc.skybox.present)) {
         // for (light : scene.infiniteLights) L += beta * light->Le(ray)
         const float4 b = ps.beta[slot], rd = ps.ray_d[slot];
         float4 L = ps.L[slot];
-        V3 add = V3(b.x, b.y, b.z) * env_Le(sc.env, V3(rd.x, rd.y, rd.z));
+        const V3 dir(rd.x, rd.y, rd.z);
+        V3 add = V3(b.x, b.y, b.z) * (sc.skybox.present ? scene_le_cold(sc, t.o, dir) : env_Le(sc.env, dir));
         L.x += add.x; L.y += add.y; L.z += add.z;
         ps.L[slot] = L;
     }
@@ -177,7 +178,10 @@ struct ShadeOut {
 #else
 #define GNX_STAGE_SYNC() do { } while (0)
 #endif
-template <int MAXL, bool SYNC = false>
+// NEXT: the scene holds PointLight / SpotLight / DistantLight / SkyBoxLight records as well (EstimateDirect's delta
+// branch, core/Integrator.cpp:148,159; SkyBoxLight::Pdf_Li is 0, so its BSDF-sampling half contributes nothing).  A
+// template parameter so that the area + environment scenes of the BASELINE configs keep their code size.
+template <int MAXL, bool SYNC = false, bool NEXT = false>
 GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, ShadeOut &out, bool valid = true) {
     const int kNonSpec = BSDF_ALL & ~BSDF_SPECULAR;
     out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
@@ -229,13 +233,15 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
     }
     const gnx_light &light = sc.lights[lightNum];
     const bool isEnv = sc.n_lights > 0 && light.type == GNX_LIGHT_INFINITE;
+    const bool isArea = !NEXT ? !isEnv : (sc.n_lights > 0 && light.type == GNX_LIGHT_AREA_TRI);
+    bool lsDelta = false;
     V3 wi(0.f), f(0.f);
     float pdf = 0;
     int flags = 0;
 #pragma unroll 1
     for (int pass = P_LIGHT; pass <= P_CONT; ++pass) {
         GNX_STAGE_SYNC();
-        const bool run = live && (pass == P_CONT || selPdf != 0);
+        const bool run = live && (pass == P_CONT || (selPdf != 0 && (pass == P_LIGHT || isEnv || isArea)));
         const int lobeFlags = pass == P_CONT ? BSDF_ALL : kNonSpec;
         const int matching = pass == P_CONT ? bsdf.num_components(BSDF_ALL) : nNonSpec;
         const V3 woW = pass == P_CONT ? -rayD : s.wo;  // isect.wo is normalized, PathIntegrator's wo = -ray.d is not
@@ -249,7 +255,13 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
         flags = 0;
         if (!run) {
         } else if (pass == P_LIGHT) {
-            const bool ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
+            bool ok;
+            if (NEXT && !isEnv && !isArea) {
+                WLightSample wl;
+                ok = w_sample_li(sc, light, s.p, ul0, ul1, &wl);
+                ls.wi = wl.wi; ls.Li = wl.Li; ls.pdf = wl.pdf; ls.pl = wl.target; ls.nl = wl.targetN; ls.plError = wl.targetErr;
+                lsDelta = wl.delta;
+            } else ok = isEnv ? env_sample_li(sc.env, ul0, ul1, &ls) : area_sample_li(sc, light, s.p, ul0, ul1, &ls);
             have = ok && ls.pdf > 0 && !is_black(ls.Li) && wo.z != 0;
             wi = ls.wi;
             wiL = bsdf.to_local(wi);
@@ -276,10 +288,11 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
             const float scatteringPdf = pdf;
             if (!is_black(f)) {
                 V3 origin, dirv;
-                if (isEnv) {
+                if (isEnv || (NEXT && !isArea)) {
                     // VisibilityTester(ref, Interaction(ref.p + wi * (2 * worldRadius), ...)): the far
                     // point has neither normal nor error bound, so SpawnRayTo's target is the point itself
-                    V3 p1 = s.p + ls.wi * (2 * sc.env.world_radius);
+                    // (likewise the position of a point / spot light and the far point of a distant / skybox light)
+                    V3 p1 = isEnv ? s.p + ls.wi * (2 * sc.env.world_radius) : ls.pl;
                     origin = offset_ray_origin(s.p, s.pError, s.n, p1 - s.p);
                     dirv = p1 - origin;
                 } else {
@@ -287,8 +300,9 @@ GNX_D void shade_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
                     V3 target = offset_ray_origin(ls.pl, ls.plError, ls.nl, origin - ls.pl);
                     dirv = target - origin;
                 }
+                // IsDeltaLight: no MIS weight (core/Integrator.cpp:157-163)
                 float weight = (ls.pdf * ls.pdf) / (ls.pdf * ls.pdf + scatteringPdf * scatteringPdf);
-                V3 Ld = div_each(f * ls.Li * weight, ls.pdf);
+                V3 Ld = (NEXT && lsDelta) ? div_each(f * ls.Li, ls.pdf) : div_each(f * ls.Li * weight, ls.pdf);
                 V3 c = beta * div_each(Ld, selPdf);
                 out.shA.o_tmax = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
                 out.shA.d_path = make_float4(dirv.x, dirv.y, dirv.z, i2f(slot));
@@ -447,7 +461,14 @@ GNX_D void build_spatial_voxel(const DeviceScene &sc, int vox, float *func, floa
         for (int j = 0; j < nL; ++j) {
             const gnx_light &l = sc.lights[j];
             LightSample ls;
-            bool ok = l.type == GNX_LIGHT_INFINITE ? env_sample_li(sc.env, u0, u1, &ls) : area_sample_li(sc, l, po, u0, u1, &ls);
+            bool ok;
+            if (l.type == GNX_LIGHT_INFINITE) ok = env_sample_li(sc.env, u0, u1, &ls);
+            else if (l.type == GNX_LIGHT_AREA_TRI) ok = area_sample_li(sc, l, po, u0, u1, &ls);
+            else {
+                WLightSample wl;
+                ok = w_sample_li(sc, l, po, u0, u1, &wl);
+                ls.pdf = wl.pdf; ls.Li = wl.Li;
+            }
             if (ok && ls.pdf > 0) fv[j] += lum_y(ls.Li) / ls.pdf;
         }
     }

@@ -264,6 +264,10 @@ int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
         d = &reordered.desc;
     }
     const gnx_geometry &g = d->geom;
+    {
+        std::string verr;
+        if (!validate_scene_desc(*d, &verr)) { if (lbvhNodes) cudaFree(lbvhNodes); return fail(ctx, GNX_ERR_INVALID, verr); }
+    }
     if (d->n_materials > (1 << 20) - 2) return fail(ctx, GNX_ERR_UNSUPPORTED, "too many materials");
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type < 0 || d->materials[i].type > GNX_MAT_DISNEY)
@@ -611,8 +615,11 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     const bool recursive = p->integrator >= GNX_INTEGRATOR_WHITTED;
     if (p->integrator == GNX_INTEGRATOR_DIRECT_ALL && 5 + 4 * (long long)p->max_depth * ctx->sc.n_lights + 64 > 1000)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "UniformSampleAll: the sample arrays of maxDepth x lights need more Halton dimensions than the sampler has (1000)");
-    if (!recursive && ctx->has_next_lights)
-        return fail(ctx, GNX_ERR_UNSUPPORTED, "point / spot / distant / skybox lights are rendered by GNX_INTEGRATOR_WHITTED and GNX_INTEGRATOR_DIRECT");
+    if (p->integrator == GNX_INTEGRATOR_VOLPATH && ctx->has_next_lights)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "point / spot / distant / skybox lights are rendered by the Path, Whitted and DirectLighting integrators, not by VolPath");
+    // the recursive integrators keep their depth-first frames in a fixed array (gnx_whitted.cuh, kMaxRecDepth)
+    if (recursive && p->max_depth > kMaxRecDepth)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting: max_depth above 16 is not supported (fixed recursion frame stack)");
     if (recursive && ctx->sc.smp.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use the Halton sampler");
     if (recursive && ctx->sc.n_media > 0) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting ignore participating media");
     if (recursive && ctx->n_textures_host > 0)
@@ -628,9 +635,10 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (p->film != GNX_FILM_BOX && !(p->filter_radius > 0.f && p->filter_radius <= 16.f && p->filter_alpha >= 0.f))
         return fail(ctx, GNX_ERR_INVALID, "Gaussian film: filter_radius must be in (0, 16] and filter_alpha >= 0");
     // the Halton index must fit the 32-bit path state
-    unsigned long long maxIdx = (unsigned long long)(p->first_sample + p->spp) * (unsigned long long)ctx->sc.smp.stride;
+    const unsigned long long lastSample = (unsigned long long)p->first_sample + (unsigned long long)p->spp;
+    unsigned long long maxIdx = lastSample * (unsigned long long)ctx->sc.smp.stride;
     if (ctx->sc.smp.type == GNX_SAMPLER_HALTON && maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
-    if (ctx->sc.smp.type == GNX_SAMPLER_PCG32 && p->first_sample + p->spp >= (1 << 20)) return fail(ctx, GNX_ERR_UNSUPPORTED, "PCG32 stream ids hold 20 bits of sample number");
+    if (ctx->sc.smp.type == GNX_SAMPLER_PCG32 && lastSample >= (1ull << 20)) return fail(ctx, GNX_ERR_UNSUPPORTED, "PCG32 stream ids hold 20 bits of sample number");
     return GNX_OK;
 }
 
@@ -682,7 +690,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / npix));
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix))) return rc;
 
-    cudaStream_t st = userStream ? userStream : ctx->stream;
+    cudaStream_t st = userStream;  // gnx_render_device maps a NULL stream to the legacy default stream (see gnxrt.h)
     set_l2_window(ctx, st);
     const DeviceScene &sc = ctx->sc;
     // the second accumulator is only needed when shadow A and B rays share a launch
@@ -784,7 +792,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
-                if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
+                if (ctx->has_next_lights) {  // point / spot / distant / skybox records: the variant with every Light::Sample_Li
+                    if (t == GNX_MAT_DISNEY) k_shade<8, true><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
+                    else k_shade<2, true><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
+                } else if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
                 else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
                 ++launches;
             }
@@ -868,7 +879,7 @@ double gnx_bvh_build_ms(const gnx_ctx *ctx) { return ctx ? (double)ctx->bvh_buil
 int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, gnx_stats *stats) {
     if (!ctx || !rgba_out) return GNX_ERR_INVALID;
     // the device-to-host copy is queued right behind the film kernel; one synchronisation at the end
-    int rc = render_impl(ctx, params, nullptr, nullptr, stats, true);
+    int rc = render_impl(ctx, params, nullptr, ctx->stream, stats, true);
     if (rc) return rc;
     const size_t bytes = (size_t)params->width * params->height * sizeof(float4);
     GNX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->rgba, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -878,7 +889,9 @@ int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, g
 
 int gnx_render_device(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_dev, void *stream, gnx_stats *stats) {
     if (!ctx || !rgba_dev) return GNX_ERR_INVALID;
-    return render_impl(ctx, params, rgba_dev, (cudaStream_t)stream, stats);
+    // stream 0 is the CALLER's default stream (cudaStreamLegacy), not a private one: work queued by the caller before and
+    // after this call on that stream is ordered with the render, whatever the caller's stream flags are
+    return render_impl(ctx, params, rgba_dev, stream ? (cudaStream_t)stream : cudaStreamLegacy, stats);
 }
 
 int gnx_primary_hits(gnx_ctx *ctx, const gnx_render_params *p, int32_t sample, int32_t *prim_id_out) {

@@ -462,4 +462,148 @@ GNX_D int choose_light(const DeviceScene &sc, V3 p, float u, float *pdf) {
     return offset;
 }
 
+// ---- every light type behind one interface (Light::Sample_Li / Pdf_Li / Le, lights/*.cpp): DiffuseAreaLight and
+// InfiniteAreaLight above, plus PointLight, SpotLight, DistantLight and SkyBoxLight.  Used by the wavefront
+// PathIntegrator's shade stage when the scene holds one of the latter four, by the spatial light-table build, and by the
+// Whitted / DirectLighting kernels (gnx_whitted.cuh).
+struct WLightSample {
+    V3 wi, Li;
+    float pdf;
+    V3 target, targetN, targetErr;  // VisibilityTester p1 (normal and error zero for points in space)
+    bool delta;                     // IsDeltaLight(flags)
+};
+
+// SpotLight::Falloff, lights/SpotLight.cpp:33-43
+GNX_D float spot_falloff(const gnx_light &l, V3 w) {
+    M44 w2l;
+    for (int i = 0; i < 16; ++i) w2l.m[i] = l.world_to_light[i];
+    V3 wl = normalize(xform_vector(w2l, w));
+    float cosTheta = wl.z;
+    if (cosTheta < l.cos_total) return 0;
+    if (cosTheta >= l.cos_falloff) return 1;
+    float delta = (cosTheta - l.cos_total) / (l.cos_falloff - l.cos_total);
+    return (delta * delta) * (delta * delta);
+}
+
+// SkyBoxLight::getLightValue, lights/SkyBoxLight.cpp:27-43
+GNX_D V3 skybox_value(const DevSkybox &sb, float u, float v) {
+    V3 Lv(0.f);
+    if (sb.data) {
+        int w = (int)(u * sb.w), h = (int)(v * sb.h);
+        int offset = (w + h * sb.w) * sb.nc;
+        const float scale = 1.0f / 10.0f;
+        Lv = V3(ldg(sb.data + offset) * scale, ldg(sb.data + offset + 1) * scale, ldg(sb.data + offset + 2) * scale);
+    }
+    return Lv;
+}
+// SkyBoxLight::Le, lights/SkyBoxLight.cpp:57-86 (the reference mixes float and double here: b, t)
+GNX_D V3 skybox_le(const DevSkybox &sb, V3 o, V3 d) {
+    V3 oc = o - sb.center;
+    float a = dot(d, d);
+    float b = (float)(2.0 * (double)dot(oc, d));
+    float c = dot(oc, oc) - sb.radius * sb.radius;
+    float discriminant = b * b - 4 * a * c;
+    if (discriminant < 0) return V3(0.f);
+    float t = (float)(((double)(-b) + sqrt((double)discriminant)) / (2.0 * (double)a));
+    V3 hitPos = o + t * d;
+    V3 hp = hitPos - sb.center;
+    V3 q = div_each(hp, sb.radius);
+    // get_sphere_uv: atan2 / asin are the double overloads in the reference (float arguments promoted)
+    float phi = (float)atan2((double)q.z, (double)q.x);
+    float theta = (float)asin((double)q.y);
+    float u = 1 - (phi + kPi) * kInv2Pi;
+    float v = (theta + kPiOver2) * kInvPi;
+    if (sb.data) return skybox_value(sb, u, v);
+    return V3((hp.x + sb.radius) / (2.f * sb.radius), (hp.y + sb.radius) / (2.f * sb.radius), (hp.z + sb.radius) / (2.f * sb.radius));
+}
+
+// Light::Le summed over the scene's lights for a ray that escapes (only the two infinite kinds return non-zero)
+GNX_D V3 scene_le(const DeviceScene &sc, V3 o, V3 d) {
+    V3 L(0.f);
+    // scene.lights order: whichever infinite light comes first is added first
+    const bool envFirst = !sc.skybox.present || (sc.env.present && sc.env.light_index < sc.skybox.light_index);
+    if (envFirst) {
+        if (sc.env.present) L += env_Le(sc.env, d);
+        if (sc.skybox.present) L += skybox_le(sc.skybox, o, d);
+    } else {
+        L += skybox_le(sc.skybox, o, d);
+        if (sc.env.present) L += env_Le(sc.env, d);
+    }
+    return L;
+}
+
+// scene_le out of line: the traversal kernels call it for escaped rays of scenes with a SkyBoxLight only, and its
+// double-precision atan2 / asin must not cost the hot loop registers.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ V3 scene_le_cold(const DeviceScene &sc, V3 o, V3 d) { return scene_le(sc, o, d); }
+#else
+inline V3 scene_le_cold(const DeviceScene &sc, V3 o, V3 d) { return scene_le(sc, o, d); }
+#endif
+
+// Light::Sample_Li for every light type (lights/*.cpp)
+GNX_D bool w_sample_li(const DeviceScene &sc, const gnx_light &l, V3 refP, float u0, float u1, WLightSample *o) {
+    o->delta = false;
+    o->targetN = V3(0.f);
+    o->targetErr = V3(0.f);
+    switch (l.type) {
+    case GNX_LIGHT_AREA_TRI: {
+        LightSample ls;
+        bool ok = area_sample_li(sc, l, refP, u0, u1, &ls);
+        o->wi = ls.wi; o->Li = ls.Li; o->pdf = ls.pdf;
+        o->target = ls.pl; o->targetN = ls.nl; o->targetErr = ls.plError;
+        return ok;
+    }
+    case GNX_LIGHT_INFINITE: {
+        LightSample ls;
+        bool ok = env_sample_li(sc.env, u0, u1, &ls);
+        o->wi = ls.wi; o->Li = ls.Li; o->pdf = ls.pdf;
+        o->target = refP + ls.wi * (2 * sc.env.world_radius);
+        return ok;
+    }
+    case GNX_LIGHT_POINT:
+    case GNX_LIGHT_SPOT: {
+        const V3 pLight(l.p[0], l.p[1], l.p[2]);
+        o->wi = normalize(pLight - refP);
+        o->pdf = 1.f;
+        o->target = pLight;
+        o->delta = true;
+        V3 I(l.L[0], l.L[1], l.L[2]);
+        if (l.type == GNX_LIGHT_SPOT) I = I * spot_falloff(l, -o->wi);
+        o->Li = div_each(I, length_sq(pLight - refP));
+        return true;
+    }
+    case GNX_LIGHT_DISTANT: {
+        const V3 wLight(l.p[0], l.p[1], l.p[2]);
+        o->wi = wLight;
+        o->pdf = 1;
+        o->target = refP + wLight * (2 * l.area);  // area: the scene's bounding-sphere radius (Preprocess)
+        o->delta = true;
+        o->Li = V3(l.L[0], l.L[1], l.L[2]);
+        return true;
+    }
+    case GNX_LIGHT_SKYBOX: {
+        float theta = u1 * kPi, phi = u0 * 2 * kPi;
+        float cosTheta = cosf(theta), sinTheta = sinf(theta);
+        float sinPhi = sinf(phi), cosPhi = cosf(phi);
+        M44 l2w;
+        for (int i = 0; i < 16; ++i) l2w.m[i] = l.world_to_light[i];  // SKYBOX: LightToWorld
+        o->wi = xform_vector(l2w, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));
+        o->pdf = 1.f / (4 * kPi);
+        o->target = refP + o->wi * (2 * sc.skybox.radius);
+        o->Li = 16 * skybox_value(sc.skybox, u0, u1);
+        return true;
+    }
+    default:
+        o->pdf = 0; o->Li = V3(0.f);
+        return false;
+    }
+}
+
+// Light::Pdf_Li for the BSDF-sampling half of EstimateDirect (0 for SkyBoxLight and the delta lights)
+GNX_D float w_pdf_li(const DeviceScene &sc, const gnx_light &l, V3 refP, V3 rayO, V3 wi) {
+    if (l.type == GNX_LIGHT_AREA_TRI) return area_pdf_li(sc, l, refP, rayO, wi);
+    if (l.type == GNX_LIGHT_INFINITE) return env_pdf_li(sc.env, wi);
+    return 0.f;
+}
+
 }  // namespace gnx

@@ -689,6 +689,57 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
         }
         sc->cam_eye[2] = 6.5; sc->cam_look[1] = -0.4f;
         sc->finalize(soup, width, height, spp, false, Mat4::identity());
+    } else if (nm == "ui" || nm.rfind("ui3d:", 0) == 0) {
+        // The reference UI's live scene (ui/RenderThread.cpp:60-164), same recipe as oracle/ref_harness.cpp::BuildUI: the
+        // mesh (Matte sigma 60) inside the five-wall Cornell box (Oren-Nayar sigma 60), the two-triangle area light with
+        // the mesh's material, a SkyBoxLight of radius 10 without an image.  Every camera ray hits a surface.
+        // p1 x p2 knot quads (0 = 2048 x 213); "ui3d:<path>" reads the mesh from a .3d file instead.
+        auto matte = [&](float r, float g, float b) { gnx_material m = make_material(GNX_MAT_MATTE, GNX_MATF_BUMP_IDENTITY); set_rgb(m, 0, r, g, b); m.f[0] = 60.f; return m; };
+        sc->materials.push_back(matte(0.2f, 0.8f, 0.2f));     // 0 mesh + light quad
+        sc->materials.push_back(matte(0.91f, 0.91f, 0.91f));  // 1 white
+        sc->materials.push_back(matte(0.9f, 0.1f, 0.17f));    // 2 red
+        sc->materials.push_back(matte(0.14f, 0.21f, 0.87f));  // 3 blue
+        const float T[3] = {0.f, -2.9f, 0.f};
+        if (nm == "ui") add_mesh(soup, gnxsk::torus_knot(p1 > 0 ? p1 : 2048, p2 > 0 ? p2 : 213), 20.f, T, 0);
+        else {
+            gnxsk::Mesh file;
+            if (!gnxsk::load_3d(nm.substr(5), &file, &sc->error)) return sc;
+            if (file.nTris() == 0) { sc->error = "mesh file without triangles"; return sc; }
+            add_mesh(soup, file, 20.f, T, 0);
+        }
+        gnxsk::Mesh walls = gnxsk::cornell_walls(5.0f);
+        const float boxT[3] = {-2.5f, -2.5f, -2.5f};
+        for (int i = 0; i < 10; ++i) {
+            gnxsk::Mesh one;
+            for (int v = 0; v < 3; ++v) { one.P.insert(one.P.end(), {walls.P[9 * i + 3 * v], walls.P[9 * i + 3 * v + 1], walls.P[9 * i + 3 * v + 2]}); one.idx.push_back(v); }
+            add_mesh(soup, one, 1.f, boxT, (i == 6 || i == 7) ? 2 : (i == 8 || i == 9) ? 3 : 1);
+        }
+        const float lightT[3] = {0.0f, 2.45f, 0.0f};
+        int firstLight = soup.count();
+        add_mesh(soup, gnxsk::area_light_quad(1.4f), 1.f, lightT, 0);
+        for (int k = firstLight; k < soup.count(); ++k) {
+            const float *p = &soup.p[(size_t)k * 9];
+            Vec3d a{p[3] - p[0], p[4] - p[1], p[5] - p[2]}, b{p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+            Vec3d c = crs(a, b);
+            float cx = (float)c.x, cy = (float)c.y, cz = (float)c.z;
+            gnx_light l{};
+            l.type = GNX_LIGHT_AREA_TRI; l.prim = k; l.two_sided = 0; l.medium = -1;
+            l.L[0] = l.L[1] = l.L[2] = 5.0f;
+            l.area = 0.5f * std::sqrt(cx * cx + cy * cy + cz * cz);
+            sc->lights.push_back(l);
+        }
+        {
+            gnx_light l{};
+            l.type = GNX_LIGHT_SKYBOX; l.prim = -1; l.medium = -1;
+            to_float16(Mat4::identity(), l.world_to_light);  // SKYBOX: LightToWorld
+            sc->lights.push_back(l);
+            gnx_skybox &k = sc->desc.skybox;
+            k.present = 1; k.light_index = (int32_t)sc->lights.size() - 1;
+            k.width = k.height = k.channels = 0; k.data = nullptr;
+            k.center[0] = k.center[1] = k.center[2] = 0.f;
+            k.radius = 10.f;
+        }
+        sc->finalize(soup, width, height, spp, false, Mat4::identity());
     } else if (nm == "dragon" || nm.rfind("dragon3d:", 0) == 0 || nm.rfind("obj:", 0) == 0) {
         // "dragon3d:<path>": the mesh comes from a .3d file, placed like ui/ModelList.cpp:49-69 (plyInfo's x20, then
         // Translate(0, -2.9, 0)); "obj:<path>": a Wavefront OBJ fitted into a sphere of radius 2.5 around (0, -0.4, 0)

@@ -336,7 +336,9 @@ int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, g
 
 /* Same, but the result stays in device memory owned by the caller (a CUDA device pointer to
  * width*height*4 floats, e.g. a torch tensor) so a multi-GPU host can reduce it with NCCL
- * without a host round trip.  stream is a cudaStream_t (or 0). */
+ * without a host round trip.  stream is the cudaStream_t the render is queued on; 0 means the caller's legacy default
+ * stream (cudaStreamLegacy).  The call returns once the work is QUEUED (unless stats are requested, which waits for it):
+ * consumers must be ordered behind it on the same stream, or synchronise that stream. */
 int gnx_render_device(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_dev,
                       void *stream, gnx_stats *stats);
 

@@ -394,6 +394,54 @@ bool BuildSmoke(HarnessScene &hs, int variant) {
     return true;
 }
 
+// The UI's live scene (ui/RenderThread.cpp:60-164): the mesh (Matte sigma 60, green) INSIDE the Cornell box whose five
+// walls are Oren-Nayar sigma 60, the two-triangle area light carrying the mesh's material (ui/ModelList.cpp:140-146), a
+// SkyBoxLight of radius 10 whose image file "1" does not exist (procedural colours through the box's open front),
+// HaltonSampler, and the integrator of ui/RenderThread.cpp:163 (Whitted, maxDepth 5) or :164 (Path, maxDepth 15).
+// The camera looks into the open front of the box: every camera ray hits a surface (100 % coverage).
+// dragon.3d is stripped from the reference snapshot: the mesh is the same torus-knot stand-in as config 2.
+bool BuildUI(HarnessScene &hs, int integrator, int nu, int nv, const std::string &file3d = "") {
+    const float sigma = 60.0f;
+    auto dragonMat = Matte(0.2f, 0.8f, 0.2f, sigma);
+    auto white = Matte(0.91f, 0.91f, 0.91f, sigma);
+    auto red = Matte(0.9f, 0.1f, 0.17f, sigma);
+    auto blue = Matte(0.14f, 0.21f, 0.87f, sigma);
+    if (!file3d.empty()) {
+        FILE *fp = fopen(file3d.c_str(), "rb");
+        if (!fp) { hs.error = "missing mesh " + file3d; return false; }
+        fclose(fp);
+        plyInfo plyi(file3d);
+        gnxsk::Mesh m;
+        for (int i = 0; i < plyi.nVertices; ++i) for (int c = 0; c < 3; ++c) m.P.push_back(plyi.vertexArray[i][c]);
+        m.idx.assign(plyi.vertexIndices, plyi.vertexIndices + 3 * plyi.nTriangles);
+        plyi.Release();
+        AddMesh(hs, m, Translate(Vector3f(0.f, -2.9f, 0.f)), dragonMat, nullptr);
+    } else {
+        gnxsk::Mesh knot = gnxsk::torus_knot(nu, nv);
+        for (float &x : knot.P) x *= 20;
+        AddMesh(hs, knot, Translate(Vector3f(0.f, -2.9f, 0.f)), dragonMat, nullptr);
+    }
+    gnxsk::Mesh walls = gnxsk::cornell_walls(5.0f);
+    Transform box2world = Translate(Vector3f(-2.5f, -2.5f, -2.5f));
+    for (int i = 0; i < 10; ++i) {
+        gnxsk::Mesh one;
+        for (int v = 0; v < 3; ++v) {
+            one.P.insert(one.P.end(), {walls.P[9 * i + 3 * v], walls.P[9 * i + 3 * v + 1], walls.P[9 * i + 3 * v + 2]});
+            one.idx.push_back(v);
+        }
+        AddMesh(hs, one, box2world, (i == 6 || i == 7) ? red : (i == 8 || i == 9) ? blue : white, nullptr);
+    }
+    Spectrum Le(5.0f);
+    AddMesh(hs, gnxsk::area_light_quad(1.4f), Translate(Vector3f(0.0f, 2.45f, 0.0f)), dragonMat, &Le);
+    // ui/ModelList.cpp:163-170: SkyBoxLight(Transform(), (0,0,0), 10, "1", 1)
+    hs.lights.push_back(std::make_shared<SkyBoxLight>(Transform(), Point3f(0.f, 0.f, 0.f), 10.0f, "1", 1));
+    stbi_set_flip_vertically_on_load(0);
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    hs.integrator = (integrator == 2 || integrator == 3) ? integrator : 0;
+    Finish(hs);
+    return true;
+}
+
 void IndexPrims(HarnessScene &hs) {
     if (!hs.cuda || !hs.cuda->flat()) return;
     const auto &ptrs = hs.cuda->flat()->prim_ptr;
@@ -409,6 +457,7 @@ extern "C" {
 //       "dragon"  (p0 = variant, p1 = nu, p2 = nv)
 //       "nano"    (p0 = variant, p1 = nu, p2 = nv)
 //       "smoke"   (p0 = variant)   -> VolPathIntegrator
+//       "ui"      (p0 = gnx_integrator: 0 Path, 2 Whitted, 3 DirectLighting; p1 = nu, p2 = nv)  the UI's live scene
 //       "whitted" / "direct" (p0 = light mask, p1 = sphere subdivision) -> WhittedIntegrator / DirectLightingIntegrator
 void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0, int p1, int p2) {
     auto *hs = new HarnessScene;
@@ -419,6 +468,13 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     else if (hs->name.rfind("dragon3d:", 0) == 0) BuildDragon(*hs, p0, 0, 0, "MonValley1000.hdr", hs->name.substr(9));
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else if (hs->name == "smoke") BuildSmoke(*hs, p0);
+    else if (hs->name == "ui") BuildUI(*hs, p0, p1 > 0 ? p1 : 2048, p2 > 0 ? p2 : 213);
+    else if (hs->name.rfind("ui3d:", 0) == 0) BuildUI(*hs, p0, 0, 0, hs->name.substr(5));
+    else if (hs->name == "lights_path") {
+        // the same room under the wavefront PathIntegrator: delta lights + SkyBoxLight through EstimateDirect
+        BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);
+        hs->integrator = 0;
+    }
     else if (hs->name == "whitted" || hs->name == "direct" || hs->name == "lights") {
         // "lights": the scene kit's name for the same room, p2 = gnx_integrator (2 Whitted, 3 DirectLighting)
         BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);

@@ -34,13 +34,23 @@ SCENES = {
     # LightStrategy::UniformSampleAll: every light at every vertex, samples out of the sampler's 2-D arrays
     "direct_all": ("direct", 31, 2, 4),
     "direct_all_area": ("direct", 1, 2, 4),         # two area-light triangles with nSamples = 5 each
+    # the reference UI's live scene (ui/RenderThread.cpp:60-164): mesh inside the Cornell box, area light + SkyBoxLight;
+    # p0 = gnx_integrator (0: the commented-in PathIntegrator line :164, 2: the default WhittedIntegrator :163)
+    "lights_path": ("lights_path", 31, 2, 0),       # PathIntegrator with area + point + spot + distant + skybox lights
+    "lights_path_img": ("lights_path", 1 | 2 | 32, 2, 0),
+    "ui_path": ("ui", 0, 256, 32),
+    "ui_whitted": ("ui", 2, 256, 32),
+    "ui_path_full": ("ui", 0, 2048, 213),
+    "ui_whitted_full": ("ui", 2, 2048, 213),
 }
 INTEGRATOR_OF = {"whitted": 2, "direct": 3, "smoke": 1}
 
 
 def integrator_of(preset):
     """gnx_integrator of a preset (p2 = 4 selects DirectLightingIntegrator with UniformSampleAll)."""
-    name, _, _, p2 = SCENES[preset]
+    name, p0, _, p2 = SCENES[preset]
+    if name == "ui":
+        return p0
     return 4 if name == "direct" and p2 == 4 else INTEGRATOR_OF.get(name, 0)
 
 

@@ -31,6 +31,7 @@ struct EmulScene {
     std::vector<uint4> dims;
     std::vector<uint16_t> perms;
     unsigned typeMask = 0;
+    bool hasNext = false;  // point / spot / distant / skybox lights present
     float wb[6];
     std::string err;
 };
@@ -59,6 +60,7 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.textures = e.textures.data();
     sc.lights = d->lights;
     sc.n_lights = d->n_lights;
+    for (int i = 0; i < d->n_lights; ++i) e.hasNext |= d->lights[i].type >= GNX_LIGHT_POINT;
     sc.light_nsamples = d->light_n_samples;
     if (g.prim_medium_in && g.prim_medium_out) {
         e.media.resize(g.n_prims);
@@ -200,6 +202,10 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         ShadeOut out;
         out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;
         if (type == kNumShadeTypes - 1) out.alive = shade_null_slot(sc, ps, rc, 0);
+        else if (e.hasNext) {
+            if (type == GNX_MAT_DISNEY) shade_slot<8, false, true>(sc, ps, rc, 0, out);
+            else shade_slot<2, false, true>(sc, ps, rc, 0, out);
+        }
         else if (type == GNX_MAT_DISNEY) shade_slot<8>(sc, ps, rc, 0, out);
         else shade_slot<2>(sc, ps, rc, 0, out);
         if (out.haveShadowA) { ++rays[1]; shadow_item(sc, ps, &out.shA, stack, 1, cnt); }

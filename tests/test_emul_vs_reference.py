@@ -156,3 +156,50 @@ def test_uniform_and_power_light_distributions(ref, emul, strategy):
     assert np.mean(rel < 1e-4) >= 0.999, f"per-sample radiance parity {np.mean(rel < 1e-4)}"
     assert np.mean(np.abs(other - rgb).max(axis=1) / scale < 1e-4) < 0.9, "the strategies should sample differently"
     rs.close(); es.close()
+
+
+@pytest.mark.parametrize("preset,depth", [("ui_path", 15), ("ui_whitted", 5), ("lights_path", 5), ("lights_path_img", 5)])
+def test_ui_scene_and_delta_skybox_lights_under_path(ref, emul, preset, depth):
+    """The reference UI's live scene (ui/RenderThread.cpp:60-164: mesh inside the Cornell box, area light + SkyBoxLight)
+    under the integrator lines :163 (Whitted, maxDepth 5) and :164 (Path, maxDepth 15), and the lights room under the
+    wavefront PathIntegrator: EstimateDirect's delta branch (core/Integrator.cpp:148,159) and SkyBoxLight (Pdf_Li = 0, Le
+    on escape).  Per-sample radiance against the reference's own Li, image against its Render, all three strategies."""
+    from _harness import integrator_of
+    res = 40
+    integ = integrator_of(preset)
+    rs = ref.scene(preset, res, res, 4)
+    es = emul.scene(rs.desc)
+    px, py = grid(res, res)
+    p = RenderParams.make(res, res, 4, max_depth=depth, integrator=integ)
+    sm = np.full(px.size, 2, np.int32)
+    rgb, prim = rs.reference_samples(px, py, sm, max_depth=depth)
+    assert np.mean(rs.to_original(es.primary_hits(res, res, 2)) == prim) >= 0.9999
+    if preset.startswith("ui"):
+        assert np.all(prim >= 0), "the UI camera looks into the box: every camera ray hits"
+    mine = es.samples(p, px, py, sm)
+    scale = np.maximum(np.abs(rgb).max(axis=1), 1e-3)
+    assert np.mean(np.abs(mine - rgb).max(axis=1) / scale < 1e-4) >= 0.999
+    img_ref, _ = rs.render_reference(max_depth=depth)
+    img, st = es.render(p)
+    assert rel_mse(img, img_ref) <= 1e-6 and st.rays_shadow > 0
+    if integ == 0:
+        for strategy in (0, 2):
+            rs.set_light_strategy(strategy)
+            a, _ = rs.render_reference(max_depth=depth)
+            b, _ = emul.scene(rs.desc).render(RenderParams.make(res, res, 4, max_depth=depth, light_strategy=strategy))
+            assert rel_mse(b, a) <= 1e-6
+    rs.close(); es.close()
+
+
+def test_scene_kit_ui_scene_equals_the_harness_one(ref, emul):
+    """The kit's own "ui" scene (what bench.py's U1 workloads render) against the reference's render of the harness one."""
+    from gnxraytracer_b200.api import SceneKit
+    res = 40
+    rs = ref.scene("ui_path", res, res, 4)
+    img_ref, _ = rs.render_reference(max_depth=15)
+    sk = SceneKit("ui", res, res, 4, 0, 256, 32)
+    img, _ = emul.scene(sk.desc).render(RenderParams.make(res, res, 4, max_depth=15))
+    # (another BVH: rays through the room's edges hit either of two walls at the same distance)
+    assert rel_mse(img, img_ref) <= 1e-3
+    assert np.mean(np.abs(img[..., :3] - img_ref[..., :3]).max(axis=2) < 1e-5) >= 0.99
+    rs.close(); sk.close()
