@@ -8,13 +8,17 @@ One step = one full render = W*H*spp camera paths.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm   (CUDA, libgnxrt.so)
   python bench.py --impl reference [...]                         reference arm (the UNMODIFIED reference's
-                                                                  OpenMP PathIntegrator::Render on the host cores)
+                                                                  OpenMP Render on the host cores)
 
-Under torchrun (N > 1) every rank renders the full per-GPU workload on its own slice of the Halton
-sequence (weak scaling: N * 64 spp in total) and the partial framebuffers are sum-reduced to rank 0
-with NCCL inside the timed region.  Prints ONE JSON line on rank 0.
+N > 1 (torchrun, one rank per GPU): every rank attaches its context to ONE job through the library's own
+communicator (gnx_comm_attach; torch.distributed only carries the 128-byte id and the timing reduction).  The job is
+the per-GPU workload times N (weak scaling: N * 64 spp), dealt out as sample ranges by the library, summed onto rank 0
+by ncclReduce queued behind each rank's last film kernel, inside the timed region.  The same line carries a second
+record, "strong_scaling": BASELINE config 5 (3840 x 2160 x 1024 spp, ONE fixed job) split over the N ranks.
+Prints ONE JSON line on rank 0.
 """
 import argparse
+import csv
 import ctypes
 import json
 import os
@@ -40,29 +44,33 @@ def emit(obj):
 
 
 METRIC = "Mpaths/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the six k_trace<3|4> launches of one
-# C2 step: 1676 + 1491 + 941 + 519 + 251 + 82 MB), from the ncu pass of this command kept in profiles/r01_dram_trace.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"c2": 4959e6 / 6}
+# gnx_integrator values (include/gnxrt.h)
+PATH, VOLPATH, WHITTED, DIRECT, DIRECT_ALL = 0, 1, 2, 3, 4
 WORKLOADS = {
-    # name: (scene, p0, p1, p2, width, height, spp, max_depth, description)
-    "c2": ("dragon", 0, 0, 0, 1024, 1024, 64, 5,
-           "C2: dragon-class mesh 872448 tris (torus-knot stand-in for dragon.3d), Plastic, InfiniteAreaLight MonValley1000.hdr, 1024x1024, 64 spp, maxDepth 5, PathIntegrator+Halton"),
-    "c3": ("nano", 0, 0, 0, 1920, 1080, 128, 5,
-           "C3: UV-mapped smooth-shaded mesh (~90k tris, stand-in for nanosuit), DisneyMaterial + ImageTexture, InfiniteAreaLight TropicalRuins1000.hdr, 1920x1080, 128 spp, maxDepth 5"),
-    "c4": ("smoke", 0, 0, 0, 1024, 1024, 64, 5,
-           "C4: VolPathIntegrator, GridDensityMedium density_render.70.volume inside HomogeneousMedium fog, Matte ground, MonValley env, 1024x1024, 64 spp, maxDepth 5, PCG32 stream sampler"),
-    "c1": ("cornell", 0, 3, 0, 512, 512, 16, 5,
-           "C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
+    "c2": dict(scene="dragon", args=(0, 0, 0), w=1024, h=1024, spp=64, depth=5, integ=PATH,
+               desc="C2: dragon-class mesh 872448 tris (torus-knot stand-in for dragon.3d), Plastic, InfiniteAreaLight MonValley1000.hdr, 1024x1024, 64 spp, maxDepth 5, PathIntegrator+Halton"),
+    "c3": dict(scene="nano", args=(0, 0, 0), w=1920, h=1080, spp=128, depth=5, integ=PATH,
+               desc="C3: UV-mapped smooth-shaded mesh (~90k tris, stand-in for nanosuit), DisneyMaterial + ImageTexture, InfiniteAreaLight TropicalRuins1000.hdr, 1920x1080, 128 spp, maxDepth 5"),
+    "c4": dict(scene="smoke", args=(0, 0, 0), w=1024, h=1024, spp=64, depth=5, integ=VOLPATH,
+               desc="C4: VolPathIntegrator, GridDensityMedium density_render.70.volume inside HomogeneousMedium fog, Matte ground, MonValley env, 1024x1024, 64 spp, maxDepth 5, PCG32 stream sampler"),
+    "c1": dict(scene="cornell", args=(0, 3, 0), w=512, h=512, spp=16, depth=5, integ=PATH,
+               desc="C1: Cornell box + 2 icospheres (Mirror, Glass), DiffuseAreaLight, 512x512, 16 spp, maxDepth 5"),
     # BASELINE config 5: ONE fixed job split across the ranks by sample range (strong scaling, "scaling": "strong")
-    "c5": ("dragon", 0, 0, 0, 3840, 2160, 1024, 5,
-           "C5: dragon-class mesh 872448 tris, Plastic, MonValley env, 3840x2160, 1024 spp in total, sample ranges dealt to the ranks, maxDepth 5"),
-    # SURVEY 8f rank 1 (the UI's default integrator): not a BASELINE config, measured to the same bar
-    "w1": ("lights", 31, 4, 2, 1024, 1024, 16, 5,
-           "W1: WhittedIntegrator, Cornell room + Mirror / Glass / Plastic spheres (11 532 tris), area + Point + Spot + Distant + SkyBox lights, 1024x1024, 16 spp, maxDepth 5"),
-    "d1": ("lights", 31, 4, 3, 1024, 1024, 16, 5,
-           "D1: DirectLightingIntegrator (UniformSampleOne), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
-    "da1": ("lights", 31, 4, 4, 1024, 1024, 16, 5,
-            "DA1: DirectLightingIntegrator (UniformSampleAll: every light at every vertex, 5 samples per area-light triangle), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
+    "c5": dict(scene="dragon", args=(0, 0, 0), w=3840, h=2160, spp=1024, depth=5, integ=PATH, strong=True,
+               desc="C5: dragon-class mesh 872448 tris, Plastic, MonValley env, 3840x2160, 1024 spp in total, sample ranges dealt to the ranks, maxDepth 5"),
+    # The reference UI's live scene (ui/RenderThread.cpp:60-164): the mesh INSIDE the Cornell box, area light + SkyBoxLight,
+    # every camera ray hits a surface.  u1p = the PathIntegrator line (:164, maxDepth 15), u1w = the default Whitted (:163).
+    "u1p": dict(scene="ui", args=(PATH, 0, 0), w=1024, h=1024, spp=32, depth=15, integ=PATH,
+                desc="U1p: the UI's live scene (872448-tri mesh Matte sigma 60 inside the Oren-Nayar Cornell box, area light + SkyBoxLight; ui/RenderThread.cpp:60-164), PathIntegrator maxDepth 15 (line :164), HaltonSampler 32 spp, 1024x1024"),
+    "u1w": dict(scene="ui", args=(WHITTED, 0, 0), w=1024, h=1024, spp=32, depth=5, integ=WHITTED,
+                desc="U1w: the UI's live scene, WhittedIntegrator maxDepth 5 (the UI's default, ui/RenderThread.cpp:163), HaltonSampler 32 spp, 1024x1024"),
+    # not BASELINE configs, measured to the same bar
+    "w1": dict(scene="lights", args=(31, 4, WHITTED), w=1024, h=1024, spp=16, depth=5, integ=WHITTED,
+               desc="W1: WhittedIntegrator, Cornell room + Mirror / Glass / Plastic spheres (11 532 tris), area + Point + Spot + Distant + SkyBox lights, 1024x1024, 16 spp, maxDepth 5"),
+    "d1": dict(scene="lights", args=(31, 4, DIRECT), w=1024, h=1024, spp=16, depth=5, integ=DIRECT,
+               desc="D1: DirectLightingIntegrator (UniformSampleOne), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
+    "da1": dict(scene="lights", args=(31, 4, DIRECT_ALL), w=1024, h=1024, spp=16, depth=5, integ=DIRECT_ALL,
+                desc="DA1: DirectLightingIntegrator (UniformSampleAll: every light at every vertex, 5 samples per area-light triangle), same scene as W1, 1024x1024, 16 spp, maxDepth 5"),
 }
 
 
@@ -74,6 +82,56 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_evidence(workload):
+    """Figures that only a profiler can give, read from the committed ncu summaries of THIS command (never measured under
+    the timer): per-launch DRAM bytes of the traversal launches and their lane / issue statistics."""
+    out = {"traffic": None, "traffic_source": None}
+    for name in ("r02_dram_trace_%s.csv" % workload, "r01_dram_trace.csv" if workload == "c2" else None):
+        path = os.path.join(ROOT, "profiles", name) if name else None
+        if not path or not os.path.exists(path):
+            continue
+        per_launch = {}
+        try:
+            with open(path) as f:
+                rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
+            hdr = rows[0]
+            ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+            for r in rows[1:]:
+                if "k_trace<3>" in r[ik] or "k_trace<4>" in r[ik] or "k_trace<0>" in r[ik] or "k_vol" in r[ik] or "k_recursive" in r[ik]:
+                    if r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        per_launch[r[iid]] = per_launch.get(r[iid], 0.0) + float(r[iv].replace(",", ""))
+            if per_launch:
+                out["traffic"] = sum(per_launch.values()) / len(per_launch)
+                out["traffic_source"] = "profiles/" + name + f" ({len(per_launch)} launches)"
+                break
+        except Exception:
+            continue
+    path = os.path.join(ROOT, "profiles", "r02_trace_metrics.json")
+    if os.path.exists(path):
+        try:
+            out["issue"] = json.load(open(path)).get(workload)
+        except Exception:
+            pass
+    return out
+
+
+def host_cpu():
+    model, phys = None, set()
+    try:
+        pid = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and model is None:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("physical id"):
+                pid = line.split(":", 1)[1].strip()
+            elif line.startswith("core id"):
+                phys.add((pid, line.split(":", 1)[1].strip()))
+    except Exception:
+        pass
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return {"model": model, "physical_cores": len(phys) or None, "threads": threads}
 
 
 class ClockSampler:
@@ -119,44 +177,61 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def scene_args(wl):
+    """(scene name, p0, p1, p2) for the scene kit and for the oracle harness (same names on both sides)."""
+    p0, p1, p2 = wl["args"]
+    if wl["scene"] in ("dragon",) or wl["scene"].startswith("dragon3d:"):
+        p1, p2 = p1 or 2048, p2 or 213
+    return wl["scene"], p0, p1, p2
+
+
 def run_reference(args, wl):
-    """Reference arm: the unmodified reference's PathIntegrator::Render (oracle/_ref, built from
-    /root/reference by oracle/Makefile) on all host threads, printf no-op'ed (core/Integrator.cpp:143).
-    Each step is a bounded sample of the workload: the same scene and resolution at a reduced spp
-    (per-sample cost is independent of spp, core/Integrator.cpp:274-291)."""
+    """Reference arm: the unmodified reference's own Render (oracle/_ref/libgnxref.so, built from /root/reference by
+    oracle/Makefile; that library links nothing of this repo's product) on all host threads, printf no-op'ed
+    (core/Integrator.cpp:143).  Each step is a bounded sample of the workload: the same scene and resolution at a reduced
+    spp (per-sample cost is independent of spp, core/Integrator.cpp:274-291).  value = best of the timed steps
+    (best of 3), OMP_PROC_BIND=spread OMP_PLACES=cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # before libgomp initialises (it is loaded with libgnxref.so)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    cpu = host_cpu()
+    os.environ["OMP_NUM_THREADS"] = str(cpu["threads"])  # all the host threads the process may use (torchrun sets it to 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _harness
-    scene, p0, p1, p2, W, H, spp, depth, desc = wl
+    W, H, spp, depth, desc = wl["w"], wl["h"], wl["spp"], wl["depth"], wl["desc"]
     if not os.path.exists(_harness.REF_LIB):
         emit({"impl": "reference", "unavailable": "oracle/_ref/libgnxref.so was not built (no /root/reference at build time)"})
         return 0
     ref = _harness.Ref()
-    # all the host threads the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    sample_spp = args.ref_spp
+    cores = cpu["threads"]
+    sample_spp = min(args.ref_spp, spp)
     lib = ref.lib
-    h = lib.gnxh_scene_create(scene.encode(), W, H, sample_spp, p0, p1 or (2048 if scene == "dragon" else 0), p2 or (213 if scene == "dragon" else 0))
+    scene, p0, p1, p2 = scene_args(wl)
+    h = lib.gnxh_scene_create(scene.encode(), W, H, sample_spp, p0, p1, p2)
     err = lib.gnxh_scene_error(h).decode()
     if err:
         emit({"impl": "reference", "unavailable": err})
         return 0
     rs = _harness.RefScene(lib, h, W, H, sample_spp)
     times = []
-    for i in range(args.warmup + args.steps):
+    steps = max(args.steps, 1)
+    for i in range(args.warmup + steps):
         _, sec = rs.render_reference(max_depth=depth, threads=cores)
         if i >= args.warmup:
             times.append(sec)
-    t = sum(times) / len(times)
+    t = min(times)
     paths = W * H * sample_spp
     value = paths / t / 1e6
-    sample = f"{W}x{H} x {sample_spp} spp of the {spp}-spp workload per step, best-effort all {cores} threads, reference timeConsume, printf interposed"
+    sample = (f"{W}x{H} x {sample_spp} spp of the {spp}-spp workload per step, best of {len(times)} steps (mean {sum(times) / len(times) * 1e3:.0f} ms), "
+              f"{cores} OpenMP threads on {cpu['physical_cores']} physical cores ({cpu['model']}), OMP_PROC_BIND={os.environ['OMP_PROC_BIND']} "
+              f"OMP_PLACES={os.environ['OMP_PLACES']}, reference timeConsume, -O2 -fopenmp, printf interposed")
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": desc, "sample": sample, "bvh_build_s": lib.gnxh_scene_bvh_seconds(h)},
+            "config": {"workload": desc, "sample": sample, "bvh_build_s": lib.gnxh_scene_bvh_seconds(h), "host_cpu": cpu},
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -167,40 +242,65 @@ def cpu_baseline(wl, budget_s=15.0):
     """The reference on this box's host cores, bounded to ~budget_s seconds (rank 0, N = 1 only)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _harness
-    import numpy as np
     if not os.path.exists(_harness.REF_LIB):
         return None, None
-    scene, p0, p1, p2, W, H, spp, depth, _ = wl
+    W, H, spp, depth = wl["w"], wl["h"], wl["spp"], wl["depth"]
     ref = _harness.Ref()
     lib = ref.lib
-    full = (2048, 213) if scene == "dragon" else (p1, p2)
+    scene, p0, p1, p2 = scene_args(wl)
     t0 = time.time()
-    h = lib.gnxh_scene_create(scene.encode(), W, H, 1, p0, p1 or full[0], p2 or full[1])
+    h = lib.gnxh_scene_create(scene.encode(), W, H, 1, p0, p1, p2)
     if lib.gnxh_scene_error(h):
         return None, None
     rs = _harness.RefScene(lib, h, W, H, 1)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cpu = host_cpu()
+    cores = cpu["threads"]
     _, sec1 = rs.render_reference(max_depth=depth, threads=cores)           # 1 spp probe (also warms the light tables)
     n = int(max(1, min(spp, budget_s / max(sec1, 1e-3))))
     rs.close()
-    h = lib.gnxh_scene_create(scene.encode(), W, H, n, p0, p1 or full[0], p2 or full[1])
+    h = lib.gnxh_scene_create(scene.encode(), W, H, n, p0, p1, p2)
     rs = _harness.RefScene(lib, h, W, H, n)
     img, sec = rs.render_reference(max_depth=depth, threads=cores)
     val = W * H * n / sec / 1e6
-    info = {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "reference",
+    info = {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "host_cpu": cpu,
             "sample": f"{W}x{H} x {n} spp of the {spp}-spp workload, one render, reference timeConsume {sec:.2f} s, "
                       f"-O2 -fopenmp, printf interposed, scene+BVH build {time.time() - t0 - sec - sec1:.1f} s untimed"}
     return info, (rs, img, n)
 
 
-def run_ours(args, wl):
+def bridge_e2e(wl, steps):
+    """Wall time of gnx::CUDAPathIntegrator::Render itself — the call a reference app makes (ui/RenderThread.cpp:169-175) —
+    on the reference's own pbr::Scene, FrameBuffer::fbuffer / ubuffer complete on return.  Needs the reference's classes,
+    i.e. oracle/_ref/libgnxbridge.so; reported next to the C-ABI e2e, which needs nothing outside the product."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _harness
+    if not (os.path.exists(_harness.REF_LIB) and os.path.exists(_harness.BRIDGE_LIB)):
+        return None
+    scene, p0, p1, p2 = scene_args(wl)
+    ref = _harness.Ref()
+    h = ref.lib.gnxh_scene_create(scene.encode(), wl["w"], wl["h"], wl["spp"], p0, p1, p2)
+    if ref.lib.gnxh_scene_error(h):
+        return None
+    rs = _harness.RefScene(ref.lib, h, wl["w"], wl["h"], wl["spp"])
+    try:
+        sec = rs.time_cuda_render(steps, max_depth=wl["depth"])
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+    finally:
+        pass
+    paths = wl["w"] * wl["h"] * wl["spp"]
+    rs.close()
+    return {"value": paths / sec / 1e6, "unit": "Mpaths/s", "ms_per_call": sec * 1e3,
+            "call": "gnx::CUDAPathIntegrator::Render(const pbr::Scene&, double&) on the reference's own Scene / Camera / Sampler / FrameBuffer objects (oracle/_ref/libgnxbridge.so)"}
+
+
+def run_ours(args, wl, name):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from gnxraytracer_b200.api import FILM_BOX, FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS, Context, RenderParams, SceneKit
-    from gnxraytracer_b200.dist import reduce_filtered_sums, reduce_framebuffer, sample_range, weak_sample_range
+    from gnxraytracer_b200.api import FILM_BOX, FILM_GAUSSIAN, Context, RenderParams, SceneKit
 
-    scene, p0, p1, p2, W, H, spp, depth, desc = wl
+    W, H, spp, depth, desc, integ = wl["w"], wl["h"], wl["spp"], wl["depth"], wl["desc"], wl["integ"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,122 +311,205 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = Context(local)
-    t0 = time.time()
-    sk = SceneKit(scene, W, H, spp, p0, p1, p2)
-    t_build = time.time() - t0
-    t0 = time.time()
-    ctx.upload(sk.desc)
-    t_upload = time.time() - t0
+    if world > 1:
+        # ONE job over all ranks, inside the library: rank 0's communicator id travels over torch.distributed (plumbing),
+        # every rank attaches its context; from here on the renders are collective and the library deals out the samples
+        box = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_attach(world, rank, box[0])
 
-    strong = args.workload == "c5"
-    first, count = sample_range(spp, rank, world) if strong else weak_sample_range(spp, rank)
-    # VolPathIntegrator for the participating-media config; "lights" carries its gnx_integrator in p2
-    integ = 1 if scene == "smoke" else (p2 if scene == "lights" else 0)
-    # --film gaussian: GaussianFilter(radius 2, alpha 2) reconstruction instead of the reference's box average; N > 1 ranks
-    # exchange the unresolved sums (gnxraytracer_b200.dist.reduce_filtered_sums)
+    def load(wl_):
+        t0 = time.time()
+        sc, p0, p1, p2 = scene_args(wl_)
+        sk_ = SceneKit(sc, wl_["w"], wl_["h"], wl_["spp"], p0, p1, p2)
+        tb = time.time() - t0
+        t0 = time.time()
+        ctx.upload(sk_.desc)
+        return sk_, tb, time.time() - t0
+
+    sk, t_build, t_upload = load(wl)
+    strong = bool(wl.get("strong"))
     gauss = args.film == "gaussian"
-    film = (FILM_GAUSSIAN_SUMS if world > 1 else FILM_GAUSSIAN) if gauss else FILM_BOX
-    params = RenderParams.make(W, H, count, max_depth=depth, first_sample=first, spp_normalize=spp if strong else spp * world, integrator=integ,
-                               film=film, filter_radius=2.0 if gauss else 0.0, filter_alpha=2.0 if gauss else 0.0)
+    # the whole job, identical on every rank: weak scaling = N times the per-GPU samples of every pixel
+    job_spp = spp if strong else spp * world
+    params = RenderParams.make(W, H, job_spp, max_depth=depth, integrator=integ, film=FILM_GAUSSIAN if gauss else FILM_BOX,
+                               filter_radius=2.0 if gauss else 0.0, filter_alpha=2.0 if gauss else 0.0,
+                               partition=1 if args.partition == "tiles" else 0)
     fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-
-    def step_device(want_stats=False):
-        st = ctx.render_device(params, fb.data_ptr(), stream, want_stats=want_stats)
-        if world > 1:
-            (reduce_filtered_sums if gauss else reduce_framebuffer)(fb, 0)
-        return st
+    host_u8 = np.zeros((H, W, 4), np.uint8)
+    host_f = np.zeros((H, W, 4), np.float32)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device(p, steps, warmup):
+        for _ in range(warmup):
+            ctx.render_device(p, fb.data_ptr(), stream, want_stats=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ctx.render_device(p, fb.data_ptr(), stream, want_stats=False)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
     # ---- device-resident throughput ("value") -----------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     clocks = ClockSampler(local)
+    for _ in range(args.warmup):
+        ctx.render_device(params, fb.data_ptr(), stream, want_stats=False)
+    barrier()
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = timed_device(params, args.steps, 0)
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- one instrumented step: per-stage CUDA events, ray / byte counters ----------------------------------
-    st = step_device(want_stats=True)
+    # ---- one instrumented step: per-stage CUDA events, ray / byte counters (this rank's share) ---------------------
+    st = ctx.render_device(params, fb.data_ptr(), stream, want_stats=True)
     barrier()
-    paths_step = W * H * count
-    # ---- end to end: the call a user makes (gnx_render into HOST memory), D2H inside the timed region ------
+    # ---- end to end: host buffers in and out, copies inside the timed region ---------------------------------------
+    #   N = 1: gnx_render_framebuffer, the call the drop-in class makes — float running mean + tonemapped 8-bit image into
+    #          (pageable) host arrays of the FrameBuffer's shape;  N > 1: gnx_render on the attached contexts, the image
+    #          reduced onto rank 0 and copied to pinned host memory there (no host -> device bounce anywhere)
+    def e2e_call():
+        if world == 1:
+            ctx.render_framebuffer(params, 1, host_f, host_u8)
+        else:
+            ctx.render_host_ptr(params, host.data_ptr() if rank == 0 else 0, want_stats=False)
+
     for _ in range(2):
-        ctx.render_host_ptr(params, host.data_ptr(), want_stats=False)
+        e2e_call()
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.render_host_ptr(params, host.data_ptr(), want_stats=False)
-        if world > 1:
-            hb = host.cuda(non_blocking=True)
-            (reduce_filtered_sums if gauss else reduce_framebuffer)(hb, 0)
+        e2e_call()
     barrier()
-    e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    t = torch.tensor([e2e_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3 / args.steps)
+    # the plain float-RGBA call as well (round 1's e2e), for continuity
+    e2e_plain_ms = None
+    if world == 1:
+        ctx.render_host_ptr(params, host.data_ptr(), want_stats=False)
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.render_host_ptr(params, host.data_ptr(), want_stats=False)
+        e2e_plain_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+
+    hit_coverage = None
+    if rank == 0:
+        one = Context(local)  # (primary hits are a single-device parity hook)
+        one.upload(sk.desc)
+        hit_coverage = float(np.mean(one.primary_hits(RenderParams.make(W, H, 1, max_depth=depth, integrator=integ), 0) >= 0))
+        one.close()
+
+    # ---- second record: BASELINE config 5 as ONE fixed job over the N ranks (strong scaling) ------------------------
+    strong_rec = None
+    if args.strong_record and not strong and name == "c2":
+        wl5 = WORKLOADS["c5"]
+        sk5, _, _ = load(wl5)
+        p5 = RenderParams.make(wl5["w"], wl5["h"], wl5["spp"], max_depth=wl5["depth"], integrator=wl5["integ"])
+        fb5 = torch.zeros((wl5["h"], wl5["w"], 4), dtype=torch.float32, device="cuda")
+
+        def timed5(steps, warmup):
+            for _ in range(warmup):
+                ctx.render_device(p5, fb5.data_ptr(), stream, want_stats=False)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                ctx.render_device(p5, fb5.data_ptr(), stream, want_stats=False)
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / steps
+        ms5 = timed5(2, 1)
+        paths5 = wl5["w"] * wl5["h"] * wl5["spp"]
+        strong_rec = {"workload": wl5["desc"], "scaling": "strong", "n_gpus": world, "value": paths5 / ms5 / 1e3, "unit": "Mpaths/s",
+                      "ms_per_step": ms5, "steps": 2, "warmup": 1,
+                      "note": "the 1024 samples of every pixel are dealt to the ranks as contiguous ranges by the library (gnx_comm_attach), 133 MB ncclReduce to rank 0 inside the timed region; speed-up = this value / the N=1 line's"}
+        del fb5
+        sk5.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        total_paths = W * H * spp if strong else paths_step * world  # all ranks together
-        value = total_paths / ms_step / 1e3  # Mpaths/s
+        paths_rank = int(st.paths)                # camera paths of this rank's share in the instrumented step
+        total_paths = W * H * job_spp             # all ranks together
+        value = total_paths / ms_step / 1e3       # Mpaths/s
         e2e_val = total_paths / e2e_ms / 1e3
         ext_ms = st.ms_extend / max(1, st.extend_launches)
         ext_bytes = st.extend_bytes / max(1, st.extend_launches)
         achieved = (ext_bytes / (ext_ms * 1e-3)) / 1e9 if ext_ms > 0 else None
+        ev = ncu_evidence(name)
+        kernel = {PATH: "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)", VOLPATH: "the VolPath launches",
+                  }.get(integ, "k_recursive (Whitted / DirectLighting, one launch per batch)")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc + (", Gaussian film (radius 2, alpha 2)" if gauss else ""), "paths_per_step_per_gpu": paths_step, "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_step * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_step * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
-                       "sample_range": (f"the {spp} samples of every pixel are dealt out as {world} contiguous ranges; NCCL sum-reduce to rank 0 inside the timed region" if strong else f"rank r renders Halton samples [{spp}r, {spp}r+{spp}) of every pixel; NCCL sum-reduce to rank 0 inside the timed region") if world > 1 else f"samples [0, {spp})",
+            "config": {"workload": desc + (", Gaussian film (radius 2, alpha 2)" if gauss else ""),
+                       "hit_coverage": hit_coverage,
+                       "hit_coverage_note": "fraction of the pixels whose camera ray (sample 0) hits a surface; the others read the environment and end",
+                       "paths_per_step_per_gpu": paths_rank,
+                       "l2_policy": f"inputs larger than L2 (126 MB): every step rewrites {paths_rank * 16 / 1e9:.2f} GB of per-sample radiance plus the path state and queues of the paths that hit something (buffers sized {paths_rank * 288 / 1e9:.1f} GB for the wavefront integrators) between launches",
+                       "job": (f"ONE job of {job_spp} spp per pixel over {world} ranks, dealt out by the library ({args.partition}); ncclReduce to rank 0 queued behind each rank's film kernel, inside the timed region"
+                               if world > 1 else f"samples [0, {spp})"),
                        "scene_build_s": round(t_build, 3), "bvh_build_s": round(sk.build_seconds, 3), "scene_upload_s": round(t_upload, 3),
                        "num_prims": sk.num_prims},
             "mrays_per_s": st.rays * (total_paths / max(1, st.paths)) / ms_step / 1e3,
-            "rays_per_path": st.rays / st.paths,
+            "rays_per_path": st.rays / max(1, st.paths),
             "stage_ms": {"raygen": st.ms_raygen, "extend": st.ms_extend, "shade": st.ms_shade, "shadow": st.ms_shadow, "film": st.ms_film,
                          "device_total": st.device_ms,
-                         "note": "extend = the k_trace<3|4|0> launches: camera rays, then per bounce the extension rays TOGETHER WITH the previous bounce's shadow / environment-MIS rays (one mixed launch); shadow = the any-hit launch after the last bounce and the area-light MIS probes"},
-            "roofline": {"bound": "hbm", "kernel": "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_dram_trace.csv)", "peak_source": peak_src,
+                         "note": "rank 0's share; extend = the k_trace<3|4|0> launches: camera rays, then per bounce the extension rays TOGETHER WITH the previous bounce's shadow / environment-MIS rays (one mixed launch); shadow = the any-hit launch after the last bounce and the area-light MIS probes"},
+            "roofline": {"bound": "latency+issue (dependent L1/L2 gathers); NOT hbm: see traffic", "bound_contract": "hbm",
+                         "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": ev["traffic"],
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), " + str(ev["traffic_source"]), "peak_source": peak_src,
                          "launches_per_step": st.extend_launches, "avg_launch_ms": ext_ms,
                          "algorithmic_bytes_per_launch": ext_bytes,
-                         "note": "algorithmic bytes = 32 B x BVH nodes popped + 48 B x triangles tested + 48 B x rays (ray read + hit write), counted by the kernel itself; the scene (97 MB of nodes+triangles) is L2-resident, so DRAM traffic is ~17x below the algorithmic bytes (no re-reads from HBM) and the kernel is bound by instruction issue and L1 wavefronts (profiles/README.md), not by HBM"},
-            "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": ctypes.sizeof(params), "d2h_bytes_per_step": W * H * 16,
-                    "ms_per_step": e2e_ms, "note": "gnx_render(): params in, float RGBA framebuffer out to pinned host memory; scene uploaded once (like the reference, which excludes scene build from timeConsume)"},
+                         "issue": ev.get("issue"),
+                         "note": "achieved = ALGORITHMIC bytes / launch time: 32 B x BVH nodes popped + 48 B x triangles tested + 48 B x rays (ray read + hit write), counted by the kernel itself.  The scene (97 MB of nodes + triangles for C2) is L2-resident, so real DRAM traffic (`traffic`) is an order of magnitude below the algorithmic bytes: frac is NOT a fraction of HBM bandwidth in use; the kernel is bound by instruction issue and L1 wavefronts of the per-lane node gathers (`issue`: active lanes per instruction, issue-slot use from the ncu capture under profiles/)"},
+            "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": ctypes.sizeof(params),
+                    "d2h_bytes_per_step": W * H * (16 + 4) if world == 1 else W * H * 16,
+                    "ms_per_step": e2e_ms,
+                    "call": ("gnx_render_framebuffer(): params in; the FrameBuffer's float running mean (16 B/pixel) and its tonemapped 8-bit image (4 B/pixel) out, unpacked into pageable host arrays of the FrameBuffer's layout — the call gnx::CUDAPathIntegrator::Render makes"
+                             if world == 1 else "gnx_render() on contexts attached to one job: every rank renders its sample range, ncclReduce to rank 0, float RGBA copied to pinned host memory on rank 0 only"),
+                    "note": "scene uploaded once (like the reference, which excludes scene build from timeConsume)"},
             "gpu_launches": int(st.kernel_launches) * args.steps,
             "clocks": clk,
         }
+        if e2e_plain_ms:
+            line["e2e"]["gnx_render_float_rgba_ms"] = e2e_plain_ms
+        if strong_rec:
+            line["strong_scaling"] = strong_rec
         if world == 1 and not args.no_cpu_baseline:
             info, extra = cpu_baseline(wl)
             if info:
                 line["cpu_baseline"] = info
                 rs, img_ref, n = extra
                 # parity at the baseline's spp: same scene through the bridge-free scene kit
-                img, _ = ctx.render(RenderParams.make(W, H, n, max_depth=depth, integrator=integ))
+                one = Context(local)
+                one.upload(sk.desc)
+                img, _ = one.render(RenderParams.make(W, H, n, max_depth=depth, integrator=integ))
+                one.close()
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 import _harness
                 line["rel_mse_vs_cpu_ref"] = _harness.rel_mse(img, img_ref)
                 line["rel_mse_spp"] = n
+                rs.close()
+            if not args.no_bridge:
+                br = bridge_e2e(wl, max(2, args.steps))
+                if br:
+                    line["e2e"]["bridge_render"] = br
+                    if br.get("ms_per_call"):
+                        line["e2e"]["bridge_over_c_abi"] = br["ms_per_call"] / e2e_ms
         emit(line)
     if world > 1:
         dist.barrier()
@@ -344,20 +527,24 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one reference-arm step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bridge", action="store_true", help="skip the CUDAPathIntegrator::Render timing (needs oracle/_ref)")
+    ap.add_argument("--no-strong-record", dest="strong_record", action="store_false", help="skip the config-5 strong-scaling record")
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"], help="how an N-rank job is dealt out (gnx_partition)")
     ap.add_argument("--mesh", default=None, help="a .3d mesh file (the reference's format) to render in place of C2's stand-in mesh")
     ap.add_argument("--film", default="box", choices=["box", "gaussian"], help="box = the reference's film (the headline); gaussian = GaussianFilter(2, 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
     if args.mesh:
-        # the real asset when the user has it: C2 with the mesh read from a .3d file (shape/plyRead.h layout) by the scene kit's
+        # the real asset when the user has it: C2 / U1 with the mesh read from a .3d file (shape/plyRead.h layout) by the scene kit's
         # reader (our arm) and by the reference's plyInfo (reference arm), placed as ui/ModelList.cpp:49-69 places dragon.3d
-        if args.workload != "c2":
-            ap.error("--mesh replaces the mesh of workload c2")
-        wl = ("dragon3d:" + os.path.abspath(args.mesh),) + wl[1:8] + (wl[8].replace("872448 tris (torus-knot stand-in for dragon.3d)", "from " + os.path.basename(args.mesh)),)
+        if args.workload not in ("c2", "u1p", "u1w"):
+            ap.error("--mesh replaces the mesh of workloads c2 / u1p / u1w")
+        wl["scene"] = ("dragon3d:" if args.workload == "c2" else "ui3d:") + os.path.abspath(args.mesh)
+        wl["desc"] = wl["desc"].replace("872448 tris (torus-knot stand-in for dragon.3d)", "from " + os.path.basename(args.mesh))
     if args.impl == "reference":
         return run_reference(args, wl)
-    return run_ours(args, wl)
+    return run_ours(args, wl, args.workload)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,8 @@ from .build import repo_root
 c_int32, c_float, c_u64, c_double, c_void_p = ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 
 LIGHTS_UNIFORM, LIGHTS_SPATIAL, LIGHTS_POWER = 0, 1, 2
-INTEGRATOR_PATH, INTEGRATOR_VOLPATH = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_VOLPATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT, INTEGRATOR_DIRECT_ALL = 0, 1, 2, 3, 4
+PARTITION_SAMPLES, PARTITION_TILES = 0, 1
 FILM_BOX, FILM_GAUSSIAN, FILM_GAUSSIAN_SUMS = 0, 1, 2
 
 STATUS = {0: "GNX_OK", -1: "GNX_ERR_INVALID", -2: "GNX_ERR_NO_DEVICE", -3: "GNX_ERR_CUDA", -4: "GNX_ERR_UNSUPPORTED",
@@ -32,15 +33,15 @@ class RenderParams(ctypes.Structure):
         ("width", c_int32), ("height", c_int32), ("spp", c_int32), ("first_sample", c_int32),
         ("spp_normalize", c_int32), ("max_depth", c_int32), ("rr_threshold", c_float), ("integrator", c_int32),
         ("light_strategy", c_int32), ("film", c_int32), ("filter_radius", c_float), ("filter_alpha", c_float),
-        ("batch_spp", c_int32),
+        ("batch_spp", c_int32), ("partition", c_int32),
     ]
 
     @classmethod
     def make(cls, width, height, spp, max_depth=5, first_sample=0, spp_normalize=0, rr_threshold=1.0,
              light_strategy=LIGHTS_SPATIAL, integrator=INTEGRATOR_PATH, batch_spp=0, film=FILM_BOX, filter_radius=0.0,
-             filter_alpha=0.0):
+             filter_alpha=0.0, partition=0):
         return cls(width, height, spp, first_sample, spp_normalize, max_depth, rr_threshold, integrator,
-                   light_strategy, film, filter_radius, filter_alpha, batch_spp)
+                   light_strategy, film, filter_radius, filter_alpha, batch_spp, partition)
 
 
 class Stats(ctypes.Structure):
@@ -64,7 +65,8 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["gnx_abi_version", "gnx_device_count", "gnx_create", "gnx_destroy", "gnx_last_error", "gnx_upload_scene", "gnx_bvh_build_ms",
-           "gnx_render", "gnx_render_device", "gnx_primary_hits", "gnx_sample_dimensions", "gnx_tonemap_rgba8"]
+           "gnx_render", "gnx_render_device", "gnx_primary_hits", "gnx_sample_dimensions", "gnx_tonemap_rgba8",
+           "gnx_create_multi", "gnx_num_devices", "gnx_comm_unique_id", "gnx_comm_attach", "gnx_render_framebuffer"]
 
 _lib = None
 
@@ -96,20 +98,47 @@ def load_library():
     lib.gnx_primary_hits.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_int32, c_void_p]
     lib.gnx_sample_dimensions.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     lib.gnx_tonemap_rgba8.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
+    lib.gnx_render_framebuffer.argtypes = [c_void_p, ctypes.POINTER(RenderParams), c_int32, c_void_p, c_void_p, ctypes.POINTER(Stats)]
+    lib.gnx_create_multi.argtypes = [ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    lib.gnx_num_devices.argtypes = [c_void_p]
+    lib.gnx_comm_unique_id.argtypes = [c_void_p]
+    lib.gnx_comm_attach.argtypes = [c_void_p, ctypes.c_int, ctypes.c_int, c_void_p]
     _lib = lib
     return lib
 
 
 class Context:
-    """One gnx_ctx == one GPU."""
+    """One gnx_ctx: one GPU (device = int), or several GPUs of this node driven from this process (devices = [ids],
+    gnx_create_multi: the library replicates the scene, splits every render and reduces onto devices[0])."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.lib = load_library()
         self.h = c_void_p()
-        rc = self.lib.gnx_create(ctypes.byref(self.h), device)
+        if devices is not None:
+            ids = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.gnx_create_multi(ctypes.byref(self.h), ids, len(devices))
+            device = devices[0]
+        else:
+            rc = self.lib.gnx_create(ctypes.byref(self.h), device)
         if rc != 0:
             raise GnxError(rc, self.lib.gnx_last_error(None).decode())
         self.device = device
+
+    @property
+    def num_devices(self):
+        return self.lib.gnx_num_devices(self.h)
+
+    def comm_unique_id(self):
+        """128-byte id for gnx_comm_attach (rank 0 creates it, the host program hands it to every rank)."""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.gnx_comm_unique_id(buf)
+        if rc != 0:
+            raise GnxError(rc, self.lib.gnx_last_error(None).decode())
+        return bytes(buf.raw)
+
+    def comm_attach(self, n_ranks, rank, comm_id):
+        """Joins this single-device context to an n_ranks-process job: renders become collective (see gnxrt.h)."""
+        self._check(self.lib.gnx_comm_attach(self.h, n_ranks, rank, ctypes.c_char_p(comm_id)))
 
     def _check(self, rc):
         if rc != 0:
@@ -131,6 +160,16 @@ class Context:
         st = Stats()
         self._check(self.lib.gnx_render(self.h, ctypes.byref(params), out.ctypes.data, ctypes.byref(st) if want_stats else None))
         return out, st
+
+    def render_framebuffer(self, params, pass_count, fbuffer, ubuffer, want_stats=False):
+        """gnx_render_framebuffer: the reference FrameBuffer's running mean + 8-bit tonemapped image, computed on the
+        device; fbuffer float32[h, w, 4] (in/out, colour channels only), ubuffer uint8[h, w, 4] (out)."""
+        st = Stats()
+        fp = fbuffer.ctypes.data if hasattr(fbuffer, "ctypes") else fbuffer
+        up = ubuffer.ctypes.data if hasattr(ubuffer, "ctypes") else ubuffer
+        self._check(self.lib.gnx_render_framebuffer(self.h, ctypes.byref(params), int(pass_count), c_void_p(int(fp)) if fp else None,
+                                                    c_void_p(int(up)) if up else None, ctypes.byref(st) if want_stats else None))
+        return st
 
     def render_host_ptr(self, params, host_ptr, want_stats=True):
         """Like render(), into caller-owned (e.g. pinned) host memory."""

@@ -507,7 +507,8 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
 CUDAPathIntegrator::CUDAPathIntegrator(int maxDepth, std::shared_ptr<const Camera> camera,
                                        std::shared_ptr<Sampler> sampler, const Bounds2i &pixelBounds,
                                        FrameBuffer *pFrameBuffer, Float rrThreshold,
-                                       const std::string &lightSampleStrategy, bool volumetric, int device)
+                                       const std::string &lightSampleStrategy, bool volumetric, int device,
+                                       const std::vector<int> &devices)
     : maxDepth_(maxDepth),
       camera_(std::move(camera)),
       sampler_(std::move(sampler)),
@@ -516,7 +517,20 @@ CUDAPathIntegrator::CUDAPathIntegrator(int maxDepth, std::shared_ptr<const Camer
       rrThreshold_(rrThreshold),
       lightSampleStrategy_(lightSampleStrategy),
       integrator_(volumetric ? GNX_INTEGRATOR_VOLPATH : GNX_INTEGRATOR_PATH) {
-    int rc = gnx_create(&ctx_, device);
+    // the GPUs of this integrator: the constructor argument, else GNX_DEVICES ("all" or a comma-separated list), else `device`
+    std::vector<int> ids = devices;
+    if (ids.empty())
+        if (const char *env = getenv("GNX_DEVICES")) {
+            if (!strcmp(env, "all")) for (int g = 0; g < gnx_device_count(); ++g) ids.push_back(g);
+            else for (const char *c = env; *c;) {
+                char *end = nullptr;
+                long v = strtol(c, &end, 10);
+                if (end == c) break;
+                ids.push_back((int)v);
+                c = *end ? end + 1 : end;
+            }
+        }
+    int rc = ids.size() > 1 ? gnx_create_multi(&ctx_, ids.data(), (int)ids.size()) : gnx_create(&ctx_, ids.empty() ? device : ids[0]);
     if (rc != GNX_OK) {
         error_ = std::string("gnx_create failed: ") + gnx_last_error(nullptr);
         ctx_ = nullptr;
@@ -543,12 +557,29 @@ gnx_render_params CUDAPathIntegrator::MakeParams() const {
                        : lightSampleStrategy_ == "power" ? GNX_LIGHTS_POWER : GNX_LIGHTS_SPATIAL;
     p.film = filterRadius_ > 0 ? GNX_FILM_GAUSSIAN : GNX_FILM_BOX;
     p.filter_radius = filterRadius_; p.filter_alpha = filterAlpha_;
+    p.partition = partition_;
     return p;
+}
+
+// What identifies an uploaded scene besides its address: a Scene rebuilt at the same address, another light list,
+// another sampler or camera all change it (edits INSIDE those objects need Invalidate()).
+static size_t SceneFingerprint(const Scene &scene, const Camera *camera, const Sampler *sampler) {
+    size_t h = 1469598103934665603ull;
+    auto mix = [&](size_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix((size_t)scene.aggregate.get());
+    mix(scene.lights.size());
+    for (const auto &l : scene.lights) mix((size_t)l.get());
+    mix((size_t)camera);
+    mix((size_t)sampler);
+    mix((size_t)sampler->samplesPerPixel);
+    return h;
 }
 
 bool CUDAPathIntegrator::EnsureUploaded(const Scene &scene) {
     if (!ctx_) return false;
-    if (uploaded_ == &scene) return true;
+    const size_t fp = SceneFingerprint(scene, camera_.get(), sampler_.get());
+    if (uploaded_ == &scene && fingerprint_ == fp) return true;
+    uploaded_ = nullptr;
     flat_.reset(new FlatScene);
     if (!FlattenScene(scene, *camera_, *sampler_, flat_.get())) {
         error_ = "FlattenScene: " + flat_->error;
@@ -559,6 +590,7 @@ bool CUDAPathIntegrator::EnsureUploaded(const Scene &scene) {
         return false;
     }
     uploaded_ = &scene;
+    fingerprint_ = fp;
     return true;
 }
 
@@ -570,26 +602,37 @@ void CUDAPathIntegrator::Render(const Scene &scene, double &timeConsume) {
         return;
     }
     gnx_render_params p = MakeParams();
-    std::vector<float> rgba((size_t)p.width * p.height * 4);
     auto t0 = std::chrono::steady_clock::now();
-    int rc = gnx_render(ctx_, &p, rgba.data(), &stats_);
-    auto t1 = std::chrono::steady_clock::now();
+    // Same sink as core/Integrator.cpp:230,307-310: one more pass in the FrameBuffer's running mean.  The mean and its
+    // tonemapped 8-bit copy are computed on the device and land in FrameBuffer::fbuffer / ubuffer directly (this
+    // translation unit sees the private members); a FrameBuffer of another shape goes through the setters.
+    fb_->renderCountIncrease();
+    const int pass = fb_->curRenderCount;
+    if (progressive_) p.first_sample = (pass - 1) * p.spp;
+    const bool direct = fb_->fbuffer && fb_->ubuffer && fb_->width == p.width && fb_->height >= p.height && fb_->channals == 4;
+    int rc;
+    std::vector<float> rgba;
+    if (direct) rc = gnx_render_framebuffer(ctx_, &p, pass, fb_->fbuffer, fb_->ubuffer, &stats_);
+    else {
+        rgba.resize((size_t)p.width * p.height * 4);
+        rc = gnx_render(ctx_, &p, rgba.data(), &stats_);
+    }
     if (rc != GNX_OK) {
-        error_ = std::string("gnx_render: ") + gnx_last_error(ctx_);
+        error_ = std::string(direct ? "gnx_render_framebuffer: " : "gnx_render: ") + gnx_last_error(ctx_);
         fprintf(stderr, "[CUDAPathIntegrator] %s\n", error_.c_str());
+        fb_->curRenderCount = pass - 1;  // the pass did not happen
         return;
     }
-    timeConsume = std::chrono::duration<double>(t1 - t0).count();
-    // Same sink as core/Integrator.cpp:230,307-310.
-    fb_->renderCountIncrease();
-    for (int j = 0; j < p.height; ++j)
-        for (int i = 0; i < p.width; ++i) {
-            const float *px = &rgba[((size_t)i + (size_t)j * p.width) * 4];
-            fb_->update_f_u_c(i, j, 0, px[0]);
-            fb_->update_f_u_c(i, j, 1, px[1]);
-            fb_->update_f_u_c(i, j, 2, px[2]);
-            fb_->set_uc(i, j, 3, 255);
-        }
+    if (!direct)
+        for (int j = 0; j < p.height; ++j)
+            for (int i = 0; i < p.width; ++i) {
+                const float *px = &rgba[((size_t)i + (size_t)j * p.width) * 4];
+                fb_->update_f_u_c(i, j, 0, px[0]);
+                fb_->update_f_u_c(i, j, 1, px[1]);
+                fb_->update_f_u_c(i, j, 2, px[2]);
+                fb_->set_uc(i, j, 3, 255);
+            }
+    timeConsume = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 bool CUDAPathIntegrator::PrimaryHits(const Scene &scene, int sample, std::vector<int32_t> *ordered) {

@@ -7,8 +7,10 @@
 //     std::make_shared<gnx::CUDAPathIntegrator>(5, camera, sampler, bounds, fb)
 // in ui/RenderThread.cpp:163-164 is the whole integration.  Render() flattens
 // the existing pbr::Scene into the plain buffers of include/gnxrt.h, hands them to libgnxrt.so
-// and writes the result into the FrameBuffer through the same setters the reference uses
-// (core/Integrator.cpp:307-310).
+// and receives the FrameBuffer's two images — the running mean over Render() calls and its 8-bit
+// tonemapped copy, both computed on the device with update_f_u_c's formulas (ui/FrameBuffer.h:127-149) —
+// straight into FrameBuffer::fbuffer / ubuffer (gnx_render_framebuffer).  With `devices` (or the
+// environment variable GNX_DEVICES=all | 0,1,..) one Render() call uses several GPUs of the box.
 //
 // This translation unit is the only one compiled against the reference's headers; it contains no
 // rendering code.
@@ -56,7 +58,7 @@ class CUDAPathIntegrator : public pbr::Integrator {
                        std::shared_ptr<pbr::Sampler> sampler, const pbr::Bounds2i &pixelBounds,
                        FrameBuffer *pFrameBuffer, pbr::Float rrThreshold = 1,
                        const std::string &lightSampleStrategy = "spatial", bool volumetric = false,
-                       int device = 0);
+                       int device = 0, const std::vector<int> &devices = {});
     ~CUDAPathIntegrator() override;
 
     // Integrator interface.  Synchronous like the reference: the FrameBuffer is complete on return.
@@ -75,6 +77,16 @@ class CUDAPathIntegrator : public pbr::Integrator {
     // Reconstruct the image with the reference's GaussianFilter(Vector2f(radius, radius), alpha)
     // (filters/GaussianFilter.h:12-33) instead of Render()'s box average; radius <= 0 switches back to the box.
     void SetGaussianFilter(pbr::Float radius, pbr::Float alpha) { filterRadius_ = radius; filterAlpha_ = alpha; }
+    // gnx_partition of a multi-GPU Render(): GNX_PARTITION_SAMPLES (default) or GNX_PARTITION_TILES
+    void SetPartition(int gnxPartition) { partition_ = gnxPartition; }
+    // The reference's UI calls Render() in a loop and averages the passes, every pass drawing the SAME samples
+    // (ui/RenderThread.cpp:169-175, core/Integrator.cpp:262-291).  Progressive: pass k renders samples
+    // [k spp, (k+1) spp) of every pixel, so the running mean converges instead of repeating itself.  Off by default.
+    void SetProgressive(bool on) { progressive_ = on; }
+    // The flattened copy is keyed on the Scene's address and a fingerprint of what hangs off it (aggregate, lights,
+    // sampler, camera); call this after editing materials / transforms in place to force a new upload.
+    void Invalidate() { uploaded_ = nullptr; }
+    int NumDevices() const { return ctx_ ? gnx_num_devices(ctx_) : 0; }
 
   private:
     bool EnsureUploaded(const pbr::Scene &scene);
@@ -89,7 +101,10 @@ class CUDAPathIntegrator : public pbr::Integrator {
     int integrator_;  // gnx_integrator
     pbr::Float filterRadius_ = 0, filterAlpha_ = 0;
     gnx_ctx *ctx_ = nullptr;
+    int partition_ = 0;
+    bool progressive_ = false;
     const pbr::Scene *uploaded_ = nullptr;
+    size_t fingerprint_ = 0;
     std::unique_ptr<FlatScene> flat_;
     gnx_stats stats_{};
     std::string error_;

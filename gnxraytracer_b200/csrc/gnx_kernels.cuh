@@ -160,11 +160,14 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                 if (!active) {
                     const int i = base + __popc(idle & ((1u << lane) - 1));
                     if (i < n) {
+                        bool valid = true;
                         if (KIND == 3) {
                             item = i;
-                            int pixel, sample;
+                            int pixel, sample, px, py;
                             slot_to_sample(rc, i, &pixel, &sample);
-                            primary_begin(sc, pixel % rc.width, pixel / rc.width, sample, &hidx, &camD, t);
+                            valid = pixel_xy(rc, pixel, &px, &py);
+                            if (valid) primary_begin(sc, px, py, sample, &hidx, &camD, t);
+                            else ps.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // pixel of an edge tile outside the image
                         } else if (kMixed) {
                             shLane = i >= nE;
                             if (shLane) { item = i - nE; shadow_begin(sc, shadowItem(item), t); ++raysSh; if (item >= firstB) ++raysB; }
@@ -172,8 +175,10 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                         } else if (KIND == 0) { item = inList[i]; extend_begin(sc, ps, item, t); }
                         else if (KIND == 1) { item = i; shadow_begin(sc, shadowItem(i), t); if (i >= firstB) ++raysB; }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
-                        active = true;
-                        ++rays;
+                        if (valid) {
+                            active = true;
+                            ++rays;
+                        }
                     }
                 }
                 exhausted = base + __popc(idle) >= n;
@@ -300,9 +305,10 @@ __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, Pat
         if (base >= n) break;
         const int slot = base + lane;
         if (slot < n) {
-            int pixel, sample;
+            int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
-            V3 L = volpath_li(sc, rc, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, vc);
+            V3 L(0.f);
+            if (pixel_xy(rc, pixel, &px, &py)) L = volpath_li(sc, rc, px, py, sample, stack, kBlock, cnt, vc);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();
@@ -333,9 +339,10 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
         if (base >= n) break;
         const int slot = base + lane;
         if (slot < n) {
-            int pixel, sample;
+            int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
-            V3 L = recursive_li<8, DIRECT>(sc, rc, pixel % rc.width, pixel / rc.width, sample, stack, kBlock, cnt, rcnt);
+            V3 L(0.f);
+            if (pixel_xy(rc, pixel, &px, &py)) L = recursive_li<8, DIRECT>(sc, rc, px, py, sample, stack, kBlock, cnt, rcnt);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();
@@ -371,7 +378,7 @@ __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts 
         int pixel, sample;
         slot_to_sample(rc, slot, &pixel, &sample);
         float u0, u1;
-        film_sample_offset(sc, rc.width, pixel % rc.width, pixel / rc.width, sample, &u0, &u1);
+        film_sample_offset(sc, rc.width, pixel % rc.width, pixel / rc.width, sample, &u0, &u1);  // (no tile partition with the Gaussian film)
         ps.ray_o[slot] = make_float4(u0, u1, 0.f, 0.f);
         float4 L = ps.L[slot];
         if (L.w != 0.f) {
@@ -470,11 +477,36 @@ __global__ void k_film_gauss(const float4 *accum, float4 *rgba, int npix, int re
         rgba[pixel] = resolve ? gaussian_resolve(accum[pixel]) : accum[pixel];
 }
 
-// colObj / samplesPerPixel, alpha 1 (core/Integrator.cpp:293,307-310)
-__global__ void k_film(const float4 *accum, float4 *rgba, int npix, float spp) {
+// colObj / samplesPerPixel, alpha 1 (core/Integrator.cpp:293,307-310).  alpha: 1, or 0 on the non-root devices of an
+// N-device job whose partial framebuffers are summed afterwards.
+__global__ void k_film(const float4 *accum, float4 *rgba, int npix, float spp, float alpha) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x) {
         const float4 a = accum[pixel];
-        rgba[pixel] = make_float4(a.x / spp, a.y / spp, a.z / spp, 1.f);
+        rgba[pixel] = make_float4(a.x / spp, a.y / spp, a.z / spp, alpha);
+    }
+}
+// Tile partition: this device's tiles scattered into the (zeroed) full frame; the sum over the devices' frames is the
+// image, every pixel being x + 0 + ... + 0: bit-equal to the single-device render.
+__global__ void k_film_tiles(const float4 *accum, float4 *rgba, RenderConsts rc, float spp) {
+    for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
+        int px, py;
+        if (!pixel_xy(rc, pixel, &px, &py)) continue;
+        const float4 a = accum[pixel];
+        rgba[(size_t)py * rc.width + px] = make_float4(a.x / spp, a.y / spp, a.z / spp, 1.f);
+    }
+}
+// The N-device reduce as ONE kernel on the root: partial frames of the peers are read through peer-to-peer loads over
+// NVLink and summed in device order (deterministic), in place into the root's frame.
+constexpr int kMaxDevices = 16;
+struct PeerFrames { const float4 *part[kMaxDevices]; int n; };
+__global__ void k_reduce_peers(float4 *out, PeerFrames pf, int npix) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        float4 a = out[i];
+        for (int g = 0; g < pf.n; ++g) {
+            const float4 b = pf.part[g][i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
     }
 }
 
@@ -495,6 +527,24 @@ __global__ void k_build_spatial(const DeviceScene sc, float *func, float *cdf, f
     const int nv = sc.ld.nvox[0] * sc.ld.nvox[1] * sc.ld.nvox[2];
     for (int vox = blockIdx.x * blockDim.x + threadIdx.x; vox < nv; vox += gridDim.x * blockDim.x)
         build_spatial_voxel(sc, vox, func, cdf, fint);
+}
+
+// FrameBuffer::update_f_u_c for a whole pass (ui/FrameBuffer.h:127-149): running mean over Render() calls, then the
+// exposure tonemap of the updated value; set_uc(.., 3, 255) for the alpha byte.  `weight` = 1 / curRenderCount.
+__global__ void k_framebuffer_update(const float4 *frame, float4 *state, uchar4 *u8, int npix, float weight) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float4 v = frame[i];
+        float4 f = state[i];
+        f.x = weight * v.x + (1.0f - weight) * f.x;
+        f.y = weight * v.y + (1.0f - weight) * f.y;
+        f.z = weight * v.z + (1.0f - weight) * f.z;
+        state[i] = f;
+        const float exposure = 0.75f;
+        const float r = 1.0f - expf(-f.x * 1.0f / (1 - exposure));
+        const float g = 1.0f - expf(-f.y * 1.0f / (1 - exposure));
+        const float b = 1.0f - expf(-f.z * 1.0f / (1 - exposure));
+        u8[i] = make_uchar4((unsigned char)(r * 255), (unsigned char)(g * 255), (unsigned char)(b * 255), 255);
+    }
 }
 
 // FrameBuffer::update_f_u_c's tonemap on the first pass (ui/FrameBuffer.h:141-147)

@@ -21,7 +21,30 @@ struct RenderConsts {
     int batch_spp;       // samples per pixel in this batch
     int first_sample;    // sample number of the batch's first sample
     int capacity;        // path slots
+    // Interleaved-tile partition of an N-device job (SURVEY 8e mode 2): this device renders the kTile x kTile tiles
+    // number tile_dev, tile_dev + tile_n, ... of the skewed row-major tile order; npix is then its LOCAL pixel count
+    // (tiles x kTile^2, pixels of edge tiles outside the image included and skipped).  tile_n == 0: the whole image.
+    int tile_n, tile_dev, tiles_x, tiles_y;
 };
+constexpr int kTile = 32;
+
+// Local pixel index -> image coordinates; false for the pixels of an edge tile that lie outside the image.
+// Tile number t of the order sits in tile row t / tiles_x, shifted by its row number (a skew, so that one device's
+// tiles form diagonals instead of columns).
+GNX_D bool pixel_xy(const RenderConsts &rc, int pixel, int *px, int *py) {
+    if (rc.tile_n == 0) { *px = pixel % rc.width; *py = pixel / rc.width; return true; }
+    const int lt = pixel / (kTile * kTile), li = pixel % (kTile * kTile);
+    const int gt = lt * rc.tile_n + rc.tile_dev;
+    const int ty = gt / rc.tiles_x, tx = (gt % rc.tiles_x + ty) % rc.tiles_x;
+    *px = tx * kTile + li % kTile;
+    *py = ty * kTile + li / kTile;
+    return gt < rc.tiles_x * rc.tiles_y && *px < rc.width && *py < rc.height;
+}
+// Tiles of the order that device `dev` of `n` owns.
+GNX_HD int local_tile_count(int tiles_x, int tiles_y, int n, int dev) {
+    const int total = tiles_x * tiles_y;
+    return total > dev ? (total - dev + n - 1) / n : 0;
+}
 
 // Camera ray for (pixel, halton index): Sampler::GetCameraSample + PerspectiveCamera::GenerateRay +
 // Transform::operator()(Ray) (core/Transform.h:230-244).

@@ -1,11 +1,15 @@
 // gnx_render.cu — the C ABI of include/gnxrt.h: context, scene upload (host SoA -> HBM layout),
 // the wavefront render loop and the parity hooks.  All compute is in gnx_kernels.cuh; there is no
 // CPU code path for any of it.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gnx_kernels.cuh"
@@ -16,7 +20,52 @@ using namespace gnx;
 
 namespace {
 thread_local std::string g_create_error;
+
+// ---- NCCL, loaded at run time: the single-GPU product has no dependency on it, an N-device job uses it for the one
+// collective the path has (the framebuffer sum-reduce) and falls back to peer-to-peer loads without it.
+// The few types are restated (nccl.h: ncclUniqueId is 128 opaque bytes, ncclFloat32 = 7, ncclSum = 0, ncclSuccess = 0).
+typedef void *NcclComm;
+struct NcclId { char internal[GNX_COMM_ID_BYTES]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclId, int) = nullptr;
+    int (*CommInitAll)(NcclComm *, int, const int *) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("GNX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names)
+            if (n && n[0] && (api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!api.h) return;
+        bool ok = true;
+        auto sym = [&](const char *name) { void *p = dlsym(api.h, name); ok = ok && p; return p; };
+        api.GetUniqueId = (int (*)(NcclId *))sym("ncclGetUniqueId");
+        api.CommInitRank = (int (*)(NcclComm *, int, NcclId, int))sym("ncclCommInitRank");
+        api.CommInitAll = (int (*)(NcclComm *, int, const int *))sym("ncclCommInitAll");
+        api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+        api.Reduce = (int (*)(const void *, void *, size_t, int, int, int, NcclComm, cudaStream_t))sym("ncclReduce");
+        api.GroupStart = (int (*)())sym("ncclGroupStart");
+        api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+        api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+        if (!ok) { dlclose(api.h); api.h = nullptr; }
+    });
+    return api.h ? &api : nullptr;
 }
+}  // namespace
+
+// Share of an N-device job that one device renders (gnx_render_params::partition).
+struct Share {
+    int n = 1, idx = 0, partition = GNX_PARTITION_SAMPLES;
+};
 
 struct gnx_ctx {
     int device = 0;
@@ -59,6 +108,25 @@ struct gnx_ctx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_stage;  // stage id of pair i (events 2i, 2i+1)
     size_t ev_used = 0;
+    // ---- N-device jobs.  gnx_create_multi: this context is the root (device_ids[0]) and owns one full single-device
+    // context per further GPU; gnx_comm_attach: this context is rank `rank` of an n_ranks-process job.
+    std::vector<gnx_ctx *> peers;
+    std::vector<void *> comms;     // single process: NCCL communicator of the root, then of every peer; attached: [0] = this rank's
+    int n_ranks = 1, rank = 0;
+    int reduce_mode = 0;           // GNX_REDUCE: 0 = NCCL when it can be loaded, else peer-to-peer; 1 = nccl; 2 = p2p
+    bool p2p_direct = false;       // the root can load from every peer's memory (cudaDeviceEnablePeerAccess)
+    cudaEvent_t ev_done = nullptr; // this device's share is queued up to here
+    float4 *stage = nullptr;       // root, without direct peer access: copies of the peers' frames
+    size_t stage_pixels = 0;
+    double ms_reduce = 0;          // device time of the last reduce (root)
+    // ---- gnx_render_framebuffer: the FrameBuffer's running mean on the device, the 8-bit image, pinned staging
+    float4 *fb_state = nullptr;
+    uchar4 *fb_u8 = nullptr;
+    size_t fb_pixels = 0;          // allocation
+    int fb_w = 0, fb_h = 0;        // image the state belongs to (0: no state)
+    void *fb_pinned = nullptr;     // pinned host staging: float4[pixels] then uchar4[pixels]
+    size_t fb_pinned_pixels = 0;
+    cudaEvent_t fb_ev[8] = {};
 };
 
 enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
@@ -142,6 +210,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->d_stats, sizeof(DevStats))) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
@@ -167,6 +236,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
     if (const char *fc = getenv("GNX_FILM_CHUNK")) ctx->film_chunk = atoi(fc);
     if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
+    if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
     *out = ctx;
@@ -175,7 +245,18 @@ int gnx_create(gnx_ctx **out, int device) {
 
 void gnx_destroy(gnx_ctx *ctx) {
     if (!ctx) return;
+    if (NcclApi *nc = ctx->comms.empty() ? nullptr : nccl_api())
+        for (void *c : ctx->comms) if (c) nc->CommDestroy(c);
+    ctx->comms.clear();
+    for (gnx_ctx *p : ctx->peers) gnx_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->fb_state) cudaFree(ctx->fb_state);
+    if (ctx->fb_u8) cudaFree(ctx->fb_u8);
+    if (ctx->fb_pinned) cudaFreeHost(ctx->fb_pinned);
+    for (cudaEvent_t e : ctx->fb_ev) if (e) cudaEventDestroy(e);
     free_pool(ctx->scene_allocs);
     free_pool(ctx->wave_allocs);
     if (ctx->accum) cudaFree(ctx->accum);
@@ -230,8 +311,25 @@ struct ReorderedGeometry {
     }
 };
 
+static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in);
+
+// The scene is replicated on every device of a multi-device context: one host thread per GPU.
 int gnx_upload_scene(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     if (!ctx || !d_in) return GNX_ERR_INVALID;
+    if (ctx->peers.empty()) return upload_one(ctx, d_in);
+    std::vector<int> rcs(ctx->peers.size(), GNX_OK);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < ctx->peers.size(); ++g)
+        th.emplace_back([&, g] { rcs[g] = upload_one(ctx->peers[g], d_in); });
+    int rc = upload_one(ctx, d_in);
+    for (std::thread &t : th) t.join();
+    for (size_t g = 0; g < rcs.size(); ++g)
+        if (rc == GNX_OK && rcs[g] != GNX_OK) { rc = rcs[g]; ctx->err = "device " + std::to_string(ctx->peers[g]->device) + ": " + ctx->peers[g]->err; }
+    if (rc != GNX_OK) { ctx->has_scene = false; for (gnx_ctx *p : ctx->peers) p->has_scene = false; }
+    return rc;
+}
+
+static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     if (d_in->abi_version != GNX_ABI_VERSION) return fail(ctx, GNX_ERR_INVALID, "abi_version mismatch");
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
     free_pool(ctx->scene_allocs);
@@ -567,7 +665,7 @@ static int ensure_light_distribution(gnx_ctx *ctx, int strategy) {
     return GNX_OK;
 }
 
-static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix) {
+static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix, int npixFrame) {
     if (capacity > ctx->capacity) {
         free_pool(ctx->wave_allocs);
         ctx->capacity = 0;
@@ -594,6 +692,7 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix) {
         ctx->capacity = capacity;
         GNX_CUDA(ctx, cudaDeviceSynchronize());
     }
+    npix = std::max(npix, npixFrame);
     if (npix > ctx->film_pixels) {
         if (ctx->accum) cudaFree(ctx->accum);
         if (ctx->rgba) cudaFree(ctx->rgba);
@@ -634,6 +733,11 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
         return fail(ctx, GNX_ERR_INVALID, "unknown film");
     if (p->film != GNX_FILM_BOX && !(p->filter_radius > 0.f && p->filter_radius <= 16.f && p->filter_alpha >= 0.f))
         return fail(ctx, GNX_ERR_INVALID, "Gaussian film: filter_radius must be in (0, 16] and filter_alpha >= 0");
+    if (p->partition != GNX_PARTITION_SAMPLES && p->partition != GNX_PARTITION_TILES) return fail(ctx, GNX_ERR_INVALID, "unknown partition");
+    const int nShare = ctx->peers.empty() ? ctx->n_ranks : 1 + (int)ctx->peers.size();
+    if (nShare > 1 && p->partition == GNX_PARTITION_TILES && p->film != GNX_FILM_BOX)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "the tile partition finishes every pixel on one device: box film only (use GNX_PARTITION_SAMPLES with a Gaussian film)");
+    (void)nShare;
     // the Halton index must fit the 32-bit path state
     const unsigned long long lastSample = (unsigned long long)p->first_sample + (unsigned long long)p->spp;
     unsigned long long maxIdx = lastSample * (unsigned long long)ctx->sc.smp.stride;
@@ -662,14 +766,38 @@ static void set_l2_window(gnx_ctx *ctx, cudaStream_t st) {
     cudaGetLastError();
 }
 
-static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats,
-                       bool callerSyncs = false) {
-    int rc = validate_params(ctx, p);
+// Queues one device's share of a render on `userStream`.  share.n == 1: the whole job.  Otherwise p_in describes the
+// WHOLE job and this device renders its sample range (its frame then holds sum / total spp, alpha 1 on share 0 and 0
+// elsewhere) or its interleaved tiles (scattered into a zeroed full frame); the caller sums the frames.
+static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_dev_out, cudaStream_t userStream, gnx_stats *stats,
+                       bool callerSyncs = false, Share share = Share()) {
+    int rc = validate_params(ctx, p_in);
     if (rc) return rc;
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    gnx_render_params pv = *p_in;
+    const gnx_render_params *p = &pv;
+    const int npixFrame = p->width * p->height;
+    const bool tiles = share.n > 1 && share.partition == GNX_PARTITION_TILES;
+    int tilesX = 0, tilesY = 0;
+    if (share.n > 1 && !tiles) {
+        // contiguous sample range of share idx (the first spp % n shares take one sample more)
+        const int base = p_in->spp / share.n, rem = p_in->spp % share.n;
+        pv.spp = base + (share.idx < rem ? 1 : 0);
+        pv.first_sample = p_in->first_sample + share.idx * base + std::min(share.idx, rem);
+        pv.spp_normalize = p_in->spp_normalize > 0 ? p_in->spp_normalize : p_in->spp;
+        if (pv.spp == 0) {  // fewer samples than devices: an empty share contributes zeros
+            float *o = rgba_dev_out;
+            if (!o) { if ((rc = ensure_wavefront(ctx, 0, 0, npixFrame))) return rc; o = (float *)ctx->rgba; }
+            GNX_CUDA(ctx, cudaMemsetAsync(o, 0, (size_t)npixFrame * sizeof(float4), userStream));
+            if (stats) memset(stats, 0, sizeof(*stats));
+            return GNX_OK;
+        }
+    }
+    if (tiles) { tilesX = (p->width + kTile - 1) / kTile; tilesY = (p->height + kTile - 1) / kTile; }
     const bool recursiveInteg = p->integrator >= GNX_INTEGRATOR_WHITTED;
     if (!recursiveInteg && (rc = ensure_light_distribution(ctx, p->light_strategy))) return rc;
-    const int npix = p->width * p->height;
+    // pixels this device renders: the image, or its tiles (edge tiles padded to kTile x kTile)
+    const int npix = tiles ? local_tile_count(tilesX, tilesY, share.n, share.idx) * kTile * kTile : npixFrame;
     // Paths in flight per wavefront batch.  Late bounces carry few rays and every launch has a tail, so
     // the batch is made as large as memory comfortably allows (profiles/README.md: 4 M -> 64 M slots took
     // C2 from 126 ms to 71 ms): up to 64 M slots, and never more than a quarter of the free HBM.
@@ -684,11 +812,11 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
         }
-        batch_spp = (int)std::max(1ll, slots / npix);
+        batch_spp = (int)std::max(1ll, slots / std::max(1, npix));
     }
     batch_spp = std::min(batch_spp, p->spp);
-    if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / npix));
-    if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix))) return rc;
+    if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / std::max(1, npix)));
+    if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix, npixFrame))) return rc;
 
     cudaStream_t st = userStream;  // gnx_render_device maps a NULL stream to the legacy default stream (see gnxrt.h)
     set_l2_window(ctx, st);
@@ -754,6 +882,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
         rcn.batch_spp = std::min(batch_spp, p->spp - done);
         rcn.first_sample = p->first_sample + done;
         rcn.capacity = ctx->capacity;
+        if (tiles) { rcn.tile_n = share.n; rcn.tile_dev = share.idx; rcn.tiles_x = tilesX; rcn.tiles_y = tilesY; }
+        if (npix == 0) break;  // more devices than tiles
         if (p->integrator != GNX_INTEGRATOR_PATH) {
             k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
             tm.begin(ST_EXTEND);
@@ -831,7 +961,13 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     const float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
     float4 *out = rgba_dev_out ? (float4 *)rgba_dev_out : ctx->rgba;
     if (gaussian) k_film_gauss<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, p->film == GNX_FILM_GAUSSIAN);
-    else k_film<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, norm);
+    else if (tiles) {
+        RenderConsts rct{};
+        rct.width = p->width; rct.height = p->height; rct.npix = npix;
+        rct.tile_n = share.n; rct.tile_dev = share.idx; rct.tiles_x = tilesX; rct.tiles_y = tilesY;
+        GNX_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)npixFrame * sizeof(float4), st));
+        if (npix > 0) k_film_tiles<<<gridWide, 256, 0, st>>>(ctx->accum, out, rct, norm);
+    } else k_film<<<gridWide, 256, 0, st>>>(ctx->accum, out, npix, norm, share.idx == 0 ? 1.f : 0.f);
     ++launches;
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     GNX_CUDA(ctx, cudaGetLastError());
@@ -872,12 +1008,142 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p, float *rgba_dev
     return GNX_OK;
 }
 
+static void add_stats(gnx_stats *a, const gnx_stats &b) {
+    a->paths += b.paths; a->rays_extend += b.rays_extend; a->rays_shadow += b.rays_shadow; a->rays_mis += b.rays_mis;
+    a->nodes_visited += b.nodes_visited; a->tris_tested += b.tris_tested; a->kernel_launches += b.kernel_launches;
+    a->bytes_algorithmic += b.bytes_algorithmic; a->extend_nodes += b.extend_nodes; a->extend_tris += b.extend_tris;
+    a->extend_launches = std::max(a->extend_launches, b.extend_launches); a->extend_bytes += b.extend_bytes;
+    // times: the slowest device bounds the job
+    a->device_ms = std::max(a->device_ms, b.device_ms); a->ms_raygen = std::max(a->ms_raygen, b.ms_raygen);
+    a->ms_extend = std::max(a->ms_extend, b.ms_extend); a->ms_shade = std::max(a->ms_shade, b.ms_shade);
+    a->ms_shadow = std::max(a->ms_shadow, b.ms_shadow); a->ms_film = std::max(a->ms_film, b.ms_film);
+}
+
+// One render on every GPU of a multi-device context (single process): the shares are queued from one host thread per
+// device, the partial frames are summed onto the root — ncclReduce queued on every device's stream right behind its
+// last film kernel, or one kernel on the root that loads the peers' frames over NVLink — and the root alone copies to
+// the host.  Exactly one of host_out / dev_out (memory of the root device) is given.
+static int render_multi(gnx_ctx *root, const gnx_render_params *p, float *host_out, float *dev_out, gnx_stats *stats, bool keepOnRoot = false) {
+    if (!host_out && !dev_out && !keepOnRoot) return GNX_ERR_INVALID;
+    int rc = validate_params(root, p);
+    if (rc) return rc;
+    const int G = 1 + (int)root->peers.size();
+    const size_t npix = (size_t)p->width * p->height;
+    // Gaussian film: the shares produce the unresolved sums (sum L f, sum f), the root divides after the reduce
+    gnx_render_params pShare = *p;
+    const bool resolveAfter = p->film == GNX_FILM_GAUSSIAN;
+    if (resolveAfter) pShare.film = GNX_FILM_GAUSSIAN_SUMS;
+    const gnx_render_params *pj = &pShare;
+    std::vector<int> rcs(G, GNX_OK);
+    std::vector<gnx_stats> sts(stats ? G : 0);
+    auto ctxOf = [&](int g) { return g == 0 ? root : root->peers[g - 1]; };
+    auto run = [&](int g) {
+        gnx_ctx *c = ctxOf(g);
+        Share sh;
+        sh.n = G; sh.idx = g; sh.partition = p->partition;
+        rcs[g] = render_impl(c, pj, g == 0 ? dev_out : nullptr, c->stream, stats ? &sts[g] : nullptr, true, sh);
+        if (rcs[g] == GNX_OK && cudaEventRecord(c->ev_done, c->stream) != cudaSuccess) { c->err = "cudaEventRecord failed"; rcs[g] = GNX_ERR_CUDA; }
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) th.emplace_back(run, g);
+    run(0);
+    for (std::thread &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != GNX_OK) {
+            if (g > 0) root->err = "device " + std::to_string(ctxOf(g)->device) + ": " + ctxOf(g)->err;
+            for (int k = 0; k < G; ++k) { cudaSetDevice(ctxOf(k)->device); cudaStreamSynchronize(ctxOf(k)->stream); }
+            return rcs[g];
+        }
+    GNX_CUDA(root, cudaSetDevice(root->device));
+    float4 *frame0 = dev_out ? (float4 *)dev_out : root->rgba;
+    GNX_CUDA(root, cudaEventRecord(root->ev0, root->stream));
+    NcclApi *nc = root->comms.empty() ? nullptr : nccl_api();
+    if (nc) {
+        int r = nc->GroupStart();
+        for (int g = 0; g < G && r == 0; ++g) {
+            gnx_ctx *c = ctxOf(g);
+            const float4 *send = g == 0 ? frame0 : c->rgba;
+            r = nc->Reduce(send, g == 0 ? (void *)frame0 : nullptr, npix * 4, kNcclFloat32, kNcclSum, 0, root->comms[g], c->stream);
+        }
+        int r2 = nc->GroupEnd();
+        if (r == 0) r = r2;
+        if (r != 0) return fail(root, GNX_ERR_CUDA, std::string("ncclReduce: ") + nc->GetErrorString(r));
+        GNX_CUDA(root, cudaSetDevice(root->device));
+    } else {
+        PeerFrames pf{};
+        pf.n = G - 1;
+        if (!root->p2p_direct && root->stage_pixels < npix * (size_t)(G - 1)) {
+            if (root->stage) cudaFree(root->stage);
+            root->stage = nullptr; root->stage_pixels = 0;
+            GNX_CUDA(root, cudaMalloc((void **)&root->stage, npix * (size_t)(G - 1) * sizeof(float4)));
+            root->stage_pixels = npix * (size_t)(G - 1);
+        }
+        for (int g = 1; g < G; ++g) {
+            gnx_ctx *c = ctxOf(g);
+            GNX_CUDA(root, cudaStreamWaitEvent(root->stream, c->ev_done, 0));
+            if (root->p2p_direct) pf.part[g - 1] = c->rgba;
+            else {
+                float4 *dst = root->stage + npix * (size_t)(g - 1);
+                GNX_CUDA(root, cudaMemcpyPeerAsync(dst, root->device, c->rgba, c->device, npix * sizeof(float4), root->stream));
+                pf.part[g - 1] = dst;
+            }
+        }
+        k_reduce_peers<<<root->sm_count * 8, 256, 0, root->stream>>>(frame0, pf, (int)npix);
+        GNX_CUDA(root, cudaGetLastError());
+    }
+    if (resolveAfter) {
+        k_film_gauss<<<root->sm_count * 8, 256, 0, root->stream>>>(frame0, frame0, (int)npix, 1);
+        GNX_CUDA(root, cudaGetLastError());
+    }
+    GNX_CUDA(root, cudaEventRecord(root->ev1, root->stream));
+    if (host_out) GNX_CUDA(root, cudaMemcpyAsync(host_out, frame0, npix * sizeof(float4), cudaMemcpyDeviceToHost, root->stream));
+    if (host_out || stats) GNX_CUDA(root, cudaStreamSynchronize(root->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int g = 0; g < G; ++g) add_stats(stats, sts[g]);
+        stats->paths = (uint64_t)npix * (uint64_t)p->spp;  // (tile shares count the padding of their edge tiles)
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, root->ev0, root->ev1) == cudaSuccess) { root->ms_reduce = ms; stats->device_ms += ms; stats->ms_film += ms; }
+        stats->kernel_launches += 1;
+    }
+    return GNX_OK;
+}
+
+// The same job across processes (gnx_comm_attach): this rank renders its share on `st`, ncclReduce to rank 0 behind it.
+static int render_attached(gnx_ctx *ctx, const gnx_render_params *p, float *host_out, float *dev_out, cudaStream_t st, gnx_stats *stats) {
+    NcclApi *nc = nccl_api();
+    if (!nc || ctx->comms.empty()) return fail(ctx, GNX_ERR_INVALID, "the context is not attached to a communicator");
+    if (ctx->rank == 0 && !host_out && !dev_out) return GNX_ERR_INVALID;
+    if (!p) return GNX_ERR_INVALID;
+    Share sh;
+    sh.n = ctx->n_ranks; sh.idx = ctx->rank; sh.partition = p->partition;
+    gnx_render_params pShare = *p;
+    const bool resolveAfter = p->film == GNX_FILM_GAUSSIAN;
+    if (resolveAfter) pShare.film = GNX_FILM_GAUSSIAN_SUMS;
+    int rc = render_impl(ctx, &pShare, dev_out, st, stats, true, sh);
+    if (rc) return rc;
+    const size_t npix = (size_t)p->width * p->height;
+    float4 *frame = dev_out ? (float4 *)dev_out : ctx->rgba;
+    int r = nc->Reduce(frame, ctx->rank == 0 ? (void *)frame : nullptr, npix * 4, kNcclFloat32, kNcclSum, 0, ctx->comms[0], st);
+    if (r != 0) return fail(ctx, GNX_ERR_CUDA, std::string("ncclReduce: ") + nc->GetErrorString(r));
+    if (resolveAfter && ctx->rank == 0) {
+        k_film_gauss<<<ctx->sm_count * 8, 256, 0, st>>>(frame, frame, (int)npix, 1);
+        GNX_CUDA(ctx, cudaGetLastError());
+    }
+    if (host_out && ctx->rank == 0) GNX_CUDA(ctx, cudaMemcpyAsync(host_out, frame, npix * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (host_out || stats) GNX_CUDA(ctx, cudaStreamSynchronize(st));
+    return GNX_OK;
+}
+
 extern "C" {
 
 double gnx_bvh_build_ms(const gnx_ctx *ctx) { return ctx ? (double)ctx->bvh_build_ms : 0.0; }
 
 int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, gnx_stats *stats) {
-    if (!ctx || !rgba_out) return GNX_ERR_INVALID;
+    if (!ctx) return GNX_ERR_INVALID;
+    if (!ctx->peers.empty()) return render_multi(ctx, params, rgba_out, nullptr, stats);
+    if (ctx->n_ranks > 1) return render_attached(ctx, params, rgba_out, nullptr, ctx->stream, stats);
+    if (!rgba_out) return GNX_ERR_INVALID;
     // the device-to-host copy is queued right behind the film kernel; one synchronisation at the end
     int rc = render_impl(ctx, params, nullptr, ctx->stream, stats, true);
     if (rc) return rc;
@@ -888,10 +1154,161 @@ int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, g
 }
 
 int gnx_render_device(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_dev, void *stream, gnx_stats *stats) {
-    if (!ctx || !rgba_dev) return GNX_ERR_INVALID;
+    if (!ctx) return GNX_ERR_INVALID;
     // stream 0 is the CALLER's default stream (cudaStreamLegacy), not a private one: work queued by the caller before and
     // after this call on that stream is ordered with the render, whatever the caller's stream flags are
-    return render_impl(ctx, params, rgba_dev, stream ? (cudaStream_t)stream : cudaStreamLegacy, stats);
+    cudaStream_t st = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+    if (!ctx->peers.empty()) return rgba_dev ? render_multi(ctx, params, nullptr, rgba_dev, stats) : GNX_ERR_INVALID;
+    if (ctx->n_ranks > 1) return (rgba_dev || ctx->rank != 0) ? render_attached(ctx, params, nullptr, rgba_dev, st, stats) : GNX_ERR_INVALID;
+    if (!rgba_dev) return GNX_ERR_INVALID;
+    return render_impl(ctx, params, rgba_dev, st, stats);
+}
+
+int gnx_render_framebuffer(gnx_ctx *ctx, const gnx_render_params *params, int32_t pass_count, float *fbuffer, uint8_t *ubuffer,
+                           gnx_stats *stats) {
+    if (!ctx || pass_count < 1) return GNX_ERR_INVALID;
+    if (ctx->n_ranks > 1) return fail(ctx, GNX_ERR_UNSUPPORTED, "gnx_render_framebuffer on a context attached to a multi-process job");
+    int rc = validate_params(ctx, params);
+    if (rc) return rc;
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)params->width * params->height;
+    if (npix > ctx->fb_pixels) {
+        if (ctx->fb_state) cudaFree(ctx->fb_state);
+        if (ctx->fb_u8) cudaFree(ctx->fb_u8);
+        ctx->fb_state = nullptr; ctx->fb_u8 = nullptr; ctx->fb_pixels = 0; ctx->fb_w = ctx->fb_h = 0;
+        GNX_CUDA(ctx, cudaMalloc((void **)&ctx->fb_state, npix * sizeof(float4)));
+        GNX_CUDA(ctx, cudaMalloc((void **)&ctx->fb_u8, npix * sizeof(uchar4)));
+        ctx->fb_pixels = npix;
+    }
+    if (npix > ctx->fb_pinned_pixels) {
+        if (ctx->fb_pinned) cudaFreeHost(ctx->fb_pinned);
+        ctx->fb_pinned = nullptr; ctx->fb_pinned_pixels = 0;
+        GNX_CUDA(ctx, cudaHostAlloc(&ctx->fb_pinned, npix * (sizeof(float4) + sizeof(uchar4)), cudaHostAllocDefault));
+        ctx->fb_pinned_pixels = npix;
+    }
+    for (cudaEvent_t &e : ctx->fb_ev) if (!e) GNX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    float4 *pinF = (float4 *)ctx->fb_pinned;
+    uchar4 *pinU = (uchar4 *)((char *)ctx->fb_pinned + ctx->fb_pinned_pixels * sizeof(float4));
+    cudaStream_t st = ctx->stream;
+    const bool haveState = ctx->fb_w == params->width && ctx->fb_h == params->height;
+    if (pass_count == 1 || (!haveState && !fbuffer)) {
+        GNX_CUDA(ctx, cudaMemsetAsync(ctx->fb_state, 0, npix * sizeof(float4), st));  // (1 - 1/1) * f: the first pass forgets f
+    } else if (!haveState) {
+        // the running mean of passes this context has not seen: taken from the caller's FrameBuffer
+        memcpy(pinF, fbuffer, npix * sizeof(float4));
+        GNX_CUDA(ctx, cudaMemcpyAsync(ctx->fb_state, pinF, npix * sizeof(float4), cudaMemcpyHostToDevice, st));
+    }
+    ctx->fb_w = params->width; ctx->fb_h = params->height;
+    // the render itself, result in ctx->rgba on this (the root) device
+    if (!ctx->peers.empty()) rc = render_multi(ctx, params, nullptr, (float *)nullptr, stats, true);
+    else rc = render_impl(ctx, params, nullptr, st, stats, true);
+    if (rc) { ctx->fb_w = ctx->fb_h = 0; return rc; }
+    k_framebuffer_update<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->rgba, ctx->fb_state, ctx->fb_u8, (int)npix, 1.0f / (float)pass_count);
+    GNX_CUDA(ctx, cudaGetLastError());
+    // device -> pinned staging in row chunks, each chunk unpacked into the caller's (pageable) buffers while the next
+    // one is in flight: colour channels only for the float image, all four bytes for the 8-bit one
+    const int nChunks = 8;
+    const size_t per = (npix + nChunks - 1) / nChunks;
+    for (int c = 0; c < nChunks; ++c) {
+        const size_t a = std::min(npix, per * c), b = std::min(npix, per * (c + 1));
+        if (b > a) {
+            if (fbuffer) GNX_CUDA(ctx, cudaMemcpyAsync(pinF + a, ctx->fb_state + a, (b - a) * sizeof(float4), cudaMemcpyDeviceToHost, st));
+            if (ubuffer) GNX_CUDA(ctx, cudaMemcpyAsync(pinU + a, ctx->fb_u8 + a, (b - a) * sizeof(uchar4), cudaMemcpyDeviceToHost, st));
+        }
+        GNX_CUDA(ctx, cudaEventRecord(ctx->fb_ev[c], st));
+    }
+    for (int c = 0; c < nChunks; ++c) {
+        GNX_CUDA(ctx, cudaEventSynchronize(ctx->fb_ev[c]));
+        const size_t a = std::min(npix, per * c), b = std::min(npix, per * (c + 1));
+        if (fbuffer)
+            for (size_t i = a; i < b; ++i) memcpy(fbuffer + 4 * i, &pinF[i], 3 * sizeof(float));
+        if (ubuffer && b > a) memcpy(ubuffer + 4 * a, pinU + a, (b - a) * sizeof(uchar4));
+    }
+    return GNX_OK;
+}
+
+int gnx_num_devices(const gnx_ctx *ctx) { return ctx ? (ctx->peers.empty() ? ctx->n_ranks : 1 + (int)ctx->peers.size()) : 0; }
+
+int gnx_create_multi(gnx_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) { g_create_error = "gnx_create_multi: out is NULL"; return GNX_ERR_INVALID; }
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > kMaxDevices) { g_create_error = "gnx_create_multi: n_devices must be in [1, 16]"; return GNX_ERR_INVALID; }
+    // A device may be listed more than once: its shares then time-share that GPU (tests of the partition logic on a
+    // one-GPU box, oversubscription); NCCL cannot put one GPU into a communicator twice, so the reduce is the kernel then.
+    std::vector<int> ids(n_devices);
+    bool dup = false;
+    for (int g = 0; g < n_devices; ++g) {
+        ids[g] = device_ids ? device_ids[g] : g;
+        for (int k = 0; k < g; ++k) dup = dup || ids[k] == ids[g];
+    }
+    gnx_ctx *root = nullptr;
+    int rc = gnx_create(&root, ids[0]);
+    if (rc) return rc;
+    for (int g = 1; g < n_devices; ++g) {
+        gnx_ctx *p = nullptr;
+        if ((rc = gnx_create(&p, ids[g]))) { gnx_destroy(root); return rc; }
+        root->peers.push_back(p);
+    }
+    if (n_devices > 1) {
+        // peer-to-peer loads from every peer (NVLink / NVSwitch on a B200 box), for the one-kernel reduce
+        cudaSetDevice(ids[0]);
+        root->p2p_direct = true;
+        for (int g = 1; g < n_devices; ++g) {
+            int can = 0;
+            if (ids[g] == ids[0]) continue;  // the root's own memory
+            if (cudaDeviceCanAccessPeer(&can, ids[0], ids[g]) != cudaSuccess || !can) { root->p2p_direct = false; continue; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ids[g], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) root->p2p_direct = false;
+        }
+        cudaGetLastError();
+        if (dup && root->reduce_mode == 1) { g_create_error = "GNX_REDUCE=nccl with a device listed twice"; gnx_destroy(root); return GNX_ERR_INVALID; }
+        NcclApi *nc = (root->reduce_mode == 2 || dup) ? nullptr : nccl_api();
+        if (nc) {
+            root->comms.assign(n_devices, nullptr);
+            int r = nc->CommInitAll(root->comms.data(), n_devices, ids.data());
+            if (r != 0) {
+                std::string why = std::string("ncclCommInitAll: ") + nc->GetErrorString(r);
+                root->comms.clear();
+                if (root->reduce_mode == 1) { g_create_error = why; gnx_destroy(root); return GNX_ERR_CUDA; }
+            }
+            cudaSetDevice(ids[0]);
+        } else if (root->reduce_mode == 1) {
+            g_create_error = "GNX_REDUCE=nccl, but libnccl could not be loaded";
+            gnx_destroy(root);
+            return GNX_ERR_UNSUPPORTED;
+        }
+    }
+    *out = root;
+    return GNX_OK;
+}
+
+int gnx_comm_unique_id(void *id_out) {
+    if (!id_out) return GNX_ERR_INVALID;
+    NcclApi *nc = nccl_api();
+    if (!nc) { g_create_error = "libnccl could not be loaded"; return GNX_ERR_UNSUPPORTED; }
+    NcclId id;
+    int r = nc->GetUniqueId(&id);
+    if (r != 0) { g_create_error = std::string("ncclGetUniqueId: ") + nc->GetErrorString(r); return GNX_ERR_CUDA; }
+    memcpy(id_out, &id, sizeof(id));
+    return GNX_OK;
+}
+
+int gnx_comm_attach(gnx_ctx *ctx, int n_ranks, int rank, const void *id) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return GNX_ERR_INVALID;
+    if (!ctx->peers.empty() || ctx->n_ranks > 1) return fail(ctx, GNX_ERR_INVALID, "the context already belongs to an N-device job");
+    if (n_ranks == 1) return GNX_OK;
+    NcclApi *nc = nccl_api();
+    if (!nc) return fail(ctx, GNX_ERR_UNSUPPORTED, "libnccl could not be loaded");
+    GNX_CUDA(ctx, cudaSetDevice(ctx->device));
+    NcclId nid;
+    memcpy(&nid, id, sizeof(nid));
+    NcclComm comm = nullptr;
+    int r = nc->CommInitRank(&comm, n_ranks, nid, rank);
+    if (r != 0) return fail(ctx, GNX_ERR_CUDA, std::string("ncclCommInitRank: ") + nc->GetErrorString(r));
+    ctx->comms.assign(1, comm);
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return GNX_OK;
 }
 
 int gnx_primary_hits(gnx_ctx *ctx, const gnx_render_params *p, int32_t sample, int32_t *prim_id_out) {

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GNX_ABI_VERSION 3
+#define GNX_ABI_VERSION 4
 
 typedef enum gnx_status {
     GNX_OK = 0,
@@ -293,7 +293,19 @@ typedef struct gnx_render_params {
     int32_t film;               /* gnx_film; BOX == the reference (core/Integrator.cpp:293)       */
     float filter_radius, filter_alpha; /* GAUSSIAN films: radius in pixels (both axes), falloff alpha  */
     int32_t batch_spp;          /* samples per pixel in flight per wavefront batch; 0 = auto      */
+    int32_t partition;          /* gnx_partition: how an N-device job (gnx_create_multi / gnx_comm_attach) is dealt
+                                   out; ignored by a single-device context                         */
 } gnx_render_params;
+
+/* Partition of ONE render over the GPUs of a multi-device context.  params describe the WHOLE job
+ * (spp = all samples of a pixel); the library deals out the work and sums the partial framebuffers onto the root. */
+typedef enum gnx_partition {
+    GNX_PARTITION_SAMPLES = 0, /* device g renders a contiguous range of every pixel's samples (Sampler::SetSampleNumber
+                                  semantics, core/Sampler.cpp:155-160); perfect balance; float sum-reduce (differs from the
+                                  single-device sum by the rounding of the regrouped additions)                            */
+    GNX_PARTITION_TILES = 1    /* interleaved 32 x 32 pixel tiles, every pixel finished on one device; the reduce only adds
+                                  zeros: bit-equal to the single-device render.  Box film only                             */
+} gnx_partition;
 
 typedef struct gnx_stats {
     uint64_t paths;             /* camera samples started                                         */
@@ -318,6 +330,21 @@ typedef struct gnx_ctx gnx_ctx;
 int gnx_abi_version(void);
 int gnx_device_count(void);                              /* 0 when no CUDA device is usable   */
 int gnx_create(gnx_ctx **out, int device);               /* one context == one GPU            */
+/* One context driving n_devices GPUs of this node from ONE process (what a reference app calling
+ * integrator->Render(scene, t) needs to use a whole 8-GPU box, ui/RenderThread.cpp:169-175): the scene is replicated by
+ * gnx_upload_scene, gnx_render splits the job (gnx_render_params::partition) over one stream per device, the partial
+ * framebuffers are summed onto device_ids[0] — ncclReduce over NVLink queued behind each device's last film kernel
+ * (libnccl is loaded at run time), or one peer-to-peer kernel on the root (GNX_REDUCE=p2p, and when NCCL is not
+ * available) — and only the root copies to the host.  device_ids == NULL: devices 0 .. n_devices-1. */
+int gnx_create_multi(gnx_ctx **out, const int *device_ids, int n_devices);
+int gnx_num_devices(const gnx_ctx *ctx);
+/* The same job partition across PROCESSES (one rank per GPU, e.g. under torchrun): rank 0 obtains an id, the host
+ * program distributes its 128 bytes to every rank (any transport), each rank attaches its single-device context.
+ * From then on gnx_render / gnx_render_device on these contexts are collective: params describe the whole job on every
+ * rank, each rank renders its share, ncclReduce leaves the image on rank 0 (rgba_out may be NULL elsewhere). */
+#define GNX_COMM_ID_BYTES 128
+int gnx_comm_unique_id(void *id_out);
+int gnx_comm_attach(gnx_ctx *ctx, int n_ranks, int rank, const void *id);
 void gnx_destroy(gnx_ctx *ctx);
 const char *gnx_last_error(const gnx_ctx *ctx);          /* ctx may be NULL: last create error */
 
@@ -342,6 +369,19 @@ int gnx_render(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_out, g
 int gnx_render_device(gnx_ctx *ctx, const gnx_render_params *params, float *rgba_dev,
                       void *stream, gnx_stats *stats);
 
+/* Render + the reference's output sink in one call: what SamplerIntegrator::Render does to the FrameBuffer it was
+ * given (core/Integrator.cpp:230,293-310, ui/FrameBuffer.h:127-149), with the running mean over Render() calls and the
+ * exposure tonemap computed on the device behind the film kernel:
+ *     f   = (1 / pass_count) * mean + (1 - 1 / pass_count) * f          per colour channel (update_f_u_c)
+ *     u8  = (1 - exp(-f / (1 - 0.75))) * 255, alpha byte 255              (update_f_u_c, set_uc)
+ * fbuffer is the HOST float[width*height*4] of the FrameBuffer (only its three colour channels are written, the float
+ * alpha stays the caller's), ubuffer the HOST uint8[width*height*4]; either may be NULL.  pass_count is
+ * FrameBuffer::curRenderCount after renderCountIncrease(), i.e. 1 on the first pass.  The running mean lives on the
+ * device between calls (the library owns pinned staging for the copies); a call with pass_count > 1 on a context that
+ * has no state of that size yet reads it from fbuffer first. */
+int gnx_render_framebuffer(gnx_ctx *ctx, const gnx_render_params *params, int32_t pass_count, float *fbuffer,
+                           uint8_t *ubuffer, gnx_stats *stats);
+
 /* Parity hook: id (gnx_geometry::prim_id) of the primitive hit by the camera ray of sample
  * `sample` of every pixel, -1 for a miss; prim_id_out is HOST int32[width*height]. */
 int gnx_primary_hits(gnx_ctx *ctx, const gnx_render_params *params, int32_t sample,
@@ -352,7 +392,8 @@ int gnx_sample_dimensions(gnx_ctx *ctx, int32_t n, const int64_t *index, const i
                           float *out);
 
 /* Tonemap + 8-bit pack identical to FrameBuffer::update_f_u_c (ui/FrameBuffer.h:141-147):
- * u8 = (1 - exp(-x / (1 - 0.75))) * 255, alpha 255.  Host buffers. */
+ * u8 = (1 - exp(-x / (1 - 0.75))) * 255, alpha 255.  Host buffers (a utility for images that are already on the host;
+ * the render path tonemaps on the device, gnx_render_framebuffer). */
 int gnx_tonemap_rgba8(gnx_ctx *ctx, const float *rgba, int32_t n_pixels, uint8_t *rgba8_out);
 
 #ifdef __cplusplus

@@ -4,10 +4,10 @@
 // ui/ModelList.cpp, ui/MaterialList.cpp and ui/RenderThread.cpp cannot be compiled without Qt, so
 // its recipes are re-expressed here with the same numbers), renders them with the UNMODIFIED
 // reference integrators and exposes parity hooks over a small C interface used by tests/ and by
-// bench.py's cpu_baseline / --impl reference legs via ctypes.  It also instantiates the product's
-// CUDAPathIntegrator on the very same pbr::Scene, which is how the drop-in boundary is tested.
+// bench.py's cpu_baseline / --impl reference legs via ctypes.
 //
-// Linked into oracle/_ref/libgnxref.so together with the reference objects (oracle/Makefile).
+// Linked into oracle/_ref/libgnxref.so together with the reference objects (oracle/Makefile); that library links nothing
+// of the product (the drop-in class is instantiated on these scenes by oracle/bridge_harness.cpp, libgnxbridge.so).
 // Nothing in the product library depends on this file.
 #include <dlfcn.h>
 #include <omp.h>
@@ -50,7 +50,7 @@
 #include "textures/ConstantTexture.h"
 #include "textures/ImageTexture.h"
 
-#include "gnxraytracer_b200/bridge/CUDAPathIntegrator.h"
+#include "ref_harness.h"
 #include "gnxraytracer_b200/host/scenekit_mesh.h"
 
 using namespace pbr;
@@ -72,35 +72,6 @@ std::string ResourceDir() {
     }
     return "Resources/";
 }
-
-struct HarnessScene {
-    int width = 0, height = 0, spp = 0;
-    std::string name;
-    std::vector<std::unique_ptr<Transform>> transforms;  // Triangle keeps raw pointers to these
-    std::vector<std::shared_ptr<Primitive>> prims;       // original (pre-BVH) order
-    std::vector<std::shared_ptr<Light>> lights;
-    std::vector<std::shared_ptr<Medium>> media;
-    std::unique_ptr<Transform> cam2world;
-    std::unique_ptr<AnimatedTransform> animated;
-    std::shared_ptr<const Camera> camera;
-    std::shared_ptr<Sampler> sampler;
-    int integrator = 0;  // gnx_integrator: 0 Path, 1 VolPath, 2 Whitted, 3 DirectLighting (UniformSampleOne)
-    std::unique_ptr<Scene> scene;
-    std::unique_ptr<FrameBuffer> fb;
-    std::unique_ptr<gnx::CUDAPathIntegrator> cuda;
-    int cudaMaxDepth = -1;
-    float filterRadius = 0, filterAlpha = 0;  // CUDAPathIntegrator::SetGaussianFilter
-    std::string strategy = "spatial";  // lightSampleStrategy handed to both integrators
-    std::unordered_map<const Primitive *, int> orderedIndex;  // BVH-ordered index of each primitive
-    std::unordered_map<const Primitive *, int> originalIndex; // position in `prims` (the caller's order)
-    std::string error;
-    double bvhSeconds = 0;
-
-    const Transform *keep(const Transform &t) {
-        transforms.emplace_back(new Transform(t));
-        return transforms.back().get();
-    }
-};
 
 // A Sampler for integrators whose number of draws per sample is unbounded (VolPath + GridDensityMedium:
 // the reference's Halton tables stop at dimension 1000 and are read out of range beyond that, SURVEY.md
@@ -442,13 +413,6 @@ bool BuildUI(HarnessScene &hs, int integrator, int nu, int nv, const std::string
     return true;
 }
 
-void IndexPrims(HarnessScene &hs) {
-    if (!hs.cuda || !hs.cuda->flat()) return;
-    const auto &ptrs = hs.cuda->flat()->prim_ptr;
-    hs.orderedIndex.clear();
-    for (size_t k = 0; k < ptrs.size(); ++k) hs.orderedIndex[(const Primitive *)ptrs[k]] = (int)k;
-}
-
 }  // namespace
 
 extern "C" {
@@ -490,13 +454,13 @@ int gnxh_scene_num_prims(void *h) { return (int)((HarnessScene *)h)->prims.size(
 void gnxh_scene_set_light_strategy(void *h, int strategy) {
     auto *hs = (HarnessScene *)h;
     hs->strategy = strategy == 0 ? "uniform" : strategy == 2 ? "power" : "spatial";
-    hs->cuda.reset();
+    hs->DropExt();
 }
 // Image reconstruction of the drop-in class: GaussianFilter(radius, alpha); radius <= 0 = the reference's box average.
 void gnxh_scene_set_gaussian_filter(void *h, float radius, float alpha) {
     auto *hs = (HarnessScene *)h;
     hs->filterRadius = radius; hs->filterAlpha = alpha;
-    hs->cuda.reset();
+    hs->DropExt();
 }
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
 
@@ -518,19 +482,26 @@ static SamplerIntegrator *MakeReferenceIntegrator(HarnessScene *hs, int maxDepth
 
 // The reference's own render: PathIntegrator::Render with `threads` OpenMP threads (0 = default).
 // rgba_out receives FrameBuffer's float buffer; *seconds the reference's own timeConsume.
-int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, double *seconds) {
+// n_passes Render() calls on a cleared FrameBuffer, as the UI's loop makes them (ui/RenderThread.cpp:169-175): rgba_out /
+// u8_out receive the float and the 8-bit buffer (running mean + tonemap of ui/FrameBuffer.h:127-149), *seconds the
+// timeConsume of the last pass.
+int gnxh_render_reference_passes(void *h, int maxDepth, int threads, int n_passes, float *rgba_out, unsigned char *u8_out, double *seconds) {
     auto *hs = (HarnessScene *)h;
     if (!hs->scene) return -1;
     if (threads > 0) omp_set_num_threads(threads);
     hs->fb->InitBuffer(hs->width, hs->height, 4);
     hs->fb->renderCountClear();
-    Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
     std::unique_ptr<SamplerIntegrator> integ(MakeReferenceIntegrator(hs, maxDepth));
     double t = 0;
-    integ->Render(*hs->scene, t);
+    for (int k = 0; k < n_passes; ++k) integ->Render(*hs->scene, t);
     if (seconds) *seconds = t;
-    if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * 4 * hs->width * hs->height);
+    const size_t n = (size_t)4 * hs->width * hs->height;
+    if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * n);
+    if (u8_out) memcpy(u8_out, hs->fb->getUCbuffer(), n);
     return 0;
+}
+int gnxh_render_reference(void *h, int maxDepth, int threads, float *rgba_out, double *seconds) {
+    return gnxh_render_reference_passes(h, maxDepth, threads, 1, rgba_out, nullptr, seconds);
 }
 
 // Li of individual camera samples (pixel, sample number) straight from PathIntegrator::Li, and the
@@ -652,73 +623,6 @@ int64_t gnxh_reference_sample_index(void *h, int px, int py, int sample) {
     s->StartPixel(Point2i(px, py));
     auto *hal = dynamic_cast<HaltonSampler *>(s.get());
     return hal ? hal->GetIndexForSample(sample) : -1;
-}
-
-// ---- the product side, through the drop-in class -----------------------------------------------------
-static gnx::CUDAPathIntegrator *EnsureCuda(HarnessScene *hs, int maxDepth) {
-    if (!hs->cuda || hs->cudaMaxDepth != maxDepth) {
-        Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
-        hs->cuda.reset(new gnx::CUDAPathIntegrator(maxDepth, hs->camera, hs->sampler, bounds, hs->fb.get(), 1.f, hs->strategy,
-                                                   hs->integrator == 1));
-        hs->cuda->SetIntegrator(hs->integrator);
-        hs->cuda->SetGaussianFilter(hs->filterRadius, hs->filterAlpha);
-        hs->cudaMaxDepth = maxDepth;
-    }
-    return hs->cuda.get();
-}
-
-// Flatten only (no GPU needed): returns the gnx_scene_desc the bridge would upload, or NULL.
-const gnx_scene_desc *gnxh_flatten(void *h) {
-    auto *hs = (HarnessScene *)h;
-    static thread_local std::unique_ptr<gnx::FlatScene> keep;
-    auto *flat = new gnx::FlatScene;
-    if (!gnx::FlattenScene(*hs->scene, *hs->camera, *hs->sampler, flat)) {
-        hs->error = flat->error;
-        delete flat;
-        return nullptr;
-    }
-    hs->orderedIndex.clear();
-    for (size_t k = 0; k < flat->prim_ptr.size(); ++k) hs->orderedIndex[(const Primitive *)flat->prim_ptr[k]] = (int)k;
-    keep.reset(flat);
-    return &flat->desc;
-}
-
-int gnxh_render_cuda(void *h, int maxDepth, float *rgba_out, double *seconds, gnx_stats *stats) {
-    auto *hs = (HarnessScene *)h;
-    gnx::CUDAPathIntegrator *c = EnsureCuda(hs, maxDepth);
-    hs->fb->InitBuffer(hs->width, hs->height, 4);
-    hs->fb->renderCountClear();
-    double t = 0;
-    c->Render(*hs->scene, t);
-    if (!c->error().empty()) { hs->error = c->error(); return -1; }
-    IndexPrims(*hs);
-    if (seconds) *seconds = t;
-    if (stats) *stats = c->lastStats();
-    if (rgba_out) memcpy(rgba_out, hs->fb->getFbuffer(), sizeof(float) * 4 * hs->width * hs->height);
-    return 0;
-}
-
-int gnxh_cuda_primary_hits(void *h, int sample, int *ordered_out) {
-    auto *hs = (HarnessScene *)h;
-    gnx::CUDAPathIntegrator *c = EnsureCuda(hs, hs->cudaMaxDepth < 0 ? 5 : hs->cudaMaxDepth);
-    std::vector<int32_t> v;
-    if (!c->PrimaryHits(*hs->scene, sample, &v)) { hs->error = c->error(); return -1; }
-    IndexPrims(*hs);
-    memcpy(ordered_out, v.data(), v.size() * sizeof(int));
-    return 0;
-}
-
-// Maps BVH-ordered primitive indices (gnx_geometry::prim_id of a bridge-flattened scene) to the
-// scene's original primitive order; -1 stays -1.  Requires gnxh_flatten or a CUDA call before.
-int gnxh_ordered_to_original(void *h, int n, const int *ordered, int *original) {
-    auto *hs = (HarnessScene *)h;
-    std::vector<int> map(hs->orderedIndex.size(), -2);
-    for (auto &kv : hs->orderedIndex) {
-        auto it = hs->originalIndex.find(kv.first);
-        if (kv.second >= 0 && kv.second < (int)map.size() && it != hs->originalIndex.end()) map[kv.second] = it->second;
-    }
-    for (int i = 0; i < n; ++i) original[i] = ordered[i] < 0 ? -1 : (ordered[i] < (int)map.size() ? map[ordered[i]] : -2);
-    return 0;
 }
 
 int gnxh_max_threads(void) { return omp_get_max_threads(); }

@@ -8,7 +8,8 @@ import numpy as np
 from gnxraytracer_b200.api import RenderParams, Stats
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgnxref.so")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgnxref.so")        # the unmodified reference + scene harness
+BRIDGE_LIB = os.path.join(ROOT, "oracle", "_ref", "libgnxbridge.so")  # the product's drop-in class on those scenes
 EMUL_LIB = os.path.join(ROOT, "tests", "emul", "_build", "libgnxemul.so")
 vp, ci = ctypes.c_void_p, ctypes.c_int
 
@@ -60,16 +61,44 @@ def grid(width, height):
     return xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)
 
 
+_bridge = None
+
+
+def bridge_lib():
+    """oracle/_ref/libgnxbridge.so: gnx::CUDAPathIntegrator + harness hooks (pulls in libgnxref.so and libgnxrt.so).
+    Loaded on first use, so that callers of the reference alone (bench.py --impl reference) map nothing of the product."""
+    global _bridge
+    if _bridge is None:
+        ctypes.CDLL(REF_LIB)
+        b = ctypes.CDLL(BRIDGE_LIB)
+        b.gnxh_flatten.restype = vp
+        b.gnxh_flatten.argtypes = [vp]
+        b.gnxh_render_cuda.argtypes = [vp, ci, vp, vp, vp]
+        b.gnxh_render_cuda_passes.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+        b.gnxh_time_cuda_render.argtypes = [vp, ci, ci]
+        b.gnxh_time_cuda_render.restype = ctypes.c_double
+        b.gnxh_cuda_primary_hits.argtypes = [vp, ci, vp]
+        b.gnxh_ordered_to_original.argtypes = [vp, ci, vp, vp]
+        b.gnxh_cuda_set_devices.argtypes = [vp, ci, vp, ci]
+        b.gnxh_cuda_set_progressive.argtypes = [vp, ci]
+        _bridge = b
+    return _bridge
+
+
 class RefScene:
     def __init__(self, lib, h, width, height, spp):
         self.lib, self.h, self.width, self.height, self.spp = lib, h, width, height, spp
         self._desc = None
 
     @property
+    def blib(self):
+        return bridge_lib()
+
+    @property
     def desc(self):
         """gnx_scene_desc* produced by the bridge's FlattenScene from the live pbr::Scene."""
         if self._desc is None:
-            self._desc = self.lib.gnxh_flatten(self.h)
+            self._desc = self.blib.gnxh_flatten(self.h)
             if not self._desc:
                 raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
         return self._desc
@@ -77,10 +106,12 @@ class RefScene:
     def set_light_strategy(self, strategy):
         """lightSampleStrategy of the reference integrators and of the drop-in class: LIGHTS_UNIFORM / SPATIAL / POWER."""
         self.lib.gnxh_scene_set_light_strategy(self.h, int(strategy))
+        self._desc = None  # the product-side state (and the flattened description it owns) is dropped with the setting
 
     def set_gaussian_filter(self, radius, alpha):
         """Film of the drop-in class: GaussianFilter(radius, alpha); radius <= 0 = the reference's box average."""
         self.lib.gnxh_scene_set_gaussian_filter(self.h, float(radius), float(alpha))
+        self._desc = None
 
     def reference_gaussian_film(self, radius, alpha, max_depth=5):
         """Film::AddSample splat of the reference's own samples / Li / GaussianFilter::Evaluate: (image, sums)."""
@@ -120,14 +151,49 @@ class RefScene:
         out = np.zeros((self.height, self.width, 4), np.float32)
         sec = ctypes.c_double()
         st = Stats()
-        rc = self.lib.gnxh_render_cuda(self.h, max_depth, out.ctypes.data, ctypes.byref(sec), ctypes.byref(st))
+        rc = self.blib.gnxh_render_cuda(self.h, max_depth, out.ctypes.data, ctypes.byref(sec), ctypes.byref(st))
         if rc != 0:
             raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
         return out, sec.value, st
 
+    def render_cuda_passes(self, n_passes, max_depth=5):
+        """n_passes calls of CUDAPathIntegrator::Render on a cleared FrameBuffer: (float buffer, 8-bit buffer, wall seconds
+        of the last call)."""
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        u8 = np.zeros((self.height, self.width, 4), np.uint8)
+        sec, wall = ctypes.c_double(), ctypes.c_double()
+        rc = self.blib.gnxh_render_cuda_passes(self.h, max_depth, n_passes, out.ctypes.data, u8.ctypes.data, ctypes.byref(sec),
+                                               ctypes.byref(wall), None)
+        if rc != 0:
+            raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
+        return out, u8, wall.value
+
+    def render_reference_passes(self, n_passes, max_depth=5, threads=0):
+        """n_passes calls of the reference's Render on a cleared FrameBuffer: (float buffer, 8-bit buffer)."""
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        u8 = np.zeros((self.height, self.width, 4), np.uint8)
+        rc = self.lib.gnxh_render_reference_passes(self.h, max_depth, threads, n_passes, out.ctypes.data, u8.ctypes.data, None)
+        assert rc == 0
+        return out, u8
+
+    def time_cuda_render(self, n_calls, max_depth=5):
+        """Wall seconds per CUDAPathIntegrator::Render call on the uploaded scene (after one warm-up call)."""
+        t = self.blib.gnxh_time_cuda_render(self.h, max_depth, n_calls)
+        if t < 0:
+            raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
+        return t
+
+    def set_devices(self, devices, partition=0):
+        """GPUs the drop-in class drives ([] = device 0 alone) and the gnx_partition of its renders."""
+        ids = (ctypes.c_int * max(1, len(devices)))(*devices)
+        self.blib.gnxh_cuda_set_devices(self.h, len(devices), ids, partition)
+
+    def set_progressive(self, on):
+        self.blib.gnxh_cuda_set_progressive(self.h, 1 if on else 0)
+
     def cuda_primary_hits(self, sample=0):
         out = np.zeros(self.width * self.height, np.int32)
-        rc = self.lib.gnxh_cuda_primary_hits(self.h, sample, out.ctypes.data)
+        rc = self.blib.gnxh_cuda_primary_hits(self.h, sample, out.ctypes.data)
         if rc != 0:
             raise RuntimeError(self.lib.gnxh_scene_error(self.h).decode())
         return out
@@ -136,7 +202,7 @@ class RefScene:
         """BVH-ordered primitive indices (a bridge-flattened scene's prim_id) -> original scene order."""
         ordered = np.ascontiguousarray(ordered, np.int32).ravel()
         out = np.zeros(ordered.size, np.int32)
-        self.lib.gnxh_ordered_to_original(self.h, ordered.size, ordered.ctypes.data, out.ctypes.data)
+        self.blib.gnxh_ordered_to_original(self.h, ordered.size, ordered.ctypes.data, out.ctypes.data)
         return out
 
     def close(self):
@@ -160,16 +226,12 @@ class Ref:
         l.gnxh_reference_gaussian_film.argtypes = [vp, ci, ctypes.c_float, ctypes.c_float, vp, vp]
         l.gnxh_reference_gaussian_eval.argtypes = [ctypes.c_float, ctypes.c_float, ci, vp, vp, vp]
         l.gnxh_scene_bvh_seconds.restype = ctypes.c_double
-        l.gnxh_flatten.restype = vp
-        l.gnxh_flatten.argtypes = [vp]
         l.gnxh_render_reference.argtypes = [vp, ci, ci, vp, vp]
+        l.gnxh_render_reference_passes.argtypes = [vp, ci, ci, ci, vp, vp, vp]
         l.gnxh_reference_samples.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
         l.gnxh_reference_sample_dims.argtypes = [vp, ci, vp, vp, vp]
         l.gnxh_reference_sample_index.restype = ctypes.c_int64
         l.gnxh_reference_sample_index.argtypes = [vp, ci, ci, ci]
-        l.gnxh_render_cuda.argtypes = [vp, ci, vp, vp, vp]
-        l.gnxh_cuda_primary_hits.argtypes = [vp, ci, vp]
-        l.gnxh_ordered_to_original.argtypes = [vp, ci, vp, vp]
         self.lib = l
 
     def scene(self, preset, width, height, spp):
@@ -203,6 +265,12 @@ class EmulScene:
         self.lib.gnxe_render(self.h, ctypes.byref(params), out.ctypes.data, ctypes.byref(st))
         return out, st
 
+    def render_share(self, params, n_shares, share):
+        """The frame share `share` of an n_shares-device job hands to the reduce (the library's partition arithmetic)."""
+        out = np.zeros((params.height, params.width, 4), np.float32)
+        self.lib.gnxe_render_share(self.h, ctypes.byref(params), n_shares, share, out.ctypes.data)
+        return out
+
     def samples(self, params, px, py, sample):
         rgb = np.zeros((px.size, 3), np.float32)
         self.lib.gnxe_samples(self.h, ctypes.byref(params), px.size, px.ctypes.data, py.ctypes.data, sample.ctypes.data, rgb.ctypes.data)
@@ -235,6 +303,7 @@ class Emul:
         l.gnxe_destroy.argtypes = [vp]
         l.gnxe_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, ctypes.POINTER(Stats)]
         l.gnxe_samples.argtypes = [vp, ctypes.POINTER(RenderParams), ci, vp, vp, vp, vp]
+        l.gnxe_render_share.argtypes = [vp, ctypes.POINTER(RenderParams), ci, ci, vp]
         l.gnxe_primary_hits.argtypes = [vp, ci, ci, ci, vp]
         l.gnxe_gaussian_eval.argtypes = [ctypes.c_float, ctypes.c_float, ci, vp, vp, vp]
         l.gnxe_sample_dims.argtypes = [vp, ci, vp, vp, vp]

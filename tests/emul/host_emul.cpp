@@ -282,6 +282,48 @@ int gnxe_render(void *h, const gnx_render_params *p, float *rgba_out, gnx_stats 
     return 0;
 }
 
+// One device's share of an N-device job, with the library's own partition arithmetic (gnx_path.cuh pixel_xy /
+// local_tile_count, the sample-range split of gnx_render.cu): the frame a device hands to the reduce.  The sum of the
+// shares' frames must be the single-device image — bit for bit with the tile partition.
+int gnxe_render_share(void *h, const gnx_render_params *p, int n_shares, int share, float *rgba_out) {
+    auto *e = (EmulScene *)h;
+    if (p->integrator < GNX_INTEGRATOR_WHITTED) ensure_spatial(*e, p->light_strategy);
+    const int W = p->width, H = p->height;
+    memset(rgba_out, 0, sizeof(float) * 4 * (size_t)W * H);
+    const float norm = (float)(p->spp_normalize > 0 ? p->spp_normalize : p->spp);
+    if (p->partition == GNX_PARTITION_TILES) {
+        RenderConsts rc{};
+        rc.width = W; rc.height = H;
+        rc.tile_n = n_shares; rc.tile_dev = share;
+        rc.tiles_x = (W + kTile - 1) / kTile; rc.tiles_y = (H + kTile - 1) / kTile;
+        const int npix = local_tile_count(rc.tiles_x, rc.tiles_y, n_shares, share) * kTile * kTile;
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int lp = 0; lp < npix; ++lp) {
+            int px, py;
+            if (!pixel_xy(rc, lp, &px, &py)) continue;
+            V3 sum(0.f);
+            TraversalCounters cnt{0, 0};
+            unsigned long long rays[3] = {0, 0, 0};
+            for (int s = 0; s < p->spp; ++s) sum += trace_sample(*e, *p, px, py, p->first_sample + s, cnt, rays);
+            float *o = rgba_out + 4 * ((size_t)py * W + px);
+            o[0] = sum.x / norm; o[1] = sum.y / norm; o[2] = sum.z / norm; o[3] = 1.f;
+        }
+        return 0;
+    }
+    const int base = p->spp / n_shares, rem = p->spp % n_shares;
+    const int count = base + (share < rem ? 1 : 0), first = p->first_sample + share * base + (share < rem ? share : rem);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int pixel = 0; pixel < W * H; ++pixel) {
+        V3 sum(0.f);
+        TraversalCounters cnt{0, 0};
+        unsigned long long rays[3] = {0, 0, 0};
+        for (int s = 0; s < count; ++s) sum += trace_sample(*e, *p, pixel % W, pixel / W, first + s, cnt, rays);
+        float *o = rgba_out + 4 * (size_t)pixel;
+        o[0] = sum.x / norm; o[1] = sum.y / norm; o[2] = sum.z / norm; o[3] = share == 0 ? 1.f : 0.f;
+    }
+    return 0;
+}
+
 int gnxe_samples(void *h, const gnx_render_params *p, int n, const int *px, const int *py, const int *sample, float *rgb_out) {
     auto *e = (EmulScene *)h;
     if (p->integrator < GNX_INTEGRATOR_WHITTED) ensure_spatial(*e, p->light_strategy);

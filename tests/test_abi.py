@@ -24,7 +24,7 @@ def test_libgnxrt_exports_every_declared_symbol():
     assert len(names) >= 11
     for n in names:
         assert hasattr(lib, n), f"libgnxrt.so does not export {n}"
-    assert lib.gnx_abi_version() == 3
+    assert lib.gnx_abi_version() == 4
 
 
 def test_scenekit_exports_every_declared_symbol():

@@ -321,15 +321,40 @@ def test_device_built_bvh_tiny_scenes(ctx):
         sk.close()
 
 
-def test_new_lights_are_refused_by_the_path_integrator(ref, ctx):
+@pytest.mark.parametrize("preset,depth", [("lights_path", 5), ("lights_path_img", 5), ("ui_path", 15), ("ui_whitted", 5)])
+def test_delta_and_skybox_lights_under_the_path_integrator(ref, emul, preset, depth):
+    """EstimateDirect's delta branch and SkyBoxLight in the wavefront PathIntegrator (core/Integrator.cpp:93-210,
+    lights/SkyBoxLight.cpp:45-86), and the reference UI's live scene under both of its integrator lines
+    (ui/RenderThread.cpp:163-164): through the drop-in class against the reference's own Render."""
+    from _harness import integrator_of
+    res, spp = 128, 8
+    rs = ref.scene(preset, res, res, spp)
+    img_ref, _ = rs.render_reference(max_depth=depth)
+    img, _, st = rs.render_cuda(max_depth=depth)
+    assert st.paths == res * res * spp and st.rays_shadow > 0
+    assert rel_mse(img, img_ref) <= 1e-3
+    px, py = grid(res, res)
+    _, prim = rs.reference_samples(px, py, np.zeros(px.size, np.int32), max_depth=depth, want_rgb=False)
+    assert float(np.mean(rs.to_original(rs.cuda_primary_hits(0)) == prim)) >= 0.9999
+    sel = np.random.default_rng(9).choice(px.size, 512, replace=False)
+    samples = np.stack([rs.reference_samples(px[sel], py[sel], np.full(sel.size, s, np.int32), max_depth=depth, want_prim=False)[0] for s in range(spp)])
+    sigma = samples.std(axis=0, ddof=1) / np.sqrt(spp) + 1e-4
+    assert np.mean(np.abs(img.reshape(-1, 4)[sel, :3] - img_ref.reshape(-1, 4)[sel, :3]) <= 3 * sigma) >= 0.999
+    emu, _ = emul.scene(rs.desc).render(RenderParams.make(res, res, spp, max_depth=depth, integrator=integrator_of(preset)))
+    assert rel_mse(img, emu) <= 1e-6
+    rs.close()
+
+
+def test_recursion_depth_limit_is_an_error_not_a_clamp(ref, ctx):
+    """Whitted / DirectLighting keep 16 recursion frames: deeper requests are refused instead of silently cut."""
     from gnxraytracer_b200.api import GnxError
     rs = ref.scene("whitted", 32, 32, 2)
     ctx.upload(rs.desc)
+    img, _ = ctx.render(RenderParams.make(32, 32, 2, integrator=2, max_depth=16))
+    assert np.isfinite(img).all()
     with pytest.raises(GnxError) as e:
-        ctx.render(RenderParams.make(32, 32, 2, integrator=0))
+        ctx.render(RenderParams.make(32, 32, 2, integrator=2, max_depth=17))
     assert e.value.code == -4
-    img, st = ctx.render(RenderParams.make(32, 32, 2, integrator=2))
-    assert np.isfinite(img).all() and img[..., :3].mean() > 0.01
     rs.close()
 
 

@@ -40,7 +40,7 @@ def test_scenekit_bvh_is_well_formed():
     sk = SceneKit("cornell", 16, 16, 1, 0, 1, 0)
     # gnx_scene_desc begins with abi_version (u32, padded) then gnx_geometry {n_nodes, nodes*, n_prims, ...}
     raw = ctypes.cast(sk.desc, ctypes.POINTER(ctypes.c_int32))
-    assert raw[0] == 3  # GNX_ABI_VERSION
+    assert raw[0] == 4  # GNX_ABI_VERSION
     n_nodes = raw[2]
     nodes_ptr = ctypes.cast(sk.desc + 16, ctypes.POINTER(ctypes.c_void_p))[0]
     n_prims = ctypes.cast(sk.desc + 24, ctypes.POINTER(ctypes.c_int32))[0]
