@@ -214,7 +214,8 @@ class Context:
 
 
 # ---- host-side scene kit (include/gnx_scenekit.h): builds gnx_scene_desc for the BASELINE configs ----
-SCENEKIT_EXPORTS = ["gnxsk_create", "gnxsk_destroy", "gnxsk_desc", "gnxsk_error", "gnxsk_num_prims", "gnxsk_build_seconds", "gnxsk_strip_bvh"]
+SCENEKIT_EXPORTS = ["gnxsk_create", "gnxsk_destroy", "gnxsk_desc", "gnxsk_error", "gnxsk_num_prims", "gnxsk_build_seconds", "gnxsk_strip_bvh",
+                    "gnxsk_corrupt"]
 _sk = None
 
 
@@ -244,6 +245,7 @@ def load_scenekit():
     sk.gnxsk_build_seconds.restype = c_double
     sk.gnxsk_strip_bvh.argtypes = [c_void_p]
     sk.gnxsk_strip_bvh.restype = None
+    sk.gnxsk_corrupt.argtypes = [c_void_p, ctypes.c_int]
     ip = ctypes.POINTER(ctypes.c_int)
     sk.gnxsk_mesh_info.argtypes = [ctypes.c_char_p, ip, ip, ip, ip, ctypes.c_char_p, ctypes.c_int]
     sk.gnxsk_write_knot_3d.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
@@ -306,6 +308,10 @@ class SceneKit:
     def strip_bvh(self):
         """Drop the host-built BVH: the library then builds one on the GPU at upload."""
         self.sk.gnxsk_strip_bvh(self.h)
+
+    def corrupt(self, kind):
+        """Damage the description (see gnx_scenekit.h) — for tests of the upload validation."""
+        return self.sk.gnxsk_corrupt(self.h, int(kind))
 
     def close(self):
         if self.h:

@@ -141,11 +141,15 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                 needFinish = false;
             }
             // shade-queue pushes, one atomic per warp and queue
-            if (__any_sync(kFull, pendType >= 0)) {
+            if (__any_sync(kFull, pendType != -1)) {
 #pragma unroll
                 for (int ty = 0; ty < kNumShadeTypes; ++ty) {
                     int idx = warp_push(&q.counts[kCntShade0 + ty], pendType == ty);
                     if (idx >= 0) q.shade_q[(size_t)ty * q.capacity + idx] = pendSlot;
+                }
+                if (q.miss_q) {  // scenes with a SkyBoxLight: escaped rays wait for k_escape
+                    int idx = warp_push(&q.counts[kCntMiss], pendType == kPendEscape);
+                    if (idx >= 0) q.miss_q[idx] = pendSlot;
                 }
                 pendType = -1;
             }
@@ -229,6 +233,12 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
         if ((threadIdx.x & 31) == 0 && raysSh) atomicAdd(&st->shadow_rays_in_extend_launches, (unsigned long long)raysSh);
     } else flush_stats(st, kExtend ? 0 : 2, cnt.nodes, cnt.tris, rays);
     if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+}
+
+// Escaped rays of a scene with a SkyBoxLight (queued by the traversal kernel): L += beta * Le(ray).
+__global__ void k_escape(const DeviceScene sc, PathState ps, Queues q) {
+    const int n = q.counts[kCntMiss];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) escape_slot(sc, ps, q.miss_q[i]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,

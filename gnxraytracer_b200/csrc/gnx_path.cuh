@@ -93,6 +93,7 @@ GNX_D void slot_to_sample(const RenderConsts &rc, int slot, int *pixel, int *sam
 }
 
 GNX_D int shade_type_of(unsigned matWord) { return (int)((matWord >> 20) & 0xfu); }
+constexpr int kPendEscape = -2;  // primary_finish / extend_finish: "queue the slot for k_escape" (scenes with a SkyBoxLight)
 
 // Camera sample `sample` of pixel (px, py): the ray is generated in registers and traversed at once
 // (no ray round trip through HBM for the ~90 % of C2's camera rays that never touch the mesh).
@@ -111,7 +112,16 @@ GNX_D void primary_begin(const DeviceScene &sc, int px, int py, int sample, uint
 GNX_D int primary_finish(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, uint32_t hidx, V3 d,
                          const Trav &t) {
     if (!t.hit) {
-        V3 Le = sc.skybox.present ? scene_le_cold(sc, t.o, d) : (sc.env.present ? env_Le(sc.env, d) : V3(0.f));
+        if (sc.skybox.present) {
+            // SkyBoxLight::Le needs the ray and double-precision atan2 / asin: escaped rays of such scenes are queued
+            // for k_escape instead of paying for that code (and its registers) inside the traversal kernel
+            ps.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ps.ray_o[slot] = make_float4(t.o.x, t.o.y, t.o.z, GNX_INF);
+            ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 1.f);
+            ps.beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+            return kPendEscape;
+        }
+        V3 Le = sc.env.present ? env_Le(sc.env, d) : V3(0.f);
         ps.L[slot] = make_float4(Le.x, Le.y, Le.z, 0.f);
         return -1;
     }
@@ -144,23 +154,34 @@ GNX_D int extend_finish(const DeviceScene &sc, const PathState &ps, const Render
         ps.hit[slot] = make_float4(t.h.b0, t.h.b1, t.h.b2, i2f(t.prim));
         return shade_type_of(matWord);
     }
-    if (emitOk && (sc.env.present || sc.skybox.present)) {
+    if (emitOk && sc.skybox.present) return kPendEscape;  // -> k_escape (ray and throughput are in the path state)
+    if (emitOk && sc.env.present) {
         // for (light : scene.infiniteLights) L += beta * light->Le(ray)
         const float4 b = ps.beta[slot], rd = ps.ray_d[slot];
         float4 L = ps.L[slot];
-        const V3 dir(rd.x, rd.y, rd.z);
-        V3 add = V3(b.x, b.y, b.z) * (sc.skybox.present ? scene_le_cold(sc, t.o, dir) : env_Le(sc.env, dir));
+        V3 add = V3(b.x, b.y, b.z) * env_Le(sc.env, V3(rd.x, rd.y, rd.z));
         L.x += add.x; L.y += add.y; L.z += add.z;
         ps.L[slot] = L;
     }
     return -1;
+}
+// An escaped ray of a scene with a SkyBoxLight: for (light : scene.infiniteLights) L += beta * light->Le(ray)
+// (PathIntegrator.cpp:112-116), both infinite kinds in the order of scene.lights.
+GNX_D void escape_slot(const DeviceScene &sc, const PathState &ps, int slot) {
+    const float4 b = ps.beta[slot], ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+    float4 L = ps.L[slot];
+    V3 add = V3(b.x, b.y, b.z) * scene_le(sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z));
+    L.x += add.x; L.y += add.y; L.z += add.z;
+    ps.L[slot] = L;
 }
 GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderConsts &rc, int slot, int2 *stack, int stride,
                       TraversalCounters &cnt) {
     TravLocal t;
     extend_begin(sc, ps, slot, t);
     while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
-    return extend_finish(sc, ps, rc, slot, t);
+    int type = extend_finish(sc, ps, rc, slot, t);
+    if (type == kPendEscape) { escape_slot(sc, ps, slot); type = -1; }  // sequential callers: at once
+    return type;
 }
 
 // Surfaces without a material are medium boundaries: PathIntegrator re-spawns the ray in the same

@@ -688,6 +688,7 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix, int npixFrame)
         if ((rc = dupload<ShadowItem>(ctx, pool, nullptr, n * 2, &ctx->q.shadow_q))) return rc;
         if ((rc = dupload<ProbeItem>(ctx, pool, nullptr, n, &ctx->q.probe_q))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, kNumCounters, &ctx->q.counts))) return rc;
+        ctx->q.miss_q = nullptr;
         ctx->q.capacity = capacity;
         ctx->capacity = capacity;
         GNX_CUDA(ctx, cudaDeviceSynchronize());
@@ -818,6 +819,11 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / std::max(1, npix)));
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix, npixFrame))) return rc;
 
+    // escaped rays of scenes with a SkyBoxLight are queued for k_escape
+    if (ctx->sc.skybox.present && p->integrator == GNX_INTEGRATOR_PATH && !ctx->q.miss_q && ctx->capacity > 0)
+        if ((rc = dupload<int>(ctx, ctx->wave_allocs, nullptr, (size_t)ctx->capacity, &ctx->q.miss_q))) return rc;
+    Queues qv = ctx->q;
+    if (!ctx->sc.skybox.present) qv.miss_q = nullptr;
     cudaStream_t st = userStream;  // gnx_render_device maps a NULL stream to the legacy default stream (see gnxrt.h)
     set_l2_window(ctx, st);
     const DeviceScene &sc = ctx->sc;
@@ -885,12 +891,12 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         if (tiles) { rcn.tile_n = share.n; rcn.tile_dev = share.idx; rcn.tiles_x = tilesX; rcn.tiles_y = tilesY; }
         if (npix == 0) break;  // more devices than tiles
         if (p->integrator != GNX_INTEGRATOR_PATH) {
-            k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, 1);
+            k_reset_counts<<<1, 32, 0, st>>>(qv.counts, 1);
             tm.begin(ST_EXTEND);
-            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
-            else if (p->integrator == GNX_INTEGRATOR_WHITTED) k_recursive<0><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
-            else if (p->integrator == GNX_INTEGRATOR_DIRECT) k_recursive<1><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
-            else k_recursive<2><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, ctx->d_stats);
+            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            else if (p->integrator == GNX_INTEGRATOR_WHITTED) k_recursive<0><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            else if (p->integrator == GNX_INTEGRATOR_DIRECT) k_recursive<1><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            else k_recursive<2><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
             tm.end();
             tm.begin(ST_FILM);
             launches += accumulate(psv, rcn);
@@ -909,27 +915,28 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         // have them keep iterating until the queue drains.
         for (int iter = 0;; ++iter) {
             const int out = 1 - in;
-            if (mixed && iter > 0) k_reset_counts_keep_rays<<<1, 32, 0, st>>>(ctx->q.counts, out);
-            else k_reset_counts<<<1, 32, 0, st>>>(ctx->q.counts, out);
+            if (mixed && iter > 0) k_reset_counts_keep_rays<<<1, 32, 0, st>>>(qv.counts, out);
+            else k_reset_counts<<<1, 32, 0, st>>>(qv.counts, out);
             tm.begin(ST_EXTEND);
-            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats);  // ray-gen fused in
-            else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, in, ctx->d_stats);
-            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, in, ctx->d_stats);
+            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 0, ctx->d_stats);  // ray-gen fused in
+            else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
             ++extendLaunches;
-            if (mixed && iter > 0) { k_reset_ray_counts<<<1, 32, 0, st>>>(ctx->q.counts); ++launches; }
+            if (qv.miss_q) { k_escape<<<gridWide, 256, 0, st>>>(sc, psv, qv); ++launches; }
+            if (mixed && iter > 0) { k_reset_ray_counts<<<1, 32, 0, st>>>(qv.counts); ++launches; }
             tm.begin(ST_SHADE);
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
                 if (ctx->has_next_lights) {  // point / spot / distant / skybox records: the variant with every Light::Sample_Li
-                    if (t == GNX_MAT_DISNEY) k_shade<8, true><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
-                    else k_shade<2, true><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
-                } else if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
-                else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, ctx->q, rcn, t, out);
+                    if (t == GNX_MAT_DISNEY) k_shade<8, true><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, qv, rcn, t, out);
+                    else k_shade<2, true><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, qv, rcn, t, out);
+                } else if (t == GNX_MAT_DISNEY) k_shade<8><<<ctx->grid_shade8, kShadeBlock, 0, st>>>(sc, psv, qv, rcn, t, out);
+                else k_shade<2><<<gridShade, kShadeBlock, 0, st>>>(sc, psv, qv, rcn, t, out);
                 ++launches;
             }
-            if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, out); ++launches; }
+            if (hasNull) { k_shade_null<<<gridShade, kBlock, 0, st>>>(sc, psv, qv, rcn, out); ++launches; }
             tm.end();
             tm.begin(ST_SHADOW);
             const bool last = iter >= p->max_depth && !hasNull;
@@ -938,18 +945,18 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
                 // accumulators (ps.L / ps.Lb), so the two rays of a path do not race.  In mixed mode they wait for the
                 // next bounce's extension launch, except after the last bounce.
                 if (!mixed || last) {
-                    k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, (psv.Lb && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
+                    k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, (psv.Lb && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
                     ++launches;
-                    if (sc.env.present && !(psv.Lb && ctx->merge_shadow)) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 1, ctx->d_stats); ++launches; }
+                    if (sc.env.present && !(psv.Lb && ctx->merge_shadow)) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 1, ctx->d_stats); ++launches; }
                 }
-                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, psv, ctx->q, rcn, 0, ctx->d_stats); ++launches; }
+                if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 0, ctx->d_stats); ++launches; }
             }
             tm.end();
             in = out;
             if (iter >= p->max_depth) {
                 if (!hasNull) break;
                 int remaining = 0;
-                GNX_CUDA(ctx, cudaMemcpyAsync(&remaining, ctx->q.counts + in, sizeof(int), cudaMemcpyDeviceToHost, st));
+                GNX_CUDA(ctx, cudaMemcpyAsync(&remaining, qv.counts + in, sizeof(int), cudaMemcpyDeviceToHost, st));
                 GNX_CUDA(ctx, cudaStreamSynchronize(st));
                 if (remaining == 0 || iter > p->max_depth + 4096) break;
             }
@@ -1217,13 +1224,27 @@ int gnx_render_framebuffer(gnx_ctx *ctx, const gnx_render_params *params, int32_
         }
         GNX_CUDA(ctx, cudaEventRecord(ctx->fb_ev[c], st));
     }
-    for (int c = 0; c < nChunks; ++c) {
-        GNX_CUDA(ctx, cudaEventSynchronize(ctx->fb_ev[c]));
-        const size_t a = std::min(npix, per * c), b = std::min(npix, per * (c + 1));
-        if (fbuffer)
-            for (size_t i = a; i < b; ++i) memcpy(fbuffer + 4 * i, &pinF[i], 3 * sizeof(float));
-        if (ubuffer && b > a) memcpy(ubuffer + 4 * a, pinU + a, (b - a) * sizeof(uchar4));
-    }
+    // (four host threads share the chunks: one thread unpacks ~8 GB/s, the copies arrive at ~25 GB/s)
+    const int nWorkers = npix >= (1u << 18) ? 4 : 1;
+    std::vector<cudaError_t> werr(nWorkers, cudaSuccess);
+    auto unpack = [&](int wk) {
+        for (int c = wk; c < nChunks; c += nWorkers) {
+            cudaError_t e = cudaEventSynchronize(ctx->fb_ev[c]);
+            if (e != cudaSuccess) { werr[wk] = e; return; }
+            const size_t a = std::min(npix, per * c), b = std::min(npix, per * (c + 1));
+            if (fbuffer) {
+                const float4 *src = pinF + a;
+                float *dst = fbuffer + 4 * a;
+                for (size_t i = 0; i < b - a; ++i) { dst[4 * i] = src[i].x; dst[4 * i + 1] = src[i].y; dst[4 * i + 2] = src[i].z; }
+            }
+            if (ubuffer && b > a) memcpy(ubuffer + 4 * a, pinU + a, (b - a) * sizeof(uchar4));
+        }
+    };
+    std::vector<std::thread> workers;
+    for (int wk = 1; wk < nWorkers; ++wk) workers.emplace_back(unpack, wk);
+    unpack(0);
+    for (std::thread &t : workers) t.join();
+    for (cudaError_t e : werr) GNX_CUDA(ctx, e);
     return GNX_OK;
 }
 

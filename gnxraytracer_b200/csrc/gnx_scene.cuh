@@ -130,6 +130,7 @@ struct Queues {
     int *shade_q;            // [n_mat_types][capacity] lists per material type
     ShadowItem *shadow_q;
     ProbeItem *probe_q;
+    int *miss_q;             // escaped rays of scenes with a SkyBoxLight (k_escape); null otherwise
     // counters: [0..1] extend ping/pong, [2..2+NT) shade per type, then shadow, probe
     int *counts;
     int capacity;
@@ -138,7 +139,7 @@ constexpr int kNumShadeTypes = 7;  // 6 gnx_material_type + "no material" (mediu
 // queue counters: extend ping/pong, one per shade type, shadow A (light samples), shadow B (environment MIS
 // probes), probe (area-light MIS probes); then the dynamic-fetch cursors of the four traversal launches
 constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCntShade0 + kNumShadeTypes,
-              kCntProbe = kCntShadow + 2, kCntFetch = kCntProbe + 1, kNumCounters = kCntFetch + 4;
+              kCntProbe = kCntShadow + 2, kCntFetch = kCntProbe + 1, kCntMiss = kCntFetch + 4, kNumCounters = kCntMiss + 1;
 
 struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
     unsigned long long rays[3], nodes[3], tris[3], paths;

@@ -532,23 +532,6 @@ GNX_D V3 scene_le(const DeviceScene &sc, V3 o, V3 d) {
     return L;
 }
 
-// scene_le for the traversal kernels' escaped rays: the SkyBoxLight part (double-precision atan2 / asin) out of line, so
-// that it costs the hot loop neither registers nor instruction-cache lines.  The record travels by value: taking the
-// address of a member of the kernel's by-value DeviceScene parameter would make the compiler keep a local copy of it.
-#if defined(__CUDA_ARCH__)
-__device__ __noinline__ V3 skybox_le_cold(DevSkybox sb, V3 o, V3 d) { return skybox_le(sb, o, d); }
-#else
-inline V3 skybox_le_cold(DevSkybox sb, V3 o, V3 d) { return skybox_le(sb, o, d); }
-#endif
-GNX_D V3 scene_le_cold(const DeviceScene &sc, V3 o, V3 d) {
-    V3 L(0.f);
-    const bool envFirst = !sc.skybox.present || (sc.env.present && sc.env.light_index < sc.skybox.light_index);
-    if (envFirst && sc.env.present) L += env_Le(sc.env, d);
-    if (sc.skybox.present) L += skybox_le_cold(sc.skybox, o, d);
-    if (!envFirst && sc.env.present) L += env_Le(sc.env, d);
-    return L;
-}
-
 // Light::Sample_Li for every light type (lights/*.cpp)
 GNX_D bool w_sample_li(const DeviceScene &sc, const gnx_light &l, V3 refP, float u0, float u1, WLightSample *o) {
     o->delta = false;

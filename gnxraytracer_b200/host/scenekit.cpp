@@ -117,7 +117,8 @@ static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3],
 struct Box { float lo[3], hi[3]; };
 static Box empty_box() { return {{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}}; }
 static void grow(Box &b, const float *p) { for (int c = 0; c < 3; ++c) { b.lo[c] = std::min(b.lo[c], p[c]); b.hi[c] = std::max(b.hi[c], p[c]); } }
-static void grow(Box &b, const Box &o) { grow(b, o.lo); grow(b, o.hi); }
+// (component-wise: an EMPTY box {+inf, -inf} must leave b unchanged — growing by its corners as points would not)
+static void grow(Box &b, const Box &o) { for (int c = 0; c < 3; ++c) { b.lo[c] = std::min(b.lo[c], o.lo[c]); b.hi[c] = std::max(b.hi[c], o.hi[c]); } }
 static float area(const Box &b) {
     float d[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
     return 2 * (d[0] * d[1] + d[0] * d[2] + d[1] * d[2]);
@@ -893,6 +894,26 @@ int gnxsk_mesh_info(const char *path, int *n_vertices, int *n_triangles, int *ha
     }
     return io_result(ok, e, err, err_len);
 }
+// Damages the description in one specific way (tests of the library's upload validation): 1 = a BVH leaf whose
+// primitive range leaves the array, 2 = prim_light past the light list, 3 = a texture index below -1, 4 = materials NULL
+// with a non-zero count, 5 = prim_light pointing at a light that is not an area light.  Returns 0 when applied.
+int gnxsk_corrupt(gnxsk_scene *s, int kind) {
+    if (!s || !s->error.empty()) return -1;
+    gnx_scene_desc &d = s->desc;
+    if (kind == 1) {
+        for (gnx_bvh_node &n : s->nodes) if (n.n_prims > 0) { n.offset = d.geom.n_prims - n.n_prims + 1; return 0; }
+        return -1;
+    }
+    if (kind == 2 && !s->prim_light.empty()) { s->prim_light[0] = d.n_lights; return 0; }
+    if (kind == 3 && !s->materials.empty()) { s->materials[0].rgb_tex[0] = -5; return 0; }
+    if (kind == 4) { d.materials = nullptr; return 0; }
+    if (kind == 5 && !s->prim_light.empty()) {
+        for (int i = 0; i < d.n_lights; ++i) if (s->lights[i].type != GNX_LIGHT_AREA_TRI) { s->prim_light[0] = i; return 0; }
+        return -1;
+    }
+    return -1;
+}
+
 void gnxsk_strip_bvh(gnxsk_scene *s) {
     if (!s) return;
     s->desc.geom.n_nodes = 0;

@@ -45,6 +45,11 @@ double gnxsk_build_seconds(const gnxsk_scene *s);      /* BVH build wall time   
 /* Drops the kit's host-built BVH from the description (geom.n_nodes = 0): gnx_upload_scene then builds the
  * hierarchy on the GPU.  The primitive arrays stay as they are (any order is valid without nodes). */
 void gnxsk_strip_bvh(gnxsk_scene *s);
+/* Damages the description in one specific way so that tests can check that gnx_upload_scene refuses it with
+ * GNX_ERR_INVALID instead of reading out of range on the device: kind 1 = a BVH leaf whose primitive range leaves the
+ * array, 2 = prim_light past the light list, 3 = a texture index below -1, 4 = materials NULL with a non-zero count,
+ * 5 = prim_light pointing at a light that is not an area light.  Returns 0 when applied. */
+int gnxsk_corrupt(gnxsk_scene *s, int kind);
 
 /* Mesh files on their own.  Both return 0, or -1 with the reason copied into err (NUL-terminated, err_len bytes).
  * gnxsk_mesh_info parses a .3d file (or a Wavefront OBJ when the path ends in ".obj") and reports its counts;

