@@ -448,7 +448,27 @@ def run_ours(args, wl, name):
         ext_bytes = st.extend_bytes / max(1, st.extend_launches)
         achieved = (ext_bytes / (ext_ms * 1e-3)) / 1e9 if ext_ms > 0 else None
         ev = ncu_evidence(name)
-        kernel = {PATH: "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)", VOLPATH: "the VolPath launches",
+        vp_stages = None
+        if integ == VOLPATH and sum(st.vp_items) > 0:
+            # VolPath wavefront: one roofline line per stage.  ALGORITHMIC bytes: path state 100 B per load
+            # or store, walk state 144 B per load or store, 48 B triangle + 136 B material + 132 B environment tables at a vertex,
+            # 32 B per BVH node and 48 B per triangle of the stage's rays, 32 B of grid reads per tracking step
+            rays = max(1, st.rays)
+            trav = (32.0 * st.nodes_visited + 48.0 * st.tris_tested) / rays
+            it, ms = list(st.vp_items), list(st.vp_ms)
+            by = [it[0] * 200 + st.rays_extend * trav,
+                  it[1] * (200 + 144 + 48 + 136 + 132),
+                  it[2] * (200 + 288) + st.rays_shadow * trav,
+                  it[3] * (200 + 288 + 48 + 136) + st.rays_mis * trav,
+                  st.vp_track_steps * 32 + it[4] * 56]
+            names = ["k_vp_logic<extend>", "k_vp_logic<vertex>", "k_vp_logic<shadow walk>", "k_vp_logic<MIS walk + continuation>", "k_vp_track"]
+            vp_stages = [{"kernel": names[k], "ms": ms[k], "items": it[k], "algorithmic_bytes": by[k],
+                          "achieved": (by[k] / (ms[k] * 1e-3) / 1e9) if ms[k] > 0 else None,
+                          "frac": (by[k] / (ms[k] * 1e-3) / 1e9 / peak) if ms[k] > 0 else None} for k in range(5)]
+            dom = max(range(5), key=lambda k: ms[k])
+            achieved, ext_ms, ext_bytes = vp_stages[dom]["achieved"], ms[dom] / max(1, st.vp_rounds), by[dom] / max(1, st.vp_rounds)
+        kernel = {PATH: "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)",
+                  VOLPATH: (vp_stages[dom]["kernel"] + " (the stage with the largest share of the step; every stage under `stages`)") if vp_stages else "k_volpath",
                   }.get(integ, "k_recursive (Whitted / DirectLighting, one launch per batch)")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -474,7 +494,8 @@ def run_ours(args, wl, name):
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), " + str(ev["traffic_source"]), "peak_source": peak_src,
                          "launches_per_step": st.extend_launches, "avg_launch_ms": ext_ms,
                          "algorithmic_bytes_per_launch": ext_bytes,
-                         "issue": ev.get("issue"),
+                         "issue": ev.get("issue"), "stages": vp_stages,
+                         "vp_rounds": int(st.vp_rounds) if vp_stages else None, "vp_track_steps": int(st.vp_track_steps) if vp_stages else None,
                          "note": "achieved = ALGORITHMIC bytes / launch time: 32 B x BVH nodes popped + 48 B x triangles tested + 48 B x rays (ray read + hit write), counted by the kernel itself.  The scene (97 MB of nodes + triangles for C2) is L2-resident, so real DRAM traffic (`traffic`) is an order of magnitude below the algorithmic bytes: frac is NOT a fraction of HBM bandwidth in use; the kernel is bound by instruction issue and L1 wavefronts of the per-lane node gathers (`issue`: active lanes per instruction, issue-slot use from the ncu capture under profiles/)"},
             "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": ctypes.sizeof(params),
                     "d2h_bytes_per_step": W * H * (16 + 4) if world == 1 else W * H * 16,

@@ -52,6 +52,7 @@ class Stats(ctypes.Structure):
         ("ms_extend", c_double), ("ms_shade", c_double), ("ms_shadow", c_double), ("ms_film", c_double),
         ("kernel_launches", c_u64), ("bytes_algorithmic", c_u64),
         ("extend_nodes", c_u64), ("extend_tris", c_u64), ("extend_launches", c_u64), ("extend_bytes", c_u64),
+        ("vp_ms", c_double * 5), ("vp_items", c_u64 * 5), ("vp_track_steps", c_u64), ("vp_rounds", c_u64),
     ]
 
     @property
@@ -59,7 +60,7 @@ class Stats(ctypes.Structure):
         return self.rays_extend + self.rays_shadow + self.rays_mis
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: (list(getattr(self, k)) if k in ("vp_ms", "vp_items") else getattr(self, k)) for k, _ in self._fields_}
         d["rays"] = self.rays
         return d
 

@@ -9,6 +9,7 @@
 // memory (24 KB per 128-thread block).
 #pragma once
 #include "gnx_whitted.cuh"
+#include "gnx_volwave.cuh"
 #include "gnx_film.cuh"
 
 namespace gnx {
@@ -329,6 +330,142 @@ __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, Pat
     flush_stats(st, 1, 0, 0, vc.shadow);
     flush_stats(st, 2, 0, 0, vc.mis);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+}
+
+// ---- VolPathIntegrator as a staged wavefront (gnx_volwave.cuh) -------------------------------------------------------
+// Queues (the PathIntegrator's arrays, re-used): walks waiting for k_vp_track in extend_q[0] as (slot << 1 | mode), count
+// in counts[0]; paths waiting for a logic kernel in shade_q[VolQueue], counts in counts[kCntShade0 + queue].  One fetch
+// cursor (counts[kCntFetch]) serves every launch: k_vp_reset zeroes it, and the count of the queue the previous launch
+// has consumed, between two launches.
+__global__ void k_vp_reset(int *counts, int consumed) {
+    const int i = threadIdx.x;
+    if (consumed == -1) { if (i < kNumCounters) counts[i] = 0; }  // before the start launch: everything
+    else if (i == consumed || i == kCntFetch) counts[i] = 0;      // (-2: the cursor only)
+}
+
+// One logic kernel (VolKernel) over one of its queues; queue < 0: the camera samples of the batch (VP_START).
+#ifndef GNX_VP_LOGIC_BLOCKS
+#define GNX_VP_LOGIC_BLOCKS 6
+#endif
+template <int KERNEL>
+__global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const DeviceScene sc, PathState ps, VolWave vw, Queues q, RenderConsts rc, int queue,
+                                                        DevStats *st) {
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
+    const int n = queue < 0 ? rc.npix * rc.batch_spp : q.counts[kCntShade0 + queue];
+    const int *list = queue < 0 ? nullptr : q.shade_q + (size_t)queue * q.capacity;
+    const int entry = queue < 0 ? VP_START : vol_queue_phase(queue);
+    int *cursor = &q.counts[kCntFetch];
+    const int lane = threadIdx.x & 31;
+    TraversalCounters cnt{0, 0};
+    VolCounters vc{0, 0, 0};
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        const int i = base + lane;
+        int slot = 0, y = VY_DONE;
+        if (i < n) {
+            slot = list ? list[i] : i;
+            y = vol_advance<8>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
+        }
+        __syncwarp();
+        int idx = warp_push(&q.counts[kCntExtend0], y == VY_TRACK_MAIN || y == VY_TRACK_SUB);
+        if (idx >= 0) q.extend_q[0][idx] = (slot << 1) | (y == VY_TRACK_SUB ? 1 : 0);
+#pragma unroll
+        for (int k = 0; k < VQ_COUNT; ++k) {
+            if (vol_queue_kernel(k) == KERNEL) continue;  // a kernel never queues for itself
+            idx = warp_push(&q.counts[kCntShade0 + k], y == VY_QUEUE0 + k);
+            if (idx >= 0) q.shade_q[(size_t)k * q.capacity + idx] = slot;
+        }
+    }
+    flush_stats(st, 0, cnt.nodes, cnt.tris, vc.extend);
+    flush_stats(st, 1, 0, 0, vc.shadow);
+    flush_stats(st, 2, 0, 0, vc.mis);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (queue < 0) atomicAdd(&st->paths, (unsigned long long)n);
+        atomicAdd(&st->vp_items[KERNEL], (unsigned long long)n);
+    }
+}
+
+// The tracking walks of GridDensityMedium (delta tracking for the medium sample of a path segment, ratio tracking for a
+// shadow / MIS walk segment): persistent lanes, each holding one walk; every iteration of the inner loop is ONE tracking
+// step for all lanes that hold a walk, and lanes whose walk has ended take the next queue entry as soon as kTrackRefill
+// of them are idle — the lanes stay full whatever the lengths of the individual walks.
+#ifndef GNX_TRACK_REFILL
+#define GNX_TRACK_REFILL 8
+#endif
+#ifndef GNX_TRACK_BURST
+#define GNX_TRACK_BURST 8
+#endif
+__global__ void __launch_bounds__(kBlock, 8) k_vp_track(const DeviceScene sc, PathState ps, VolWave vw, Queues q, RenderConsts rc, DevStats *st) {
+    const int n = q.counts[kCntExtend0];
+    const int *list = q.extend_q[0];
+    int *cursor = &q.counts[kCntFetch];
+    const int lane = threadIdx.x & 31;
+    TrackLane tl;
+    tl.slot = 0; tl.mode = 0; tl.medium = 0;
+    PathSampler smp(sc.smp, 0, 0);
+    bool active = false, exhausted = false;
+    int pendQueue = -1, pendSlot = 0;   // finished walk: resume queue of its path
+    unsigned long long steps = 0;
+    while (true) {
+        // paths whose walk ended since the last visit go to the queue of their resume phase, one atomic per warp and queue
+        if (__any_sync(kFull, pendQueue >= 0)) {
+#pragma unroll
+            for (int k = 0; k < VQ_COUNT; ++k) {
+                if (k != VQ_VERTEX && k != VQ_SHADOW_RESUME && k != VQ_MIS_RESUME) continue;
+                const int idx = warp_push(&q.counts[kCntShade0 + k], pendQueue == k);
+                if (idx >= 0) q.shade_q[(size_t)k * q.capacity + idx] = pendSlot;
+            }
+            pendQueue = -1;
+        }
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (!exhausted && __popc(idle) >= GNX_TRACK_REFILL) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(cursor, __popc(idle));
+            base = __shfl_sync(kFull, base, leader);
+            if (!active) {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                if (i < n) {
+                    const int item = list[i];
+                    const int slot = item >> 1, mode = item & 1;
+                    int pixel, sample, px, py;
+                    slot_to_sample(rc, slot, &pixel, &sample);
+                    pixel_xy(rc, pixel, &px, &py);
+                    smp.take(vol_load_sampler(sc, rc, ps, vw, slot, px, py, sample));
+                    if (vol_track_begin(sc, ps, vw, slot, mode, tl)) active = true;
+                    else {  // the ray misses the medium's box: no steps, no draws
+                        vol_track_finish(sc, ps, vw, tl, smp);
+                        pendSlot = slot;
+                        pendQueue = vol_resume_queue(mode, (int)(ps.meta[slot] & kVolPhaseMask));
+                    }
+                }
+            }
+            exhausted = base + __popc(idle) >= n;
+        }
+        if (!__any_sync(kFull, active || pendQueue >= 0)) { if (exhausted) break; else continue; }
+#pragma unroll 1
+        for (int k = 0; k < GNX_TRACK_BURST; ++k) {
+            if (active) {
+                ++steps;
+                if (track_step(sc.media[tl.medium], tl.ts, smp)) {
+                    vol_track_finish(sc, ps, vw, tl, smp);
+                    pendSlot = tl.slot;
+                    pendQueue = vol_resume_queue(tl.mode, (int)(ps.meta[tl.slot] & kVolPhaseMask));
+                    active = false;
+                }
+            }
+            // stop the burst early once enough lanes are idle to be worth a refill (or nobody is left)
+            const unsigned act = __ballot_sync(kFull, active);
+            if (act == 0 || (!exhausted && 32 - __popc(act) >= GNX_TRACK_REFILL)) break;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(kFull, steps, o);
+    if (lane == 0 && steps) atomicAdd(&st->track_steps, steps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->vp_items[4], (unsigned long long)n);
 }
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame

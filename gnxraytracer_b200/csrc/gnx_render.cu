@@ -99,6 +99,11 @@ struct gnx_ctx {
     int capacity = 0;
     PathState ps{};
     Queues q{};
+    VolWave vw{};                  // VolPath wavefront state (allocated on the first VolPath render)
+    int vw_capacity = 0;
+    std::vector<void *> vw_allocs;
+    bool vol_megakernel = false;   // GNX_VOLPATH_MEGAKERNEL=1: the per-lane kernel k_volpath instead of the staged wavefront
+    int grid_vp_logic = 148 * 4, grid_vp_track = 148 * 8;
     std::vector<void *> wave_allocs;
     float4 *accum = nullptr, *rgba = nullptr;
     int film_pixels = 0;
@@ -129,7 +134,7 @@ struct gnx_ctx {
     cudaEvent_t fb_ev[8] = {};
 };
 
-enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_VP_EXTEND, ST_VP_VERTEX, ST_VP_SHADOW, ST_VP_MIS, ST_VP_TRACK, ST_COUNT };
 
 // RAII-free helper: brackets the launches issued between begin() and end() with two events.
 struct StageTimer {
@@ -223,6 +228,8 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_logic = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_track, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_track = ctx->sm_count * b;
     }
     // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
@@ -236,6 +243,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
     if (const char *fc = getenv("GNX_FILM_CHUNK")) ctx->film_chunk = atoi(fc);
     if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
+    if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
@@ -259,6 +267,7 @@ void gnx_destroy(gnx_ctx *ctx) {
     for (cudaEvent_t e : ctx->fb_ev) if (e) cudaEventDestroy(e);
     free_pool(ctx->scene_allocs);
     free_pool(ctx->wave_allocs);
+    free_pool(ctx->vw_allocs);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->rgba) cudaFree(ctx->rgba);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
@@ -706,6 +715,22 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix, int npixFrame)
     return GNX_OK;
 }
 
+static int ensure_volwave(gnx_ctx *ctx, int capacity) {
+    if (capacity <= ctx->vw_capacity) return GNX_OK;
+    free_pool(ctx->vw_allocs);
+    ctx->vw_capacity = 0;
+    std::vector<void *> &pool = ctx->vw_allocs;
+    const size_t n = (size_t)capacity;
+    int rc;
+    VolWave &v = ctx->vw;
+    if ((rc = dupload<uint2>(ctx, pool, nullptr, n, &v.rng))) return rc;
+    if ((rc = dupload<float>(ctx, pool, nullptr, n, &v.tmi))) return rc;
+    float4 **arrs[] = {&v.sub_o, &v.sub_d, &v.sub_hit, &v.sub_tr, &v.w0, &v.w1, &v.w2, &v.w3, &v.w4};
+    for (float4 **a : arrs) if ((rc = dupload<float4>(ctx, pool, nullptr, n, a))) return rc;
+    ctx->vw_capacity = capacity;
+    return GNX_OK;
+}
+
 static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (!ctx->has_scene) return fail(ctx, GNX_ERR_NO_SCENE, "no scene uploaded");
     if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
@@ -809,7 +834,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         // (cudaMemGetInfo costs ~0.5 ms: only asked when the buffers of an earlier call do not already cover the batch)
         const long long want = std::min(slots, (long long)npix * p->spp);
         if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            const long long bytesPerSlot = 320;  // PathState 124 B + queues 180 B, rounded up
+            // PathState 124 B + queues 180 B, rounded up; the VolPath wavefront keeps 156 B more per path
+            const long long bytesPerSlot = (p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel) ? 480 : 320;
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
         }
@@ -818,6 +844,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     batch_spp = std::min(batch_spp, p->spp);
     if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / std::max(1, npix)));
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix, npixFrame))) return rc;
+    const bool volWave = p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel;
+    if (volWave && (rc = ensure_volwave(ctx, ctx->capacity))) return rc;
 
     // escaped rays of scenes with a SkyBoxLight are queued for k_escape
     if (ctx->sc.skybox.present && p->integrator == GNX_INTEGRATOR_PATH && !ctx->q.miss_q && ctx->capacity > 0)
@@ -843,7 +871,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     StageTimer tm{ctx, st, stats != nullptr && ctx->stage_timers};
     ctx->ev_used = 0;
     ctx->ev_stage.clear();
-    unsigned long long extendLaunches = 0;
+    unsigned long long extendLaunches = 0, vpRounds = 0;
     GNX_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     GNX_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)npix * sizeof(float4), st));
 
@@ -890,6 +918,60 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         rcn.capacity = ctx->capacity;
         if (tiles) { rcn.tile_n = share.n; rcn.tile_dev = share.idx; rcn.tiles_x = tilesX; rcn.tiles_y = tilesY; }
         if (npix == 0) break;  // more devices than tiles
+        if (volWave) {
+            // VolPath as a staged wavefront (gnx_volwave.cuh): the start launch carries every path to its first tracking
+            // walk (or its end); then rounds of { k_vp_track over the queued walks, k_vp_logic per resume phase } until no
+            // walk is queued any more.  The queue length is read back every few rounds (the loop has no fixed depth:
+            // medium boundaries do not count as bounces).
+            const int gl = ctx->grid_vp_logic, gt = ctx->grid_vp_track;
+            k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -1);
+            tm.begin(ST_VP_EXTEND);
+            k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, -1, ctx->d_stats);
+            tm.end();
+            launches += 2;
+            auto logic = [&](int queue) {
+                tm.begin(ST_VP_EXTEND + vol_queue_kernel(queue));
+                k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -2);  // (the cursor only)
+                switch (vol_queue_kernel(queue)) {
+                case VK_EXTEND: k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                case VK_VERTEX: k_vp_logic<VK_VERTEX><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                case VK_SHADOW: k_vp_logic<VK_SHADOW><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                default: k_vp_logic<VK_MIS><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                }
+                k_vp_reset<<<1, 32, 0, st>>>(qv.counts, kCntShade0 + queue);
+                tm.end();
+                launches += 3;
+            };
+            for (int round = 0; round < 100000; ++round) {
+                // one round: the queued tracking walks, then every logic kernel once, in the order a path flows through them
+                tm.begin(ST_VP_TRACK);
+                k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -2);
+                k_vp_track<<<gt, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, ctx->d_stats);
+                k_vp_reset<<<1, 32, 0, st>>>(qv.counts, kCntExtend0);
+                tm.end();
+                logic(VQ_VERTEX);
+                logic(VQ_SHADOW_RESUME);
+                logic(VQ_SHADOW);
+                logic(VQ_MIS_RESUME);
+                logic(VQ_MIS);
+                logic(VQ_EXTEND);
+                launches += 3;
+                ++extendLaunches;
+                ++vpRounds;
+                if (round % 4 == 3 || round >= 16) {
+                    int hc[kNumCounters];
+                    GNX_CUDA(ctx, cudaMemcpyAsync(hc, qv.counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+                    GNX_CUDA(ctx, cudaStreamSynchronize(st));
+                    int remaining = hc[kCntExtend0];
+                    for (int k = 0; k < VQ_COUNT; ++k) remaining += hc[kCntShade0 + k];
+                    if (remaining == 0) break;
+                }
+            }
+            tm.begin(ST_FILM);
+            launches += accumulate(psv, rcn);
+            tm.end();
+            continue;
+        }
         if (p->integrator != GNX_INTEGRATOR_PATH) {
             k_reset_counts<<<1, 32, 0, st>>>(qv.counts, 1);
             tm.begin(ST_EXTEND);
@@ -1004,13 +1086,18 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         stats->extend_launches = extendLaunches;
         // (mixed launches trace the previous bounce's any-hit rays as well: their nodes / triangles are in nodes[0] / tris[0])
         stats->extend_bytes = 32ull * hs.nodes[0] + 48ull * hs.tris[0] + 48ull * (hs.rays[0] + hs.shadow_rays_in_extend_launches);
-        double acc[ST_COUNT] = {0, 0, 0, 0, 0};
+        double acc[ST_COUNT] = {};
         for (size_t i = 0; i * 2 + 1 < ctx->ev_used + 0 && i < ctx->ev_stage.size(); ++i) {
             float t = 0;
             if (cudaEventElapsedTime(&t, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) == cudaSuccess) acc[ctx->ev_stage[i]] += t;
         }
-        stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND]; stats->ms_shade = acc[ST_SHADE];
-        stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
+        // the VolPath wavefront's stages are also folded into the classic ones: extend, shade = vertex + MIS, shadow = shadow walk + tracking
+        stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND] + acc[ST_VP_EXTEND];
+        stats->ms_shade = acc[ST_SHADE] + acc[ST_VP_VERTEX] + acc[ST_VP_MIS];
+        stats->ms_shadow = acc[ST_SHADOW] + acc[ST_VP_SHADOW] + acc[ST_VP_TRACK]; stats->ms_film = acc[ST_FILM];
+        for (int k = 0; k < 5; ++k) { stats->vp_ms[k] = acc[ST_VP_EXTEND + k]; stats->vp_items[k] = hs.vp_items[k]; }
+        stats->vp_track_steps = hs.track_steps;
+        stats->vp_rounds = vpRounds;
     }
     return GNX_OK;
 }
@@ -1024,6 +1111,8 @@ static void add_stats(gnx_stats *a, const gnx_stats &b) {
     a->device_ms = std::max(a->device_ms, b.device_ms); a->ms_raygen = std::max(a->ms_raygen, b.ms_raygen);
     a->ms_extend = std::max(a->ms_extend, b.ms_extend); a->ms_shade = std::max(a->ms_shade, b.ms_shade);
     a->ms_shadow = std::max(a->ms_shadow, b.ms_shadow); a->ms_film = std::max(a->ms_film, b.ms_film);
+    for (int k = 0; k < 5; ++k) { a->vp_ms[k] = std::max(a->vp_ms[k], b.vp_ms[k]); a->vp_items[k] += b.vp_items[k]; }
+    a->vp_track_steps += b.vp_track_steps; a->vp_rounds = std::max(a->vp_rounds, b.vp_rounds);
 }
 
 // One render on every GPU of a multi-device context (single process): the shares are queued from one host thread per

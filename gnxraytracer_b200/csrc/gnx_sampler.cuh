@@ -193,6 +193,8 @@ struct PathSampler {
         p.rng.set_sequence(sequence);
         return p;
     }
+    // takes over another view's position in the stream (the table reference stays: both views are of the same sampler)
+    GNX_D void take(const PathSampler &o) { index = o.index; dim = o.dim; pcg = o.pcg; rng = o.rng; }
     GNX_D float get1d() {
         if (pcg) { ++dim; return rng.uniform_float(); }
         return halton_sample_dimension(s, index, dim++);

@@ -144,6 +144,8 @@ constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCn
 struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
     unsigned long long rays[3], nodes[3], tris[3], paths;
     unsigned long long shadow_rays_in_extend_launches;  // any-hit rays traced by the mixed launches (booked under nodes[0] / tris[0])
+    unsigned long long track_steps;                     // VolPath: tracking steps taken by k_vp_track
+    unsigned long long vp_items[5];                     // VolPath: items per stage (extend, vertex, shadow, MIS, track)
 };
 
 }  // namespace gnx

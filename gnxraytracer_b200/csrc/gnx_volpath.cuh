@@ -94,67 +94,96 @@ GNX_D float grid_density(const DevMedium &m, V3 p) {
 
 GNX_D V3 vexp(V3 a) { return V3(expf(a.x), expf(a.y), expf(a.z)); }
 
+// ---- GridDensityMedium tracking loops, one step at a time ------------------------------------------------------
+// Delta tracking (GridDensityMedium::Sample, media/GridDensityMedium.cpp:31-55) and ratio tracking
+// (GridDensityMedium::Tr, :57-87) share the walk: t -= log(1 - u) * invMaxDensity / sigma_t, density lookup at
+// ray(t).  Written as begin / step so that the wavefront tracking kernel (k_vp_track) can run one step per lane and
+// refill lanes whose walk has ended; the sequential callers below loop over the same functions.
+struct TrackState {
+    V3 o, d;          // the ray in medium space (direction normalised in world space before the transform)
+    float t, tMax;
+    float Tr;         // ratio tracking: transmittance so far
+    int mode;         // 0 = delta tracking (sample an interaction), 1 = ratio tracking (transmittance)
+    bool sampled;     // delta tracking: an interaction was sampled at parameter t
+};
+// false: the ray misses the medium's unit box (no interaction / Tr = 1, no sampler draws)
+GNX_D bool track_begin(const DevMedium &m, V3 ro, V3 rd, float rtMax, int mode, TrackState &ts) {
+    float tMaxM, tMin, tMax;
+    xform_ray(m.w2m, ro, normalize(rd), rtMax * length(rd), &ts.o, &ts.d, &tMaxM);
+    ts.mode = mode; ts.Tr = 1; ts.sampled = false;
+    if (!unit_box_interval(ts.o, ts.d, tMaxM, &tMin, &tMax)) return false;
+    ts.t = tMin; ts.tMax = tMax;
+    return true;
+}
+// One tracking step; true when the walk has ended (ts.sampled / ts.t, or ts.Tr, hold the result).
+GNX_D bool track_step(const DevMedium &m, TrackState &ts, PathSampler &smp) {
+    ts.t -= logf(1 - smp.get1d()) * m.inv_max_density / m.sigma_t_scalar;
+    if (ts.t >= ts.tMax) return true;
+    const float density = grid_density(m, ts.o + ts.d * ts.t);
+    if (ts.mode == 0) {
+        if (density * m.inv_max_density > smp.get1d()) { ts.sampled = true; return true; }
+        return false;
+    }
+    ts.Tr *= 1 - fmaxf(0.f, density * m.inv_max_density);
+    const float rrThreshold = .1f;
+    if (ts.Tr < rrThreshold) {
+        float q = fmaxf(.05f, 1 - ts.Tr);
+        if (smp.get1d() < q) { ts.Tr = 0.f; return true; }
+        ts.Tr /= 1 - q;
+    }
+    return false;
+}
+
+// HomogeneousMedium::Tr (media/HomogeneousMedium.cpp:11-15): closed form, no sampler draws
+GNX_D V3 homogeneous_tr(const DevMedium &m, V3 rd, float rtMax) {
+    const V3 st(m.sigma_t[0], m.sigma_t[1], m.sigma_t[2]);
+    return vexp(-st * fminf(rtMax * length(rd), kMaxFloat));
+}
+// HomogeneousMedium::Sample (media/HomogeneousMedium.cpp:17-43): the weight; *tOut >= 0 when an interaction was sampled
+// at ray(t) (t in the ray's own parametrisation), -1 otherwise.  Two sampler draws.
+GNX_D V3 homogeneous_sample(const DevMedium &m, V3 rd, float rtMax, PathSampler &smp, float *tOut) {
+    const V3 st(m.sigma_t[0], m.sigma_t[1], m.sigma_t[2]), ss(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+    int channel = (int)(smp.get1d() * 3);
+    if (channel > 2) channel = 2;
+    float dist = -logf(1 - smp.get1d()) / st[channel];
+    float len = length(rd);
+    float t = fminf(dist / len, rtMax);
+    bool sampledMedium = t < rtMax;
+    *tOut = sampledMedium ? t : -1.f;
+    V3 Tr = vexp(-st * fminf(t, kMaxFloat) * len);
+    V3 density = sampledMedium ? (st * Tr) : Tr;
+    float pdf = 0;
+    for (int i = 0; i < 3; ++i) pdf += density[i];
+    pdf *= 1 / (float)3;
+    if (pdf == 0) pdf = 1;
+    return sampledMedium ? div_each(Tr * ss, pdf) : div_each(Tr, pdf);
+}
+
 // Medium::Tr
 GNX_D V3 medium_tr(const DevMedium &m, const VRay &ray, PathSampler &smp) {
-    if (m.type == GNX_MEDIUM_HOMOGENEOUS) {
-        const V3 st(m.sigma_t[0], m.sigma_t[1], m.sigma_t[2]);
-        return vexp(-st * fminf(ray.tMax * length(ray.d), kMaxFloat));
-    }
-    V3 o, d;
-    float tMaxM;
-    xform_ray(m.w2m, ray.o, normalize(ray.d), ray.tMax * length(ray.d), &o, &d, &tMaxM);
-    float tMin, tMax;
-    if (!unit_box_interval(o, d, tMaxM, &tMin, &tMax)) return V3(1.f);
-    float Tr = 1, t = tMin;
-    while (true) {
-        t -= logf(1 - smp.get1d()) * m.inv_max_density / m.sigma_t_scalar;
-        if (t >= tMax) break;
-        float density = grid_density(m, o + d * t);
-        Tr *= 1 - fmaxf(0.f, density * m.inv_max_density);
-        const float rrThreshold = .1f;
-        if (Tr < rrThreshold) {
-            float q = fmaxf(.05f, 1 - Tr);
-            if (smp.get1d() < q) return V3(0.f);
-            Tr /= 1 - q;
-        }
-    }
-    return V3(Tr);
+    if (m.type == GNX_MEDIUM_HOMOGENEOUS) return homogeneous_tr(m, ray.d, ray.tMax);
+    TrackState ts;
+    if (!track_begin(m, ray.o, ray.d, ray.tMax, 1, ts)) return V3(1.f);
+    while (!track_step(m, ts, smp)) {}
+    return V3(ts.Tr);
 }
 
 // Medium::Sample; *sampled / *pMi describe the MediumInteraction when one is created
 GNX_D V3 medium_sample(const DevMedium &m, const VRay &ray, PathSampler &smp, bool *sampled, V3 *pMi) {
     *sampled = false;
     if (m.type == GNX_MEDIUM_HOMOGENEOUS) {
-        const V3 st(m.sigma_t[0], m.sigma_t[1], m.sigma_t[2]), ss(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
-        int channel = (int)(smp.get1d() * 3);
-        if (channel > 2) channel = 2;
-        float dist = -logf(1 - smp.get1d()) / st[channel];
-        float len = length(ray.d);
-        float t = fminf(dist / len, ray.tMax);
-        bool sampledMedium = t < ray.tMax;
-        if (sampledMedium) { *sampled = true; *pMi = ray.o + ray.d * t; }
-        V3 Tr = vexp(-st * fminf(t, kMaxFloat) * len);
-        V3 density = sampledMedium ? (st * Tr) : Tr;
-        float pdf = 0;
-        for (int i = 0; i < 3; ++i) pdf += density[i];
-        pdf *= 1 / (float)3;
-        if (pdf == 0) pdf = 1;
-        return sampledMedium ? div_each(Tr * ss, pdf) : div_each(Tr, pdf);
+        float t;
+        V3 w = homogeneous_sample(m, ray.d, ray.tMax, smp, &t);
+        if (t >= 0) { *sampled = true; *pMi = ray.o + ray.d * t; }
+        return w;
     }
-    V3 o, d;
-    float tMaxM;
-    xform_ray(m.w2m, ray.o, normalize(ray.d), ray.tMax * length(ray.d), &o, &d, &tMaxM);
-    float tMin, tMax;
-    if (!unit_box_interval(o, d, tMaxM, &tMin, &tMax)) return V3(1.f);
-    float t = tMin;
-    while (true) {
-        t -= logf(1 - smp.get1d()) * m.inv_max_density / m.sigma_t_scalar;
-        if (t >= tMax) break;
-        if (grid_density(m, o + d * t) * m.inv_max_density > smp.get1d()) {
-            *sampled = true;
-            *pMi = ray.o + ray.d * t;  // rWorld(t), as the reference writes it
-            return div_each(V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]), m.sigma_t_scalar);
-        }
+    TrackState ts;
+    if (!track_begin(m, ray.o, ray.d, ray.tMax, 0, ts)) return V3(1.f);
+    while (!track_step(m, ts, smp)) {}
+    if (ts.sampled) {
+        *sampled = true;
+        *pMi = ray.o + ray.d * ts.t;  // rWorld(t), as the reference writes it
+        return div_each(V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]), m.sigma_t_scalar);
     }
     return V3(1.f);
 }

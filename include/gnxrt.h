@@ -322,6 +322,13 @@ typedef struct gnx_stats {
     uint64_t extend_nodes, extend_tris; /* BVH nodes popped / triangles tested by closest-hit extension rays */
     uint64_t extend_launches;   /* number of k_extend launches; ms_extend is their CUDA-event sum   */
     uint64_t extend_bytes;      /* 32*extend_nodes + 48*extend_tris + 48*rays_extend                */
+    /* VolPath wavefront (GNX_INTEGRATOR_VOLPATH), per stage: [0] extend kernel, [1] vertex kernel, [2] shadow-walk kernel,
+     * [3] MIS-walk + continuation kernel, [4] tracking kernel.  items = paths advanced (walks for [4]); vp_track_steps =
+     * tracking steps (8 grid reads each); vp_rounds = rounds of { track, logic kernels } until every path had ended */
+    double vp_ms[5];
+    uint64_t vp_items[5];
+    uint64_t vp_track_steps;
+    uint64_t vp_rounds;
 } gnx_stats;
 
 typedef struct gnx_ctx gnx_ctx;

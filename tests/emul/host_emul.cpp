@@ -14,6 +14,7 @@
 
 #include "gnx_pack.h"
 #include "gnx_whitted.cuh"
+#include "gnx_volwave.cuh"
 #include "gnx_film.cuh"
 
 using namespace gnx;
@@ -167,7 +168,28 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         rcv.width = p.width; rcv.height = p.height; rcv.max_depth = p.max_depth; rcv.rr_threshold = p.rr_threshold;
         int2 vstack[kSmemStack];
         VolCounters vc{0, 0, 0};
-        V3 Lv = volpath_li(sc, rcv, px, py, sample, vstack, 1, cnt, vc);
+        V3 Lv;
+        if (getenv("GNX_VOLPATH_MEGAKERNEL")) Lv = volpath_li(sc, rcv, px, py, sample, vstack, 1, cnt, vc);
+        else {
+            // the staged wavefront's state machine (gnx_volwave.cuh), one slot: pixel / sample go in through the batch mapping
+            float4 ro, rd, be, Lq, hq, so, sd, sh, st, w0, w1, w2, w3, w4;
+            uint32_t hidx = 0, meta = 0;
+            int32_t med = -1;
+            uint2 rng = make_uint2(0, 0);
+            float tmi = -1;
+            PathState ps1{&ro, &rd, &be, &Lq, &hq, &hidx, &meta, &med};
+            VolWave vw1{&rng, &tmi, &so, &sd, &sh, &st, &w0, &w1, &w2, &w3, &w4};
+            rcv.batch_spp = 1; rcv.npix = p.width * p.height;
+            // slot_to_sample maps slot -> (pixel = slot, sample = first_sample): render "slot" = pixel through offset pointers
+            const int pix = py * p.width + px;
+            rcv.first_sample = sample;
+            PathState psq = ps1;
+            psq.ray_o -= pix; psq.ray_d -= pix; psq.beta -= pix; psq.L -= pix; psq.hit -= pix; psq.hidx -= pix; psq.meta -= pix; psq.medium -= pix;
+            VolWave vwq = vw1;
+            vwq.rng -= pix; vwq.tmi -= pix; vwq.sub_o -= pix; vwq.sub_d -= pix; vwq.sub_hit -= pix; vwq.sub_tr -= pix;
+            vwq.w0 -= pix; vwq.w1 -= pix; vwq.w2 -= pix; vwq.w3 -= pix; vwq.w4 -= pix;
+            Lv = volwave_li<8>(sc, rcv, psq, vwq, pix, vstack, 1, cnt, vc, getenv("GNX_VOLWAVE_INPLACE") == nullptr);
+        }
         rays[0] += vc.extend; rays[1] += vc.shadow; rays[2] += vc.mis;
         return Lv;
     }

@@ -8,7 +8,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (bench.py points fd 1 at stderr for its one-JSON-line contract: undo that here)
 from bench import WORKLOADS  # noqa: E402
+os.dup2(bench._REAL_STDOUT, 1)
 from gnxraytracer_b200.api import Context, RenderParams, SceneKit  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -18,7 +20,8 @@ ap.add_argument("--spp", type=int, default=0)
 ap.add_argument("--res", type=int, default=0)
 ap.add_argument("--batch-spp", type=int, default=0)
 a = ap.parse_args()
-scene, p0, p1, p2, W, H, spp, depth, desc = WORKLOADS[a.workload]
+wl = WORKLOADS[a.workload]
+scene, (p0, p1, p2), W, H, spp, depth, desc = wl["scene"], wl["args"], wl["w"], wl["h"], wl["spp"], wl["depth"], wl["desc"]
 if a.spp:
     spp = a.spp
 if a.res:
@@ -26,7 +29,7 @@ if a.res:
 ctx = Context(0)
 sk = SceneKit(scene, W, H, spp, p0, p1, p2)
 ctx.upload(sk.desc)
-p = RenderParams.make(W, H, spp, max_depth=depth, batch_spp=a.batch_spp, integrator=1 if scene == 'smoke' else (p2 if scene == 'lights' else 0))
+p = RenderParams.make(W, H, spp, max_depth=depth, batch_spp=a.batch_spp, integrator=wl["integ"])
 for i in range(a.steps):
     img, st = ctx.render(p)
 d = st.as_dict()
