@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kShadeBlock, GNX_SHADE_MINBLOCKS(MAXL)) k_shad
 // integrator is not cut into wavefront stages).  Lanes pull camera samples through a warp-aggregated cursor.
 // Resident blocks per SM for the two per-lane kernels (latency-bound: more warps pay despite the spills).  Measured:
 // k_volpath C4 4 blocks 2.1 s, 6: 1.97 s, 8: 1.85 s; k_recursive W1 / D1 4: 25.5 / 34.0 ms, 6: 23.9 / 32.0, 8: 25.0 / 30.2.
+template <bool TEX>
 __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, Pat
             int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
             V3 L(0.f);
-            if (pixel_xy(rc, pixel, &px, &py)) L = volpath_li(sc, rc, px, py, sample, stack, kBlock, cnt, vc);
+            if (pixel_xy(rc, pixel, &px, &py)) L = volpath_li<TEX>(sc, rc, px, py, sample, stack, kBlock, cnt, vc);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();
@@ -345,9 +346,9 @@ __global__ void k_vp_reset(int *counts, int consumed) {
 
 // One logic kernel (VolKernel) over one of its queues; queue < 0: the camera samples of the batch (VP_START).
 #ifndef GNX_VP_LOGIC_BLOCKS
-#define GNX_VP_LOGIC_BLOCKS 6
+#define GNX_VP_LOGIC_BLOCKS 4  // measured on C4: 4 blocks (128 registers) 148 ms, 6: 158 ms, 8: 177 ms — the spills cost more than the warps hide
 #endif
-template <int KERNEL>
+template <int KERNEL, bool TEX = false>
 __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const DeviceScene sc, PathState ps, VolWave vw, Queues q, RenderConsts rc, int queue,
                                                         DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const 
         int slot = 0, y = VY_DONE;
         if (i < n) {
             slot = list ? list[i] : i;
-            y = vol_advance<8>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
+            y = vol_advance<8, TEX>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
         }
         __syncwarp();
         int idx = warp_push(&q.counts[kCntExtend0], y == VY_TRACK_MAIN || y == VY_TRACK_SUB);
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_vp_track(const DeviceScene sc, Pa
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
 // stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
-template <int DIRECT>  // 0 Whitted, 1 DirectLighting UniformSampleOne, 2 UniformSampleAll
+template <int DIRECT, bool TEX>  // DIRECT: 0 Whitted, 1 DirectLighting UniformSampleOne, 2 UniformSampleAll; TEX: carry ray differentials
 __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
             int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
             V3 L(0.f);
-            if (pixel_xy(rc, pixel, &px, &py)) L = recursive_li<8, DIRECT>(sc, rc, px, py, sample, stack, kBlock, cnt, rcnt);
+            if (pixel_xy(rc, pixel, &px, &py)) L = recursive_li<8, DIRECT, TEX>(sc, rc, px, py, sample, stack, kBlock, cnt, rcnt);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();

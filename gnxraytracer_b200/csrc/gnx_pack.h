@@ -250,6 +250,59 @@ inline bool build_node4(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
     return true;
 }
 
+// MIPMap pyramid from a power-of-two level 0 (core/MIPMap.h:161-186): level i is the 2 x 2 box filter of level i - 1
+// through MIPMap::Texel's wrap rule.  `texels` receives all levels back to back, `offsets` each level's start in texels.
+// The caller's own levels (n_levels > 1: the reference's pyramid, read by the bridge) are copied as they are.
+inline void build_mip_pyramid(const gnx_texture &t, std::vector<float> &texels, std::vector<int> &offsets, int *nLevelsOut) {
+    const int nch = t.n_channels;
+    auto levelW = [&](int l) { return std::max(1, t.width >> l); };
+    auto levelH = [&](int l) { return std::max(1, t.height >> l); };
+    const bool pow2 = (t.width & (t.width - 1)) == 0 && (t.height & (t.height - 1)) == 0;
+    int nLevels = t.n_levels;
+    if (nLevels <= 1) {
+        nLevels = 1;
+        if (pow2) { int m = std::max(t.width, t.height); while ((1 << nLevels) <= m) ++nLevels; }  // 1 + Log2Int(max)
+    }
+    offsets.assign(nLevels, 0);
+    size_t total = 0;
+    for (int l = 0; l < nLevels; ++l) { offsets[l] = (int)total; total += (size_t)levelW(l) * levelH(l); }
+    texels.resize(total * nch);
+    if (t.n_levels > 1) { memcpy(texels.data(), t.texels, total * nch * sizeof(float)); *nLevelsOut = nLevels; return; }
+    memcpy(texels.data(), t.texels, (size_t)t.width * t.height * nch * sizeof(float));
+    for (int l = 1; l < nLevels; ++l) {
+        const int pw = levelW(l - 1), ph = levelH(l - 1), w = levelW(l), h = levelH(l);
+        const float *src = texels.data() + (size_t)offsets[l - 1] * nch;
+        float *dst = texels.data() + (size_t)offsets[l] * nch;
+        auto texel = [&](int s, int tt, int c) -> float {
+            if (t.wrap == GNX_WRAP_REPEAT) { s %= pw; if (s < 0) s += pw; tt %= ph; if (tt < 0) tt += ph; }
+            else if (t.wrap == GNX_WRAP_CLAMP) { s = std::min(std::max(s, 0), pw - 1); tt = std::min(std::max(tt, 0), ph - 1); }
+            else if (s < 0 || s >= pw || tt < 0 || tt >= ph) return 0.f;
+            return src[((size_t)tt * pw + s) * nch + c];
+        };
+        for (int tt = 0; tt < h; ++tt)
+            for (int ss = 0; ss < w; ++ss)
+                for (int c = 0; c < nch; ++c)
+                    dst[((size_t)tt * w + ss) * nch + c] = .25f * (texel(2 * ss, 2 * tt, c) + texel(2 * ss + 1, 2 * tt, c) +
+                                                                   texel(2 * ss, 2 * tt + 1, c) + texel(2 * ss + 1, 2 * tt + 1, c));
+    }
+    *nLevelsOut = nLevels;
+}
+// MIPMap::weightLut (core/MIPMap.h:189-196)
+inline void make_ewa_lut(float lut[128]) {
+    for (int i = 0; i < 128; ++i) {
+        float alpha = 2;
+        float r2 = float(i) / float(128 - 1);
+        lut[i] = std::exp(-alpha * r2) - std::exp(-alpha);
+    }
+}
+inline void fill_dev_texture(const gnx_texture &t, const float *texels, const std::vector<int> &offsets, int nLevels, DevTexture &o) {
+    o.w = t.width; o.h = t.height; o.nch = t.n_channels; o.wrap = t.wrap;
+    o.su = t.su; o.sv = t.sv; o.du = t.du; o.dv = t.dv;
+    o.texels = texels;
+    o.n_levels = nLevels; o.do_trilinear = t.do_trilinear; o.max_aniso = t.max_aniso;
+    for (int l = 0; l < kMaxMipLevels; ++l) o.level_off[l] = l < nLevels ? offsets[l] : 0;
+}
+
 // Index hygiene at the ABI boundary: every index the kernels will dereference is checked here, once, so that a bad
 // description is GNX_ERR_INVALID at upload instead of an out-of-range device read at render time.
 inline bool validate_scene_desc(const gnx_scene_desc &d, std::string *err) {

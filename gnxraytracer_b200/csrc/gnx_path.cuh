@@ -75,6 +75,41 @@ GNX_D void camera_ray_uv(const DeviceScene &sc, int px, int py, float u0, float 
     }
     *o = wo; *d = wd; *tMax = tm;
 }
+// The offset rays of PerspectiveCamera::GenerateRayDifferential (camera/Perspective.cpp:62-112), carried to world space
+// by Transform::operator()(RayDifferential) (core/Transform.h:246-256: the main ray with its error-bound shift, the
+// offset rays as plain points / vectors) and scaled by 1 / sqrt(samplesPerPixel) as Render does (core/Integrator.cpp:277).
+// (o, d) is the world ray camera_ray_uv returned for the same sample.
+GNX_D RayDiff camera_ray_differentials(const DeviceScene &sc, int px, int py, float u0, float u1, float l0, float l1, V3 o, V3 d) {
+    RayDiff rd;
+    rd.has = true;
+    const V3 pFilm((float)px + u0, (float)py + u1, 0.f);
+    const V3 pCamera = xform_point(sc.cam.r2c, pFilm);
+    V3 rxo(0.f), ryo(0.f), rxd, ryd;
+    if (sc.cam.lens_radius > 0) {
+        float lx, ly;
+        concentric_sample_disk(l0, l1, &lx, &ly);
+        lx *= sc.cam.lens_radius; ly *= sc.cam.lens_radius;
+        const V3 dx = normalize(pCamera + sc.cam.dx_camera);
+        float ft = sc.cam.focal_distance / dx.z;
+        V3 pFocus = V3(0.f) + (ft * dx);
+        rxo = V3(lx, ly, 0);
+        rxd = normalize(pFocus - rxo);
+        const V3 dy = normalize(pCamera + sc.cam.dy_camera);
+        ft = sc.cam.focal_distance / dy.z;
+        pFocus = V3(0.f) + (ft * dy);
+        ryo = V3(lx, ly, 0);
+        ryd = normalize(pFocus - ryo);
+    } else {
+        rxd = normalize(pCamera + sc.cam.dx_camera);
+        ryd = normalize(pCamera + sc.cam.dy_camera);
+    }
+    rxo = xform_point(sc.cam.c2w, rxo); ryo = xform_point(sc.cam.c2w, ryo);
+    rxd = xform_vector(sc.cam.c2w, rxd); ryd = xform_vector(sc.cam.c2w, ryd);
+    const float sscale = 1 / sqrtf((float)sc.smp.spp);
+    rd.rxo = o + (rxo - o) * sscale; rd.ryo = o + (ryo - o) * sscale;
+    rd.rxd = d + (rxd - d) * sscale; rd.ryd = d + (ryd - d) * sscale;
+    return rd;
+}
 GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *o, V3 *d, float *tMax) {
     float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
     float l0 = 0, l1 = 0;

@@ -80,6 +80,7 @@ struct gnx_ctx {
     // scene
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
+    bool tex_needs_pyramid = false; // an image texture came as one level that is not a power of two: no MIPMap pyramid to filter with
     bool merge_extend = true;      // GNX_MERGE_EXTEND=0: the any-hit rays of a bounce get their own launch(es)
     int film_chunk = 0;            // GNX_FILM_CHUNK: samples per pixel staged at a time by the tiled Gaussian gather (0 = auto)
     bool film_simple = false;      // GNX_FILM_SIMPLE=1: Gaussian film with the per-pixel gather instead of the tiled one
@@ -226,9 +227,9 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_logic = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_logic = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_track, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_track = ctx->sm_count * b;
     }
     // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
@@ -345,6 +346,7 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     ctx->has_scene = false;
     ctx->spatial_built = false;
     ctx->has_next_lights = false;
+    ctx->tex_needs_pyramid = false;
     ctx->bvh_build_ms = 0;
     DeviceScene sc{};
     std::vector<void *> &pool = ctx->scene_allocs;
@@ -451,9 +453,23 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
             const gnx_texture &t = d->textures[i];
             if (t.width <= 0 || t.height <= 0 || (t.n_channels != 1 && t.n_channels != 3) || !t.texels)
                 return fail(ctx, GNX_ERR_INVALID, "bad texture descriptor");
+            if (t.n_levels > kMaxMipLevels) return fail(ctx, GNX_ERR_INVALID, "texture with more than 16 MIPMap levels");
+            // the MIPMap pyramid: the caller's own levels, or built here from a power-of-two level 0
+            std::vector<float> pyr;
+            std::vector<int> offs;
+            int nLevels = 1;
+            build_mip_pyramid(t, pyr, offs, &nLevels);
+            if (nLevels == 1 && (t.width > 1 || t.height > 1)) ctx->tex_needs_pyramid = true;  // not a power of two, no levels given
             float *dtex;
-            if ((rc = dupload(ctx, pool, t.texels, (size_t)t.width * t.height * t.n_channels, &dtex))) return rc;
-            tex[i] = DevTexture{t.width, t.height, t.n_channels, t.wrap, t.su, t.sv, t.du, t.dv, dtex};
+            if ((rc = dupload(ctx, pool, pyr.data(), pyr.size(), &dtex))) return rc;
+            fill_dev_texture(t, dtex, offs, nLevels, tex[i]);
+        }
+        {
+            float lut[128];
+            make_ewa_lut(lut);
+            float *dlut;
+            if ((rc = dupload(ctx, pool, lut, (size_t)128, &dlut))) return rc;
+            sc.ewa_lut = dlut;
         }
         DevTexture *dt;
         if ((rc = dupload(ctx, pool, tex.data(), tex.size(), &dt))) return rc;
@@ -603,6 +619,8 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     sc.cam.lens_radius = d->camera.lens_radius;
     sc.cam.focal_distance = d->camera.focal_distance;
     sc.cam.medium = d->camera.medium;
+    sc.cam.dx_camera = V3(d->camera.dx_camera[0], d->camera.dx_camera[1], d->camera.dx_camera[2]);
+    sc.cam.dy_camera = V3(d->camera.dy_camera[0], d->camera.dy_camera[1], d->camera.dy_camera[2]);
 
     // ---- sampler
     const gnx_sampler &s = d->sampler;
@@ -615,6 +633,7 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     sc.smp.stride = s.sample_stride;
     sc.smp.mult_inv0 = s.mult_inverse[0]; sc.smp.mult_inv1 = s.mult_inverse[1];
     sc.smp.at_center = s.sample_at_pixel_center;
+    sc.smp.spp = s.samples_per_pixel > 0 ? s.samples_per_pixel : 1;
     sc.smp.stride_over_scale0 = s.type == GNX_SAMPLER_HALTON ? s.sample_stride / s.base_scales[0] : 0;
     sc.smp.stride_over_scale1 = s.type == GNX_SAMPLER_HALTON ? s.sample_stride / s.base_scales[1] : 0;
     {
@@ -747,14 +766,12 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
         return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting: max_depth above 16 is not supported (fixed recursion frame stack)");
     if (recursive && ctx->sc.smp.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use the Halton sampler");
     if (recursive && ctx->sc.n_media > 0) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting ignore participating media");
-    if (recursive && ctx->n_textures_host > 0)
-        return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting filter image textures with ray differentials (EWA), which is not implemented");
+    if (p->integrator != GNX_INTEGRATOR_PATH && ctx->tex_needs_pyramid)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "an image texture has a single level that is not a power of two: pass the MIPMap's own levels (gnx_texture::n_levels) for the integrators that filter with ray differentials");
     if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.smp.type != GNX_SAMPLER_HALTON)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "the wavefront PathIntegrator keeps a Halton (index, dimension) per path; the PCG32 stream sampler is for VolPath");
     if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.n_media > 0)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "scene has participating media: use GNX_INTEGRATOR_VOLPATH (PathIntegrator ignores media)");
-    if (p->integrator == GNX_INTEGRATOR_VOLPATH && ctx->n_textures_host > 0)
-        return fail(ctx, GNX_ERR_UNSUPPORTED, "VolPath with image textures needs ray-differential (EWA) filtering at the camera vertex, which is not implemented");
     if (p->film != GNX_FILM_BOX && p->film != GNX_FILM_GAUSSIAN && p->film != GNX_FILM_GAUSSIAN_SUMS)
         return fail(ctx, GNX_ERR_INVALID, "unknown film");
     if (p->film != GNX_FILM_BOX && !(p->filter_radius > 0.f && p->filter_radius <= 16.f && p->filter_alpha >= 0.f))
@@ -845,6 +862,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     if ((long long)npix * batch_spp > (1ll << 30)) batch_spp = std::max(1, (int)((1ll << 30) / std::max(1, npix)));
     if ((rc = ensure_wavefront(ctx, npix * batch_spp, npix, npixFrame))) return rc;
     const bool volWave = p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel;
+    const bool tex = ctx->n_textures_host > 0;  // image textures: integrators with a RayDifferential filter them through the MIPMap
     if (volWave && (rc = ensure_volwave(ctx, ctx->capacity))) return rc;
 
     // escaped rays of scenes with a SkyBoxLight are queued for k_escape
@@ -926,7 +944,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             const int gl = ctx->grid_vp_logic, gt = ctx->grid_vp_track;
             k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -1);
             tm.begin(ST_VP_EXTEND);
-            k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, -1, ctx->d_stats);
+            if (tex) k_vp_logic<VK_EXTEND, true><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, -1, ctx->d_stats);  // (sets the camera-differential flag)
+            else k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, -1, ctx->d_stats);
             tm.end();
             launches += 2;
             auto logic = [&](int queue) {
@@ -934,9 +953,15 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
                 k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -2);  // (the cursor only)
                 switch (vol_queue_kernel(queue)) {
                 case VK_EXTEND: k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
-                case VK_VERTEX: k_vp_logic<VK_VERTEX><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                case VK_VERTEX:
+                    if (tex) k_vp_logic<VK_VERTEX, true><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    else k_vp_logic<VK_VERTEX><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    break;
                 case VK_SHADOW: k_vp_logic<VK_SHADOW><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
-                default: k_vp_logic<VK_MIS><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                default:
+                    if (tex) k_vp_logic<VK_MIS, true><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    else k_vp_logic<VK_MIS><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    break;
                 }
                 k_vp_reset<<<1, 32, 0, st>>>(qv.counts, kCntShade0 + queue);
                 tm.end();
@@ -975,10 +1000,21 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         if (p->integrator != GNX_INTEGRATOR_PATH) {
             k_reset_counts<<<1, 32, 0, st>>>(qv.counts, 1);
             tm.begin(ST_EXTEND);
-            if (p->integrator == GNX_INTEGRATOR_VOLPATH) k_volpath<<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
-            else if (p->integrator == GNX_INTEGRATOR_WHITTED) k_recursive<0><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
-            else if (p->integrator == GNX_INTEGRATOR_DIRECT) k_recursive<1><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
-            else k_recursive<2><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            // (scenes with image textures: the variants that carry ray differentials for MIPMap::Lookup)
+            const int gr = ctx->grid_recursive;
+            if (p->integrator == GNX_INTEGRATOR_VOLPATH) {
+                if (tex) k_volpath<true><<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                else k_volpath<false><<<ctx->grid_volpath, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            } else if (p->integrator == GNX_INTEGRATOR_WHITTED) {
+                if (tex) k_recursive<0, true><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                else k_recursive<0, false><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            } else if (p->integrator == GNX_INTEGRATOR_DIRECT) {
+                if (tex) k_recursive<1, true><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                else k_recursive<1, false><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            } else {
+                if (tex) k_recursive<2, true><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                else k_recursive<2, false><<<gr, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+            }
             tm.end();
             tm.begin(ST_FILM);
             launches += accumulate(psv, rcn);

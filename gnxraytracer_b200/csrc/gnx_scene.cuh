@@ -6,10 +6,14 @@
 
 namespace gnx {
 
+constexpr int kMaxMipLevels = 16;
 struct DevTexture {
     int w, h, nch, wrap;
     float su, sv, du, dv;
-    const float *texels;  // level 0, row-major
+    const float *texels;  // level 0, row-major; the further MIPMap levels follow back to back (core/MIPMap.h:86-199)
+    int n_levels, do_trilinear;
+    float max_aniso;
+    int level_off[kMaxMipLevels];  // offset of level l in texels, in TEXELS
 };
 
 struct DevEnv {
@@ -45,6 +49,7 @@ struct DevCamera {
     M44 r2c, c2w;
     float lens_radius, focal_distance;
     int medium;
+    V3 dx_camera, dy_camera;  // PerspectiveCamera::dxCamera / dyCamera (camera/Perspective.cpp:26-32): ray differentials
 };
 
 struct DevSampler {
@@ -56,6 +61,7 @@ struct DevSampler {
     const int *primes;
     const uint4 *dims;        // per dimension {prime, PrimeSums, ceil(2^38 / prime) lo, hi}
     int n_primes;
+    int spp;                  // Sampler::samplesPerPixel: ScaleDifferentials(1 / sqrt(spp)), core/Integrator.cpp:277
 };
 
 struct DevMedium {
@@ -84,6 +90,7 @@ struct DeviceScene {
     const gnx_material *materials;
     int n_materials;
     const DevTexture *textures;
+    const float *ewa_lut;         // MIPMap::weightLut, 128 entries (core/MIPMap.h:189-196)
     const gnx_light *lights;
     int n_lights;
     const int *light_nsamples;    // [n_lights] Light::nSamples or null (= 1), UniformSampleAllLights
@@ -113,6 +120,7 @@ struct PathState {
                        // extension rays, whose escape adds the environment radiance to L (null: they go to L)
 };
 constexpr uint32_t kFlagSpecular = 1u;
+constexpr uint32_t kFlagCameraDiff = 2u;  // VolPath: the path segment is still the camera's RayDifferential
 
 struct ShadowItem {      // 48 bytes: any-hit query "add contrib to path if nothing is hit"
     float4 o_tmax;       // origin, tMax

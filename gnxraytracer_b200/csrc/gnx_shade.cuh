@@ -14,10 +14,22 @@ struct Surface {
     float u, v;
     int material, light, prim;
     unsigned flags;
+    // ray differentials (integrators that carry a RayDifferential: Whitted, DirectLighting, VolPath's camera vertex)
+    V3 dpdu, dpdv;          // geometric partial derivatives (SurfaceInteraction::dpdu / dpdv)
+    V3 dndu, dndv;          // shading.dndu / dndv (zero without vertex normals)
+    V3 dpdx, dpdy;
+    float dudx, dvdx, dudy, dvdy;
+};
+
+// RayDifferential's extra members (core/Geometry.h:856-890)
+struct RayDiff {
+    bool has;
+    V3 rxo, ryo, rxd, ryd;
 };
 
 // Triangle::Intersect from "Compute triangle partial derivatives" on (shape/Triangle.cpp:170-303),
 // for the accepted hit only.
+template <bool DIFF = false>
 GNX_D Surface make_surface(const DeviceScene &sc, int prim, float b0, float b1, float b2, V3 rayD) {
     float4 c;
     const TriVerts tv = load_tri(sc.tris, prim, &c);
@@ -60,9 +72,25 @@ GNX_D Surface make_surface(const DeviceScene &sc, int prim, float b0, float b1, 
     s.ns = s.n;
     s.dpdu_s = dpdu;
     s.dpdv_s = dpdv;
+    s.dpdu = dpdu; s.dpdv = dpdv;
+    s.dndu = V3(0.f); s.dndv = V3(0.f);
+    s.dpdx = V3(0.f); s.dpdy = V3(0.f);
+    s.dudx = s.dvdx = s.dudy = s.dvdy = 0.f;
     if (sc.tri_has_n && sc.tri_has_n[prim]) {
         const float *q = sc.tri_n + 9 * (size_t)prim;
         V3 n0(q[0], q[1], q[2]), n1(q[3], q[4], q[5]), n2(q[6], q[7], q[8]);
+        if (DIFF) {
+            // dndu / dndv of the triangle's shading geometry (shape/Triangle.cpp:262-293)
+            const V3 dn1 = n0 - n2, dn2 = n1 - n2;
+            if (degenerateUV) {
+                V3 dn = cross(n2 - n0, n1 - n0);
+                if (length_sq(dn) != 0) coordinate_system(dn, &s.dndu, &s.dndv);
+            } else {
+                float invDet = 1 / determinant;
+                s.dndu = (duv12y * dn1 - duv02y * dn2) * invDet;
+                s.dndv = (-duv12x * dn1 + duv02x * dn2) * invDet;
+            }
+        }
         V3 ns = (b0 * n0 + b1 * n1 + b2 * n2);
         if (length_sq(ns) > 0) ns = normalize(ns); else ns = s.n;
         V3 ss = normalize(dpdu);
@@ -101,17 +129,141 @@ GNX_D V3 texture_bilinear(const DevTexture &t, float su, float sv) {
     return (1 - ds) * (1 - dt) * texel_fetch(t, s0, t0) + (1 - ds) * dt * texel_fetch(t, s0, t0 + 1) +
            ds * (1 - dt) * texel_fetch(t, s0 + 1, t0) + ds * dt * texel_fetch(t, s0 + 1, t0 + 1);
 }
+// ---- MIPMap::Lookup with texture-space differentials (core/MIPMap.h:226-337): trilinear or EWA over the pyramid ----
+GNX_D int mip_w(const DevTexture &t, int level) { int w = t.w >> level; return w < 1 ? 1 : w; }
+GNX_D int mip_h(const DevTexture &t, int level) { int h = t.h >> level; return h < 1 ? 1 : h; }
+// MIPMap::Texel(level, s, t)
+GNX_D V3 mip_texel(const DevTexture &t, int level, int s, int tt) {
+    const int w = mip_w(t, level), h = mip_h(t, level);
+    if (t.wrap == GNX_WRAP_REPEAT) {
+        s = s % w; if (s < 0) s += w;
+        tt = tt % h; if (tt < 0) tt += h;
+    } else if (t.wrap == GNX_WRAP_CLAMP) {
+        s = s < 0 ? 0 : (s > w - 1 ? w - 1 : s);
+        tt = tt < 0 ? 0 : (tt > h - 1 ? h - 1 : tt);
+    } else if (s < 0 || s >= w || tt < 0 || tt >= h) {
+        return V3(0.f);
+    }
+    const float *q = t.texels + ((size_t)t.level_off[level] + (size_t)tt * w + s) * t.nch;
+    return t.nch == 3 ? V3(ldg(q), ldg(q + 1), ldg(q + 2)) : V3(ldg(q));
+}
+// MIPMap::triangle(level, st)
+GNX_D V3 mip_triangle(const DevTexture &t, int level, float su, float sv) {
+    level = level < 0 ? 0 : (level > t.n_levels - 1 ? t.n_levels - 1 : level);
+    float s = su * mip_w(t, level) - 0.5f, tt = sv * mip_h(t, level) - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(tt);
+    float ds = s - s0, dt = tt - t0;
+    return (1 - ds) * (1 - dt) * mip_texel(t, level, s0, t0) + (1 - ds) * dt * mip_texel(t, level, s0, t0 + 1) +
+           ds * (1 - dt) * mip_texel(t, level, s0 + 1, t0) + ds * dt * mip_texel(t, level, s0 + 1, t0 + 1);
+}
+GNX_D float log2_ref(float x) { return logf(x) * 1.442695040888963387004650940071f; }  // Log2(), core/GNXRayTracer.h:259-262
+// MIPMap::EWA(level, st, dst0, dst1)
+GNX_D V3 mip_ewa(const DevTexture &t, const float *lut, int level, float st0, float st1, float d00, float d01, float d10, float d11) {
+    if (level >= t.n_levels) return mip_texel(t, t.n_levels - 1, 0, 0);
+    const int w = mip_w(t, level), h = mip_h(t, level);
+    st0 = st0 * w - 0.5f; st1 = st1 * h - 0.5f;
+    d00 *= w; d01 *= h; d10 *= w; d11 *= h;
+    float A = d01 * d01 + d11 * d11 + 1;
+    float B = -2 * (d00 * d01 + d10 * d11);
+    float C = d00 * d00 + d10 * d10 + 1;
+    float invF = 1 / (A * C - B * B * 0.25f);
+    A *= invF; B *= invF; C *= invF;
+    float det = -B * B + 4 * A * C;
+    float invDet = 1 / det;
+    float uSqrt = sqrtf(det * C), vSqrt = sqrtf(A * det);
+    int s0 = (int)ceilf(st0 - 2 * invDet * uSqrt), s1 = (int)floorf(st0 + 2 * invDet * uSqrt);
+    int t0 = (int)ceilf(st1 - 2 * invDet * vSqrt), t1 = (int)floorf(st1 + 2 * invDet * vSqrt);
+    V3 sum(0.f);
+    float sumWts = 0;
+    for (int it = t0; it <= t1; ++it) {
+        float tt = it - st1;
+        for (int is = s0; is <= s1; ++is) {
+            float ss = is - st0;
+            float r2 = A * ss * ss + B * ss * tt + C * tt * tt;
+            if (r2 < 1) {
+                int index = (int)(r2 * 128);
+                if (index > 127) index = 127;
+                float weight = ldg(lut + index);
+                sum += mip_texel(t, level, is, it) * weight;
+                sumWts += weight;
+            }
+        }
+    }
+    return div_each(sum, sumWts);
+}
+// MIPMap::Lookup(st, dst0, dst1)
+GNX_D V3 mip_lookup(const DevTexture &t, const float *lut, float su, float sv, float d00, float d01, float d10, float d11) {
+    if (t.do_trilinear) {
+        float width = fmaxf(fmaxf(fabsf(d00), fabsf(d01)), fmaxf(fabsf(d10), fabsf(d11)));
+        float level = t.n_levels - 1 + log2_ref(fmaxf(width, 1e-8f));
+        if (level < 0) return mip_triangle(t, 0, su, sv);
+        if (level >= t.n_levels - 1) return mip_texel(t, t.n_levels - 1, 0, 0);
+        int iLevel = (int)floorf(level);
+        float delta = level - iLevel;
+        return (1 - delta) * mip_triangle(t, iLevel, su, sv) + delta * mip_triangle(t, iLevel + 1, su, sv);
+    }
+    if (d00 * d00 + d01 * d01 < d10 * d10 + d11 * d11) { float a = d00, b = d01; d00 = d10; d01 = d11; d10 = a; d11 = b; }
+    float majorLength = sqrtf(d00 * d00 + d01 * d01), minorLength = sqrtf(d10 * d10 + d11 * d11);
+    if (minorLength * t.max_aniso < majorLength && minorLength > 0) {
+        float scale = majorLength / (minorLength * t.max_aniso);
+        d10 *= scale; d11 *= scale;
+        minorLength *= scale;
+    }
+    if (minorLength == 0) return mip_triangle(t, 0, su, sv);
+    float lod = fmaxf(0.f, t.n_levels - 1.f + log2_ref(minorLength));
+    int ilod = (int)floorf(lod);
+    float dl = lod - ilod;
+    return (1 - dl) * mip_ewa(t, lut, ilod, su, sv, d00, d01, d10, d11) + dl * mip_ewa(t, lut, ilod + 1, su, sv, d00, d01, d10, d11);
+}
+// ImageTexture::Evaluate (textures/ImageTexture.h:55-62) through UVMapping2D::Map (core/Texture.cpp:168-175).  DIFF =
+// false: the integrator carries no ray differentials (PathIntegrator slices them off, integrators/PathIntegrator.cpp:67),
+// every lookup is MIPMap::triangle(0, st).
+template <bool DIFF>
+GNX_D V3 eval_texture(const DeviceScene &sc, const DevTexture &t, const Surface &s) {
+    const float su = t.su * s.u + t.du, sv = t.sv * s.v + t.dv;
+    if (!DIFF) return texture_bilinear(t, su, sv);
+    return mip_lookup(t, sc.ewa_lut, su, sv, t.su * s.dudx, t.sv * s.dvdx, t.su * s.dudy, t.sv * s.dvdy);
+}
+template <bool DIFF = false>
 GNX_D V3 eval_rgb(const DeviceScene &sc, const gnx_material &m, int slot, const Surface &s) {
     int tex = m.rgb_tex[slot];
     if (tex < 0) return V3(m.rgb[slot][0], m.rgb[slot][1], m.rgb[slot][2]);
-    const DevTexture &t = sc.textures[tex];
-    return texture_bilinear(t, t.su * s.u + t.du, t.sv * s.v + t.dv);
+    return eval_texture<DIFF>(sc, sc.textures[tex], s);
 }
+template <bool DIFF = false>
 GNX_D float eval_f(const DeviceScene &sc, const gnx_material &m, int slot, const Surface &s) {
     int tex = m.f_tex[slot];
     if (tex < 0) return m.f[slot];
-    const DevTexture &t = sc.textures[tex];
-    return texture_bilinear(t, t.su * s.u + t.du, t.sv * s.v + t.dv).x;
+    return eval_texture<DIFF>(sc, sc.textures[tex], s).x;
+}
+
+// SurfaceInteraction::ComputeDifferentials (core/Interaction.cpp:65-114)
+GNX_D void compute_differentials(Surface &s, const RayDiff &rd) {
+    s.dudx = s.dvdx = s.dudy = s.dvdy = 0.f;
+    s.dpdx = V3(0.f); s.dpdy = V3(0.f);
+    if (!rd.has) return;
+    const float d = dot(s.n, s.p);
+    const float tx = -(dot(s.n, rd.rxo) - d) / dot(s.n, rd.rxd);
+    if (finf(tx) || tx != tx) return;
+    const V3 px = rd.rxo + tx * rd.rxd;
+    const float ty = -(dot(s.n, rd.ryo) - d) / dot(s.n, rd.ryd);
+    if (finf(ty) || ty != ty) return;
+    const V3 py = rd.ryo + ty * rd.ryd;
+    s.dpdx = px - s.p;
+    s.dpdy = py - s.p;
+    int d0, d1;
+    if (fabsf(s.n.x) > fabsf(s.n.y) && fabsf(s.n.x) > fabsf(s.n.z)) { d0 = 1; d1 = 2; }
+    else if (fabsf(s.n.y) > fabsf(s.n.z)) { d0 = 0; d1 = 2; }
+    else { d0 = 0; d1 = 1; }
+    const float A00 = s.dpdu[d0], A01 = s.dpdv[d0], A10 = s.dpdu[d1], A11 = s.dpdv[d1];
+    const float Bx0 = px[d0] - s.p[d0], Bx1 = px[d1] - s.p[d1], By0 = py[d0] - s.p[d0], By1 = py[d1] - s.p[d1];
+    // SolveLinearSystem2x2 (core/Transform.cpp:12-20)
+    const float det = A00 * A11 - A01 * A10;
+    if (fabsf(det) < 1e-10f) return;
+    float x0 = (A11 * Bx0 - A01 * Bx1) / det, x1 = (A00 * Bx1 - A10 * Bx0) / det;
+    if (!(x0 != x0 || x1 != x1)) { s.dudx = x0; s.dvdx = x1; }
+    x0 = (A11 * By0 - A01 * By1) / det; x1 = (A00 * By1 - A10 * By0) / det;
+    if (!(x0 != x0 || x1 != x1)) { s.dudy = x0; s.dvdy = x1; }
 }
 
 GNX_D Lobe make_lobe(int kind, int type, V3 R) {
@@ -128,7 +280,7 @@ GNX_D float clamp_alpha(float a) { return fmaxf(0.001f, a); }  // TrowbridgeReit
 // (constant) bump map is attached, and fills the BSDF frame (core/Reflection.h:106-111).
 // multiLobes: the allowMultipleLobes argument (true for Path / VolPath, false for Whitted / DirectLighting; only
 // GlassMaterial looks at it, materials/GlassMaterial.cpp:31).
-template <int MAXL>
+template <int MAXL, bool DIFF = false>
 GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, Bsdf<MAXL> &b, bool multiLobes = true) {
     if (m.flags & GNX_MATF_BUMP_IDENTITY) {
         // SetShadingGeometry(dpdu, dpdv, ..., false) with unchanged dpdu/dpdv (core/Material.cpp:45-51)
@@ -143,8 +295,8 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
     b.ts = cross(b.ns, b.ss);
     switch (m.type) {
     case GNX_MAT_MATTE: {
-        V3 r = clamp0(eval_rgb(sc, m, 0, s));
-        float sig = clampf(eval_f(sc, m, 0, s), 0, 90);
+        V3 r = clamp0(eval_rgb<DIFF>(sc, m, 0, s));
+        float sig = clampf(eval_f<DIFF>(sc, m, 0, s), 0, 90);
         if (!is_black(r)) {
             if (sig == 0) b.add(make_lobe(LK_LAMBERT_R, BSDF_REFLECTION | BSDF_DIFFUSE, r));
             else {
@@ -159,16 +311,16 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
         break;
     }
     case GNX_MAT_MIRROR: {
-        V3 R = clamp0(eval_rgb(sc, m, 0, s));
+        V3 R = clamp0(eval_rgb<DIFF>(sc, m, 0, s));
         if (!is_black(R)) b.add(make_lobe(LK_SPEC_R, BSDF_REFLECTION | BSDF_SPECULAR, R));
         break;
     }
     case GNX_MAT_PLASTIC: {
-        V3 kd = clamp0(eval_rgb(sc, m, 0, s));
+        V3 kd = clamp0(eval_rgb<DIFF>(sc, m, 0, s));
         if (!is_black(kd)) b.add(make_lobe(LK_LAMBERT_R, BSDF_REFLECTION | BSDF_DIFFUSE, kd));
-        V3 ks = clamp0(eval_rgb(sc, m, 1, s));
+        V3 ks = clamp0(eval_rgb<DIFF>(sc, m, 1, s));
         if (!is_black(ks)) {
-            float rough = eval_f(sc, m, 0, s);
+            float rough = eval_f<DIFF>(sc, m, 0, s);
             if (m.flags & GNX_MATF_REMAP_ROUGHNESS) rough = roughness_to_alpha(rough);
             Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, ks);
             l.fresnel = FR_DIELECTRIC; l.e0 = 1.5f; l.e1 = 1.f;
@@ -178,20 +330,20 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
         break;
     }
     case GNX_MAT_METAL: {
-        float ur = eval_f(sc, m, 0, s), vr = eval_f(sc, m, 1, s);
+        float ur = eval_f<DIFF>(sc, m, 0, s), vr = eval_f<DIFF>(sc, m, 1, s);
         if (m.flags & GNX_MATF_REMAP_ROUGHNESS) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
         Lobe l = make_lobe(LK_MICRO_R, BSDF_REFLECTION | BSDF_GLOSSY, V3(1.f));
         l.fresnel = FR_CONDUCTOR; l.e0 = 1.f;
-        l.a = eval_rgb(sc, m, 0, s);
-        l.b = eval_rgb(sc, m, 1, s);
+        l.a = eval_rgb<DIFF>(sc, m, 0, s);
+        l.b = eval_rgb<DIFF>(sc, m, 1, s);
         l.p0 = clamp_alpha(ur); l.p1 = clamp_alpha(vr);
         b.add(l);
         break;
     }
     case GNX_MAT_GLASS: {
-        float eta = eval_f(sc, m, 2, s);
-        float ur = eval_f(sc, m, 0, s), vr = eval_f(sc, m, 1, s);
-        V3 R = clamp0(eval_rgb(sc, m, 0, s)), T = clamp0(eval_rgb(sc, m, 1, s));
+        float eta = eval_f<DIFF>(sc, m, 2, s);
+        float ur = eval_f<DIFF>(sc, m, 0, s), vr = eval_f<DIFF>(sc, m, 1, s);
+        V3 R = clamp0(eval_rgb<DIFF>(sc, m, 0, s)), T = clamp0(eval_rgb<DIFF>(sc, m, 1, s));
         b.eta = eta;
         if (is_black(R) && is_black(T)) break;
         bool isSpecular = ur == 0 && vr == 0;
@@ -228,26 +380,26 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
         break;
     }
     case GNX_MAT_DISNEY: {  // materials/DisneyMaterial.cpp:467-581
-        const V3 c = clamp0(eval_rgb(sc, m, 0, s));
-        const float metallicWeight = eval_f(sc, m, 0, s), e = eval_f(sc, m, 1, s), strans = eval_f(sc, m, 9, s);
+        const V3 c = clamp0(eval_rgb<DIFF>(sc, m, 0, s));
+        const float metallicWeight = eval_f<DIFF>(sc, m, 0, s), e = eval_f<DIFF>(sc, m, 1, s), strans = eval_f<DIFF>(sc, m, 9, s);
         const float diffuseWeight = (1 - metallicWeight) * (1 - strans);
-        const float dt = eval_f(sc, m, 11, s) / 2;
-        const float rough = eval_f(sc, m, 2, s);
+        const float dt = eval_f<DIFF>(sc, m, 11, s) / 2;
+        const float rough = eval_f<DIFF>(sc, m, 2, s);
         const float lum = lum_y(c);
         const V3 Ctint = lum > 0 ? div_each(c, lum) : V3(1.f);
-        const float sheenWeight = eval_f(sc, m, 5, s);
+        const float sheenWeight = eval_f<DIFF>(sc, m, 5, s);
         V3 Csheen(0.f);
-        if (sheenWeight > 0) { float stint = eval_f(sc, m, 6, s); Csheen = (1 - stint) * V3(1.f) + stint * Ctint; }
+        if (sheenWeight > 0) { float stint = eval_f<DIFF>(sc, m, 6, s); Csheen = (1 - stint) * V3(1.f) + stint * Ctint; }
         const bool thin = (m.flags & GNX_MATF_THIN) != 0;
         if (diffuseWeight > 0) {
             if (thin) {
-                float flat = eval_f(sc, m, 10, s);
+                float flat = eval_f<DIFF>(sc, m, 10, s);
                 b.add(make_lobe(LK_DISNEY_DIFFUSE, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * (1 - flat) * (1 - dt)) * c));
                 Lobe l = make_lobe(LK_DISNEY_FAKESS, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * flat * (1 - dt)) * c);
                 l.p0 = rough;
                 b.add(l);
             } else {
-                V3 sd = eval_rgb(sc, m, 1, s);
+                V3 sd = eval_rgb<DIFF>(sc, m, 1, s);
                 if (is_black(sd)) b.add(make_lobe(LK_DISNEY_DIFFUSE, BSDF_REFLECTION | BSDF_DIFFUSE, diffuseWeight * c));
                 else {
                     // the BSSRDF itself is compiled out of both integrators (PathIntegrator.cpp:165-192); the
@@ -262,9 +414,9 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
             b.add(r);
             if (sheenWeight > 0) b.add(make_lobe(LK_DISNEY_SHEEN, BSDF_REFLECTION | BSDF_DIFFUSE, (diffuseWeight * sheenWeight) * Csheen));
         }
-        const float aspect = (float)sqrt(1 - eval_f(sc, m, 4, s) * .9);
+        const float aspect = (float)sqrt(1 - eval_f<DIFF>(sc, m, 4, s) * .9);
         const float ax = fmaxf(.001f, (rough * rough) / aspect), ay = fmaxf(.001f, (rough * rough) * aspect);
-        const float specTint = eval_f(sc, m, 3, s);
+        const float specTint = eval_f<DIFF>(sc, m, 3, s);
         const float r0 = ((e - 1) * (e - 1)) / ((e + 1) * (e + 1));  // SchlickR0FromEta
         const V3 tintMix = (1 - specTint) * V3(1.f) + specTint * Ctint;
         const V3 Cspec0 = (1 - metallicWeight) * (r0 * tintMix) + metallicWeight * c;
@@ -275,11 +427,11 @@ GNX_D void build_bsdf(const DeviceScene &sc, const gnx_material &m, Surface &s, 
             l.p0 = clamp_alpha(ax); l.p1 = clamp_alpha(ay);
             b.add(l);
         }
-        const float cc = eval_f(sc, m, 7, s);
+        const float cc = eval_f<DIFF>(sc, m, 7, s);
         if (cc > 0) {
             Lobe l = make_lobe(LK_DISNEY_CLEARCOAT, BSDF_REFLECTION | BSDF_GLOSSY, V3(0.f));
             l.p0 = cc;
-            l.p1 = lerpf(eval_f(sc, m, 8, s), .1f, .001f);
+            l.p1 = lerpf(eval_f<DIFF>(sc, m, 8, s), .1f, .001f);
             b.add(l);
         }
         if (strans > 0) {

@@ -335,6 +335,7 @@ GNX_D V3 vol_sample_one_light(const DeviceScene &sc, const VPoint &it, const Bsd
 struct VolCounters { unsigned extend, shadow, mis; };
 
 // VolPathIntegrator::Li for camera sample `sample` of pixel (px, py).
+template <bool TEX = false>
 GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int py, int sample, int2 *stack, int stride,
                     TraversalCounters &cnt, VolCounters &vc) {
     const bool pcg = sc.smp.type == GNX_SAMPLER_PCG32;
@@ -352,6 +353,9 @@ GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int p
     V3 L(0.f), beta(1.f);
     bool specularBounce = false;
     float etaScale = 1;
+    RayDiff camDiff;
+    camDiff.has = false;
+    if (TEX) camDiff = camera_ray_differentials(sc, px, py, u0, u1, l0, l1, ray.o, ray.d);
     for (int bounces = 0;; ++bounces) {
         VHit hit;
         ++vc.extend;
@@ -375,7 +379,7 @@ GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int p
             it.p = pMi; it.pError = V3(0.f); it.n = V3(0.f);
             it.mIn = it.mOut = ray.medium;
         } else {
-            if (found) s = make_surface(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
+            if (found) s = make_surface<TEX>(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
             if (bounces == 0 || specularBounce) {
                 if (found) { if (s.light >= 0) L += beta * area_light_L(sc.lights[s.light], s.n, -ray.d); }
                 else if (sc.env.present) L += beta * env_Le(sc.env, ray.d);
@@ -384,11 +388,14 @@ GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int p
             it = surface_point(sc, s, ray.medium);
             if (s.material < 0) {
                 ray = spawn_ray(it, ray.d);
+                camDiff.has = false;
                 bounces--;
                 continue;
             }
-            build_bsdf<8>(sc, sc.materials[s.material], s, bsdf);
+            if (TEX) compute_differentials(s, camDiff);
+            build_bsdf<8, TEX>(sc, sc.materials[s.material], s, bsdf);
         }
+        camDiff.has = false;  // every ray spawned from here on is a plain Ray
         L += beta * vol_sample_one_light<8>(sc, it, miValid ? nullptr : &bsdf, miValid ? V3(0.f) : s.wo, miValid ? wo : V3(0.f), g, smp,
                                             stack, stride, cnt, vc.shadow, vc.mis);
         if (miValid) {

@@ -91,7 +91,11 @@ struct VolVertex {
 // place) until the path ends (VY_DONE), needs a tracking walk through a grid medium (VY_TRACK_MAIN: delta tracking
 // along the path segment, VY_TRACK_SUB: ratio tracking along the walk segment; the resume phase is left in the low
 // byte of ps.meta), or reaches a phase of another kernel (VY_QUEUE0 + queue).
-template <int MAXL>
+// TEX: the scene has image textures — the camera segment keeps its ray differentials (VolPathIntegrator::Li takes a
+// RayDifferential and hands it to ComputeScatteringFunctions at the first vertex; every spawned ray is a plain Ray,
+// integrators/VolPathIntegrator.cpp:30,97-105,130), so a textured surface the camera sees directly is filtered with
+// MIPMap::Lookup's trilinear / EWA path.
+template <int MAXL, bool TEX = false>
 GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathState &ps, const VolWave &vw, int slot, int phase,
                       int kernel, int2 *stack, int stride, TraversalCounters &cnt, VolCounters &vc) {
     const int kNonSpec = BSDF_ALL & ~BSDF_SPECULAR;
@@ -103,12 +107,13 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
     V3 L(0.f), beta(1.f);
     float etaScale = 1;
     int bounces = 0;
-    bool specularBounce = false;
+    bool specularBounce = false, cameraDiff = false;
     VHit hit;
     hit.prim = -1;
     bool found = false;
     PathSampler smp(sc.smp, 0, 0);
     if (phase == VP_START) {
+        cameraDiff = TEX;
         if (sc.smp.type == GNX_SAMPLER_PCG32) smp.take(PathSampler::stream(sc.smp, ((uint64_t)(rc.width * py + px) << 20) | (uint64_t)sample));
         else smp.take(PathSampler(sc.smp, halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride, 0));
         float u0, u1, l0, l1;
@@ -129,6 +134,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
         const uint32_t meta = ps.meta[slot];
         bounces = (int)((meta >> 16) & 0xff);
         specularBounce = ((meta >> 24) & kFlagSpecular) != 0;
+        cameraDiff = TEX && ((meta >> 24) & kFlagCameraDiff) != 0;
         hit.prim = f2i(h4.w); hit.h.b0 = h4.x; hit.h.b1 = h4.y; hit.h.b2 = h4.z; hit.h.t = ray.tMax;
         found = hit.prim >= 0;
         smp.take(vol_load_sampler(sc, rc, ps, vw, slot, px, py, sample));
@@ -169,9 +175,22 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
             vx.it.p = ray.o + ray.d * tmi; vx.it.pError = V3(0.f); vx.it.n = V3(0.f);
             vx.it.mIn = vx.it.mOut = ray.medium;
         } else {
-            vx.s = make_surface(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
+            vx.s = make_surface<TEX>(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
             vx.it = surface_point(sc, vx.s, ray.medium);
-            if (vx.s.material >= 0) build_bsdf<MAXL>(sc, sc.materials[vx.s.material], vx.s, vx.bsdf);
+            if (TEX && cameraDiff && vx.s.material >= 0) {
+                // the camera sample again (its five draws open the stream), for the offset rays
+                float u0, u1, l0, l1;
+                if (sc.smp.type == GNX_SAMPLER_PCG32) {
+                    PathSampler cs = PathSampler::stream(sc.smp, ((uint64_t)(rc.width * py + px) << 20) | (uint64_t)sample);
+                    cs.get2d(&u0, &u1); cs.get1d(); cs.get2d(&l0, &l1);
+                } else {
+                    const uint64_t hi = (uint64_t)ps.hidx[slot];
+                    u0 = halton_sample_dimension(sc.smp, hi, 0); u1 = halton_sample_dimension(sc.smp, hi, 1);
+                    l0 = halton_sample_dimension(sc.smp, hi, 3); l1 = halton_sample_dimension(sc.smp, hi, 4);
+                }
+                compute_differentials(vx.s, camera_ray_differentials(sc, px, py, u0, u1, l0, l1, ray.o, ray.d));
+            }
+            if (vx.s.material >= 0) build_bsdf<MAXL, TEX>(sc, sc.materials[vx.s.material], vx.s, vx.bsdf);
         }
     };
     auto storeMain = [&](int resume) {
@@ -181,7 +200,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
         ps.beta[slot] = make_float4(beta.x, beta.y, beta.z, 0.f);
         ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         ps.hit[slot] = make_float4(hit.h.b0, hit.h.b1, hit.h.b2, i2f(found ? hit.prim : -1));
-        ps.meta[slot] = (uint32_t)resume | ((uint32_t)bounces << 16) | ((specularBounce ? kFlagSpecular : 0u) << 24);
+        ps.meta[slot] = (uint32_t)resume | ((uint32_t)bounces << 16) | (((specularBounce ? kFlagSpecular : 0u) | (cameraDiff ? kFlagCameraDiff : 0u)) << 24);
         vol_store_sampler(vw, slot, smp);
     };
     auto storeSub = [&]() {
@@ -229,6 +248,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
                 if (noMaterial && !emits) {
                     const Surface s = make_surface(sc, hit.prim, hit.h.b0, hit.h.b1, hit.h.b2, ray.d);
                     ray = spawn_ray(surface_point(sc, s, ray.medium), ray.d);
+                    cameraDiff = false;
                     break;  // phase stays VP_EXTEND
                 }
             }
@@ -251,6 +271,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
                 if (!found || bounces >= rc.max_depth) { storeMain(VP_CONT); return VY_DONE; }
                 if (vx.s.material < 0) {  // medium boundary: same direction, the bounce does not count
                     ray = spawn_ray(vx.it, ray.d);
+                    cameraDiff = false;
                     phase = VP_EXTEND;
                     break;
                 }
@@ -423,6 +444,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
                 beta = div_each(beta, 1 - q);
             }
             ++bounces;
+            cameraDiff = false;
             phase = VP_EXTEND;
             break;
         }
@@ -496,12 +518,12 @@ GNX_D void vol_track_finish(const DeviceScene &sc, const PathState &ps, const Vo
 // Sequential driver (CPU emulation, tests): the same state machine for one path.  staged = true follows the path
 // through the kernels exactly as the device does — every hand-over between two logic kernels and every tracking walk goes
 // through the stored state — staged = false runs all phases in place.
-template <int MAXL>
+template <int MAXL, bool TEX = false>
 GNX_D V3 volwave_li(const DeviceScene &sc, const RenderConsts &rc, const PathState &ps, const VolWave &vw, int slot, int2 *stack, int stride,
                     TraversalCounters &cnt, VolCounters &vc, bool staged = true) {
     int phase = VP_START, kernel = staged ? VK_EXTEND : VK_ANY;
     while (true) {
-        const int y = vol_advance<MAXL>(sc, rc, ps, vw, slot, phase, kernel, stack, stride, cnt, vc);
+        const int y = vol_advance<MAXL, TEX>(sc, rc, ps, vw, slot, phase, kernel, stack, stride, cnt, vc);
         if (y == VY_DONE) break;
         if (y >= VY_QUEUE0) {
             phase = vol_queue_phase(y - VY_QUEUE0);

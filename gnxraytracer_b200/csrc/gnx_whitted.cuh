@@ -8,8 +8,9 @@
 // subtree in advance, so — like VolPath — the recursion runs per lane, as an explicit depth-first stack of frames;
 // a pending transmission frame keeps only the hit record and is re-shaded when it is popped.
 //
-// Ray differentials are carried by the reference only to filter textures; these integrators are therefore
-// refused for scenes with image textures (gnx_render.cu), everything else is independent of them.
+// Ray differentials (RayDifferential, SurfaceInteraction::ComputeDifferentials, the reflected / refracted offset rays of
+// SpecularReflect / SpecularTransmit) are carried only when the scene has image textures: they feed MIPMap::Lookup's
+// trilinear / EWA filtering and nothing else (TEX template parameter).
 #pragma once
 #include "gnx_volpath.cuh"
 
@@ -91,6 +92,7 @@ GNX_D V3 w_estimate_direct(const DeviceScene &sc, const Surface &s, const Bsdf<M
 
 // One pending piece of the recursion.
 struct RecFrame {
+    RayDiff rd;       // the ray's differentials (kind 1: of the ray that produced the hit)
     V3 o, d;          // kind 0: the ray to trace.  kind 1: d = direction of the ray that produced the hit
     V3 weight;        // product of f * |cos| / pdf down to here
     float hb0, hb1, hb2;
@@ -113,7 +115,7 @@ constexpr int kMaxRecDepth = 16;
 // start behind the arrays' (GlobalSampler::Get1D / Get2D skip [arrayStartDim, arrayEndDim), core/Sampler.cpp).
 // (direct is a template parameter: with the three integrators in one body the Whitted render measured 12 % slower —
 // the UniformSampleAll code costs registers in the hot loop even when it never runs.)
-template <int MAXL, int direct>
+template <int MAXL, int direct, bool TEX = false>
 GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int py, int sample, int2 *stack, int stride,
                       TraversalCounters &cnt, RecCounters &rcnt) {
     const uint64_t pixOffset = halton_pixel_offset(sc.smp, px, py);
@@ -130,6 +132,13 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
         RecFrame &f = frames[nf++];
         f.o = o; f.d = d; f.weight = V3(1.f); f.depth = 0; f.kind = 0; f.prim = -1;
         f.hb0 = f.hb1 = f.hb2 = 0;
+        f.rd.has = false;
+        if (TEX) {
+            const float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+            float l0 = 0, l1 = 0;
+            if (sc.cam.lens_radius > 0) { l0 = halton_sample_dimension(sc.smp, hidx, 3); l1 = halton_sample_dimension(sc.smp, hidx, 4); }
+            f.rd = camera_ray_differentials(sc, px, py, u0, u1, l0, l1, o, d);
+        }
     }
     V3 L(0.f);
     const int maxDepth = rc.max_depth < kMaxRecDepth ? rc.max_depth : kMaxRecDepth;
@@ -146,18 +155,20 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
                 TriHit h;
                 ++rcnt.extend;
                 if (!traverse<false>(sc, fr.o, fr.d, GNX_INF, stack, stride, &prim, &h, cnt)) { escaped = true; break; }
-                s = make_surface(sc, prim, h.b0, h.b1, h.b2, fr.d);
+                s = make_surface<TEX>(sc, prim, h.b0, h.b1, h.b2, fr.d);
                 fr.prim = prim; fr.hb0 = h.b0; fr.hb1 = h.b1; fr.hb2 = h.b2;
                 if (s.material >= 0) break;
-                fr.o = offset_ray_origin(s.p, s.pError, s.n, fr.d);  // isect.SpawnRay(ray.d)
+                fr.o = offset_ray_origin(s.p, s.pError, s.n, fr.d);  // isect.SpawnRay(ray.d): a plain Ray, the differentials end here
+                fr.rd.has = false;
             }
             if (escaped) { L += fr.weight * scene_le(sc, fr.o, fr.d); continue; }
             if (s.material < 0) continue;
             lit = true;
         } else {
-            s = make_surface(sc, fr.prim, fr.hb0, fr.hb1, fr.hb2, fr.d);
+            s = make_surface<TEX>(sc, fr.prim, fr.hb0, fr.hb1, fr.hb2, fr.d);
         }
-        build_bsdf<MAXL>(sc, sc.materials[s.material], s, bsdf, false);
+        if (TEX) compute_differentials(s, fr.rd);  // isect.ComputeScatteringFunctions(ray, ...) -> ComputeDifferentials(ray)
+        build_bsdf<MAXL, TEX>(sc, sc.materials[s.material], s, bsdf, false);
         const V3 ns = bsdf.ns;
         if (lit) {
             // ---- emitted light, then the direct illumination of the integrator
@@ -234,6 +245,31 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
             c.kind = 0;
             c.prim = -1;
             c.hb0 = c.hb1 = c.hb2 = 0;
+            c.rd.has = false;
+            if (TEX && fr.rd.has) {
+                // differentials of the reflected / refracted ray (core/Integrator.cpp:336-356, 381-437)
+                c.rd.has = true;
+                c.rd.rxo = s.p + s.dpdx;
+                c.rd.ryo = s.p + s.dpdy;
+                V3 nsd = ns;
+                V3 dndx = s.dndu * s.dudx + s.dndv * s.dvdx, dndy = s.dndu * s.dudy + s.dndv * s.dvdy;
+                const V3 wo = s.wo;
+                const V3 dwodx = -fr.rd.rxd - wo, dwody = -fr.rd.ryd - wo;
+                if (lit) {
+                    const float dDNdx = dot(dwodx, nsd) + dot(wo, dndx), dDNdy = dot(dwody, nsd) + dot(wo, dndy);
+                    c.rd.rxd = wi - dwodx + 2.f * (dot(wo, nsd) * dndx + dDNdx * nsd);
+                    c.rd.ryd = wi - dwody + 2.f * (dot(wo, nsd) * dndy + dDNdy * nsd);
+                } else {
+                    float eta = 1 / bsdf.eta;
+                    if (dot(wo, nsd) < 0) { eta = 1 / eta; nsd = -nsd; dndx = -dndx; dndy = -dndy; }
+                    const float dDNdx = dot(dwodx, nsd) + dot(wo, dndx), dDNdy = dot(dwody, nsd) + dot(wo, dndy);
+                    const float mu = eta * dot(wo, nsd) - absdot(wi, nsd);
+                    const float dmudx = (eta - (eta * eta * dot(wo, nsd)) / absdot(wi, nsd)) * dDNdx;
+                    const float dmudy = (eta - (eta * eta * dot(wo, nsd)) / absdot(wi, nsd)) * dDNdy;
+                    c.rd.rxd = wi - eta * dwodx + (mu * dndx + dmudx * nsd);
+                    c.rd.ryd = wi - eta * dwody + (mu * dndy + dmudy * nsd);
+                }
+            }
         }
     }
     return L;
@@ -245,7 +281,12 @@ namespace gnx {
 // run-time selection of the integrator (host emulation, tests)
 template <int MAXL>
 GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int direct, int px, int py, int sample, int2 *stack, int stride,
-                      TraversalCounters &cnt, RecCounters &rcnt) {
+                      TraversalCounters &cnt, RecCounters &rcnt, bool tex = false) {
+    if (tex) {
+        if (direct == 0) return recursive_li<MAXL, 0, true>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+        if (direct == 1) return recursive_li<MAXL, 1, true>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+        return recursive_li<MAXL, 2, true>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
+    }
     if (direct == 0) return recursive_li<MAXL, 0>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
     if (direct == 1) return recursive_li<MAXL, 1>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);
     return recursive_li<MAXL, 2>(sc, rc, px, py, sample, stack, stride, cnt, rcnt);

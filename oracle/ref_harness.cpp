@@ -197,8 +197,18 @@ void BuildCornell(HarnessScene &hs, int variant, int subdiv) {
 // box, lit by a PointLight, a SpotLight, a DistantLight, the area light and a SkyBoxLight (visible through the
 // opening and in the mirror).  lightMask selects the lights (bit 0 area, 1 point, 2 spot, 3 distant, 4 skybox,
 // 5 = skybox with the awesomeface.jpg image instead of the procedural colours).
-void BuildLightsRoom(HarnessScene &hs, int lightMask, int subdiv) {
-    auto white = Matte(0.91f, 0.91f, 0.91f, 0.f);
+// textured: 0 = constant colours; 1 / 2 = the white walls (floor, ceiling, back wall) carry awesomeface.jpg as an
+// ImageTexture filtered with EWA (1) or trilinearly (2), and the spheres get per-vertex normals — Whitted / DirectLighting
+// then exercise ray differentials: ComputeDifferentials, MIPMap::Lookup, the offset rays through SpecularReflect /
+// SpecularTransmit (core/Interaction.cpp:65-114, core/MIPMap.h:226-337, core/Integrator.cpp:321-442).
+void BuildLightsRoom(HarnessScene &hs, int lightMask, int subdiv, int textured = 0) {
+    std::shared_ptr<Material> white = Matte(0.91f, 0.91f, 0.91f, 0.f);
+    if (textured) {
+        std::unique_ptr<TextureMapping2D> map = std::make_unique<UVMapping2D>(2.f, 3.f, 0.1f, 0.2f);
+        std::shared_ptr<Texture<Spectrum>> face = std::make_shared<ImageTexture<RGBSpectrum, Spectrum>>(
+            std::move(map), ResourceDir() + "awesomeface.jpg", textured == 2, 8.f, ImageWrap::Repeat, 1.f, false);
+        white = std::make_shared<MatteMaterial>(face, ConstF(0.f), ConstF(0.0f));
+    }
     auto red = Matte(0.9f, 0.1f, 0.17f, 0.f);
     auto blue = Matte(0.14f, 0.21f, 0.87f, 30.f);
     auto mirror = std::make_shared<MirrorMaterial>(ConstSpec(0.9f, 0.9f, 0.9f), ConstF(0.0f));
@@ -206,8 +216,8 @@ void BuildLightsRoom(HarnessScene &hs, int lightMask, int subdiv) {
                                                  ConstF(0.0f), ConstF(1.5f), ConstF(0.0f), false);
     auto plastic = std::make_shared<PlasticMaterial>(ConstSpec(0.35f, 0.12f, 0.48f), ConstSpec(0.65f, 0.88f, 0.52f), ConstF(0.1f),
                                                      ConstF(0.0f), true);
-    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, -1.0f, -1.7f, -0.5f), Transform(), mirror, nullptr);
-    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, 1.0f, -1.7f, 0.8f), Transform(), glass, nullptr);
+    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, -1.0f, -1.7f, -0.5f, textured != 0), Transform(), mirror, nullptr);
+    AddMesh(hs, gnxsk::icosphere(subdiv, 0.8f, 1.0f, -1.7f, 0.8f, textured != 0), Transform(), glass, nullptr);
     AddMesh(hs, gnxsk::icosphere(subdiv > 1 ? subdiv - 1 : subdiv, 0.5f, 0.0f, -2.0f, 1.6f), Transform(), plastic, nullptr);
     gnxsk::Mesh walls = gnxsk::cornell_walls(5.0f);
     Transform box2world = Translate(Vector3f(-2.5f, -2.5f, -2.5f));
@@ -357,11 +367,19 @@ bool BuildSmoke(HarnessScene &hs, int variant) {
     const float flo[3] = {-2.4f, -2.4f, -2.4f}, fhi[3] = {2.4f, 2.4f, 2.4f};
     AddMesh(hs, gnxsk::box(flo, fhi), Transform(), nullptr, nullptr, MediumInterface(inner, nullptr));
     AddMesh(hs, gnxsk::ground_quad(2.2f, -1.5f), Transform(), Matte(0.5f, 0.5f, 0.5f, 0.f), nullptr, MediumInterface(inner));
+    if (variant >= 2) {
+        // variant 2 / 3: a large textured floor below the fog box, seen by the camera DIRECTLY in front of the box: the one
+        // place where VolPathIntegrator still holds the camera's RayDifferential (EWA / trilinear MIPMap::Lookup)
+        std::unique_ptr<TextureMapping2D> map = std::make_unique<UVMapping2D>(3.f, 3.f, 0.f, 0.f);
+        std::shared_ptr<Texture<Spectrum>> face = std::make_shared<ImageTexture<RGBSpectrum, Spectrum>>(
+            std::move(map), ResourceDir() + "awesomeface.jpg", variant == 3, 8.f, ImageWrap::Repeat, 1.f, false);
+        AddMesh(hs, gnxsk::ground_quad(9.0f, -2.45f), Transform(), std::make_shared<MatteMaterial>(face, ConstF(0.f), ConstF(0.0f)), nullptr);
+    }
     Transform l2w = RotateX(20) * RotateY(-90) * RotateX(-90);
     hs.lights.push_back(std::make_shared<InfiniteAreaLight>(l2w, Spectrum(1.0f), 10, hdr));
     SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
     hs.integrator = 1;
-    Finish(hs, variant == 0);
+    Finish(hs, variant == 0);  // the grid medium needs the unbounded PCG stream; the fog-only variants run on Halton
     return true;
 }
 
@@ -438,6 +456,11 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
         // the same room under the wavefront PathIntegrator: delta lights + SkyBoxLight through EstimateDirect
         BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2);
         hs->integrator = 0;
+    }
+    else if (hs->name == "whitted_tex" || hs->name == "direct_tex") {
+        // p2: 1 = EWA, 2 = trilinear filtering of the wall texture
+        BuildLightsRoom(*hs, p0 > 0 ? p0 : 31, p1 > 0 ? p1 : 2, p2 == 2 ? 2 : 1);
+        hs->integrator = hs->name == "whitted_tex" ? 2 : 3;
     }
     else if (hs->name == "whitted" || hs->name == "direct" || hs->name == "lights") {
         // "lights": the scene kit's name for the same room, p2 = gnx_integrator (2 Whitted, 3 DirectLighting)

@@ -37,6 +37,12 @@ SCENES = {
     "direct_all_area": ("direct", 1, 2, 4),         # two area-light triangles with nSamples = 5 each
     # the reference UI's live scene (ui/RenderThread.cpp:60-164): mesh inside the Cornell box, area light + SkyBoxLight;
     # p0 = gnx_integrator (0: the commented-in PathIntegrator line :164, 2: the default WhittedIntegrator :163)
+    # image textures under the integrators that carry ray differentials: EWA (p2 = 1) / trilinear (p2 = 2) MIPMap::Lookup
+    "whitted_tex": ("whitted_tex", 31, 2, 1),
+    "whitted_tri": ("whitted_tex", 31, 2, 2),
+    "direct_tex": ("direct_tex", 1 | 2, 2, 1),
+    "fog_tex": ("smoke", 2, 0, 0),                  # VolPath: textured floor seen directly by the camera, EWA
+    "fog_tri": ("smoke", 3, 0, 0),                  # ... trilinear
     "lights_path": ("lights_path", 31, 2, 0),       # PathIntegrator with area + point + spot + distant + skybox lights
     "lights_path_img": ("lights_path", 1 | 2 | 32, 2, 0),
     "ui_path": ("ui", 0, 256, 32),
@@ -44,7 +50,7 @@ SCENES = {
     "ui_path_full": ("ui", 0, 2048, 213),
     "ui_whitted_full": ("ui", 2, 2048, 213),
 }
-INTEGRATOR_OF = {"whitted": 2, "direct": 3, "smoke": 1}
+INTEGRATOR_OF = {"whitted": 2, "direct": 3, "smoke": 1, "whitted_tex": 2, "direct_tex": 3}
 
 
 def integrator_of(preset):

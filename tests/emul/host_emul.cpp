@@ -33,6 +33,9 @@ struct EmulScene {
     std::vector<uint16_t> perms;
     unsigned typeMask = 0;
     bool hasNext = false;  // point / spot / distant / skybox lights present
+    bool hasTex = false;   // image textures: the integrators with a RayDifferential carry it
+    std::vector<std::vector<float>> pyramids;
+    float ewa_lut[128];
     float wb[6];
     std::string err;
 };
@@ -54,11 +57,18 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.materials = d->materials;
     sc.n_materials = d->n_materials;
     e.textures.resize(d->n_textures);
+    e.pyramids.resize(d->n_textures);
     for (int i = 0; i < d->n_textures; ++i) {
         const gnx_texture &t = d->textures[i];
-        e.textures[i] = DevTexture{t.width, t.height, t.n_channels, t.wrap, t.su, t.sv, t.du, t.dv, t.texels};
+        std::vector<int> offs;
+        int nLevels = 1;
+        build_mip_pyramid(t, e.pyramids[i], offs, &nLevels);
+        fill_dev_texture(t, e.pyramids[i].data(), offs, nLevels, e.textures[i]);
     }
     sc.textures = e.textures.data();
+    make_ewa_lut(e.ewa_lut);
+    sc.ewa_lut = e.ewa_lut;
+    e.hasTex = d->n_textures > 0;
     sc.lights = d->lights;
     sc.n_lights = d->n_lights;
     for (int i = 0; i < d->n_lights; ++i) e.hasNext |= d->lights[i].type >= GNX_LIGHT_POINT;
@@ -116,7 +126,10 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.cam.lens_radius = d->camera.lens_radius;
     sc.cam.focal_distance = d->camera.focal_distance;
     sc.cam.medium = d->camera.medium;
+    sc.cam.dx_camera = V3(d->camera.dx_camera[0], d->camera.dx_camera[1], d->camera.dx_camera[2]);
+    sc.cam.dy_camera = V3(d->camera.dy_camera[0], d->camera.dy_camera[1], d->camera.dy_camera[2]);
     const gnx_sampler &s = d->sampler;
+    sc.smp.spp = s.samples_per_pixel > 0 ? s.samples_per_pixel : 1;
     sc.smp.type = s.type;
     sc.smp.base_scale0 = s.base_scales[0]; sc.smp.base_scale1 = s.base_scales[1];
     sc.smp.base_exp0 = s.base_exponents[0]; sc.smp.base_exp1 = s.base_exponents[1];
@@ -169,7 +182,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         int2 vstack[kSmemStack];
         VolCounters vc{0, 0, 0};
         V3 Lv;
-        if (getenv("GNX_VOLPATH_MEGAKERNEL")) Lv = volpath_li(sc, rcv, px, py, sample, vstack, 1, cnt, vc);
+        if (getenv("GNX_VOLPATH_MEGAKERNEL")) Lv = e.hasTex ? volpath_li<true>(sc, rcv, px, py, sample, vstack, 1, cnt, vc) : volpath_li<false>(sc, rcv, px, py, sample, vstack, 1, cnt, vc);
         else {
             // the staged wavefront's state machine (gnx_volwave.cuh), one slot: pixel / sample go in through the batch mapping
             float4 ro, rd, be, Lq, hq, so, sd, sh, st, w0, w1, w2, w3, w4;
@@ -188,7 +201,8 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
             VolWave vwq = vw1;
             vwq.rng -= pix; vwq.tmi -= pix; vwq.sub_o -= pix; vwq.sub_d -= pix; vwq.sub_hit -= pix; vwq.sub_tr -= pix;
             vwq.w0 -= pix; vwq.w1 -= pix; vwq.w2 -= pix; vwq.w3 -= pix; vwq.w4 -= pix;
-            Lv = volwave_li<8>(sc, rcv, psq, vwq, pix, vstack, 1, cnt, vc, getenv("GNX_VOLWAVE_INPLACE") == nullptr);
+            const bool staged = getenv("GNX_VOLWAVE_INPLACE") == nullptr;
+            Lv = e.hasTex ? volwave_li<8, true>(sc, rcv, psq, vwq, pix, vstack, 1, cnt, vc, staged) : volwave_li<8, false>(sc, rcv, psq, vwq, pix, vstack, 1, cnt, vc, staged);
         }
         rays[0] += vc.extend; rays[1] += vc.shadow; rays[2] += vc.mis;
         return Lv;
@@ -198,7 +212,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
         rcw.width = p.width; rcw.height = p.height; rcw.max_depth = p.max_depth; rcw.rr_threshold = p.rr_threshold;
         int2 wstack[kSmemStack];
         RecCounters rcnt{0, 0, 0};
-        V3 Lw = recursive_li<8>(sc, rcw, p.integrator - GNX_INTEGRATOR_WHITTED, px, py, sample, wstack, 1, cnt, rcnt);
+        V3 Lw = recursive_li<8>(sc, rcw, p.integrator - GNX_INTEGRATOR_WHITTED, px, py, sample, wstack, 1, cnt, rcnt, e.hasTex);
         rays[0] += rcnt.extend; rays[1] += rcnt.shadow; rays[2] += rcnt.mis;
         return Lw;
     }

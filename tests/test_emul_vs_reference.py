@@ -203,3 +203,34 @@ def test_scene_kit_ui_scene_equals_the_harness_one(ref, emul):
     assert rel_mse(img, img_ref) <= 1e-3
     assert np.mean(np.abs(img[..., :3] - img_ref[..., :3]).max(axis=2) < 1e-5) >= 0.99
     rs.close(); sk.close()
+
+
+@pytest.mark.parametrize("preset", ["whitted_tex", "whitted_tri", "direct_tex", "fog_tex", "fog_tri"])
+def test_image_textures_filtered_with_ray_differentials(ref, emul, preset):
+    """MIPMap::Lookup with ray differentials (core/MIPMap.h:226-337): EWA and trilinear filtering over the pyramid, fed by
+    SurfaceInteraction::ComputeDifferentials (core/Interaction.cpp:65-114) from the camera's offset rays
+    (camera/Perspective.cpp:62-112, scaled by 1 / sqrt(spp)) and, under Whitted / DirectLighting, from the offset rays of
+    SpecularReflect / SpecularTransmit (core/Integrator.cpp:321-442: mirror and glass spheres with vertex normals in front of
+    textured walls).  VolPath keeps the differentials for the camera segment only.  Per-sample radiance against the
+    reference's Li, the image against its Render; EWA and trilinear must differ from each other and from plain bilinear."""
+    from _harness import integrator_of
+    res = 48
+    integ = integrator_of(preset)
+    rs = ref.scene(preset, res, res, 4)
+    es = emul.scene(rs.desc)
+    px, py = grid(res, res)
+    p = RenderParams.make(res, res, 4, max_depth=5, integrator=integ)
+    sm = np.full(px.size, 1, np.int32)
+    rgb, _ = rs.reference_samples(px, py, sm, max_depth=5, want_prim=False)
+    mine = es.samples(p, px, py, sm)
+    scale = np.maximum(np.abs(rgb).max(axis=1), 1e-3)
+    assert np.mean(np.abs(mine - rgb).max(axis=1) / scale < 1e-4) >= 0.999
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, _ = es.render(p)
+    assert rel_mse(img, img_ref) <= 1e-6
+    if preset in ("whitted_tex", "fog_tex"):
+        other = ref.scene(preset.replace("_tex", "_tri"), res, res, 4)
+        img_tri, _ = other.render_reference(max_depth=5)
+        assert rel_mse(img, img_tri) > 1e-7, "EWA and trilinear filtering should not coincide"
+        other.close()
+    rs.close(); es.close()

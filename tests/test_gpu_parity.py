@@ -345,6 +345,24 @@ def test_delta_and_skybox_lights_under_the_path_integrator(ref, emul, preset, de
     rs.close()
 
 
+@pytest.mark.parametrize("preset", ["whitted_tex", "whitted_tri", "direct_tex", "fog_tex", "fog_tri"])
+def test_image_textures_with_ray_differentials_on_gpu(ref, emul, preset):
+    """EWA / trilinear MIPMap::Lookup with ray differentials (core/MIPMap.h:226-337, core/Interaction.cpp:65-114) under
+    Whitted, DirectLighting and at VolPath's camera vertex: the drop-in class against the reference's own Render."""
+    from _harness import integrator_of
+    res, spp = 128, 8
+    rs = ref.scene(preset, res, res, spp)
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, _, st = rs.render_cuda(max_depth=5)
+    assert st.paths == res * res * spp
+    assert rel_mse(img, img_ref) <= 1e-3
+    close = np.abs(img[..., :3] - img_ref[..., :3]).max(axis=2) <= 1e-3 * np.maximum(1.0, img_ref[..., :3].max(axis=2))
+    assert np.mean(close) >= 0.99
+    emu, _ = emul.scene(rs.desc).render(RenderParams.make(res, res, spp, max_depth=5, integrator=integrator_of(preset)))
+    assert rel_mse(img, emu) <= 1e-6
+    rs.close()
+
+
 def test_recursion_depth_limit_is_an_error_not_a_clamp(ref, ctx):
     """Whitted / DirectLighting keep 16 recursion frames: deeper requests are refused instead of silently cut."""
     from gnxraytracer_b200.api import GnxError
