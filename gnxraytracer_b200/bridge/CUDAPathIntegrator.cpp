@@ -78,6 +78,7 @@
 #undef protected
 
 #include "gnxraytracer_b200/bridge/CUDAPathIntegrator.h"
+#include "gnxraytracer_b200/bridge/SobolSampler.h"
 
 namespace gnx {
 
@@ -495,6 +496,16 @@ bool FlattenScene(const Scene &scene, const Camera &camera, const Sampler &sampl
         out->perms = HaltonSampler::radicalInversePermutations;
         s.n_perm_entries = (int32_t)out->perms.size();
         s.perms = out->perms.data();
+    } else if (auto *sb = dynamic_cast<const SobolSampler *>(&sampler)) {
+        // the reference's own tables, by pointer (samplers/SobolMatrices.cpp); nothing of them is copied into this repository
+        if (sb->sampleBounds.pMin.x != 0 || sb->sampleBounds.pMin.y != 0) return fl.Fail("SobolSampler: sample bounds must start at (0, 0)");
+        s.type = GNX_SAMPLER_SOBOL;
+        s.sobol_resolution = sb->resolution;
+        s.sobol_log2_resolution = sb->log2Resolution;
+        s.n_sobol_dimensions = NumSobolDimensions;
+        s.sobol_matrices32 = SobolMatrices32;
+        s.sobol_vdc = sb->log2Resolution > 0 ? VdCSobolMatrices[sb->log2Resolution - 1] : nullptr;
+        s.sobol_vdc_inv = sb->log2Resolution > 0 ? VdCSobolMatricesInv[sb->log2Resolution - 1] : nullptr;
     } else {
         // Any other sampler is mapped onto the per-pixel PCG32 stream; parity is then statistical.
         s.type = GNX_SAMPLER_PCG32;

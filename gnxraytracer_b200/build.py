@@ -15,7 +15,10 @@ NVCC_FLAGS = [
     # no FMA contraction: discrete decisions (hit / lobe / light choice) then agree with the x86 -O2
     # reference on all but grazing cases
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    # kernel templates are instantiated in one translation unit and launched from another (csrc/tu_*.cu): keep their host
+    # stubs external, which is CUDA 12's default, stated explicitly because nvcc announces a change of that default
+    "-static-global-template-stub=false", "-diag-suppress", "20281",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -45,8 +48,23 @@ def build_product(force: bool = False) -> str:
     out = os.path.join(lib, "libgnxrt.so")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(root, "include", "gnxrt.h")]
     if force or _newer(out, srcs):
+        # one object per translation unit (gnx_render.cu: host code + the light kernels; tu_*.cu: explicit instantiations
+        # of the heavy kernel templates), compiled in parallel, linked into one shared library
+        from concurrent.futures import ThreadPoolExecutor
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc, *NVCC_FLAGS, "-I", os.path.join(root, "include"), "-o", out, os.path.join(csrc, "gnx_render.cu")])
+        objdir = os.path.join(root, "build", "obj")
+        os.makedirs(objdir, exist_ok=True)
+        units = sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+        headers = [os.path.join(csrc, f) for f in os.listdir(csrc) if not f.endswith(".cu")] + [os.path.join(root, "include", "gnxrt.h")]
+
+        def compile_unit(u):
+            obj = os.path.join(objdir, u[:-3] + ".o")
+            if force or _newer(obj, [os.path.join(csrc, u)] + headers):
+                _run([nvcc, *NVCC_FLAGS, "-I", os.path.join(root, "include"), "-c", os.path.join(csrc, u), "-o", obj])
+            return obj
+        with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
+            objs = list(ex.map(compile_unit, units))
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs])
     sk = os.path.join(lib, "libgnxscenekit.so")
     sk_src = os.path.join(host, "scenekit.cpp")
     if os.path.exists(sk_src):

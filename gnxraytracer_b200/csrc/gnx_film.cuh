@@ -32,9 +32,8 @@ GNX_D void film_sample_offset(const DeviceScene &sc, int width, int px, int py, 
         PathSampler smp = PathSampler::stream(sc.smp, ((uint64_t)(width * py + px) << 20) | (uint64_t)sample);
         smp.get2d(u0, u1);
     } else {
-        uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
-        *u0 = halton_sample_dimension(sc.smp, hidx, 0);
-        *u1 = halton_sample_dimension(sc.smp, hidx, 1);
+        uint64_t hidx = sampler_index(sc.smp, px, py, (uint64_t)sample);
+        sampler_film_dimensions(sc.smp, hidx, px, py, u0, u1);
     }
 }
 

@@ -43,22 +43,28 @@ __device__ __forceinline__ void flush_stats(DevStats *st, int kind, unsigned nod
 }
 
 // Zeroes every queue counter except the extend queue that is about to be consumed.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_reset_counts(int *counts, int outExtend) {
     int i = threadIdx.x;
     if (i < kNumCounters && i != (1 - outExtend)) counts[i] = 0;
 }
+#endif
 
 // Zeroes the shadow / probe counters and the fetch cursors (between a mixed trace launch and the shade stage).
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_reset_ray_counts(int *counts) {
     int i = threadIdx.x;
     if (i >= kCntShadow && i < kNumCounters) counts[i] = 0;
 }
+#endif
 // Zeroes the counters of the queues the coming stages will fill, keeping the extend queue `in` AND the shadow queues
 // (both are consumed by the mixed trace launch that follows); fetch cursors are zeroed.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_reset_counts_keep_rays(int *counts, int outExtend) {
     int i = threadIdx.x;
     if (i < kNumCounters && i != (1 - outExtend) && !(i >= kCntShadow && i < kCntShadow + 2)) counts[i] = 0;
 }
+#endif
 
 // ---- the traversal kernel --------------------------------------------------------------------------------
 // Persistent threads with dynamic ray fetch (Aila & Laine's while-while scheme): the grid is exactly the
@@ -237,11 +243,14 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
 }
 
 // Escaped rays of a scene with a SkyBoxLight (queued by the traversal kernel): L += beta * Le(ray).
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_escape(const DeviceScene sc, PathState ps, Queues q) {
     const int n = q.counts[kCntMiss];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) escape_slot(sc, ps, q.miss_q[i]);
 }
+#endif
 
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc,
                                                         int outQ) {
     const int n = q.counts[kCntShade0 + (kNumShadeTypes - 1)];
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const DeviceScene sc, Pat
         if (idx >= 0) q.extend_q[outQ][idx] = slot;
     }
 }
+#endif
 
 #ifndef GNX_SHADE_BLOCK
 #define GNX_SHADE_BLOCK 128
@@ -338,11 +348,13 @@ __global__ void __launch_bounds__(kBlock, 8) k_volpath(const DeviceScene sc, Pat
 // in counts[0]; paths waiting for a logic kernel in shade_q[VolQueue], counts in counts[kCntShade0 + queue].  One fetch
 // cursor (counts[kCntFetch]) serves every launch: k_vp_reset zeroes it, and the count of the queue the previous launch
 // has consumed, between two launches.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_vp_reset(int *counts, int consumed) {
     const int i = threadIdx.x;
     if (consumed == -1) { if (i < kNumCounters) counts[i] = 0; }  // before the start launch: everything
     else if (i == consumed || i == kCntFetch) counts[i] = 0;      // (-2: the cursor only)
 }
+#endif
 
 // One logic kernel (VolKernel) over one of its queues; queue < 0: the camera samples of the batch (VP_START).
 #ifndef GNX_VP_LOGIC_BLOCKS
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const 
 #ifndef GNX_TRACK_BURST
 #define GNX_TRACK_BURST 8
 #endif
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void __launch_bounds__(kBlock, 8) k_vp_track(const DeviceScene sc, PathState ps, VolWave vw, Queues q, RenderConsts rc, DevStats *st) {
     const int n = q.counts[kCntExtend0];
     const int *list = q.extend_q[0];
@@ -468,6 +481,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_vp_track(const DeviceScene sc, Pa
     if (lane == 0 && steps) atomicAdd(&st->track_steps, steps);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->vp_items[4], (unsigned long long)n);
 }
+#endif
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
 // stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
@@ -503,6 +517,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
 }
 
 // colObj += Li(...) over the samples of the pixel, in sample order (core/Integrator.cpp:274-291)
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
         float4 a = accum[pixel];
@@ -517,9 +532,11 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
         accum[pixel] = a;
     }
 }
+#endif
 
 // Gaussian film, step 1 (per path slot): the sample's radiance summed into L.xyz and its film offset written into the
 // slot's ray-origin record, which is dead once the bounce loop has ended.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts rc) {
     const int n = rc.npix * rc.batch_spp;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
@@ -536,8 +553,10 @@ __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts 
         }
     }
 }
+#endif
 
 // Gaussian film, step 2 (per pixel): gather the batch's samples within the filter's reach; accum = (sum L f, sum f).
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_accumulate_gauss(PathState ps, float4 *accum, RenderConsts rc, FilmFilter f) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
         const float4 g = gaussian_gather(ps.L, ps.ray_o, rc, f, pixel % rc.width, pixel / rc.width);
@@ -546,6 +565,7 @@ __global__ void k_accumulate_gauss(PathState ps, float4 *accum, RenderConsts rc,
         accum[pixel] = a;
     }
 }
+#endif
 
 // Gaussian film, step 2 as a shared-memory tiled gather: a block owns a 32 x 8 tile of output pixels and stages, for
 // `chunk` samples per pixel at a time, the radiance of the (32 + 2 reach) x (8 + 2 reach) source pixels around it
@@ -620,21 +640,26 @@ __global__ void __launch_bounds__(kFilmTW * kFilmTH) k_accumulate_gauss_tiled(Pa
 }
 
 // resolve = 1: sum(L f) / sum(f); 0: the raw sums (N-GPU jobs reduce them across ranks before dividing)
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_film_gauss(const float4 *accum, float4 *rgba, int npix, int resolve) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)
         rgba[pixel] = resolve ? gaussian_resolve(accum[pixel]) : accum[pixel];
 }
+#endif
 
 // colObj / samplesPerPixel, alpha 1 (core/Integrator.cpp:293,307-310).  alpha: 1, or 0 on the non-root devices of an
 // N-device job whose partial framebuffers are summed afterwards.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_film(const float4 *accum, float4 *rgba, int npix, float spp, float alpha) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x) {
         const float4 a = accum[pixel];
         rgba[pixel] = make_float4(a.x / spp, a.y / spp, a.z / spp, alpha);
     }
 }
+#endif
 // Tile partition: this device's tiles scattered into the (zeroed) full frame; the sum over the devices' frames is the
 // image, every pixel being x + 0 + ... + 0: bit-equal to the single-device render.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_film_tiles(const float4 *accum, float4 *rgba, RenderConsts rc, float spp) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
         int px, py;
@@ -643,10 +668,12 @@ __global__ void k_film_tiles(const float4 *accum, float4 *rgba, RenderConsts rc,
         rgba[(size_t)py * rc.width + px] = make_float4(a.x / spp, a.y / spp, a.z / spp, 1.f);
     }
 }
+#endif
 // The N-device reduce as ONE kernel on the root: partial frames of the peers are read through peer-to-peer loads over
 // NVLink and summed in device order (deterministic), in place into the root's frame.
 constexpr int kMaxDevices = 16;
 struct PeerFrames { const float4 *part[kMaxDevices]; int n; };
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_reduce_peers(float4 *out, PeerFrames pf, int npix) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         float4 a = out[i];
@@ -657,7 +684,9 @@ __global__ void k_reduce_peers(float4 *out, PeerFrames pf, int npix) {
         out[i] = a;
     }
 }
+#endif
 
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void __launch_bounds__(kBlock) k_primary_hits(const DeviceScene sc, int width, int height, int sample, int *out) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
@@ -665,20 +694,26 @@ __global__ void __launch_bounds__(kBlock) k_primary_hits(const DeviceScene sc, i
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < npix; pixel += gridDim.x * blockDim.x)
         out[pixel] = primary_hit_id(sc, width, pixel % width, pixel / width, sample, stack, kBlock);
 }
+#endif
 
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_sample_dims(const DeviceScene sc, int n, const long long *index, const int *dim, float *out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         out[i] = halton_sample_dimension(sc.smp, (uint64_t)index[i], dim[i]);
 }
+#endif
 
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_build_spatial(const DeviceScene sc, float *func, float *cdf, float *fint) {
     const int nv = sc.ld.nvox[0] * sc.ld.nvox[1] * sc.ld.nvox[2];
     for (int vox = blockIdx.x * blockDim.x + threadIdx.x; vox < nv; vox += gridDim.x * blockDim.x)
         build_spatial_voxel(sc, vox, func, cdf, fint);
 }
+#endif
 
 // FrameBuffer::update_f_u_c for a whole pass (ui/FrameBuffer.h:127-149): running mean over Render() calls, then the
 // exposure tonemap of the updated value; set_uc(.., 3, 255) for the alpha byte.  `weight` = 1 / curRenderCount.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_framebuffer_update(const float4 *frame, float4 *state, uchar4 *u8, int npix, float weight) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         const float4 v = frame[i];
@@ -694,8 +729,10 @@ __global__ void k_framebuffer_update(const float4 *frame, float4 *state, uchar4 
         u8[i] = make_uchar4((unsigned char)(r * 255), (unsigned char)(g * 255), (unsigned char)(b * 255), 255);
     }
 }
+#endif
 
 // FrameBuffer::update_f_u_c's tonemap on the first pass (ui/FrameBuffer.h:141-147)
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_tonemap(const float4 *rgba, uchar4 *out, int npix) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         const float4 c = rgba[i];
@@ -706,5 +743,78 @@ __global__ void k_tonemap(const float4 *rgba, uchar4 *out, int npix) {
         out[i] = make_uchar4((unsigned char)(r * 255), (unsigned char)(g * 255), (unsigned char)(b * 255), 255);
     }
 }
+#endif
+
+// ---- translation units -------------------------------------------------------------------------------------------
+// The heavy kernel templates are instantiated in their own translation units (csrc/tu_*.cu, compiled in parallel): each
+// defines GNX_KERNELS_TEMPLATES_ONLY and ONE GNX_TU_<name>; gnx_render.cu (GNX_TU_MAIN) only declares them.
+#if defined(GNX_TU_MAIN)
+extern template __global__ void k_trace<0>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<1>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<2>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<3>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<4>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_shade<2, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+extern template __global__ void k_shade<2, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+extern template __global__ void k_shade<8, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+extern template __global__ void k_shade<8, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+extern template __global__ void k_recursive<0, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_recursive<0, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_recursive<1, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_recursive<1, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_recursive<2, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_recursive<2, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_MIS, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_EXTEND, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_EXTEND, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_SHADOW, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_volpath<false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_volpath<true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+#endif
+#if defined(GNX_TU_TRACE)
+template __global__ void k_trace<0>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<1>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<2>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<3>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<4>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+#endif
+#if defined(GNX_TU_SHADE2)
+template __global__ void k_shade<2, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+template __global__ void k_shade<2, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+#endif
+#if defined(GNX_TU_SHADE8)
+template __global__ void k_shade<8, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+template __global__ void k_shade<8, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
+#endif
+#if defined(GNX_TU_REC0)
+template __global__ void k_recursive<0, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_recursive<0, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+#endif
+#if defined(GNX_TU_REC1)
+template __global__ void k_recursive<1, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_recursive<1, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+#endif
+#if defined(GNX_TU_REC2)
+template __global__ void k_recursive<2, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_recursive<2, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+#endif
+#if defined(GNX_TU_VOL1)
+template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+#endif
+#if defined(GNX_TU_VOL2)
+template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_MIS, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+#endif
+#if defined(GNX_TU_VOL3)
+template __global__ void k_vp_logic<VK_EXTEND, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_EXTEND, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_SHADOW, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_volpath<false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_volpath<true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+#endif
 
 }  // namespace gnx

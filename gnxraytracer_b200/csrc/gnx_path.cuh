@@ -111,7 +111,8 @@ GNX_D RayDiff camera_ray_differentials(const DeviceScene &sc, int px, int py, fl
     return rd;
 }
 GNX_D void camera_ray(const DeviceScene &sc, int px, int py, uint64_t hidx, V3 *o, V3 *d, float *tMax) {
-    float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+    float u0, u1;
+    sampler_film_dimensions(sc.smp, hidx, px, py, &u0, &u1);
     float l0 = 0, l1 = 0;
     if (sc.cam.lens_radius > 0) { l0 = halton_sample_dimension(sc.smp, hidx, 3); l1 = halton_sample_dimension(sc.smp, hidx, 4); }
     camera_ray_uv(sc, px, py, u0, u1, l0, l1, o, d, tMax);
@@ -133,7 +134,7 @@ constexpr int kPendEscape = -2;  // primary_finish / extend_finish: "queue the s
 // Camera sample `sample` of pixel (px, py): the ray is generated in registers and traversed at once
 // (no ray round trip through HBM for the ~90 % of C2's camera rays that never touch the mesh).
 GNX_D void primary_begin(const DeviceScene &sc, int px, int py, int sample, uint32_t *hidxOut, V3 *dOut, Trav &t) {
-    uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    uint64_t hidx = sampler_index(sc.smp, px, py, (uint64_t)sample);
     V3 o, d;
     float tMax;
     camera_ray(sc, px, py, hidx, &o, &d, &tMax);
@@ -509,7 +510,7 @@ GNX_D int primary_hit_id(const DeviceScene &sc, int width, int px, int py, int s
         smp.get2d(&l0, &l1);
         camera_ray_uv(sc, px, py, u0, u1, l0, l1, &o, &d, &tMax);
     } else {
-        uint64_t hidx = halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride;
+        uint64_t hidx = sampler_index(sc.smp, px, py, (uint64_t)sample);
         camera_ray(sc, px, py, hidx, &o, &d, &tMax);
     }
     int prim = -1;

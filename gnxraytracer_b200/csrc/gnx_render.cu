@@ -12,11 +12,20 @@
 #include <thread>
 #include <vector>
 
+#define GNX_TU_MAIN
 #include "gnx_kernels.cuh"
 #include "gnx_lbvh.cuh"
 #include "gnx_pack.h"
 
 using namespace gnx;
+
+// Every translation unit has its own copy of the __constant__ Sobol' matrices (gnx_sampler.cuh) and registers an
+// uploader for it here; gnx_upload_scene calls them all.
+static std::vector<void (*)(const uint32_t *)> &sobol_uploaders() {
+    static std::vector<void (*)(const uint32_t *)> v;
+    return v;
+}
+void gnx_register_sobol_uploader(void (*fn)(const uint32_t *)) { sobol_uploaders().push_back(fn); }
 
 namespace {
 thread_local std::string g_create_error;
@@ -624,7 +633,28 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
 
     // ---- sampler
     const gnx_sampler &s = d->sampler;
-    if (s.type != GNX_SAMPLER_HALTON && s.type != GNX_SAMPLER_PCG32) return fail(ctx, GNX_ERR_INVALID, "unknown sampler type");
+    if (s.type != GNX_SAMPLER_HALTON && s.type != GNX_SAMPLER_PCG32 && s.type != GNX_SAMPLER_SOBOL) return fail(ctx, GNX_ERR_INVALID, "unknown sampler type");
+    sc.smp.sobol32 = nullptr; sc.smp.sobol_vdc = sc.smp.sobol_vdc_inv = nullptr;
+    sc.smp.sobol_dims = sc.smp.sobol_log2res = sc.smp.sobol_res = 0;
+    if (s.type == GNX_SAMPLER_SOBOL) {
+        if (!s.sobol_matrices32 || s.n_sobol_dimensions < 5 || s.sobol_log2_resolution < 0 || s.sobol_log2_resolution > 15 ||
+            s.sobol_resolution != (1 << s.sobol_log2_resolution) || (s.sobol_log2_resolution > 0 && (!s.sobol_vdc || !s.sobol_vdc_inv)))
+            return fail(ctx, GNX_ERR_INVALID, "bad Sobol parameters");
+        uint32_t *dm; uint64_t *dv;
+        if ((rc = dupload(ctx, pool, s.sobol_matrices32, (size_t)s.n_sobol_dimensions * kSobolMatrixSize, &dm))) return rc;
+        sc.smp.sobol32 = dm;
+        std::vector<uint64_t> zero(kSobolMatrixSize, 0);
+        if ((rc = dupload(ctx, pool, s.sobol_vdc ? s.sobol_vdc : zero.data(), (size_t)kSobolMatrixSize, &dv))) return rc;
+        sc.smp.sobol_vdc = dv;
+        if ((rc = dupload(ctx, pool, s.sobol_vdc_inv ? s.sobol_vdc_inv : zero.data(), (size_t)kSobolMatrixSize, &dv))) return rc;
+        sc.smp.sobol_vdc_inv = dv;
+        sc.smp.sobol_dims = s.n_sobol_dimensions; sc.smp.sobol_log2res = s.sobol_log2_resolution; sc.smp.sobol_res = s.sobol_resolution;
+        // the first dimensions' matrices in __constant__ memory (one broadcast per read: the lanes of a warp walk the index bits in step)
+        std::vector<uint32_t> head((size_t)kSobolConstDims * kSobolMatrixSize, 0u);
+        memcpy(head.data(), s.sobol_matrices32, sizeof(uint32_t) * (size_t)std::min(kSobolConstDims, s.n_sobol_dimensions) * kSobolMatrixSize);
+        for (auto fn : sobol_uploaders()) fn(head.data());
+        GNX_CUDA(ctx, cudaGetLastError());
+    }
     if (s.type == GNX_SAMPLER_HALTON && (s.base_scales[0] <= 0 || s.base_scales[1] <= 0 || s.sample_stride <= 0))
         return fail(ctx, GNX_ERR_INVALID, "bad Halton parameters");
     sc.smp.type = s.type;
@@ -764,12 +794,12 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     // the recursive integrators keep their depth-first frames in a fixed array (gnx_whitted.cuh, kMaxRecDepth)
     if (recursive && p->max_depth > kMaxRecDepth)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting: max_depth above 16 is not supported (fixed recursion frame stack)");
-    if (recursive && ctx->sc.smp.type != GNX_SAMPLER_HALTON) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use the Halton sampler");
+    if (recursive && ctx->sc.smp.type == GNX_SAMPLER_PCG32) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting use a GlobalSampler (Halton or Sobol)");
     if (recursive && ctx->sc.n_media > 0) return fail(ctx, GNX_ERR_UNSUPPORTED, "Whitted / DirectLighting ignore participating media");
     if (p->integrator != GNX_INTEGRATOR_PATH && ctx->tex_needs_pyramid)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "an image texture has a single level that is not a power of two: pass the MIPMap's own levels (gnx_texture::n_levels) for the integrators that filter with ray differentials");
-    if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.smp.type != GNX_SAMPLER_HALTON)
-        return fail(ctx, GNX_ERR_UNSUPPORTED, "the wavefront PathIntegrator keeps a Halton (index, dimension) per path; the PCG32 stream sampler is for VolPath");
+    if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.smp.type == GNX_SAMPLER_PCG32)
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "the wavefront PathIntegrator keeps a GlobalSampler (index, dimension) per path (Halton or Sobol); the PCG32 stream sampler is for VolPath");
     if (p->integrator == GNX_INTEGRATOR_PATH && ctx->sc.n_media > 0)
         return fail(ctx, GNX_ERR_UNSUPPORTED, "scene has participating media: use GNX_INTEGRATOR_VOLPATH (PathIntegrator ignores media)");
     if (p->film != GNX_FILM_BOX && p->film != GNX_FILM_GAUSSIAN && p->film != GNX_FILM_GAUSSIAN_SUMS)
@@ -785,6 +815,9 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     const unsigned long long lastSample = (unsigned long long)p->first_sample + (unsigned long long)p->spp;
     unsigned long long maxIdx = lastSample * (unsigned long long)ctx->sc.smp.stride;
     if (ctx->sc.smp.type == GNX_SAMPLER_HALTON && maxIdx >= (1ull << 32)) return fail(ctx, GNX_ERR_UNSUPPORTED, "sample index exceeds 32 bits");
+    // Sobol: index = sample << 2 log2(resolution) | pixel bits
+    if (ctx->sc.smp.type == GNX_SAMPLER_SOBOL && (lastSample << (2 * ctx->sc.smp.sobol_log2res)) >= (1ull << 32))
+        return fail(ctx, GNX_ERR_UNSUPPORTED, "Sobol sample index exceeds 32 bits (samples x resolution^2 must stay below 2^32)");
     if (ctx->sc.smp.type == GNX_SAMPLER_PCG32 && lastSample >= (1ull << 20)) return fail(ctx, GNX_ERR_UNSUPPORTED, "PCG32 stream ids hold 20 bits of sample number");
     return GNX_OK;
 }

@@ -139,8 +139,64 @@ GNX_D float radical_inverse(const DevSampler &s, int baseIndex, uint64_t a) {
     return radical_inverse_base(a, (uint32_t)ldg(s.primes + baseIndex));
 }
 
-// HaltonSampler::SampleDimension, samplers/HaltonSampler.cpp:85-94
+// ---- Sobol' (samplers/LowDiscrepancy.h:194-252) ----------------------------------------------------------------
+constexpr int kSobolMatrixSize = 52;   // samplers/SobolMatrices.h:14
+constexpr int kSobolConstDims = 192;   // dimensions whose matrices live in __constant__ memory (39 936 B); a path of
+                                       // maxDepth 5 uses 5 + 8 * 6 = 53 of them.  All lanes of a warp walk the bits of
+                                       // their indices in step, so every matrix read is one broadcast.
+#if defined(__CUDACC__)
+static __constant__ uint32_t c_sobol32[kSobolConstDims * kSobolMatrixSize];
+}  // namespace gnx
+void gnx_register_sobol_uploader(void (*fn)(const uint32_t *));  // gnx_render.cu
+namespace gnx {
+namespace {
+struct SobolConstRegistrar {
+    SobolConstRegistrar() {
+        gnx_register_sobol_uploader([](const uint32_t *head) { cudaMemcpyToSymbol(c_sobol32, head, sizeof(c_sobol32)); });
+    }
+};
+static SobolConstRegistrar g_sobol_const_registrar;  // one per translation unit: each has its own copy of the symbol
+}  // namespace
+#endif
+// SobolSampleFloat(a, dimension, scramble = 0)
+GNX_D float sobol_sample_float(const DevSampler &s, uint64_t a, int dimension) {
+    if (dimension >= s.sobol_dims) return 0.f;  // (the reference reads past its tables here)
+    uint32_t v = 0;
+#if defined(__CUDA_ARCH__)
+    if (dimension < kSobolConstDims) {
+        const uint32_t *M = c_sobol32 + dimension * kSobolMatrixSize;
+        for (int i = 0; a != 0; a >>= 1, i++) if (a & 1) v ^= M[i];
+    } else
+#endif
+    {
+        const uint32_t *M = s.sobol32 + (size_t)dimension * kSobolMatrixSize;
+        for (int i = 0; a != 0; a >>= 1, i++) if (a & 1) v ^= ldg(M + i);
+    }
+    return fminf(v * 2.3283064365386963e-10f, kOneMinusEpsilon);
+}
+// SobolIntervalToIndex(m, frame, p)
+GNX_D uint64_t sobol_interval_to_index(const DevSampler &s, uint64_t frame, int px, int py) {
+    const uint32_t m = (uint32_t)s.sobol_log2res;
+    if (m == 0) return 0;
+    const uint32_t m2 = m << 1;
+    uint64_t index = frame << m2;
+    uint64_t delta = 0;
+    for (int c = 0; frame; frame >>= 1, ++c)
+        if (frame & 1) delta ^= ldg(s.sobol_vdc + c);
+    uint64_t b = ((((uint64_t)((uint32_t)px)) << m) | ((uint32_t)py)) ^ delta;
+    for (int c = 0; b; b >>= 1, ++c)
+        if (b & 1) index ^= ldg(s.sobol_vdc_inv + c);
+    return index;
+}
+
+// GlobalSampler::GetIndexForSample(sampleNum) for pixel (px, py): HaltonSampler (samplers/HaltonSampler.cpp:63-82) or the
+// Sobol' sampler (SobolIntervalToIndex over the pixel grid of resolution 2^m).
+GNX_D uint64_t sampler_index(const DevSampler &s, int px, int py, uint64_t sampleNum);
+
+// HaltonSampler::SampleDimension, samplers/HaltonSampler.cpp:85-94 — or, for GNX_SAMPLER_SOBOL, SobolSample(index, dim)
+// WITHOUT the pixel remap of the first two dimensions (see sampler_film_dimensions)
 GNX_D float halton_sample_dimension(const DevSampler &s, uint64_t index, int dim) {
+    if (s.type == GNX_SAMPLER_SOBOL) return sobol_sample_float(s, index, dim);
     if (s.at_center && (dim == 0 || dim == 1)) return 0.5f;
     if (dim == 0) return radical_inverse_base2(index >> s.base_exp0);
     if (dim == 1)
@@ -151,6 +207,23 @@ GNX_D float halton_sample_dimension(const DevSampler &s, uint64_t index, int dim
     if (dim >= s.n_primes) return 0.f;
     uint4 rec = ldg(s.dims + dim);  // {prime, offset of its permutation, magic lo, magic hi}
     return scrambled_radical_inverse_base(index, rec.x, s.perms + rec.y, ((uint64_t)rec.w << 32) | rec.z);
+}
+
+GNX_D uint64_t sampler_index(const DevSampler &s, int px, int py, uint64_t sampleNum) {
+    if (s.type == GNX_SAMPLER_SOBOL) return sobol_interval_to_index(s, sampleNum, px, py);
+    return halton_pixel_offset(s, px, py) + sampleNum * (uint64_t)s.stride;
+}
+// Dimensions 0 and 1 of a camera sample (the film offset inside the pixel).  The Sobol' sampler stretches them over the
+// whole image and takes the part inside the current pixel: s * resolution - pixel, clamped to [0, 1).
+GNX_D void sampler_film_dimensions(const DevSampler &s, uint64_t index, int px, int py, float *u0, float *u1) {
+    *u0 = halton_sample_dimension(s, index, 0);
+    *u1 = halton_sample_dimension(s, index, 1);
+    if (s.type == GNX_SAMPLER_SOBOL) {
+        float a = *u0 * s.sobol_res + 0.f, b = *u1 * s.sobol_res + 0.f;  // + sampleBounds.pMin (the image starts at 0)
+        a -= (float)px; b -= (float)py;
+        *u0 = a < 0.f ? 0.f : (a > kOneMinusEpsilon ? kOneMinusEpsilon : a);
+        *u1 = b < 0.f ? 0.f : (b > kOneMinusEpsilon ? kOneMinusEpsilon : b);
+    }
 }
 
 // PCG32 (core/RNG.h:30-110), used as the per-pixel stream when the sampler is not Halton.
@@ -198,6 +271,12 @@ struct PathSampler {
     GNX_D float get1d() {
         if (pcg) { ++dim; return rng.uniform_float(); }
         return halton_sample_dimension(s, index, dim++);
+    }
+    // Sampler::GetCameraSample's film sample: dimensions 0 and 1 (remapped into the pixel by the Sobol' sampler)
+    GNX_D void get_film(int px, int py, float *a, float *b) {
+        if (pcg) { get2d(a, b); return; }
+        sampler_film_dimensions(s, index, px, py, a, b);
+        dim += 2;
     }
     GNX_D void get2d(float *a, float *b) {
         if (pcg) { *a = rng.uniform_float(); *b = rng.uniform_float(); dim += 2; return; }

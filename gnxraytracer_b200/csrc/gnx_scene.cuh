@@ -62,6 +62,11 @@ struct DevSampler {
     const uint4 *dims;        // per dimension {prime, PrimeSums, ceil(2^38 / prime) lo, hi}
     int n_primes;
     int spp;                  // Sampler::samplesPerPixel: ScaleDifferentials(1 / sqrt(spp)), core/Integrator.cpp:277
+    // Sobol' (GNX_SAMPLER_SOBOL): generator matrices [dims][52] (the first kSobolConstDims also in __constant__ memory),
+    // the two van der Corput rows of SobolIntervalToIndex for this resolution
+    const uint32_t *sobol32;
+    const uint64_t *sobol_vdc, *sobol_vdc_inv;
+    int sobol_dims, sobol_log2res, sobol_res;
 };
 
 struct DevMedium {

@@ -340,10 +340,10 @@ GNX_D V3 volpath_li(const DeviceScene &sc, const RenderConsts &rc, int px, int p
                     TraversalCounters &cnt, VolCounters &vc) {
     const bool pcg = sc.smp.type == GNX_SAMPLER_PCG32;
     PathSampler smp = pcg ? PathSampler::stream(sc.smp, ((uint64_t)(rc.width * py + px) << 20) | (uint64_t)sample)
-                          : PathSampler(sc.smp, halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride, 0);
+                          : PathSampler(sc.smp, sampler_index(sc.smp, px, py, (uint64_t)sample), 0);
     // Sampler::GetCameraSample: film (2), time (1), lens (2)
     float u0, u1, tm, l0, l1;
-    smp.get2d(&u0, &u1);
+    smp.get_film(px, py, &u0, &u1);
     tm = smp.get1d();
     smp.get2d(&l0, &l1);
     (void)tm;

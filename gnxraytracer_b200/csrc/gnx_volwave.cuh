@@ -115,9 +115,9 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
     if (phase == VP_START) {
         cameraDiff = TEX;
         if (sc.smp.type == GNX_SAMPLER_PCG32) smp.take(PathSampler::stream(sc.smp, ((uint64_t)(rc.width * py + px) << 20) | (uint64_t)sample));
-        else smp.take(PathSampler(sc.smp, halton_pixel_offset(sc.smp, px, py) + (uint64_t)sample * (uint64_t)sc.smp.stride, 0));
+        else smp.take(PathSampler(sc.smp, sampler_index(sc.smp, px, py, (uint64_t)sample), 0));
         float u0, u1, l0, l1;
-        smp.get2d(&u0, &u1);
+        smp.get_film(px, py, &u0, &u1);
         smp.get1d();  // time
         smp.get2d(&l0, &l1);
         camera_ray_uv(sc, px, py, u0, u1, l0, l1, &ray.o, &ray.d, &ray.tMax);
@@ -185,7 +185,7 @@ GNX_D int vol_advance(const DeviceScene &sc, const RenderConsts &rc, const PathS
                     cs.get2d(&u0, &u1); cs.get1d(); cs.get2d(&l0, &l1);
                 } else {
                     const uint64_t hi = (uint64_t)ps.hidx[slot];
-                    u0 = halton_sample_dimension(sc.smp, hi, 0); u1 = halton_sample_dimension(sc.smp, hi, 1);
+                    sampler_film_dimensions(sc.smp, hi, px, py, &u0, &u1);
                     l0 = halton_sample_dimension(sc.smp, hi, 3); l1 = halton_sample_dimension(sc.smp, hi, 4);
                 }
                 compute_differentials(vx.s, camera_ray_differentials(sc, px, py, u0, u1, l0, l1, ray.o, ray.d));

@@ -118,8 +118,7 @@ constexpr int kMaxRecDepth = 16;
 template <int MAXL, int direct, bool TEX = false>
 GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int py, int sample, int2 *stack, int stride,
                       TraversalCounters &cnt, RecCounters &rcnt) {
-    const uint64_t pixOffset = halton_pixel_offset(sc.smp, px, py);
-    const uint64_t hidx = pixOffset + (uint64_t)sample * (uint64_t)sc.smp.stride;
+    const uint64_t hidx = sampler_index(sc.smp, px, py, (uint64_t)sample);
     const int nArrays = direct == 2 ? 2 * rc.max_depth * sc.n_lights : 0;
     int arrayCursor = 0;               // Sampler::array2DOffset
     PathSampler smp(sc.smp, hidx, 5 + 2 * nArrays);  // dimensions 0-4 belong to the camera sample, then the arrays'
@@ -134,7 +133,8 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
         f.hb0 = f.hb1 = f.hb2 = 0;
         f.rd.has = false;
         if (TEX) {
-            const float u0 = halton_sample_dimension(sc.smp, hidx, 0), u1 = halton_sample_dimension(sc.smp, hidx, 1);
+            float u0, u1;
+            sampler_film_dimensions(sc.smp, hidx, px, py, &u0, &u1);
             float l0 = 0, l1 = 0;
             if (sc.cam.lens_radius > 0) { l0 = halton_sample_dimension(sc.smp, hidx, 3); l1 = halton_sample_dimension(sc.smp, hidx, 4); }
             f.rd = camera_ray_differentials(sc, px, py, u0, u1, l0, l1, o, d);
@@ -201,7 +201,7 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
                         arrayCursor += 2;
                         V3 Ld(0.f);
                         for (int k = 0; k < n; ++k) {
-                            const uint64_t idx = pixOffset + ((uint64_t)sample * (uint64_t)n + (uint64_t)k) * (uint64_t)sc.smp.stride;
+                            const uint64_t idx = sampler_index(sc.smp, px, py, (uint64_t)sample * (uint64_t)n + (uint64_t)k);
                             const float ul0 = halton_sample_dimension(sc.smp, idx, dimL), ul1 = halton_sample_dimension(sc.smp, idx, dimL + 1);
                             const float us0 = halton_sample_dimension(sc.smp, idx, dimS), us1 = halton_sample_dimension(sc.smp, idx, dimS + 1);
                             Ld += w_estimate_direct<MAXL>(sc, s, bsdf, sc.lights[j], ul0, ul1, us0, us1, stack, stride, cnt, rcnt);

@@ -220,7 +220,11 @@ typedef struct gnx_camera {
 
 typedef enum gnx_sampler_type {
     GNX_SAMPLER_HALTON = 0, /* HaltonSampler + GlobalSampler dimension bookkeeping            */
-    GNX_SAMPLER_PCG32 = 1   /* per-pixel PCG32 stream (core/RNG.h:30-110), for unbounded-dimension paths */
+    GNX_SAMPLER_PCG32 = 1,  /* per-pixel PCG32 stream (core/RNG.h:30-110), for unbounded-dimension paths */
+    GNX_SAMPLER_SOBOL = 2   /* (0,2)-sequence-in-the-first-two-dimensions Sobol' GlobalSampler built from the reference's
+                               SobolIntervalToIndex / SobolSample helpers and generator matrices
+                               (samplers/LowDiscrepancy.h:194-252, samplers/SobolMatrices.h:12-17); the reference ships
+                               no sampler class for them, gnxraytracer_b200/bridge/SobolSampler.h is that class */
 } gnx_sampler_type;
 
 typedef struct gnx_sampler {
@@ -235,6 +239,14 @@ typedef struct gnx_sampler {
     const uint16_t *perms;       /* radicalInversePermutations, or NULL: the library generates the
                                     table itself from a default-seeded PCG32 like the reference
                                     (samplers/HaltonSampler.cpp:36-39)                          */
+    /* Sobol' state (GNX_SAMPLER_SOBOL).  The generator matrices cannot be regenerated and are not copied into this
+     * repository: the caller hands over the reference's own tables by pointer (the bridge has them linked in). */
+    int32_t sobol_resolution;        /* RoundUpPow2(max(image width, height))                      */
+    int32_t sobol_log2_resolution;
+    int32_t n_sobol_dimensions;      /* NumSobolDimensions (1024)                                  */
+    const uint32_t *sobol_matrices32; /* SobolMatrices32[n_sobol_dimensions][52]                   */
+    const uint64_t *sobol_vdc;       /* VdCSobolMatrices[log2_resolution - 1][52]                  */
+    const uint64_t *sobol_vdc_inv;   /* VdCSobolMatricesInv[log2_resolution - 1][52]               */
 } gnx_sampler;
 
 /* ------------------------------------------------------------------------------------------

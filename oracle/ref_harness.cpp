@@ -51,6 +51,7 @@
 #include "textures/ImageTexture.h"
 
 #include "ref_harness.h"
+#include "gnxraytracer_b200/bridge/SobolSampler.h"  // header-only, built from the reference's own Sobol helpers and tables
 #include "gnxraytracer_b200/host/scenekit_mesh.h"
 
 using namespace pbr;
@@ -486,6 +487,15 @@ void gnxh_scene_set_gaussian_filter(void *h, float radius, float alpha) {
     hs->DropExt();
 }
 double gnxh_scene_bvh_seconds(void *h) { return ((HarnessScene *)h)->bvhSeconds; }
+// The sampler handed to both integrators: 0 = HaltonSampler (the UI's, ui/RenderThread.cpp:159), 2 = the Sobol'
+// GlobalSampler of gnxraytracer_b200/bridge/SobolSampler.h.  (The PCG stream sampler belongs to the grid-medium scene.)
+void gnxh_scene_set_sampler(void *h, int kind) {
+    auto *hs = (HarnessScene *)h;
+    Bounds2i bounds(Point2i(0, 0), Point2i(hs->width, hs->height));
+    if (kind == 2) hs->sampler = std::make_shared<gnx::SobolSampler>(hs->spp, bounds);
+    else hs->sampler = std::make_shared<HaltonSampler>(hs->spp, bounds, false);
+    hs->DropExt();
+}
 
 // Every integrator gets a fresh copy of the scene's sampler: DirectLightingIntegrator::Preprocess(UniformSampleAll) appends
 // sample-array requests to the sampler it is given, and a second Preprocess on the same object would append them again.
@@ -633,9 +643,12 @@ int gnxh_reference_gaussian_film(void *h, int maxDepth, float radius, float alph
 
 int gnxh_reference_sample_dims(void *h, int n, const int64_t *index, const int *dim, float *out) {
     auto *hs = (HarnessScene *)h;
-    auto *hal = dynamic_cast<HaltonSampler *>(hs->sampler.get());
-    if (!hal) return -1;
-    for (int i = 0; i < n; ++i) out[i] = hal->SampleDimension(index[i], dim[i]);
+    auto *gs = dynamic_cast<GlobalSampler *>(hs->sampler.get());
+    if (!gs) return -1;
+    std::unique_ptr<Sampler> own = gs->Clone(0);  // (SampleDimension of the Sobol' sampler looks at the current pixel: (0, 0) here)
+    auto *g = dynamic_cast<GlobalSampler *>(own.get());
+    g->StartPixel(Point2i(0, 0));
+    for (int i = 0; i < n; ++i) out[i] = g->SampleDimension(index[i], dim[i]);
     return 0;
 }
 
@@ -644,8 +657,8 @@ int64_t gnxh_reference_sample_index(void *h, int px, int py, int sample) {
     auto *hs = (HarnessScene *)h;
     std::unique_ptr<Sampler> s = hs->sampler->Clone(0);
     s->StartPixel(Point2i(px, py));
-    auto *hal = dynamic_cast<HaltonSampler *>(s.get());
-    return hal ? hal->GetIndexForSample(sample) : -1;
+    auto *g = dynamic_cast<GlobalSampler *>(s.get());
+    return g ? g->GetIndexForSample(sample) : -1;
 }
 
 int gnxh_max_threads(void) { return omp_get_max_threads(); }

@@ -114,6 +114,11 @@ class RefScene:
         self.lib.gnxh_scene_set_light_strategy(self.h, int(strategy))
         self._desc = None  # the product-side state (and the flattened description it owns) is dropped with the setting
 
+    def set_sampler(self, kind):
+        """0 = HaltonSampler, 2 = the Sobol' GlobalSampler (gnxraytracer_b200/bridge/SobolSampler.h) — for both integrators."""
+        self.lib.gnxh_scene_set_sampler(self.h, int(kind))
+        self._desc = None
+
     def set_gaussian_filter(self, radius, alpha):
         """Film of the drop-in class: GaussianFilter(radius, alpha); radius <= 0 = the reference's box average."""
         self.lib.gnxh_scene_set_gaussian_filter(self.h, float(radius), float(alpha))
@@ -228,6 +233,7 @@ class Ref:
         l.gnxh_scene_num_prims.argtypes = [vp]
         l.gnxh_scene_bvh_seconds.argtypes = [vp]
         l.gnxh_scene_set_light_strategy.argtypes = [vp, ci]
+        l.gnxh_scene_set_sampler.argtypes = [vp, ci]
         l.gnxh_scene_set_gaussian_filter.argtypes = [vp, ctypes.c_float, ctypes.c_float]
         l.gnxh_reference_gaussian_film.argtypes = [vp, ci, ctypes.c_float, ctypes.c_float, vp, vp]
         l.gnxh_reference_gaussian_eval.argtypes = [ctypes.c_float, ctypes.c_float, ci, vp, vp, vp]

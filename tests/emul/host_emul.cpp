@@ -130,6 +130,8 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     sc.cam.dy_camera = V3(d->camera.dy_camera[0], d->camera.dy_camera[1], d->camera.dy_camera[2]);
     const gnx_sampler &s = d->sampler;
     sc.smp.spp = s.samples_per_pixel > 0 ? s.samples_per_pixel : 1;
+    sc.smp.sobol32 = s.sobol_matrices32; sc.smp.sobol_vdc = s.sobol_vdc; sc.smp.sobol_vdc_inv = s.sobol_vdc_inv;
+    sc.smp.sobol_dims = s.n_sobol_dimensions; sc.smp.sobol_log2res = s.sobol_log2_resolution; sc.smp.sobol_res = s.sobol_resolution;
     sc.smp.type = s.type;
     sc.smp.base_scale0 = s.base_scales[0]; sc.smp.base_scale1 = s.base_scales[1];
     sc.smp.base_exp0 = s.base_exponents[0]; sc.smp.base_exp1 = s.base_exponents[1];
@@ -399,7 +401,7 @@ int gnxe_sample_dims(void *h, int n, const int64_t *index, const int *dim, float
 
 int64_t gnxe_sample_index(void *h, int px, int py, int sample) {
     auto *e = (EmulScene *)h;
-    return (int64_t)(halton_pixel_offset(e->sc.smp, px, py) + (uint64_t)sample * (uint64_t)e->sc.smp.stride);
+    return (int64_t)sampler_index(e->sc.smp, px, py, (uint64_t)sample);
 }
 
 }  // extern "C"

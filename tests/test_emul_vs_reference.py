@@ -234,3 +234,30 @@ def test_image_textures_filtered_with_ray_differentials(ref, emul, preset):
         assert rel_mse(img, img_tri) > 1e-7, "EWA and trilinear filtering should not coincide"
         other.close()
     rs.close(); es.close()
+
+
+@pytest.mark.parametrize("preset", ["cornell", "dragon", "whitted", "direct_all", "fog"])
+def test_sobol_sampler_matches_the_reference_helpers(ref, emul, preset):
+    """GNX_SAMPLER_SOBOL: the Sobol' GlobalSampler built from the reference's SobolIntervalToIndex / SobolSample and its
+    generator matrices (samplers/LowDiscrepancy.h:194-252, samplers/SobolMatrices.h:12-17; the class itself is
+    gnxraytracer_b200/bridge/SobolSampler.h, running inside the reference's own integrators on the oracle side): sample values
+    bit for bit, GetIndexForSample for pixels and samples, and the images of Path / Whitted / UniformSampleAll (sample arrays) /
+    VolPath through it."""
+    from _harness import integrator_of
+    res, spp = 40, 4
+    rs = ref.scene(preset, res, res, spp)
+    rs.set_sampler(2)
+    es = emul.scene(rs.desc)
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, 1 << 24, 20000).astype(np.int64)
+    dim = rng.integers(2, 1024, 20000).astype(np.int32)
+    assert np.array_equal(rs.sample_dims(idx, dim).view(np.uint32), es.sample_dims(idx, dim).view(np.uint32))
+    for (x, y, s) in ((0, 0, 0), (5, 7, 1), (39, 39, 3), (17, 2, 2)):
+        assert rs.sample_index(x, y, s) == es.sample_index(x, y, s)
+    img_ref, _ = rs.render_reference(max_depth=5)
+    img, _ = es.render(RenderParams.make(res, res, spp, max_depth=5, integrator=integrator_of(preset)))
+    assert rel_mse(img, img_ref) <= 1e-6
+    rs.set_sampler(0)
+    img_halton, _ = rs.render_reference(max_depth=5)
+    assert rel_mse(img, img_halton) > 1e-6, "another sampler, another image"
+    rs.close(); es.close()

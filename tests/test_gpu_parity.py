@@ -363,6 +363,30 @@ def test_image_textures_with_ray_differentials_on_gpu(ref, emul, preset):
     rs.close()
 
 
+def test_sobol_sampler_on_gpu(ref, ctx):
+    """GNX_SAMPLER_SOBOL on the device: SobolSample values bit for bit (dimensions from __constant__ memory and beyond),
+    and the images of configs 1 and 2 through the drop-in class against the reference's Render with the same sampler."""
+    rs = ref.scene("cornell_full", 128, 128, 8)
+    rs.set_sampler(2)
+    ctx.upload(rs.desc)
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, 1 << 26, 200000).astype(np.int64)
+    dim = rng.integers(2, 1024, 200000).astype(np.int32)
+    assert np.array_equal(rs.sample_dims(idx, dim).view(np.uint32), ctx.sample_dimensions(idx, dim).view(np.uint32))
+    rs.close()
+    for preset, res, spp in (("cornell_full", 256, 16), ("dragon", 256, 8), ("whitted", 128, 8)):
+        rs = ref.scene(preset, res, res, spp)
+        rs.set_sampler(2)
+        img_ref, _ = rs.render_reference(max_depth=5)
+        img, _, st = rs.render_cuda(max_depth=5)
+        assert st.paths == res * res * spp
+        assert rel_mse(img, img_ref) <= 1e-3
+        px, py = grid(res, res)
+        _, prim = rs.reference_samples(px, py, np.zeros(px.size, np.int32), want_rgb=False)
+        assert float(np.mean(rs.to_original(rs.cuda_primary_hits(0)) == prim)) >= 0.9999
+        rs.close()
+
+
 def test_recursion_depth_limit_is_an_error_not_a_clamp(ref, ctx):
     """Whitted / DirectLighting keep 16 recursion frames: deeper requests are refused instead of silently cut."""
     from gnxraytracer_b200.api import GnxError
