@@ -255,12 +255,12 @@ def load_scenekit():
 
 
 def resources_dir():
-    """Where the HDR environment maps live: GNX_RESOURCES, else the build-time copy next to the oracle
-    (oracle/_ref/Resources, filled by `make -C oracle ref` from the reference's Resources/)."""
+    """Where the HDR environment maps and the volume live: GNX_RESOURCES, else gnxraytracer_b200/resources (staged from the
+    reference's Resources/ by the build, gnxraytracer_b200.build.stage_resources)."""
     env = os.environ.get("GNX_RESOURCES")
     if env:
         return env
-    return os.path.join(repo_root(), "oracle", "_ref", "Resources")
+    return os.path.join(repo_root(), "gnxraytracer_b200", "resources")
 
 
 def mesh_info(path):

@@ -75,6 +75,24 @@ def build_product(force: bool = False) -> str:
     return out
 
 
+RESOURCE_FILES = ("MonValley1000.hdr", "TropicalRuins1000.hdr", "awesomeface.jpg", "density_render.70.volume")
+
+
+def stage_resources() -> str:
+    """The environment maps and the volume of the BASELINE configs are DATA of the reference (Resources/), not sources:
+    where the reference is present they are staged under gnxraytracer_b200/resources/ (git-ignored, travels to the GPU box
+    like the built libraries), so that the product (scene kit, bench.py, smoke()) needs nothing under oracle/."""
+    root = repo_root()
+    dst = os.path.join(root, "gnxraytracer_b200", "resources")
+    src = os.path.join(os.environ.get("GNX_REFERENCE", "/root/reference"), "Resources")
+    if os.path.isdir(src):
+        os.makedirs(dst, exist_ok=True)
+        for f in RESOURCE_FILES:
+            if os.path.exists(os.path.join(src, f)) and _newer(os.path.join(dst, f), [os.path.join(src, f)]):
+                shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+    return dst
+
+
 def build_emul(force: bool = False) -> str:
     """g++ -> tests/emul/_build/libgnxemul.so (TEST TOOL: device functions compiled for the host)."""
     root = repo_root()
@@ -101,5 +119,6 @@ def build_oracle() -> None:
 
 def build_all(force: bool = False) -> None:
     build_product(force)
+    stage_resources()
     build_emul(force)
     build_oracle()

@@ -94,7 +94,8 @@ static void add_mesh(Soup &s, const gnxsk::Mesh &m, float pre, const float t[3],
                 s.p.push_back(x + t[c]);
             }
         }
-        s.material.push_back(material);
+        // (a mesh with per-triangle materials — OBJ usemtl — indexes them behind `material`; slot `material` itself is the default)
+        s.material.push_back(m.tri_material.empty() ? material : material + 1 + m.tri_material[f]);
         s.light.push_back(-1);
         s.med_in.push_back(medIn); s.med_out.push_back(medOut); s.transition.push_back(medIn != medOut);
         if (medIn >= 0 || medOut >= 0) s.anyMedia = true;
@@ -759,8 +760,26 @@ gnxsk_scene *gnxsk_create(const char *name, int width, int height, int spp, int 
         else {
             gnxsk::Mesh file;
             const bool obj = nm[0] == 'o';
-            if (!(obj ? gnxsk::load_obj(nm.substr(4), &file, &sc->error) : gnxsk::load_3d(nm.substr(9), &file, &sc->error))) return sc;
+            std::vector<gnxsk::ObjMaterial> objMats;
+            if (!(obj ? gnxsk::load_obj(nm.substr(4), &file, &sc->error, &objMats) : gnxsk::load_3d(nm.substr(9), &file, &sc->error))) return sc;
             if (file.nTris() == 0) { sc->error = "mesh file without triangles"; return sc; }
+            // OBJ materials (MTL): one gnx_material per entry behind the default one, through the same recipe the oracle
+            // harness feeds to the reference's material classes
+            for (const gnxsk::ObjMaterial &om : objMats) {
+                const gnxsk::MaterialRecipe r = gnxsk::material_recipe(om);
+                gnx_material gm = make_material(GNX_MAT_MATTE, GNX_MATF_BUMP_IDENTITY);
+                if (r.kind == gnxsk::MaterialRecipe::Matte) { set_rgb(gm, 0, r.kd[0], r.kd[1], r.kd[2]); gm.f[0] = 0.f; }
+                else if (r.kind == gnxsk::MaterialRecipe::Plastic) {
+                    gm.type = GNX_MAT_PLASTIC;
+                    set_rgb(gm, 0, r.kd[0], r.kd[1], r.kd[2]); set_rgb(gm, 1, r.ks[0], r.ks[1], r.ks[2]); gm.f[0] = r.roughness;
+                } else if (r.kind == gnxsk::MaterialRecipe::Mirror) { gm.type = GNX_MAT_MIRROR; set_rgb(gm, 0, r.ks[0], r.ks[1], r.ks[2]); }
+                else {
+                    gm.type = GNX_MAT_GLASS;
+                    set_rgb(gm, 0, r.ks[0], r.ks[1], r.ks[2]); set_rgb(gm, 1, r.ks[0], r.ks[1], r.ks[2]);
+                    gm.f[0] = gm.f[1] = 0.f; gm.f[2] = r.index;
+                }
+                sc->materials.push_back(gm);
+            }
             if (obj) {
                 const float centre[3] = {0.f, -0.4f, 0.f}, zero[3] = {0.f, 0.f, 0.f};
                 gnxsk::fit_to_sphere(&file, 2.5f, centre);

@@ -9,6 +9,11 @@
 //   load_obj  Wavefront OBJ (v / vt / vn / f with v, v/vt, v//vn, v/vt/vn corners, negative indices, polygons fanned
 //             into triangles).  The reference has no OBJ loader (config 3 names an asset it cannot open): corners are
 //             unified into the single-index vertices TriangleMesh takes (shape/Triangle.cpp:14-60).
+//   load_mtl  the MTL library an OBJ names (newmtl / Kd / Ks / Ns / Ni / d / Tr / illum) and `material_recipe`, the mapping
+//             of an MTL entry onto the reference's material classes (materials/*.cpp): mirror for illum 3 / 5 with a black
+//             Kd, glass for illum 4 / 6 / 7 / 9 or d < 1, plastic when Ks is not black, matte otherwise.  The scene kit turns
+//             a recipe into a gnx_material, the oracle harness into the reference's own Material object — one recipe, two
+//             consumers, so both sides render the same thing.
 //   save_3d   writes a Mesh in the .3d layout (tests, tools).
 //
 // Header-only, plain C++; no dependency on the reference or on CUDA.
@@ -101,9 +106,79 @@ inline bool save_3d(const std::string &path, const Mesh &m, std::string *err) {
     return true;
 }
 
-inline bool load_obj(const std::string &path, Mesh *m, std::string *err) {
+struct ObjMaterial {
+    std::string name;
+    float Kd[3] = {0.8f, 0.8f, 0.8f}, Ks[3] = {0, 0, 0};
+    float Ns = 0, Ni = 1.5f, d = 1;
+    int illum = 2;
+};
+// What a material of the reference is built from (same constants on the kit side and on the reference side).
+struct MaterialRecipe {
+    enum Kind { Matte, Plastic, Mirror, Glass } kind = Matte;
+    float kd[3] = {0, 0, 0}, ks[3] = {0, 0, 0};
+    float roughness = 0, index = 1.5f;
+};
+inline MaterialRecipe material_recipe(const ObjMaterial &m) {
+    MaterialRecipe r;
+    const bool kdBlack = m.Kd[0] == 0 && m.Kd[1] == 0 && m.Kd[2] == 0, ksBlack = m.Ks[0] == 0 && m.Ks[1] == 0 && m.Ks[2] == 0;
+    for (int c = 0; c < 3; ++c) { r.kd[c] = m.Kd[c]; r.ks[c] = m.Ks[c]; }
+    r.index = m.Ni;
+    if (m.illum == 4 || m.illum == 6 || m.illum == 7 || m.illum == 9 || m.d < 1) {
+        r.kind = MaterialRecipe::Glass;                       // GlassMaterial(Kr = Ks or 1, Kt = 1 - (1 - d) Kd ... kept simple: Kt = Kr)
+        for (int c = 0; c < 3; ++c) r.ks[c] = ksBlack ? 1.f : m.Ks[c];
+    } else if ((m.illum == 3 || m.illum == 5) && kdBlack && !ksBlack) r.kind = MaterialRecipe::Mirror;   // MirrorMaterial(Kr = Ks)
+    else if (!ksBlack) {
+        r.kind = MaterialRecipe::Plastic;                     // PlasticMaterial(Kd, Ks, roughness), remapRoughness = false
+        r.roughness = std::sqrt(2.f / (m.Ns + 2.f));          // Blinn-Phong exponent -> microfacet alpha
+    } else r.kind = MaterialRecipe::Matte;                    // MatteMaterial(Kd, sigma = 0)
+    return r;
+}
+inline bool load_mtl(const std::string &path, std::vector<ObjMaterial> *out, std::string *err) {
     std::string buf;
     if (!read_file(path, &buf, err)) return false;
+    std::istringstream in(buf);
+    std::string line;
+    int lineNo = 0;
+    while (std::getline(in, line)) {
+        ++lineNo;
+        size_t h = line.find('#');
+        if (h != std::string::npos) line.resize(h);
+        Tokens t(line);
+        std::string w;
+        if (!t.word(&w)) continue;
+        if (w == "newmtl") {
+            out->emplace_back();
+            if (!t.word(&out->back().name)) { *err = path + ":" + std::to_string(lineNo) + ": newmtl without a name"; return false; }
+            continue;
+        }
+        if (out->empty()) continue;
+        ObjMaterial &m = out->back();
+        auto three = [&](float *v) {
+            if (!t.real(&v[0])) return false;
+            if (!t.real(&v[1])) { v[1] = v[2] = v[0]; return true; }  // "Kd r" means grey
+            return t.real(&v[2]);
+        };
+        bool ok = true;
+        if (w == "Kd") ok = three(m.Kd);
+        else if (w == "Ks") ok = three(m.Ks);
+        else if (w == "Ns") ok = t.real(&m.Ns);
+        else if (w == "Ni") ok = t.real(&m.Ni);
+        else if (w == "d") ok = t.real(&m.d);
+        else if (w == "Tr") { float tr; ok = t.real(&tr); m.d = 1 - tr; }
+        else if (w == "illum") { float f; ok = t.real(&f); m.illum = (int)f; }
+        // Ka / Ke / Tf / map_*: not part of the reference's material models
+        if (!ok) { *err = path + ":" + std::to_string(lineNo) + ": malformed '" + w + "'"; return false; }
+    }
+    return true;
+}
+
+// mats (optional): receives the materials of the OBJ's mtllib files; m->tri_material then indexes it per triangle.
+inline bool load_obj(const std::string &path, Mesh *m, std::string *err, std::vector<ObjMaterial> *mats = nullptr) {
+    std::string buf;
+    if (!read_file(path, &buf, err)) return false;
+    std::vector<int> faceMat;
+    int curMat = -1;
+    const std::string dir = path.find_last_of('/') == std::string::npos ? std::string() : path.substr(0, path.find_last_of('/') + 1);
     std::vector<float> P, T, N;
     std::map<std::tuple<int, int, int>, int> corner;  // (v, vt, vn) -> unified vertex
     *m = Mesh();
@@ -148,8 +223,27 @@ inline bool load_obj(const std::string &path, Mesh *m, std::string *err) {
                 poly.emplace_back(id[0], id[1], id[2]);
             }
             if (poly.size() < 3) return fail("face with fewer than 3 corners");
-            for (size_t k = 1; k + 1 < poly.size(); ++k) { faces.push_back(poly[0]); faces.push_back(poly[k]); faces.push_back(poly[k + 1]); }
-        }  // o / g / s / usemtl / mtllib: one material per scene-kit mesh, ignored
+            for (size_t k = 1; k + 1 < poly.size(); ++k) {
+                faces.push_back(poly[0]); faces.push_back(poly[k]); faces.push_back(poly[k + 1]);
+                faceMat.push_back(curMat);
+            }
+        } else if (w == "mtllib" && mats) {
+            std::string f;
+            // (a library that is not there is not an error: OBJ files routinely outlive their MTL; the faces then keep the
+            // scene's default material.  A library that IS there must parse.)
+            while (t.word(&f)) {
+                FILE *probe = fopen((dir + f).c_str(), "rb");
+                if (!probe) continue;
+                fclose(probe);
+                if (!load_mtl(dir + f, mats, err)) return false;
+            }
+        } else if (w == "usemtl" && mats) {
+            std::string nm;
+            t.word(&nm);
+            curMat = -1;
+            for (size_t k = 0; k < mats->size(); ++k) if ((*mats)[k].name == nm) curMat = (int)k;
+            if (curMat < 0 && !mats->empty()) return fail("usemtl names an unknown material '" + nm + "'");
+        }  // o / g / s: ignored
     }
     if (faces.empty()) return fail("no faces");
     for (auto &c : faces) {
@@ -172,6 +266,7 @@ inline bool load_obj(const std::string &path, Mesh *m, std::string *err) {
         }
         m->idx.push_back(it->second);
     }
+    if (mats && !mats->empty()) m->tri_material = faceMat;
     return true;
 }
 

@@ -24,6 +24,7 @@ struct Mesh {
     std::vector<float> N;    // 3 * nVerts or empty
     std::vector<float> UV;   // 2 * nVerts or empty
     std::vector<int> idx;    // 3 * nTris
+    std::vector<int> tri_material;  // nTris indices into the file's material list (OBJ usemtl), -1 = none; empty = one material
     int nVerts() const { return (int)(P.size() / 3); }
     int nTris() const { return (int)(idx.size() / 3); }
 };

@@ -53,6 +53,7 @@
 #include "ref_harness.h"
 #include "gnxraytracer_b200/bridge/SobolSampler.h"  // header-only, built from the reference's own Sobol helpers and tables
 #include "gnxraytracer_b200/host/scenekit_mesh.h"
+#include "gnxraytracer_b200/host/scenekit_io.h"
 
 using namespace pbr;
 
@@ -299,6 +300,49 @@ bool BuildDragon(HarnessScene &hs, int variant, int nu, int nv, const std::strin
     return true;
 }
 
+// A Wavefront OBJ (+ MTL) through the reference's classes: the reference has no OBJ loader, so the
+// file is read by the scene kit's reader and handed to TriangleMesh / GeometricPrimitive exactly like ui/ModelList.cpp:49-69
+// does for dragon.3d — one TriangleMesh per material, the MTL entries mapped onto MatteMaterial / PlasticMaterial /
+// MirrorMaterial / GlassMaterial by the same recipe the kit uses (gnxsk::material_recipe).  Placement and light as the kit's
+// "obj:" scene: fitted into a sphere of radius 2.5 around (0, -0.4, 0), MonValley environment.
+bool BuildObj(HarnessScene &hs, int variant, const std::string &path) {
+    gnxsk::Mesh file;
+    std::vector<gnxsk::ObjMaterial> objMats;
+    if (!gnxsk::load_obj(path, &file, &hs.error, &objMats)) return false;
+    if (file.nTris() == 0) { hs.error = "mesh file without triangles"; return false; }
+    const float centre[3] = {0.f, -0.4f, 0.f};
+    gnxsk::fit_to_sphere(&file, 2.5f, centre);
+    std::vector<std::shared_ptr<Material>> mats;
+    mats.push_back(variant == 1 ? YellowMetal() : PurplePlastic());  // faces without usemtl
+    for (const gnxsk::ObjMaterial &om : objMats) {
+        const gnxsk::MaterialRecipe r = gnxsk::material_recipe(om);
+        if (r.kind == gnxsk::MaterialRecipe::Matte) mats.push_back(Matte(r.kd[0], r.kd[1], r.kd[2], 0.f));
+        else if (r.kind == gnxsk::MaterialRecipe::Plastic)
+            mats.push_back(std::make_shared<PlasticMaterial>(ConstSpec(r.kd[0], r.kd[1], r.kd[2]), ConstSpec(r.ks[0], r.ks[1], r.ks[2]), ConstF(r.roughness), ConstF(0.0f), false));
+        else if (r.kind == gnxsk::MaterialRecipe::Mirror) mats.push_back(std::make_shared<MirrorMaterial>(ConstSpec(r.ks[0], r.ks[1], r.ks[2]), ConstF(0.0f)));
+        else mats.push_back(std::make_shared<GlassMaterial>(ConstSpec(r.ks[0], r.ks[1], r.ks[2]), ConstSpec(r.ks[0], r.ks[1], r.ks[2]), ConstF(0.0f), ConstF(0.0f), ConstF(r.index), ConstF(0.0f), false));
+    }
+    // one sub-mesh per material, faces in file order (the scene's primitive order is file order within each material)
+    for (size_t k = 0; k < mats.size(); ++k) {
+        gnxsk::Mesh sub;
+        sub.P = file.P; sub.N = file.N; sub.UV = file.UV;
+        for (int f = 0; f < file.nTris(); ++f) {
+            const int mi = file.tri_material.empty() ? 0 : file.tri_material[f] + 1;
+            if (mi == (int)k) for (int v = 0; v < 3; ++v) sub.idx.push_back(file.idx[3 * f + v]);
+        }
+        if (sub.nTris() > 0) AddMesh(hs, sub, Transform(), mats[k], nullptr);
+    }
+    std::string hdr = ResourceDir() + "MonValley1000.hdr";
+    FILE *f = fopen(hdr.c_str(), "rb");
+    if (!f) { hs.error = "missing resource " + hdr; return false; }
+    fclose(f);
+    Transform l2w = RotateX(20) * RotateY(-90) * RotateX(-90);
+    hs.lights.push_back(std::make_shared<InfiniteAreaLight>(l2w, Spectrum(1.0f), 10, hdr));
+    SetupCamera(hs, Point3f(0.f, 0.f, 5.0f), Point3f(0.f, 0.f, 0.0f));
+    Finish(hs);
+    return true;
+}
+
 // Config 3: textured mesh with per-vertex UVs and normals (stand-in for the stripped nanosuit: there is no
 // OBJ loader in the reference), DisneyMaterial whose colour is an ImageTexture on awesomeface.jpg exactly
 // as getSmileFacePlasticMaterial builds it (ui/MaterialList.cpp:31-46), TropicalRuins environment.
@@ -449,6 +493,7 @@ void *gnxh_scene_create(const char *name, int width, int height, int spp, int p0
     if (hs->name == "cornell") BuildCornell(*hs, p0, p1);
     else if (hs->name == "dragon") BuildDragon(*hs, p0, p1, p2, "MonValley1000.hdr");
     else if (hs->name.rfind("dragon3d:", 0) == 0) BuildDragon(*hs, p0, 0, 0, "MonValley1000.hdr", hs->name.substr(9));
+    else if (hs->name.rfind("obj:", 0) == 0) BuildObj(*hs, p0, hs->name.substr(4));
     else if (hs->name == "nano") BuildNano(*hs, p0, p1, p2);
     else if (hs->name == "smoke") BuildSmoke(*hs, p0);
     else if (hs->name == "ui") BuildUI(*hs, p0, p1 > 0 ? p1 : 2048, p2 > 0 ? p2 : 213);

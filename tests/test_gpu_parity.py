@@ -357,7 +357,9 @@ def test_image_textures_with_ray_differentials_on_gpu(ref, emul, preset):
     assert st.paths == res * res * spp
     assert rel_mse(img, img_ref) <= 1e-3
     close = np.abs(img[..., :3] - img_ref[..., :3]).max(axis=2) <= 1e-3 * np.maximum(1.0, img_ref[..., :3].max(axis=2))
-    assert np.mean(close) >= 0.99
+    # (VolPath takes many more discrete decisions per path — free-flight distances through logf, the channel choice — so more
+    # of its pixels hold a path that CUDA's libm sends another way than glibc)
+    assert np.mean(close) >= (0.97 if preset.startswith("fog") else 0.99)
     emu, _ = emul.scene(rs.desc).render(RenderParams.make(res, res, spp, max_depth=5, integrator=integrator_of(preset)))
     assert rel_mse(img, emu) <= 1e-6
     rs.close()
