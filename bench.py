@@ -182,6 +182,8 @@ def scene_args(wl):
     p0, p1, p2 = wl["args"]
     if wl["scene"] in ("dragon",) or wl["scene"].startswith("dragon3d:"):
         p1, p2 = p1 or 2048, p2 or 213
+    if wl["scene"] == "nano":   # the kit's default tessellation (the harness takes it literally)
+        p1, p2 = p1 or 320, p2 or 64
     return wl["scene"], p0, p1, p2
 
 
@@ -522,7 +524,14 @@ def run_ours(args, wl, name):
                 one.close()
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 import _harness
-                line["rel_mse_vs_cpu_ref"] = _harness.rel_mse(img, img_ref)
+                if wl["scene"] == "nano":
+                    # the kit paints a procedural colour map (no JPEG decoder), the reference side loads awesomeface.jpg: same
+                    # geometry, materials and light, another texture — the image comparison for this config is the GPU parity
+                    # test through the bridge (tests/test_gpu_fullsize.py), not this line
+                    line["rel_mse_vs_cpu_ref"] = None
+                    line["rel_mse_note"] = "not comparable: procedural texture (kit) vs awesomeface.jpg (reference side); see tests/test_gpu_fullsize.py[nano_full]"
+                else:
+                    line["rel_mse_vs_cpu_ref"] = _harness.rel_mse(img, img_ref)
                 line["rel_mse_spp"] = n
                 rs.close()
             if not args.no_bridge:
