@@ -242,6 +242,80 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
 
+// ---- the any-hit kernel over the compressed 8-wide tree (gnx_bvh8.cuh) ---------------------------------------
+// Shadow rays (queue half A) and environment-MIS rays (half B) of one bounce: same persistent scheme as k_trace (one ray
+// per lane, refill through a warp-aggregated cursor, warp-synchronous rounds), but a round is one 8-wide node per lane:
+// six 16-byte loads feed eight slab tests, the stack holds one entry per node (node, children still to visit), and there
+// is no visiting order to keep.  Leaves wait until kLeafBatch lanes hold one, like in k_trace.
+//   VARIANT 0: both queue halves (A first)
+#ifndef GNX_ANY8_BLOCKS
+#define GNX_ANY8_BLOCKS 8
+#endif
+#ifndef GNX_ANY8_REFETCH
+#define GNX_ANY8_REFETCH 24
+#endif
+template <int VARIANT>
+__global__ void __launch_bounds__(kBlock, GNX_ANY8_BLOCKS) k_anyhit8(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
+    __shared__ int2 s_stack[kSmemStack * kBlock];
+    int2 *stack = s_stack + threadIdx.x;
+    const uint32_t sb = stack_shared_base(stack);
+    const int lane = threadIdx.x & 31;
+    const int nShA = q.counts[kCntShadow], nShB = q.counts[kCntShadow + 1];
+    const int n = nShA + nShB;
+    int *cursor = &q.counts[kCntFetch + 1];
+    auto shadowItem = [&](int i) { return i >= nShA ? q.shadow_q + (size_t)q.capacity + (i - nShA) : q.shadow_q + i; };
+    TraversalCounters cnt{0, 0};
+    unsigned rays = 0, raysB = 0;
+    Trav8 t;
+    int2 spill[kSpillStack];
+    t.spill = spill;
+    t.cur = kRefNone;
+    t.gnode = 0; t.gmask = 0;
+    bool active = false, exhausted = false;
+    int item = 0;
+    while (true) {
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(kFull, !active);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(cursor, __popc(idle));
+                base = __shfl_sync(kFull, base, leader);
+                if (!active) {
+                    const int i = base + __popc(idle & ((1u << lane) - 1));
+                    if (i < n) {
+                        item = i;
+                        shadow_begin(sc, shadowItem(i), t);
+                        trav8_init(sc, t);
+                        if (i >= nShA) ++raysB;
+                        active = true;
+                        ++rays;
+                    }
+                }
+                exhausted = base + __popc(idle) >= n;
+            }
+        }
+        if (!__any_sync(kFull, active)) break;
+        while (true) {
+            if (active && trav_needs_pop(t)) trav8_next(sc, t, stack, kBlock, sb);
+            bool parked = active && trav_is_leaf(t);
+            if (active && !parked && trav_is_interior(t)) { trav8_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
+            const unsigned parkedMask = __ballot_sync(kFull, parked);
+            const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
+            if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0))
+                t.cur = trav_leaf_ref<true>(sc, t, t.cur, cnt) ? kRefNone : kRefPop;
+            if (active && trav_done(t)) {
+                shadow_finish(ps, shadowItem(item), t, item >= nShA);
+                active = false;
+            }
+            const unsigned actMask = __ballot_sync(kFull, active);
+            if (actMask == 0 || (!exhausted && __popc(actMask) < GNX_ANY8_REFETCH)) break;
+        }
+    }
+    flush_stats(st, 1, cnt.nodes, cnt.tris, rays - raysB);
+    flush_stats(st, 2, 0, 0, raysB);
+}
+
 // Escaped rays of a scene with a SkyBoxLight (queued by the traversal kernel): L += beta * Le(ray).
 #ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_escape(const DeviceScene sc, PathState ps, Queues q) {
@@ -357,6 +431,9 @@ __global__ void k_vp_reset(int *counts, int consumed) {
 #endif
 
 // One logic kernel (VolKernel) over one of its queues; queue < 0: the camera samples of the batch (VP_START).
+#ifndef GNX_VOL_MAXL
+#define GNX_VOL_MAXL 8
+#endif
 #ifndef GNX_VP_LOGIC_BLOCKS
 #define GNX_VP_LOGIC_BLOCKS 4  // measured on C4: 4 blocks (128 registers) 148 ms, 6: 158 ms, 8: 177 ms — the spills cost more than the warps hide
 #endif
@@ -381,7 +458,7 @@ __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const 
         int slot = 0, y = VY_DONE;
         if (i < n) {
             slot = list ? list[i] : i;
-            y = vol_advance<8, TEX>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
+            y = vol_advance<GNX_VOL_MAXL, TEX>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
         }
         __syncwarp();
         int idx = warp_push(&q.counts[kCntExtend0], y == VY_TRACK_MAIN || y == VY_TRACK_SUB);
@@ -764,6 +841,7 @@ extern template __global__ void k_recursive<1, false>(const DeviceScene, PathSta
 extern template __global__ void k_recursive<1, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<2, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<2, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_anyhit8<0>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
@@ -775,6 +853,7 @@ extern template __global__ void k_volpath<false>(const DeviceScene, PathState, Q
 extern template __global__ void k_volpath<true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 #endif
 #if defined(GNX_TU_TRACE)
+template __global__ void k_anyhit8<0>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 template __global__ void k_trace<0>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<1>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<2>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);

@@ -12,6 +12,7 @@
 #include "gnx_scene.cuh"
 #include "gnx_sampler.cuh"
 #include "gnx_bvh.cuh"
+#include "gnx_bvh8.cuh"
 
 namespace gnx {
 
@@ -350,6 +351,106 @@ inline bool build_nodes(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
     if (!build_node2(nodes, n, out, err)) return false;
     *count = (int)(out.size() / 4);
 #endif
+    return true;
+}
+
+// Node2 array (64-byte two-child records, gnx_bvh.cuh) -> compressed 8-wide tree (gnx_bvh8.cuh) over the same ordered
+// primitives, for the any-hit queries.  A Node8 starts from the two children of its source node and keeps replacing the
+// internal child of largest surface area by that child's own two children until it holds eight (or only leaves are
+// left); leaves keep their reference.  Child boxes are rounded OUTWARD onto the node's grid (origin = corner of the union,
+// step = the smallest power of two that spans it in 255 steps), checked in double precision.  Returns false (and leaves
+// `out` empty) for bounds that are not finite: the caller then keeps the two-child tree for every query.
+inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
+    out.clear();
+    if (count <= 0) return true;
+    struct Child { float lo[3], hi[3]; int ref; };
+    auto children2 = [&](int i, Child *c) {
+        const float4 a = n2[4 * (size_t)i], b = n2[4 * (size_t)i + 1], d = n2[4 * (size_t)i + 2], r = n2[4 * (size_t)i + 3];
+        int ref0, ref1, n = 0;
+        memcpy(&ref0, &r.x, 4); memcpy(&ref1, &r.y, 4);
+        if (ref0 != kRefNone) { c[n] = Child{{a.x, a.y, a.z}, {a.w, b.x, b.y}, ref0}; ++n; }
+        if (ref1 != kRefNone) { c[n] = Child{{b.z, b.w, d.x}, {d.y, d.z, d.w}, ref1}; ++n; }
+        return n;
+    };
+    auto area = [](const Child &c) {
+        const double dx = (double)c.hi[0] - c.lo[0], dy = (double)c.hi[1] - c.lo[1], dz = (double)c.hi[2] - c.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    std::vector<std::pair<int, int>> todo;  // (source Node2, Node8 index)
+    out.resize(kNode8Words);
+    todo.push_back({0, 0});
+    while (!todo.empty()) {
+        const auto [src, me] = todo.back();
+        todo.pop_back();
+        if (src < 0 || src >= count) { out.clear(); return false; }
+        Child c[8];
+        int n = children2(src, c);
+        while (n < 8) {
+            int pick = -1;
+            double best = -1;
+            for (int k = 0; k < n; ++k) if (c[k].ref >= 0) { const double a = area(c[k]); if (a > best || pick < 0) { best = a; pick = k; } }
+            if (pick < 0) break;
+            if (c[pick].ref >= count) { out.clear(); return false; }
+            Child g[2];
+            const int m = children2(c[pick].ref, g);
+            if (m == 0) { c[pick] = c[--n]; continue; }
+            c[pick] = g[0];
+            if (m > 1) c[n++] = g[1];
+        }
+        std::sort(c, c + n, [&](const Child &x, const Child &y) { return area(x) > area(y); });
+        float org[3];
+        int ebyte[3];
+        uint8_t qlo[3][8], qhi[3][8];
+        for (int ax = 0; ax < 3; ++ax) {
+            float lo = c[0].lo[ax], hi = c[0].hi[ax];
+            for (int k = 0; k < n; ++k) {
+                if (!std::isfinite(c[k].lo[ax]) || !std::isfinite(c[k].hi[ax]) || c[k].hi[ax] < c[k].lo[ax]) { out.clear(); return false; }
+                lo = std::min(lo, c[k].lo[ax]); hi = std::max(hi, c[k].hi[ax]);
+            }
+            org[ax] = lo;
+            const double ext = (double)hi - (double)lo;
+            int e = -126;
+            if (ext > 0) { int fe; std::frexp(ext / 255.0, &fe); e = std::max(-126, fe - 1); }  // 2^(fe-1) <= ext/255 < 2^fe
+            for (;; ++e) {
+                if (e > 127) { out.clear(); return false; }
+                const double s = std::ldexp(1.0, e);
+                bool ok = true;
+                for (int k = 0; k < n && ok; ++k) {
+                    double ql = std::floor(((double)c[k].lo[ax] - (double)lo) / s), qh = std::ceil(((double)c[k].hi[ax] - (double)lo) / s);
+                    while (ql > 0 && (double)lo + ql * s > (double)c[k].lo[ax]) ql -= 1;
+                    while ((double)lo + qh * s < (double)c[k].hi[ax]) qh += 1;
+                    if (ql < 0) ql = 0;
+                    if (qh > 255) { ok = false; break; }
+                    qlo[ax][k] = (uint8_t)ql; qhi[ax][k] = (uint8_t)qh;
+                }
+                if (ok) break;
+            }
+            ebyte[ax] = e + 127;
+        }
+        int refs[8];
+        unsigned valid = 0;
+        for (int k = 0; k < 8; ++k) {
+            refs[k] = kRefNone;
+            if (k >= n) { for (int ax = 0; ax < 3; ++ax) { qlo[ax][k] = 255; qhi[ax][k] = 0; } continue; }
+            valid |= 1u << k;
+            if (c[k].ref < 0) refs[k] = c[k].ref;
+            else {
+                refs[k] = (int)(out.size() / kNode8Words);
+                out.resize(out.size() + kNode8Words);
+                todo.push_back({c[k].ref, refs[k]});
+            }
+        }
+        auto pack4 = [](const uint8_t *b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+        uint32_t ob[3];
+        memcpy(ob, org, 12);
+        uint4 *w = out.data() + (size_t)kNode8Words * me;
+        w[0] = make_uint4(ob[0], ob[1], ob[2], (uint32_t)ebyte[0] | ((uint32_t)ebyte[1] << 8) | ((uint32_t)ebyte[2] << 16) | (valid << 24));
+        w[1] = make_uint4((uint32_t)refs[0], (uint32_t)refs[1], (uint32_t)refs[2], (uint32_t)refs[3]);
+        w[2] = make_uint4((uint32_t)refs[4], (uint32_t)refs[5], (uint32_t)refs[6], (uint32_t)refs[7]);
+        w[3] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+        w[4] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+        w[5] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    }
     return true;
 }
 

@@ -472,6 +472,20 @@ GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav
 }
 GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int2 *stack, int stride,
                        TraversalCounters &cnt) {
+    if (sc.nodes8) {  // the compressed 8-wide tree answers the any-hit queries (gnx_bvh8.cuh)
+        Trav8 t8;
+        int2 store[kSpillStack];
+        t8.spill = store;
+        shadow_begin(sc, item, t8);
+        trav8_init(sc, t8);
+        while (!trav_done(t8)) {
+            if (trav_needs_pop(t8)) trav8_next(sc, t8, stack, stride);
+            else if (trav_is_leaf(t8)) t8.cur = trav_leaf_ref<true>(sc, t8, t8.cur, cnt) ? kRefNone : kRefPop;
+            else trav8_interior(sc, t8, stack, stride, cnt);
+        }
+        shadow_finish(ps, item, t8);
+        return;
+    }
     TravLocal t;
     shadow_begin(sc, item, t);
     while (!trav_step<true>(sc, t, stack, stride, cnt)) {}

@@ -90,6 +90,11 @@ struct gnx_ctx {
     bool has_scene = false;
     bool has_next_lights = false;  // point / spot / distant / skybox lights present
     bool tex_needs_pyramid = false; // an image texture came as one level that is not a power of two: no MIPMap pyramid to filter with
+    cudaStream_t stream_any = nullptr;  // the any-hit launches of a bounce run here, next to the extension launch on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool anyhit_overlap = true;    // GNX_ANYHIT_OVERLAP=0: any-hit launch on the render stream, after the extension launch
+    int grid_anyhit8 = 148 * 8;
+    bool anyhit8 = true;           // GNX_ANYHIT_BVH8=0: any-hit rays walk the two-child tree like the closest-hit rays
     bool merge_extend = true;      // GNX_MERGE_EXTEND=0: the any-hit rays of a bounce get their own launch(es)
     int film_chunk = 0;            // GNX_FILM_CHUNK: samples per pixel staged at a time by the tiled Gaussian gather (0 = auto)
     bool film_simple = false;      // GNX_FILM_SIMPLE=1: Gaussian film with the per-pixel gather instead of the tiled one
@@ -226,6 +231,9 @@ int gnx_create(gnx_ctx **out, int device) {
     if ((e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream_any, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->d_stats, sizeof(DevStats))) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
@@ -234,6 +242,7 @@ int gnx_create(gnx_ctx **out, int device) {
     {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_anyhit8<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_anyhit8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
@@ -253,6 +262,8 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
     if (const char *fc = getenv("GNX_FILM_CHUNK")) ctx->film_chunk = atoi(fc);
     if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
+    if (const char *a8 = getenv("GNX_ANYHIT_BVH8")) ctx->anyhit8 = a8[0] != '0';
+    if (const char *a8 = getenv("GNX_ANYHIT_OVERLAP")) ctx->anyhit_overlap = a8[0] != '0';
     if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
@@ -271,6 +282,9 @@ void gnx_destroy(gnx_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream_any) cudaStreamDestroy(ctx->stream_any);
     if (ctx->fb_state) cudaFree(ctx->fb_state);
     if (ctx->fb_u8) cudaFree(ctx->fb_u8);
     if (ctx->fb_pinned) cudaFreeHost(ctx->fb_pinned);
@@ -423,6 +437,23 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
         sc.tris = dn + nodeF4;
         ctx->geom_base = dn;
         ctx->geom_bytes = (nodeF4 + tris.size()) * sizeof(float4);
+#if GNX_BVH_WIDTH == 2
+        // ---- the any-hit tree: the two-child records collapsed into compressed 8-wide nodes (gnx_bvh8.cuh).  A tree built
+        // on the device is read back for the collapse (64 bytes per interior node).
+        if (ctx->anyhit8 && nNodes > 0) {
+            std::vector<uint4> n8;
+            if (deviceBuilt) {
+                n2.resize(nodeF4);
+                GNX_CUDA(ctx, cudaMemcpy(n2.data(), dn, nodeF4 * sizeof(float4), cudaMemcpyDeviceToHost));
+            }
+            if (build_node8(n2.data(), nNodes, n8) && !n8.empty()) {
+                uint4 *d8;
+                if ((rc = dupload(ctx, pool, n8.data(), n8.size(), &d8))) return rc;
+                sc.nodes8 = d8;
+                sc.n_nodes8 = (int)(n8.size() / kNode8Words);
+            }
+        }
+#endif
     }
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
@@ -1062,6 +1093,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         // a tail of a few long rays, and the late bounces are mostly tail.  Not with material-less surfaces (the loop
         // below polls the queue from the host) and not when the caller turned it off.
         const bool mixed = ctx->merge_extend && psv.La && psv.Lb && !hasNull && sc.n_lights > 0;
+        // any-hit rays through the compressed 8-wide tree (both queue halves in one launch: needs the second accumulator)
+        const bool any8 = ctx->anyhit8 && sc.nodes8 != nullptr && ctx->merge_shadow && (psv.Lb || !sc.env.present);
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.
         for (int iter = 0;; ++iter) {
@@ -1070,7 +1103,23 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             else k_reset_counts<<<1, 32, 0, st>>>(qv.counts, out);
             tm.begin(ST_EXTEND);
             if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 0, ctx->d_stats);  // ray-gen fused in
-            else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+            else if (mixed && any8) {
+                // the any-hit rays of bounce d walk the compressed 8-wide tree in their own kernel, launched on a second
+                // stream behind the extension launch of bounce d+1: its blocks move in as the extension kernel's blocks
+                // drain (both are persistent grids), which fills the tail like the mixed launch did
+                if (ctx->anyhit_overlap) {
+                    GNX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+                    k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+                    GNX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_any, ctx->ev_fork, 0));
+                    k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, ctx->stream_any>>>(sc, psv, qv, rcn, ctx->d_stats);
+                    GNX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream_any));
+                    GNX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                } else {
+                    k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+                    k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                }
+                ++launches;
+            } else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
             else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
             tm.end();
             launches += 2;
@@ -1096,9 +1145,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
                 // accumulators (ps.L / ps.Lb), so the two rays of a path do not race.  In mixed mode they wait for the
                 // next bounce's extension launch, except after the last bounce.
                 if (!mixed || last) {
-                    k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, (psv.Lb && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
+                    if (any8) k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                    else k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, (psv.Lb && ctx->merge_shadow) ? 2 : 0, ctx->d_stats);
                     ++launches;
-                    if (sc.env.present && !(psv.Lb && ctx->merge_shadow)) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 1, ctx->d_stats); ++launches; }
+                    if (!any8 && sc.env.present && !(psv.Lb && ctx->merge_shadow)) { k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 1, ctx->d_stats); ++launches; }
                 }
                 if (sc.n_lights > (sc.env.present ? 1 : 0)) { k_trace<2><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 0, ctx->d_stats); ++launches; }
             }

@@ -84,6 +84,8 @@ struct DeviceScene {
     //   a = (p0.x p0.y p0.z p1.x)  b = (p1.y p1.z p2.x p2.y)  c = (p2.z, bits(material | type<<20 | flags<<24), bits(light), bits(prim_id))
     const float4 *nodes2;
     int n_nodes2;
+    const uint4 *nodes8;          // compressed 8-wide tree over the same ordered primitives, any-hit queries (gnx_bvh8.cuh); null: none
+    int n_nodes8;
     const float4 *tris;
     const float *tri_uv;          // [n][6] or null
     const float *tri_n;           // [n][9] or null

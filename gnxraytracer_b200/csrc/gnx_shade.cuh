@@ -3,6 +3,7 @@
 #pragma once
 #include "gnx_bsdf.cuh"
 #include "gnx_bvh.cuh"
+#include "gnx_bvh8.cuh"
 #include "gnx_sampler.cuh"
 
 namespace gnx {

@@ -24,6 +24,7 @@ namespace {
 struct EmulScene {
     DeviceScene sc{};
     std::vector<float4> tris, nodes2, env_texels;
+    std::vector<uint4> nodes8;
     std::vector<int2> media;
     std::vector<DevMedium> dev_media;
     std::vector<DevTexture> textures;
@@ -45,6 +46,14 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     const gnx_geometry &g = d->geom;
     if (!build_nodes(g.nodes, g.n_nodes, e.nodes2, &sc.n_nodes2, &e.err)) return false;
     sc.nodes2 = e.nodes2.data();
+#if GNX_BVH_WIDTH == 2
+    // the any-hit tree of the product (gnx_bvh8.cuh); GNX_ANYHIT_BVH8=0 keeps the two-child tree for every query
+    const char *a8 = getenv("GNX_ANYHIT_BVH8");
+    if (!(a8 && a8[0] == '0') && build_node8(e.nodes2.data(), sc.n_nodes2, e.nodes8) && !e.nodes8.empty()) {
+        sc.nodes8 = e.nodes8.data();
+        sc.n_nodes8 = (int)(e.nodes8.size() / kNode8Words);
+    }
+#endif
     sc.n_nodes = g.n_nodes;
     sc.n_prims = g.n_prims;
     if (!pack_triangles(*d, e.tris, &e.typeMask, &e.err)) return false;
