@@ -99,7 +99,8 @@ def ncu_evidence(workload):
             hdr = rows[0]
             ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
             for r in rows[1:]:
-                if "k_trace<3>" in r[ik] or "k_trace<4>" in r[ik] or "k_trace<0>" in r[ik] or "k_vol" in r[ik] or "k_recursive" in r[ik]:
+                kn = r[ik].replace(", 0>", ">")  # k_trace<KIND, WIDE = false>
+                if "k_trace<3>" in kn or "k_trace<4>" in kn or "k_trace<0>" in kn or "k_anyhit8<1>" in kn or "k_vol" in kn or "k_recursive" in kn:
                     if r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                         per_launch[r[iid]] = per_launch.get(r[iid], 0.0) + float(r[iv].replace(",", ""))
             if per_launch:
@@ -469,7 +470,7 @@ def run_ours(args, wl, name):
                           "frac": (by[k] / (ms[k] * 1e-3) / 1e9 / peak) if ms[k] > 0 else None} for k in range(5)]
             dom = max(range(5), key=lambda k: ms[k])
             achieved, ext_ms, ext_bytes = vp_stages[dom]["achieved"], ms[dom] / max(1, st.vp_rounds), by[dom] / max(1, st.vp_rounds)
-        kernel = {PATH: "k_trace<3|4|0> (closest-hit extension launches, incl. the any-hit rays they carry)",
+        kernel = {PATH: "k_trace<3|0> + k_anyhit8<1> (the extend stage: closest-hit extension launches on the two-child tree and, on a second stream next to them, the previous bounce's any-hit rays on the compressed 8-wide tree)",
                   VOLPATH: (vp_stages[dom]["kernel"] + " (the stage with the largest share of the step; every stage under `stages`)") if vp_stages else "k_volpath",
                   }.get(integ, "k_recursive (Whitted / DirectLighting, one launch per batch)")
         line = {
@@ -489,7 +490,7 @@ def run_ours(args, wl, name):
             "rays_per_path": st.rays / max(1, st.paths),
             "stage_ms": {"raygen": st.ms_raygen, "extend": st.ms_extend, "shade": st.ms_shade, "shadow": st.ms_shadow, "film": st.ms_film,
                          "device_total": st.device_ms,
-                         "note": "rank 0's share; extend = the k_trace<3|4|0> launches: camera rays, then per bounce the extension rays TOGETHER WITH the previous bounce's shadow / environment-MIS rays (one mixed launch); shadow = the any-hit launch after the last bounce and the area-light MIS probes"},
+                         "note": "rank 0's share; extend = camera rays (k_trace<3>), then per bounce the extension rays (k_trace<0>) with the previous bounce's shadow / environment-MIS rays next to them (k_anyhit8<1> on a second stream; scenes without the second accumulator: any-hit rays in the shadow stage); shadow = the any-hit launch after the last bounce and the area-light MIS probes"},
             "roofline": {"bound": "latency+issue (dependent L1/L2 gathers); NOT hbm: see traffic", "bound_contract": "hbm",
                          "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ev["traffic"],

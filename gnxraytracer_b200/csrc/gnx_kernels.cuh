@@ -50,6 +50,14 @@ __global__ void k_reset_counts(int *counts, int outExtend) {
 }
 #endif
 
+// After the reference-order launch over the rays a wide closest-hit launch flagged: their list (extend queue qi) and the
+// cursor that launch fetched through are free again.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
+__global__ void k_retrace_reset(int *counts, int qi) {
+    if (threadIdx.x == 0) { counts[qi] = 0; counts[kCntFetch + 3] = 0; }
+}
+#endif
+
 // Zeroes the shadow / probe counters and the fetch cursors (between a mixed trace launch and the shade stage).
 #ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_reset_ray_counts(int *counts) {
@@ -100,9 +108,18 @@ constexpr int kLeafBatch = GNX_LEAF_BATCH;  // parked lanes that trigger a joint
 #ifndef GNX_TRACE_BLOCKS
 #define GNX_TRACE_BLOCKS 8
 #endif
-template <int KIND>
-__global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int arg,
+//   WIDE (KIND 0 and 3): the closest hit through the compressed 8-wide tree (gnx_bvh8.cuh), front-to-back by octant slots.
+//           A ray whose best hit has a rival within the tie band is not finished here: its slot (KIND 0) or sample index
+//           (KIND 3) goes to the free extend queue `1 - arg` (KIND 3: queue 1), and the caller launches the reference-order
+//           kernel over that list (KIND 0 with arg = the list; KIND 3 with arg = the list instead of -1 = "all samples").
+constexpr int kPendRetrace = -3;
+#ifndef GNX_TRACE8_BLOCKS
+#define GNX_TRACE8_BLOCKS 8
+#endif
+template <int KIND, bool WIDE = false>
+__global__ void __launch_bounds__(kBlock, WIDE ? GNX_TRACE8_BLOCKS : GNX_TRACE_BLOCKS) k_trace(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int arg,
                                                       DevStats *st) {
+    static_assert(!WIDE || KIND == 0 || KIND == 3, "the wide closest-hit traversal serves extension and camera rays");
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
     const uint32_t sb = stack_shared_base(stack);
@@ -113,12 +130,17 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     // KIND 1: arg 0 = shadow A items, 1 = shadow B items, 2 = both halves in one launch (A first)
     // KIND 4: arg = extend queue; shadow items (A then B) follow the nE extension rays in the index space
     const int nShA = (KIND == 1 || kMixed) ? q.counts[kCntShadow] : 0, nShB = (KIND == 1 || kMixed) ? q.counts[kCntShadow + 1] : 0;
-    const int nE = (KIND == 0 || kMixed) ? q.counts[arg] : 0;
-    const int n = KIND == 3 ? rc.npix * rc.batch_spp
+    const int qa = KIND == 0 ? (arg & 1) : arg;  // KIND 0: bit 1 of arg marks the retrace launch of flagged rays
+    const int nE = (KIND == 0 || kMixed) ? q.counts[qa] : 0;
+    const int *primList = (KIND == 3 && !WIDE && arg >= 0) ? q.extend_q[arg] : nullptr;  // retrace of flagged camera rays
+    const int retraceQ = KIND == 3 ? 1 : 1 - (arg & 1);                                         // WIDE: where flagged rays go
+    const int n = KIND == 3 ? (primList ? q.counts[arg] : rc.npix * rc.batch_spp)
                             : (KIND == 0 ? nE : (kMixed ? nE + nShA + nShB
                                                         : (KIND == 1 ? (arg == 0 ? nShA : (arg == 1 ? nShB : nShA + nShB)) : q.counts[kCntProbe])));
-    int *cursor = &q.counts[kCntFetch + (kExtend ? 0 : (KIND == 1 ? (arg == 1 ? 2 : 1) : 3))];
-    const int *inList = (KIND == 0 || kMixed) ? q.extend_q[arg] : nullptr;
+    // (the retrace launches of flagged rays fetch through the probe cursor: the extension cursor has been used by the wide launch)
+    const bool retraceLaunch = !WIDE && ((KIND == 3 && arg >= 0) || (KIND == 0 && (arg & 2)));
+    int *cursor = &q.counts[kCntFetch + (kExtend ? (retraceLaunch ? 3 : 0) : (KIND == 1 ? (arg == 1 ? 2 : 1) : 3))];
+    const int *inList = (KIND == 0 || kMixed) ? q.extend_q[qa] : nullptr;
     const int firstB = kMixed ? nShA : (KIND == 1 ? (arg == 0 ? 0x7fffffff : (arg == 1 ? 0 : nShA)) : 0);  // shadow items from here on are B items
     bool shLane = false;  // KIND 4: the lane's ray is an any-hit ray
     unsigned raysSh = 0;
@@ -126,7 +148,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
     unsigned raysB = 0;
     TraversalCounters cnt{0, 0};
     unsigned rays = 0;
-    Trav t;
+    typename std::conditional<WIDE, Trav8, Trav>::type t;
     int2 spill[kSpillStack];
     t.spill = spill;
     t.cur = kRefNone;
@@ -142,7 +164,10 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             // of escaped rays (atan2f / acosf / bilinear fetch) and the path-state writes of hits run with as
             // many lanes as were idle instead of one lane at a time inside the traversal loop.
             if (needFinish) {
-                if (KIND == 3) pendType = primary_finish(sc, ps, rc, item, hidx, camD, t);
+                bool flagged = false;
+                if constexpr (WIDE) flagged = t.tie;
+                if (flagged) pendType = kPendRetrace;
+                else if (KIND == 3) pendType = primary_finish(sc, ps, rc, item, hidx, camD, t);
                 else pendType = extend_finish(sc, ps, rc, item, t);
                 pendSlot = item;
                 needFinish = false;
@@ -157,6 +182,10 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                 if (q.miss_q) {  // scenes with a SkyBoxLight: escaped rays wait for k_escape
                     int idx = warp_push(&q.counts[kCntMiss], pendType == kPendEscape);
                     if (idx >= 0) q.miss_q[idx] = pendSlot;
+                }
+                if constexpr (WIDE) {      // flagged rays wait for the reference-order launch
+                    int idx = warp_push(&q.counts[retraceQ], pendType == kPendRetrace);
+                    if (idx >= 0) q.extend_q[retraceQ][idx] = pendSlot;
                 }
                 pendType = -1;
             }
@@ -173,12 +202,12 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                     if (i < n) {
                         bool valid = true;
                         if (KIND == 3) {
-                            item = i;
+                            item = primList ? primList[i] : i;
                             int pixel, sample, px, py;
-                            slot_to_sample(rc, i, &pixel, &sample);
+                            slot_to_sample(rc, item, &pixel, &sample);
                             valid = pixel_xy(rc, pixel, &px, &py);
                             if (valid) primary_begin(sc, px, py, sample, &hidx, &camD, t);
-                            else ps.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // pixel of an edge tile outside the image
+                            else ps.L[item] = make_float4(0.f, 0.f, 0.f, 0.f);  // pixel of an edge tile outside the image
                         } else if (kMixed) {
                             shLane = i >= nE;
                             if (shLane) { item = i - nE; shadow_begin(sc, shadowItem(item), t); ++raysSh; if (item >= firstB) ++raysB; }
@@ -187,8 +216,9 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
                         else if (KIND == 1) { item = i; shadow_begin(sc, shadowItem(i), t); if (i >= firstB) ++raysB; }
                         else { item = i; probe_begin(sc, q.probe_q + i, t); }
                         if (valid) {
+                            if constexpr (WIDE) trav8_init(sc, t);
                             active = true;
-                            ++rays;
+                            if (!retraceLaunch) ++rays;  // a retraced ray has been counted by the wide launch
                         }
                     }
                 }
@@ -207,16 +237,22 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
             // Pops requested by the previous round's interior steps and leaves.  Any-hit rays (entries never go stale):
             // predicated at the top of the round, no divergent block (shadow stage -3 %); closest-hit rays measure
             // 1-2 % better with the divergent pop below, whose re-validation loop skips culled entries at once.
-            if (kPopRound) trav_pop_round<KIND == 1>(t, stack, kBlock, sb, active);
+            if constexpr (WIDE) { if (active && trav_needs_pop(t)) trav8_next(sc, t, stack, kBlock, sb); }
+            else if (kPopRound) trav_pop_round<KIND == 1>(t, stack, kBlock, sb, active);
             bool parked = active && trav_is_leaf(t);
-            if (active && !parked && trav_is_interior(t)) { trav_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
+            if (active && !parked && trav_is_interior(t)) {
+                if constexpr (WIDE) trav8_interior<true>(sc, t, stack, kBlock, cnt, sb);
+                else trav_interior(sc, t, stack, kBlock, cnt, sb);
+                parked = trav_is_leaf(t);
+            }
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
             if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0)) {
-                trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
+                if constexpr (WIDE) { trav8_leaf_closest(sc, t, t.cur, cnt); t.cur = kRefPop; }
+                else trav_leaf<KIND == 1>(sc, t, stack, kBlock, cnt);
                 if (kMixed && shLane && t.hit) t.cur = kRefNone;  // any-hit ray in a mixed launch
             }
-            if (!kPopRound && active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb);
+            if constexpr (!WIDE) { if (!kPopRound && active && trav_needs_pop(t)) trav_pop<KIND == 1>(t, stack, kBlock, sb); }
             if (active && trav_done(t)) {
                 if (kExtend && !(kMixed && shLane)) needFinish = true;
                 else if (KIND == 1 || kMixed) shadow_finish(ps, shadowItem(item), t, item >= firstB);
@@ -239,7 +275,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
         for (int o = 16; o > 0; o >>= 1) raysSh += __shfl_down_sync(kFull, raysSh, o);
         if ((threadIdx.x & 31) == 0 && raysSh) atomicAdd(&st->shadow_rays_in_extend_launches, (unsigned long long)raysSh);
     } else flush_stats(st, kExtend ? 0 : 2, cnt.nodes, cnt.tris, rays);
-    if (KIND == 3 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+    if (KIND == 3 && !retraceLaunch && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
 
 // ---- the any-hit kernel over the compressed 8-wide tree (gnx_bvh8.cuh) ---------------------------------------
@@ -247,7 +283,7 @@ __global__ void __launch_bounds__(kBlock, GNX_TRACE_BLOCKS) k_trace(const Device
 // per lane, refill through a warp-aggregated cursor, warp-synchronous rounds), but a round is one 8-wide node per lane:
 // six 16-byte loads feed eight slab tests, the stack holds one entry per node (node, children still to visit), and there
 // is no visiting order to keep.  Leaves wait until kLeafBatch lanes hold one, like in k_trace.
-//   VARIANT 0: both queue halves (A first)
+//   VARIANT 0: both queue halves (A first); VARIANT 1: the same, launched next to an extension launch (booked to that stage)
 #ifndef GNX_ANY8_BLOCKS
 #define GNX_ANY8_BLOCKS 8
 #endif
@@ -299,7 +335,7 @@ __global__ void __launch_bounds__(kBlock, GNX_ANY8_BLOCKS) k_anyhit8(const Devic
         while (true) {
             if (active && trav_needs_pop(t)) trav8_next(sc, t, stack, kBlock, sb);
             bool parked = active && trav_is_leaf(t);
-            if (active && !parked && trav_is_interior(t)) { trav8_interior(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
+            if (active && !parked && trav_is_interior(t)) { trav8_interior<false>(sc, t, stack, kBlock, cnt, sb); parked = trav_is_leaf(t); }
             const unsigned parkedMask = __ballot_sync(kFull, parked);
             const unsigned advMask = __ballot_sync(kFull, active && !parked && !trav_done(t));
             if (parked && (__popc(parkedMask) >= kLeafBatch || advMask == 0))
@@ -314,6 +350,19 @@ __global__ void __launch_bounds__(kBlock, GNX_ANY8_BLOCKS) k_anyhit8(const Devic
     }
     flush_stats(st, 1, cnt.nodes, cnt.tris, rays - raysB);
     flush_stats(st, 2, 0, 0, raysB);
+    if (VARIANT == 1) {  // launched inside the extend stage: its work belongs to that stage's algorithmic bytes
+        unsigned nn = cnt.nodes, nt = cnt.tris;
+        for (int o = 16; o > 0; o >>= 1) {
+            rays += __shfl_down_sync(kFull, rays, o);
+            nn += __shfl_down_sync(kFull, nn, o);
+            nt += __shfl_down_sync(kFull, nt, o);
+        }
+        if (lane == 0 && rays) {
+            atomicAdd(&st->shadow_rays_in_extend_launches, (unsigned long long)rays);
+            atomicAdd(&st->any_nodes_in_extend, (unsigned long long)nn);
+            atomicAdd(&st->any_tris_in_extend, (unsigned long long)nt);
+        }
+    }
 }
 
 // Escaped rays of a scene with a SkyBoxLight (queued by the traversal kernel): L += beta * Le(ray).
@@ -831,6 +880,8 @@ extern template __global__ void k_trace<1>(const DeviceScene, PathState, Queues,
 extern template __global__ void k_trace<2>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_trace<3>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_trace<4>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<0, true>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_trace<3, true>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_shade<2, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
 extern template __global__ void k_shade<2, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
 extern template __global__ void k_shade<8, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
@@ -842,6 +893,7 @@ extern template __global__ void k_recursive<1, true>(const DeviceScene, PathStat
 extern template __global__ void k_recursive<2, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<2, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_anyhit8<0>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_anyhit8<1>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
@@ -854,11 +906,14 @@ extern template __global__ void k_volpath<true>(const DeviceScene, PathState, Qu
 #endif
 #if defined(GNX_TU_TRACE)
 template __global__ void k_anyhit8<0>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_anyhit8<1>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 template __global__ void k_trace<0>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<1>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<2>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<3>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_trace<4>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<0, true>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_trace<3, true>(const DeviceScene, PathState, Queues, RenderConsts, int, DevStats *);
 #endif
 #if defined(GNX_TU_SHADE2)
 template __global__ void k_shade<2, false>(const DeviceScene, PathState, Queues, RenderConsts, int, int);

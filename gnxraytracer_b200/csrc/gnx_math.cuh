@@ -14,8 +14,15 @@
 
 namespace gnx {
 
+#ifdef __CUDACC__
 #define GNX_HD __host__ __device__ __forceinline__
 #define GNX_D __host__ __device__ __forceinline__
+#else
+// host compilers (the scene kit, the CPU emulation under tests/): plain inline — with always_inline everywhere g++ -O2
+// took up to 15 minutes over the emulation's single translation unit
+#define GNX_HD inline
+#define GNX_D inline
+#endif
 // One out-of-line copy for the large switch-over-lobe-kind functions: the shade kernel calls each of them from
 // several places, and fully inlined it grew to 54 K SASS instructions (870 KB) against a 32 KB L1.5 / ~128 KB
 // instruction cache — ncu showed 46 % icache hit rate and stall_no_instruction as the top stall.

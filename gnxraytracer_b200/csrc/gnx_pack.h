@@ -357,7 +357,7 @@ inline bool build_nodes(const gnx_bvh_node *nodes, int n, std::vector<float4> &o
 // Node2 array (64-byte two-child records, gnx_bvh.cuh) -> compressed 8-wide tree (gnx_bvh8.cuh) over the same ordered
 // primitives, for the any-hit queries.  A Node8 starts from the two children of its source node and keeps replacing the
 // internal child of largest surface area by that child's own two children until it holds eight (or only leaves are
-// left); leaves keep their reference.  Child boxes are rounded OUTWARD onto the node's grid (origin = corner of the union,
+// left); leaves keep their reference; the children then take octant slots (front-to-back visiting order by XOR).  Child boxes are rounded OUTWARD onto the node's grid (origin = corner of the union,
 // step = the smallest power of two that spans it in 255 steps), checked in double precision.  Returns false (and leaves
 // `out` empty) for bounds that are not finite: the caller then keeps the two-child tree for every query.
 inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
@@ -385,6 +385,7 @@ inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
         if (src < 0 || src >= count) { out.clear(); return false; }
         Child c[8];
         int n = children2(src, c);
+        if (n == 0) { out.clear(); return false; }
         while (n < 8) {
             int pick = -1;
             double best = -1;
@@ -397,15 +398,50 @@ inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
             c[pick] = g[0];
             if (m > 1) c[n++] = g[1];
         }
-        std::sort(c, c + n, [&](const Child &x, const Child &y) { return area(x) > area(y); });
+        // octant slots (gnx_bvh8.cuh): the child lying furthest towards (+-x, +-y, +-z) of the node's centre takes that
+        // corner's slot, greedily over the 8 x n (child, slot) pairs
+        {
+            double ctr[3], cc[8][3];
+            for (int ax = 0; ax < 3; ++ax) {
+                double lo = c[0].lo[ax], hi = c[0].hi[ax];
+                for (int k = 1; k < n; ++k) { lo = std::min(lo, (double)c[k].lo[ax]); hi = std::max(hi, (double)c[k].hi[ax]); }
+                ctr[ax] = 0.5 * (lo + hi);
+                for (int k = 0; k < n; ++k) cc[k][ax] = 0.5 * ((double)c[k].lo[ax] + (double)c[k].hi[ax]) - ctr[ax];
+            }
+            Child placed[8];
+            bool slotUsed[8] = {}, childUsed[8] = {};
+            int slotOf[8];
+            for (int round = 0; round < n; ++round) {
+                int bc = -1, bs = -1;
+                double best = 0;
+                for (int k = 0; k < n; ++k) {
+                    if (childUsed[k]) continue;
+                    for (int sl = 0; sl < 8; ++sl) {
+                        if (slotUsed[sl]) continue;
+                        const double v = ((sl & 1) ? cc[k][0] : -cc[k][0]) + ((sl & 2) ? cc[k][1] : -cc[k][1]) + ((sl & 4) ? cc[k][2] : -cc[k][2]);
+                        if (bc < 0 || v > best) { best = v; bc = k; bs = sl; }
+                    }
+                }
+                childUsed[bc] = true; slotUsed[bs] = true; slotOf[bc] = bs;
+            }
+            for (int k = 0; k < n; ++k) placed[slotOf[k]] = c[k];
+            for (int sl = 0; sl < 8; ++sl) if (!slotUsed[sl]) { placed[sl] = c[0]; placed[sl].ref = kRefNone; }  // empty slot
+            for (int sl = 0; sl < 8; ++sl) c[sl] = placed[sl];
+        }
         float org[3];
         int ebyte[3];
         uint8_t qlo[3][8], qhi[3][8];
+        bool occ[8];
+        for (int k = 0; k < 8; ++k) occ[k] = c[k].ref != kRefNone;
         for (int ax = 0; ax < 3; ++ax) {
-            float lo = c[0].lo[ax], hi = c[0].hi[ax];
-            for (int k = 0; k < n; ++k) {
+            float lo = 0, hi = 0;
+            bool first = true;
+            for (int k = 0; k < 8; ++k) {
+                if (!occ[k]) continue;
                 if (!std::isfinite(c[k].lo[ax]) || !std::isfinite(c[k].hi[ax]) || c[k].hi[ax] < c[k].lo[ax]) { out.clear(); return false; }
-                lo = std::min(lo, c[k].lo[ax]); hi = std::max(hi, c[k].hi[ax]);
+                lo = first ? c[k].lo[ax] : std::min(lo, c[k].lo[ax]);
+                hi = first ? c[k].hi[ax] : std::max(hi, c[k].hi[ax]);
+                first = false;
             }
             org[ax] = lo;
             const double ext = (double)hi - (double)lo;
@@ -415,7 +451,8 @@ inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
                 if (e > 127) { out.clear(); return false; }
                 const double s = std::ldexp(1.0, e);
                 bool ok = true;
-                for (int k = 0; k < n && ok; ++k) {
+                for (int k = 0; k < 8 && ok; ++k) {
+                    if (!occ[k]) { qlo[ax][k] = 255; qhi[ax][k] = 0; continue; }
                     double ql = std::floor(((double)c[k].lo[ax] - (double)lo) / s), qh = std::ceil(((double)c[k].hi[ax] - (double)lo) / s);
                     while (ql > 0 && (double)lo + ql * s > (double)c[k].lo[ax]) ql -= 1;
                     while ((double)lo + qh * s < (double)c[k].hi[ax]) qh += 1;
@@ -431,7 +468,7 @@ inline bool build_node8(const float4 *n2, int count, std::vector<uint4> &out) {
         unsigned valid = 0;
         for (int k = 0; k < 8; ++k) {
             refs[k] = kRefNone;
-            if (k >= n) { for (int ax = 0; ax < 3; ++ax) { qlo[ax][k] = 255; qhi[ax][k] = 0; } continue; }
+            if (!occ[k]) continue;
             valid |= 1u << k;
             if (c[k].ref < 0) refs[k] = c[k].ref;
             else {

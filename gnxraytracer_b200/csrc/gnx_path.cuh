@@ -214,7 +214,7 @@ GNX_D int extend_slot(const DeviceScene &sc, const PathState &ps, const RenderCo
                       TraversalCounters &cnt) {
     TravLocal t;
     extend_begin(sc, ps, slot, t);
-    while (!trav_step<false>(sc, t, stack, stride, cnt)) {}
+    closest_hit_run(sc, t, stack, stride, cnt);  // the 8-wide tree when the scene routes closest hits there
     int type = extend_finish(sc, ps, rc, slot, t);
     if (type == kPendEscape) { escape_slot(sc, ps, slot); type = -1; }  // sequential callers: at once
     return type;
@@ -472,7 +472,7 @@ GNX_D void shadow_finish(const PathState &ps, const ShadowItem *item, const Trav
 }
 GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowItem *item, int2 *stack, int stride,
                        TraversalCounters &cnt) {
-    if (sc.nodes8) {  // the compressed 8-wide tree answers the any-hit queries (gnx_bvh8.cuh)
+    if (sc.nodes8 && sc.wide_any) {  // the compressed 8-wide tree answers the any-hit queries (gnx_bvh8.cuh)
         Trav8 t8;
         int2 store[kSpillStack];
         t8.spill = store;
@@ -481,7 +481,7 @@ GNX_D void shadow_item(const DeviceScene &sc, const PathState &ps, const ShadowI
         while (!trav_done(t8)) {
             if (trav_needs_pop(t8)) trav8_next(sc, t8, stack, stride);
             else if (trav_is_leaf(t8)) t8.cur = trav_leaf_ref<true>(sc, t8, t8.cur, cnt) ? kRefNone : kRefPop;
-            else trav8_interior(sc, t8, stack, stride, cnt);
+            else trav8_interior<false>(sc, t8, stack, stride, cnt);
         }
         shadow_finish(ps, item, t8);
         return;

@@ -93,7 +93,11 @@ struct gnx_ctx {
     cudaStream_t stream_any = nullptr;  // the any-hit launches of a bounce run here, next to the extension launch on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool anyhit_overlap = true;    // GNX_ANYHIT_OVERLAP=0: any-hit launch on the render stream, after the extension launch
-    int grid_anyhit8 = 148 * 8;
+    int grid_anyhit8 = 148 * 8, grid_trace8 = 148 * 8, grid_trace8p = 148 * 8;
+    bool closest8 = false;         // GNX_CLOSEST_BVH8=1: extension / camera rays through the 8-wide tree too (k_trace<., true> + retrace of
+                                   // flagged rays).  Bit-equal, but measured SLOWER than the two-child tree (C2 extend 16.9 -> 18.3 ms, U1p
+                                   // 81.4 -> 84.8 ms, C3 46.9 -> 52.9 ms): the kernel is bound by instruction issue, and decoding eight
+                                   // quantised boxes costs about as many instructions as the three two-child nodes it replaces
     bool anyhit8 = true;           // GNX_ANYHIT_BVH8=0: any-hit rays walk the two-child tree like the closest-hit rays
     bool merge_extend = true;      // GNX_MERGE_EXTEND=0: the any-hit rays of a bounce get their own launch(es)
     int film_chunk = 0;            // GNX_FILM_CHUNK: samples per pixel staged at a time by the tiled Gaussian gather (0 = auto)
@@ -243,6 +247,8 @@ int gnx_create(gnx_ctx **out, int device) {
         int b = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_anyhit8<0>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_anyhit8 = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<0, true>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace8 = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<3, true>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_trace8p = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<2>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
@@ -264,6 +270,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *me = getenv("GNX_MERGE_EXTEND")) ctx->merge_extend = me[0] != '0';
     if (const char *a8 = getenv("GNX_ANYHIT_BVH8")) ctx->anyhit8 = a8[0] != '0';
     if (const char *a8 = getenv("GNX_ANYHIT_OVERLAP")) ctx->anyhit_overlap = a8[0] != '0';
+    if (const char *c8 = getenv("GNX_CLOSEST_BVH8")) ctx->closest8 = c8[0] == '1';
     if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
@@ -440,7 +447,7 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
 #if GNX_BVH_WIDTH == 2
         // ---- the any-hit tree: the two-child records collapsed into compressed 8-wide nodes (gnx_bvh8.cuh).  A tree built
         // on the device is read back for the collapse (64 bytes per interior node).
-        if (ctx->anyhit8 && nNodes > 0) {
+        if ((ctx->anyhit8 || ctx->closest8) && nNodes > 0) {
             std::vector<uint4> n8;
             if (deviceBuilt) {
                 n2.resize(nodeF4);
@@ -451,6 +458,8 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
                 if ((rc = dupload(ctx, pool, n8.data(), n8.size(), &d8))) return rc;
                 sc.nodes8 = d8;
                 sc.n_nodes8 = (int)(n8.size() / kNode8Words);
+                sc.wide_any = ctx->anyhit8;
+                sc.wide_closest = ctx->closest8;
             }
         }
 #endif
@@ -1094,7 +1103,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         // below polls the queue from the host) and not when the caller turned it off.
         const bool mixed = ctx->merge_extend && psv.La && psv.Lb && !hasNull && sc.n_lights > 0;
         // any-hit rays through the compressed 8-wide tree (both queue halves in one launch: needs the second accumulator)
-        const bool any8 = ctx->anyhit8 && sc.nodes8 != nullptr && ctx->merge_shadow && (psv.Lb || !sc.env.present);
+        const bool close8 = sc.wide_closest && sc.nodes8 != nullptr;
+        const bool any8 = sc.wide_any && sc.nodes8 != nullptr && ctx->merge_shadow && (psv.Lb || !sc.env.present);
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.
         for (int iter = 0;; ++iter) {
@@ -1102,25 +1112,42 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             if (mixed && iter > 0) k_reset_counts_keep_rays<<<1, 32, 0, st>>>(qv.counts, out);
             else k_reset_counts<<<1, 32, 0, st>>>(qv.counts, out);
             tm.begin(ST_EXTEND);
-            if (iter == 0) k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 0, ctx->d_stats);  // ray-gen fused in
-            else if (mixed && any8) {
+            // Closest hits through the compressed 8-wide tree (k_trace<., true>); the rays it flags (two candidates within
+            // the tie band: the reference's answer depends on its visiting order) are traced again in reference order by a
+            // launch over the list the wide launch left in the free extend queue.
+            auto extendRays = [&](int inq) {
+                if (close8) {
+                    k_trace<0, true><<<ctx->grid_trace8, kBlock, 0, st>>>(sc, psv, qv, rcn, inq, ctx->d_stats);
+                    k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, (1 - inq) | 2, ctx->d_stats);
+                    k_retrace_reset<<<1, 32, 0, st>>>(qv.counts, 1 - inq);
+                    launches += 2;
+                } else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, inq, ctx->d_stats);
+            };
+            if (iter == 0) {  // ray-gen fused in
+                if (close8) {
+                    k_trace<3, true><<<ctx->grid_trace8p, kBlock, 0, st>>>(sc, psv, qv, rcn, -1, ctx->d_stats);
+                    k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, 1, ctx->d_stats);
+                    k_retrace_reset<<<1, 32, 0, st>>>(qv.counts, 1);
+                    launches += 2;
+                } else k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, -1, ctx->d_stats);
+            } else if (mixed && any8) {
                 // the any-hit rays of bounce d walk the compressed 8-wide tree in their own kernel, launched on a second
                 // stream behind the extension launch of bounce d+1: its blocks move in as the extension kernel's blocks
                 // drain (both are persistent grids), which fills the tail like the mixed launch did
                 if (ctx->anyhit_overlap) {
                     GNX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-                    k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+                    extendRays(in);
                     GNX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_any, ctx->ev_fork, 0));
-                    k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, ctx->stream_any>>>(sc, psv, qv, rcn, ctx->d_stats);
+                    k_anyhit8<1><<<ctx->grid_anyhit8, kBlock, 0, ctx->stream_any>>>(sc, psv, qv, rcn, ctx->d_stats);
                     GNX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream_any));
                     GNX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
                 } else {
-                    k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
-                    k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
+                    extendRays(in);
+                    k_anyhit8<1><<<ctx->grid_anyhit8, kBlock, 0, st>>>(sc, psv, qv, rcn, ctx->d_stats);
                 }
                 ++launches;
             } else if (mixed) k_trace<4><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
-            else k_trace<0><<<gridTrace, kBlock, 0, st>>>(sc, psv, qv, rcn, in, ctx->d_stats);
+            else extendRays(in);
             tm.end();
             launches += 2;
             ++extendLaunches;
@@ -1204,7 +1231,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         stats->extend_tris = hs.tris[0];
         stats->extend_launches = extendLaunches;
         // (mixed launches trace the previous bounce's any-hit rays as well: their nodes / triangles are in nodes[0] / tris[0])
-        stats->extend_bytes = 32ull * hs.nodes[0] + 48ull * hs.tris[0] + 48ull * (hs.rays[0] + hs.shadow_rays_in_extend_launches);
+        // (likewise the k_anyhit8 launches that run next to an extension launch, inside the extend stage's timers)
+        stats->extend_bytes = 32ull * (hs.nodes[0] + hs.any_nodes_in_extend) + 48ull * (hs.tris[0] + hs.any_tris_in_extend) +
+                              48ull * (hs.rays[0] + hs.shadow_rays_in_extend_launches);
         double acc[ST_COUNT] = {};
         for (size_t i = 0; i * 2 + 1 < ctx->ev_used + 0 && i < ctx->ev_stage.size(); ++i) {
             float t = 0;

@@ -86,6 +86,7 @@ struct DeviceScene {
     int n_nodes2;
     const uint4 *nodes8;          // compressed 8-wide tree over the same ordered primitives, any-hit queries (gnx_bvh8.cuh); null: none
     int n_nodes8;
+    int wide_any, wide_closest;   // which queries go through nodes8 (the rest, and flagged closest-hit rays, walk nodes2)
     const float4 *tris;
     const float *tri_uv;          // [n][6] or null
     const float *tri_n;           // [n][9] or null
@@ -159,6 +160,7 @@ constexpr int kCntExtend0 = 0, kCntExtend1 = 1, kCntShade0 = 2, kCntShadow = kCn
 struct DevStats {  // index 0 = extension rays, 1 = shadow rays, 2 = MIS probe rays
     unsigned long long rays[3], nodes[3], tris[3], paths;
     unsigned long long shadow_rays_in_extend_launches;  // any-hit rays traced by the mixed launches (booked under nodes[0] / tris[0])
+    unsigned long long any_nodes_in_extend, any_tris_in_extend;  // k_anyhit8 launched next to an extension launch: its share of nodes[1] / tris[1]
     unsigned long long track_steps;                     // VolPath: tracking steps taken by k_vp_track
     unsigned long long vp_items[5];                     // VolPath: items per stage (extend, vertex, shadow, MIS, track)
 };

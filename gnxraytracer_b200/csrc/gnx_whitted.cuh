@@ -29,6 +29,8 @@ GNX_D bool w_unoccluded(const DeviceScene &sc, const Surface &s, const WLightSam
     int prim;
     TriHit h;
     ++rcnt.shadow;
+    // any-hit: the compressed 8-wide tree when the scene has one (gnx_bvh8.cuh; the answer does not depend on the visiting order)
+    if (sc.nodes8 && sc.wide_any) return !traverse8_any(sc, origin, d, 1 - kShadowEpsilon, stack, stride, cnt);
     return !traverse<true>(sc, origin, d, 1 - kShadowEpsilon, stack, stride, &prim, &h, cnt);
 }
 

@@ -47,11 +47,15 @@ bool build(const gnx_scene_desc *d, EmulScene &e) {
     if (!build_nodes(g.nodes, g.n_nodes, e.nodes2, &sc.n_nodes2, &e.err)) return false;
     sc.nodes2 = e.nodes2.data();
 #if GNX_BVH_WIDTH == 2
-    // the any-hit tree of the product (gnx_bvh8.cuh); GNX_ANYHIT_BVH8=0 keeps the two-child tree for every query
-    const char *a8 = getenv("GNX_ANYHIT_BVH8");
-    if (!(a8 && a8[0] == '0') && build_node8(e.nodes2.data(), sc.n_nodes2, e.nodes8) && !e.nodes8.empty()) {
+    // the compressed 8-wide tree of the product (gnx_bvh8.cuh); GNX_ANYHIT_BVH8=0 keeps the two-child tree for the
+    // any-hit queries, GNX_CLOSEST_BVH8=1 sends the closest-hit queries through the wide tree as well
+    const char *a8 = getenv("GNX_ANYHIT_BVH8"), *c8 = getenv("GNX_CLOSEST_BVH8");
+    const bool any8 = !(a8 && a8[0] == '0'), close8 = c8 && c8[0] == '1';  // the product's defaults
+    if ((any8 || close8) && build_node8(e.nodes2.data(), sc.n_nodes2, e.nodes8) && !e.nodes8.empty()) {
         sc.nodes8 = e.nodes8.data();
         sc.n_nodes8 = (int)(e.nodes8.size() / kNode8Words);
+        sc.wide_any = any8;
+        sc.wide_closest = close8;
     }
 #endif
     sc.n_nodes = g.n_nodes;
@@ -243,7 +247,7 @@ V3 trace_sample(const EmulScene &e, const gnx_render_params &p, int px, int py, 
     V3 d;
     primary_begin(sc, px, py, sample, &hidx, &d, t);
     ++rays[0];
-    while (!trav_step<false>(sc, t, stack, 1, cnt)) {}
+    closest_hit_run(sc, t, stack, 1, cnt);
     int type = primary_finish(sc, ps, rc, 0, hidx, d, t);
     if (type == kPendEscape) { escape_slot(sc, ps, 0); type = -1; }
     for (int iter = 0; iter < 100000 && type >= 0; ++iter) {

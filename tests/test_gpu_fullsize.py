@@ -78,3 +78,29 @@ def test_config5_primary_hits_at_3840x2160(ref):
     assert agree >= 0.9999, f"primary-hit agreement {agree} over {width * height} pixels"
     assert 0.03 < coverage < 0.5
     rs.close()
+
+
+@pytest.mark.parametrize("scene,arg0,res,spp,depth", [("dragon", 0, 1024, 2, 5), ("ui", 0, 1024, 1, 15)])
+def test_wide_closest_hit_is_bit_equal_at_full_size(scene, arg0, res, spp, depth):
+    """GNX_CLOSEST_BVH8=1 (camera and extension rays through the compressed 8-wide tree, flagged rays traced again in
+    reference order; gnx_bvh8.cuh) against the default (reference-order two-child tree) on the full-size meshes of C2 and
+    U1: every pixel bit-equal.  1024 x 1024 includes the ray through the exact image centre (d = (0, 0, -1)), whose
+    infinite 1 / d once made the wide traversal visit every node."""
+    import os
+    from gnxraytracer_b200.api import Context, RenderParams, SceneKit
+    sk = SceneKit(scene, res, res, spp, arg0, 0, 0)
+    p = RenderParams.make(res, res, spp, max_depth=depth)
+    imgs = []
+    for wide in ("0", "1"):
+        os.environ["GNX_CLOSEST_BVH8"] = wide
+        try:
+            c = Context(0)
+        finally:
+            del os.environ["GNX_CLOSEST_BVH8"]
+        c.upload(sk.desc)
+        img, st = c.render(p)
+        assert st.paths == res * res * spp
+        imgs.append(img)
+        c.close()
+    assert np.array_equal(imgs[0], imgs[1])
+    sk.close()

@@ -193,20 +193,30 @@ def test_gpu_counters_match_the_restated_reference_traversal(ref, ctx):
     res = 128
     rs = ref.scene("dragon", res, res, 4)
     p = RenderParams.make(res, res, 4, max_depth=5)
-    # the counters are compared with every query on the reference-order two-child tree; the product's default sends the
-    # any-hit queries through the compressed 8-wide tree (gnx_bvh8.cuh), which must not change a single pixel
+    # the counters are compared with every query on the reference-order two-child tree.  The product's default sends the
+    # any-hit queries through the compressed 8-wide tree (gnx_bvh8.cuh), GNX_CLOSEST_BVH8=1 the camera and extension rays
+    # as well (rays whose best hit has a rival within the tie band are traced again in reference order): not a pixel changes
+    def ctx_with(**env):
+        os.environ.update(env)
+        try:
+            return Context(0)
+        finally:
+            for k in env:
+                del os.environ[k]
     ctx.upload(rs.desc)
     img8, st8 = ctx.render(p)
-    os.environ["GNX_ANYHIT_BVH8"] = "0"
-    try:
-        ctx2 = Context(0)
-    finally:
-        del os.environ["GNX_ANYHIT_BVH8"]
+    ctxc = ctx_with(GNX_CLOSEST_BVH8="1")
+    ctxc.upload(rs.desc)
+    imgc, stc = ctxc.render(p)
+    ctxc.close()
+    ctx2 = ctx_with(GNX_ANYHIT_BVH8="0", GNX_CLOSEST_BVH8="0")
     ctx2.upload(rs.desc)
     img, st = ctx2.render(p)
     ctx2.close()
-    assert np.array_equal(img8, img)
-    assert int(st8.rays_extend) == int(st.rays_extend) and int(st8.rays_shadow) == int(st.rays_shadow)
+    assert np.array_equal(img8, img) and np.array_equal(imgc, img)
+    assert int(st8.rays_extend) == int(st.rays_extend) == int(stc.rays_extend)
+    assert int(st8.rays_shadow) == int(st.rays_shadow) == int(stc.rays_shadow)
+    assert int(stc.nodes_visited) < int(st.nodes_visited)  # the wide tree fetches fewer node bytes
     ro = _harness.Restate().scene(rs.desc)
     img_r, c = ro.render(p)
     assert rel_mse(img, img_r) <= 1e-5

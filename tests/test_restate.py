@@ -82,7 +82,21 @@ def test_restate_and_emulated_kernels_agree_on_counters(ref, restate, emul):
     r = ref.scene("cornell", 48, 48, 4)
     p = RenderParams.make(48, 48, 4, max_depth=5)
     a, ca = restate.scene(r.desc).render(p)
-    b, sb = emul.scene(r.desc).render(p)
+    # counters of the reference-order traversal: every query on the two-child tree.  The default build sends the any-hit
+    # queries through the compressed 8-wide tree (gnx_bvh8.cuh), GNX_CLOSEST_BVH8=1 the closest-hit queries as well (rays
+    # whose best hit has a rival within the tie band are traced again in reference order): the very same image each time
+    def emul_with(**env):
+        os.environ.update(env)
+        try:
+            return emul.scene(r.desc)
+        finally:
+            for k in env:
+                del os.environ[k]
+    b8, sb8 = emul.scene(r.desc).render(p)
+    bc, sbc = emul_with(GNX_CLOSEST_BVH8="1").render(p)
+    b, sb = emul_with(GNX_ANYHIT_BVH8="0", GNX_CLOSEST_BVH8="0").render(p)
+    assert np.array_equal(b8, b) and np.array_equal(bc, b)
+    assert sb8.rays_extend == sb.rays_extend == sbc.rays_extend and sb8.rays_shadow == sb.rays_shadow == sbc.rays_shadow
     assert rel_mse(b, a) <= 1e-6
     assert ca["rays_extend"] == sb.rays_extend and ca["rays_shadow"] == sb.rays_shadow
     assert ca["tris_tested"] == sb.tris_tested

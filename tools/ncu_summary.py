@@ -15,7 +15,7 @@ for w in ("c2", "u1p", "c4"):
     rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
     launches = collections.OrderedDict()
     for r in rows:
-        launches.setdefault((r["ID"], re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")), {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+        launches.setdefault((r["ID"], re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace(", 0>", ">")), {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
     agg = collections.OrderedDict()
     for (_, name), m in launches.items():
         a = agg.setdefault(name, collections.defaultdict(float))
