@@ -213,6 +213,23 @@ GNX_D bool traverse8_closest(const DeviceScene &sc, V3 o, V3 d, float tMax, int2
     return t.hit;
 }
 
+// Closest hit for the per-lane kernels (Whitted / DirectLighting recursion, VolPath): GNX_PERLANE_CLOSEST8=1 sends them
+// through the wide tree first (same tie rule).
+#ifndef GNX_PERLANE_CLOSEST8
+#define GNX_PERLANE_CLOSEST8 0
+#endif
+GNX_D bool closest_hit(const DeviceScene &sc, V3 o, V3 d, float tMax, int2 *stack, int stride, int *primOut, TriHit *hitOut,
+                       TraversalCounters &cnt) {
+#if GNX_PERLANE_CLOSEST8
+    if (sc.nodes8) {
+        bool tie;
+        const bool found = traverse8_closest(sc, o, d, tMax, stack, stride, primOut, hitOut, &tie, cnt);
+        if (!tie) return found;
+    }
+#endif
+    return traverse<false>(sc, o, d, tMax, stack, stride, primOut, hitOut, cnt);
+}
+
 // Closest hit of the ray `t` has been set up for (trav_init): the 8-wide tree when the scene routes closest-hit queries
 // there, the reference-order two-child tree otherwise and for a flagged ray (sequential callers).
 GNX_D void closest_hit_run(const DeviceScene &sc, TravLocal &t, int2 *stack, int stride, TraversalCounters &cnt) {

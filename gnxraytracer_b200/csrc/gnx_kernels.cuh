@@ -615,7 +615,9 @@ template <int DIRECT, bool TEX>  // DIRECT: 0 Whitted, 1 DirectLighting UniformS
 __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
     int2 *stack = s_stack + threadIdx.x;
-    const int n = rc.npix * rc.batch_spp;
+    // rc.rec_list: only the samples the staged first vertex turned down (k_whitted_vertex), counted by the camera-ray launch
+    const int *list = rc.rec_list ? q.extend_q[rc.rec_list - 1] : nullptr;
+    const int n = list ? q.counts[rc.rec_list - 1] : rc.npix * rc.batch_spp;
     const int lane = threadIdx.x & 31;
     int *cursor = &q.counts[kCntFetch];
     TraversalCounters cnt{0, 0};
@@ -625,8 +627,8 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
         if (lane == 0) base = atomicAdd(cursor, 32);
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
-        const int slot = base + lane;
-        if (slot < n) {
+        if (base + lane < n) {
+            const int slot = list ? list[base + lane] : base + lane;
             int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
             V3 L(0.f);
@@ -639,8 +641,67 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
     flush_stats(st, 0, nodes, tris, rcnt.extend);
     flush_stats(st, 1, 0, 0, rcnt.shadow);
     flush_stats(st, 2, 0, 0, rcnt.mis);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
+    if (!list && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->paths, (unsigned long long)n);
 }
+
+// WhittedIntegrator's first vertex as a stage (gnx_whitted.cuh): over the camera rays' hits of one shade queue.  A vertex
+// without specular lobes gets its emitted light into ps.L and one shadow item per light that can contribute (plane index
+// light * capacity + slot in d_path.w); the others are listed in extend queue 0 for k_recursive.
+template <bool TEX>
+__global__ void __launch_bounds__(kBlock, 4) k_whitted_vertex(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, int type) {
+    const int n = q.counts[kCntShade0 + type];
+    const int *list = q.shade_q + (size_t)type * q.capacity;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {
+        const int i = base + threadIdx.x;
+        int slot = 0;
+        bool staged = false, recurse = false;
+        WhittedVertex<8> v;
+        if (i < n) {
+            slot = list[i];
+            int pixel, sample, px, py;
+            slot_to_sample(rc, slot, &pixel, &sample);
+            pixel_xy(rc, pixel, &px, &py);
+            const float4 hit = ps.hit[slot];
+            V3 Le;
+            staged = whitted_vertex_begin<8, TEX>(sc, px, py, sample, f2i(hit.w), hit.x, hit.y, hit.z, v, &Le);
+            recurse = !staged;
+            if (staged) ps.L[slot] = make_float4(Le.x, Le.y, Le.z, 0.f);
+        }
+        int idx = warp_push(&q.counts[kCntExtend0], recurse);
+        if (idx >= 0) q.extend_q[0][idx] = slot;
+        for (int j = 0; j < sc.n_lights; ++j) {
+            ShadowItem it;
+            const bool have = staged && whitted_vertex_light<8>(sc, v, j, &it);
+            idx = warp_push(&q.counts[kCntShadow], have);
+            if (idx >= 0) {
+                it.d_path.w = i2f(j * q.capacity + slot);
+                q.shadow_q[idx] = it;
+            }
+        }
+    }
+}
+
+// L = Le + lightL, lightL = the visible lights' contributions in light order (WhittedIntegrator.cpp:42-60).  Slots the
+// stage did not handle have zero planes: escaped rays keep their radiance, recursion slots are overwritten afterwards.
+#ifndef GNX_KERNELS_TEMPLATES_ONLY
+__global__ void k_whitted_sum(float4 *L, const float4 *planes, int nLights, int capacity, int n) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+        for (int j = 0; j < nLights; ++j) {
+            const float4 c = planes[(size_t)j * capacity + slot];
+            lx += c.x; ly += c.y; lz += c.z;
+        }
+        float4 v = L[slot];
+        v.x += lx; v.y += ly; v.z += lz;
+        v.w = 0.f;
+        L[slot] = v;
+    }
+}
+__global__ void k_zero_counter(int *counts, int i) {
+    if (threadIdx.x == 0) counts[i] = 0;
+}
+#endif
 
 // colObj += Li(...) over the samples of the pixel, in sample order (core/Integrator.cpp:274-291)
 #ifndef GNX_KERNELS_TEMPLATES_ONLY
@@ -888,6 +949,8 @@ extern template __global__ void k_shade<8, false>(const DeviceScene, PathState, 
 extern template __global__ void k_shade<8, true>(const DeviceScene, PathState, Queues, RenderConsts, int, int);
 extern template __global__ void k_recursive<0, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<0, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+extern template __global__ void k_whitted_vertex<false>(const DeviceScene, PathState, Queues, RenderConsts, int);
+extern template __global__ void k_whitted_vertex<true>(const DeviceScene, PathState, Queues, RenderConsts, int);
 extern template __global__ void k_recursive<1, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<1, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 extern template __global__ void k_recursive<2, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
@@ -926,6 +989,8 @@ template __global__ void k_shade<8, true>(const DeviceScene, PathState, Queues, 
 #if defined(GNX_TU_REC0)
 template __global__ void k_recursive<0, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
 template __global__ void k_recursive<0, true>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);
+template __global__ void k_whitted_vertex<false>(const DeviceScene, PathState, Queues, RenderConsts, int);
+template __global__ void k_whitted_vertex<true>(const DeviceScene, PathState, Queues, RenderConsts, int);
 #endif
 #if defined(GNX_TU_REC1)
 template __global__ void k_recursive<1, false>(const DeviceScene, PathState, Queues, RenderConsts, DevStats *);

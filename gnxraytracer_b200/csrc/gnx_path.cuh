@@ -25,6 +25,7 @@ struct RenderConsts {
     // number tile_dev, tile_dev + tile_n, ... of the skewed row-major tile order; npix is then its LOCAL pixel count
     // (tiles x kTile^2, pixels of edge tiles outside the image included and skipped).  tile_n == 0: the whole image.
     int tile_n, tile_dev, tiles_x, tiles_y;
+    int rec_list;        // k_recursive: 0 = every camera sample of the batch, 1 + q = the samples listed in extend queue q
 };
 constexpr int kTile = 32;
 

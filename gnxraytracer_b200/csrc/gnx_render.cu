@@ -121,6 +121,13 @@ struct gnx_ctx {
     VolWave vw{};                  // VolPath wavefront state (allocated on the first VolPath render)
     int vw_capacity = 0;
     std::vector<void *> vw_allocs;
+    // WhittedIntegrator with its first vertex staged (k_whitted_vertex): one shadow item and one contribution plane per light and path
+    ShadowItem *ww_items = nullptr;
+    float4 *ww_planes = nullptr;
+    size_t ww_slots = 0;           // capacity x lights the two buffers hold
+    std::vector<void *> ww_allocs;
+    bool whitted_staged = true;    // GNX_WHITTED_STAGED=0: every sample through the per-lane recursion (k_recursive<0>)
+    int grid_whitted_vertex = 148 * 4;
     bool vol_megakernel = false;   // GNX_VOLPATH_MEGAKERNEL=1: the per-lane kernel k_volpath instead of the staged wavefront
     int grid_vp_logic = 148 * 4, grid_vp_track = 148 * 8;
     std::vector<void *> wave_allocs;
@@ -253,6 +260,7 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<8>, kShadeBlock, 0) == cudaSuccess && b > 0) ctx->grid_shade8 = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_volpath<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_volpath = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_whitted_vertex<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_whitted_vertex = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_logic = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_track, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_track = ctx->sm_count * b;
     }
@@ -272,6 +280,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *a8 = getenv("GNX_ANYHIT_OVERLAP")) ctx->anyhit_overlap = a8[0] != '0';
     if (const char *c8 = getenv("GNX_CLOSEST_BVH8")) ctx->closest8 = c8[0] == '1';
     if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
+    if (const char *ws = getenv("GNX_WHITTED_STAGED")) ctx->whitted_staged = ws[0] != '0';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
@@ -299,6 +308,7 @@ void gnx_destroy(gnx_ctx *ctx) {
     free_pool(ctx->scene_allocs);
     free_pool(ctx->wave_allocs);
     free_pool(ctx->vw_allocs);
+    free_pool(ctx->ww_allocs);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->rgba) cudaFree(ctx->rgba);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
@@ -820,6 +830,18 @@ static int ensure_volwave(gnx_ctx *ctx, int capacity) {
     return GNX_OK;
 }
 
+static int ensure_whitted(gnx_ctx *ctx, int capacity, int nLights) {
+    const size_t need = (size_t)capacity * (size_t)nLights;
+    if (need <= ctx->ww_slots) return GNX_OK;
+    free_pool(ctx->ww_allocs);
+    ctx->ww_slots = 0;
+    int rc;
+    if ((rc = dupload<ShadowItem>(ctx, ctx->ww_allocs, nullptr, need, &ctx->ww_items))) return rc;
+    if ((rc = dupload<float4>(ctx, ctx->ww_allocs, nullptr, need, &ctx->ww_planes))) return rc;
+    ctx->ww_slots = need;
+    return GNX_OK;
+}
+
 static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
     if (!ctx->has_scene) return fail(ctx, GNX_ERR_NO_SCENE, "no scene uploaded");
     if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->first_sample < 0 || p->max_depth < 0 || p->max_depth > 250)
@@ -917,6 +939,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     // Paths in flight per wavefront batch.  Late bounces carry few rays and every launch has a tail, so
     // the batch is made as large as memory comfortably allows (profiles/README.md: 4 M -> 64 M slots took
     // C2 from 126 ms to 71 ms): up to 64 M slots, and never more than a quarter of the free HBM.
+    // WhittedIntegrator with the first vertex staged: needs per-light buffers, so only with a handful of lights (the reference
+    // UI's scene has 3, the W1 workload 6); a plane index light * capacity + slot must also fit the item's int
+    const bool whittedStaged = p->integrator == GNX_INTEGRATOR_WHITTED && ctx->whitted_staged &&
+                               ctx->sc.n_lights >= 1 && ctx->sc.n_lights <= 8;
     int batch_spp = p->batch_spp;
     if (batch_spp <= 0) {
         size_t freeB = 0, totalB = 0;
@@ -925,7 +951,8 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         const long long want = std::min(slots, (long long)npix * p->spp);
         if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
             // PathState 124 B + queues 180 B, rounded up; the VolPath wavefront keeps 156 B more per path
-            const long long bytesPerSlot = (p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel) ? 480 : 320;
+            long long bytesPerSlot = (p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel) ? 480 : 320;
+            if (whittedStaged) bytesPerSlot += 64ll * ctx->sc.n_lights;  // a shadow item and a contribution per light
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);
             slots = std::max(1ll << 20, std::min(slots, avail));
         }
@@ -937,9 +964,10 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     const bool volWave = p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel;
     const bool tex = ctx->n_textures_host > 0;  // image textures: integrators with a RayDifferential filter them through the MIPMap
     if (volWave && (rc = ensure_volwave(ctx, ctx->capacity))) return rc;
+    if (whittedStaged && (rc = ensure_whitted(ctx, ctx->capacity, ctx->sc.n_lights))) return rc;
 
     // escaped rays of scenes with a SkyBoxLight are queued for k_escape
-    if (ctx->sc.skybox.present && p->integrator == GNX_INTEGRATOR_PATH && !ctx->q.miss_q && ctx->capacity > 0)
+    if (ctx->sc.skybox.present && (p->integrator == GNX_INTEGRATOR_PATH || whittedStaged) && !ctx->q.miss_q && ctx->capacity > 0)
         if ((rc = dupload<int>(ctx, ctx->wave_allocs, nullptr, (size_t)ctx->capacity, &ctx->q.miss_q))) return rc;
     Queues qv = ctx->q;
     if (!ctx->sc.skybox.present) qv.miss_q = nullptr;
@@ -1068,6 +1096,49 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             tm.begin(ST_FILM);
             launches += accumulate(psv, rcn);
             tm.end();
+            continue;
+        }
+        if (whittedStaged) {
+            // camera rays -> first vertices (emitted light + one shadow item per light) -> any-hit -> sum in light order;
+            // the samples whose vertex has specular lobes go through the recursion (gnx_whitted.cuh)
+            const int nL = sc.n_lights, nSlots = rcn.npix * rcn.batch_spp;
+            GNX_CUDA(ctx, cudaMemsetAsync(qv.counts, 0, sizeof(int) * kNumCounters, st));
+            GNX_CUDA(ctx, cudaMemsetAsync(ctx->ww_planes, 0, (size_t)nL * ctx->capacity * sizeof(float4), st));
+            PathState psw = psv;
+            psw.La = psw.Lb = nullptr;
+            Queues qw = qv;
+            qw.shadow_q = ctx->ww_items;
+            tm.begin(ST_EXTEND);
+            k_trace<3><<<gridTrace, kBlock, 0, st>>>(sc, psw, qw, rcn, -1, ctx->d_stats);
+            tm.end();
+            if (qw.miss_q) k_escape<<<gridWide, 256, 0, st>>>(sc, psw, qw);
+            tm.begin(ST_SHADE);
+            for (int t = 0; t < kNumShadeTypes; ++t) {
+                if (!((ctx->shade_type_mask >> t) & 1u)) continue;
+                if (tex) k_whitted_vertex<true><<<ctx->grid_whitted_vertex, kBlock, 0, st>>>(sc, psw, qw, rcn, t);
+                else k_whitted_vertex<false><<<ctx->grid_whitted_vertex, kBlock, 0, st>>>(sc, psw, qw, rcn, t);
+                ++launches;
+            }
+            tm.end();
+            tm.begin(ST_SHADOW);
+            PathState psl = psw;
+            psl.La = ctx->ww_planes;  // shadow_finish: planes[light * capacity + slot] = contribution when nothing is hit
+            if (sc.nodes8 && sc.wide_any) k_anyhit8<0><<<ctx->grid_anyhit8, kBlock, 0, st>>>(sc, psl, qw, rcn, ctx->d_stats);
+            else k_trace<1><<<gridTrace, kBlock, 0, st>>>(sc, psl, qw, rcn, 0, ctx->d_stats);
+            k_whitted_sum<<<gridWide, 256, 0, st>>>(psw.L, ctx->ww_planes, nL, ctx->capacity, nSlots);
+            tm.end();
+            tm.begin(ST_EXTEND);
+            k_zero_counter<<<1, 32, 0, st>>>(qw.counts, kCntFetch);
+            RenderConsts rcl = rcn;
+            rcl.rec_list = 1;  // extend queue 0
+            if (tex) k_recursive<0, true><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psw, qw, rcl, ctx->d_stats);
+            else k_recursive<0, false><<<ctx->grid_recursive, kBlock, 0, st>>>(sc, psw, qw, rcl, ctx->d_stats);
+            tm.end();
+            tm.begin(ST_FILM);
+            launches += accumulate(psw, rcn);
+            tm.end();
+            launches += 8;
+            ++extendLaunches;
             continue;
         }
         if (p->integrator != GNX_INTEGRATOR_PATH) {

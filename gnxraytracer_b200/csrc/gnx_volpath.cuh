@@ -211,7 +211,7 @@ GNX_D float hg_sample_p(V3 wo, V3 *wi, float u0, float u1, float g) {
 struct VHit { int prim; TriHit h; };
 
 GNX_D bool vol_intersect(const DeviceScene &sc, VRay &ray, VHit *hit, int2 *stack, int stride, TraversalCounters &cnt) {
-    bool found = traverse<false>(sc, ray.o, ray.d, ray.tMax, stack, stride, &hit->prim, &hit->h, cnt);
+    bool found = closest_hit(sc, ray.o, ray.d, ray.tMax, stack, stride, &hit->prim, &hit->h, cnt);
     if (found) ray.tMax = hit->h.t;
     return found;
 }

@@ -29,8 +29,8 @@ GNX_D bool w_unoccluded(const DeviceScene &sc, const Surface &s, const WLightSam
     int prim;
     TriHit h;
     ++rcnt.shadow;
-    // any-hit: the compressed 8-wide tree when the scene has one (gnx_bvh8.cuh; the answer does not depend on the visiting order)
-    if (sc.nodes8 && sc.wide_any) return !traverse8_any(sc, origin, d, 1 - kShadowEpsilon, stack, stride, cnt);
+    // (the two-child tree: inside this per-lane kernel the wide tree measured SLOWER — U1w 68 -> 89 ms, W1 23.9 -> 27.1 ms;
+    // the staged first vertex sends its shadow rays through k_anyhit8 instead)
     return !traverse<true>(sc, origin, d, 1 - kShadowEpsilon, stack, stride, &prim, &h, cnt);
 }
 
@@ -77,7 +77,7 @@ GNX_D V3 w_estimate_direct(const DeviceScene &sc, const Surface &s, const Bsdf<M
             int prim;
             TriHit h;
             ++rcnt.mis;
-            bool found = traverse<false>(sc, o, wi, GNX_INF, stack, stride, &prim, &h, cnt);
+            bool found = closest_hit(sc, o, wi, GNX_INF, stack, stride, &prim, &h, cnt);
             V3 Li(0.f);
             if (found) {
                 if (light.type == GNX_LIGHT_AREA_TRI && prim == light.prim) {
@@ -156,7 +156,7 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
                 int prim;
                 TriHit h;
                 ++rcnt.extend;
-                if (!traverse<false>(sc, fr.o, fr.d, GNX_INF, stack, stride, &prim, &h, cnt)) { escaped = true; break; }
+                if (!closest_hit(sc, fr.o, fr.d, GNX_INF, stack, stride, &prim, &h, cnt)) { escaped = true; break; }
                 s = make_surface<TEX>(sc, prim, h.b0, h.b1, h.b2, fr.d);
                 fr.prim = prim; fr.hb0 = h.b0; fr.hb1 = h.b1; fr.hb2 = h.b2;
                 if (s.material >= 0) break;
@@ -275,6 +275,70 @@ GNX_D V3 recursive_li(const DeviceScene &sc, const RenderConsts &rc, int px, int
         }
     }
     return L;
+}
+
+// ---- WhittedIntegrator, first vertex as a wavefront stage ---------------------------------------------------
+// Most camera samples of a Whitted render end at their first vertex: emitted light plus one shadow ray per light
+// (WhittedIntegrator.cpp:36-58); only surfaces with specular lobes recurse (:59-64).  The staged form (gnx_render.cu):
+// k_trace<3> finds the camera rays' hits, k_whitted_vertex runs this function over them, the any-hit kernel answers the
+// shadow rays of ALL lights at once, k_whitted_sum adds the surviving contributions in light order, and the samples this
+// function turns down (specular lobes, surfaces without a material) go through recursive_li as before.
+//
+// Per light j a vertex yields either nothing (contribution zero) or a shadow item whose contribution f * Li * |cos| / pdf
+// the any-hit kernel stores in plane j of the light planes when the light is visible (d_path.w = j * capacity + slot).
+template <int MAXL>
+struct WhittedVertex {
+    Surface s;
+    Bsdf<MAXL> bsdf;
+    uint64_t hidx;
+};
+// The vertex of camera sample (px, py, sample) at hit (prim, b0 b1 b2).  False: the sample needs the recursion.
+template <int MAXL, bool TEX>
+GNX_D bool whitted_vertex_begin(const DeviceScene &sc, int px, int py, int sample, int prim, float b0, float b1, float b2,
+                                WhittedVertex<MAXL> &v, V3 *LeOut) {
+    v.hidx = sampler_index(sc.smp, px, py, (uint64_t)sample);
+    V3 o, d;
+    float tMax;
+    camera_ray(sc, px, py, v.hidx, &o, &d, &tMax);
+    v.s = make_surface<TEX>(sc, prim, b0, b1, b2, d);
+    if (v.s.material < 0) return false;
+    if (TEX) {
+        float u0, u1;
+        sampler_film_dimensions(sc.smp, v.hidx, px, py, &u0, &u1);
+        float l0 = 0, l1 = 0;
+        if (sc.cam.lens_radius > 0) { l0 = halton_sample_dimension(sc.smp, v.hidx, 3); l1 = halton_sample_dimension(sc.smp, v.hidx, 4); }
+        const RayDiff rd = camera_ray_differentials(sc, px, py, u0, u1, l0, l1, o, d);
+        compute_differentials(v.s, rd);
+    }
+    build_bsdf<MAXL, TEX>(sc, sc.materials[v.s.material], v.s, v.bsdf, false);
+    for (int i = 0; i < v.bsdf.n; ++i) if (v.bsdf.lobes[i].type & BSDF_SPECULAR) return false;  // SpecularReflect / Transmit would recurse
+    *LeOut = v.s.light >= 0 ? area_light_L(sc.lights[v.s.light], v.s.n, v.s.wo) : V3(0.f);
+    return true;
+}
+// Light j of that vertex (WhittedIntegrator.cpp:44-57; the j-th Get2D of the sample = dimensions 5 + 2j, 5 + 2j + 1).
+// True: *it is the shadow ray to trace (d_path.w left for the caller's plane index).
+template <int MAXL>
+GNX_D bool whitted_vertex_light(const DeviceScene &sc, const WhittedVertex<MAXL> &v, int j, ShadowItem *it) {
+    const Surface &s = v.s;
+    const float u0 = halton_sample_dimension(sc.smp, v.hidx, 5 + 2 * j), u1 = halton_sample_dimension(sc.smp, v.hidx, 5 + 2 * j + 1);
+    WLightSample ls;
+    w_sample_li(sc, sc.lights[j], s.p, u0, u1, &ls);
+    if (is_black(ls.Li) || ls.pdf == 0) return false;
+    V3 f;
+    float pdfUnused;
+    bsdf_f_pdf(v.bsdf, s.wo, ls.wi, BSDF_ALL, &f, &pdfUnused);
+    if (is_black(f)) return false;
+    // VisibilityTester::Unoccluded (w_unoccluded above): the segment from the offset origin to the offset target
+    V3 origin = offset_ray_origin(s.p, s.pError, s.n, ls.target - s.p);
+    V3 target = ls.target;
+    if (ls.targetN.x != 0 || ls.targetN.y != 0 || ls.targetN.z != 0 || ls.targetErr.x != 0 || ls.targetErr.y != 0 || ls.targetErr.z != 0)
+        target = offset_ray_origin(ls.target, ls.targetErr, ls.targetN, origin - ls.target);
+    const V3 sd = target - origin;
+    const V3 c = div_each(f * ls.Li * absdot(ls.wi, v.bsdf.ns), ls.pdf);
+    it->o_tmax = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
+    it->d_path = make_float4(sd.x, sd.y, sd.z, 0.f);
+    it->contrib = make_float4(c.x, c.y, c.z, 0.f);
+    return true;
 }
 
 }  // namespace gnx

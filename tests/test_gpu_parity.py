@@ -506,3 +506,30 @@ def test_config2_full_size_properties(ctx):
     assert 0.03 < frac < 0.9
     # pixels whose 4 primary rays all miss show the bilinear environment: strictly positive radiance
     sk.close()
+
+
+@pytest.mark.parametrize("scene,args,res,spp", [("ui", (2, 0, 0), 192, 4), ("lights", (31, 4, 2), 160, 4)])
+def test_whitted_staged_first_vertex_is_bit_equal_to_the_recursion(scene, args, res, spp):
+    """WhittedIntegrator with its first vertex as wavefront stages (camera rays -> k_whitted_vertex -> any-hit kernel ->
+    k_whitted_sum, the samples with specular lobes through k_recursive; csrc/gnx_whitted.cuh) against the per-lane recursion
+    over every sample (GNX_WHITTED_STAGED=0): same operations in the same order, so not a bit may differ.  `ui` = the
+    reference UI's scene (no specular surface: every sample staged), `lights` = mirror / glass spheres and six lights."""
+    import os
+    from gnxraytracer_b200.api import INTEGRATOR_WHITTED
+    sk = SceneKit(scene, res, res, spp, *args)
+    p = RenderParams.make(res, res, spp, max_depth=5, integrator=INTEGRATOR_WHITTED)
+    out = []
+    for staged in ("1", "0"):
+        os.environ["GNX_WHITTED_STAGED"] = staged
+        try:
+            c = Context(0)
+        finally:
+            del os.environ["GNX_WHITTED_STAGED"]
+        c.upload(sk.desc)
+        img, st = c.render(p)
+        out.append((img, int(st.paths), int(st.rays_shadow)))
+        c.close()
+    assert out[0][1] == out[1][1] == res * res * spp
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][2] > 0
+    sk.close()
