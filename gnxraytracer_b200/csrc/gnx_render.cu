@@ -121,6 +121,17 @@ struct gnx_ctx {
     VolWave vw{};                  // VolPath wavefront state (allocated on the first VolPath render)
     int vw_capacity = 0;
     std::vector<void *> vw_allocs;
+    // shade queues put back into slot order before shading (k_qs_*): bitmap over the path slots + per-block counts
+    unsigned *qs_bits = nullptr;
+    int *qs_blocks = nullptr;
+    size_t qs_words = 0;
+    std::vector<void *> qs_allocs;
+    bool sort_queues = true;       // GNX_SORT_QUEUES=0: shade in the completion order of the traversal kernel
+    // Sorting pays on dense queues only (kQsMinDensity).  The kernels check that themselves, but in a scene where few camera
+    // rays hit anything even their empty launches cost ~1 %: the previous render call's hit count of the first batch (copied
+    // to pinned memory without a synchronisation) lets the host skip the launches altogether.  Results do not depend on it.
+    int *qs_probe_dev = nullptr;
+    volatile int *qs_probe_host = nullptr;  // [0] hits, [1] slots of that batch; slots 0 = nothing known yet
     // WhittedIntegrator with its first vertex staged (k_whitted_vertex): one shadow item and one contribution plane per light and path
     ShadowItem *ww_items = nullptr;
     float4 *ww_planes = nullptr;
@@ -281,6 +292,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *c8 = getenv("GNX_CLOSEST_BVH8")) ctx->closest8 = c8[0] == '1';
     if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
     if (const char *ws = getenv("GNX_WHITTED_STAGED")) ctx->whitted_staged = ws[0] != '0';
+    if (const char *sq = getenv("GNX_SORT_QUEUES")) ctx->sort_queues = sq[0] != '0';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
@@ -304,11 +316,14 @@ void gnx_destroy(gnx_ctx *ctx) {
     if (ctx->fb_state) cudaFree(ctx->fb_state);
     if (ctx->fb_u8) cudaFree(ctx->fb_u8);
     if (ctx->fb_pinned) cudaFreeHost(ctx->fb_pinned);
+    if (ctx->qs_probe_host) cudaFreeHost((void *)ctx->qs_probe_host);
+    if (ctx->qs_probe_dev) cudaFree(ctx->qs_probe_dev);
     for (cudaEvent_t e : ctx->fb_ev) if (e) cudaEventDestroy(e);
     free_pool(ctx->scene_allocs);
     free_pool(ctx->wave_allocs);
     free_pool(ctx->vw_allocs);
     free_pool(ctx->ww_allocs);
+    free_pool(ctx->qs_allocs);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->rgba) cudaFree(ctx->rgba);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
@@ -735,6 +750,7 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     }
     ctx->sc = sc;
     ctx->has_scene = true;
+    if (ctx->qs_probe_host) ctx->qs_probe_host[1] = 0;  // another scene: its hit density is not known yet
     return GNX_OK;
 }
 
@@ -827,6 +843,23 @@ static int ensure_volwave(gnx_ctx *ctx, int capacity) {
     float4 **arrs[] = {&v.sub_o, &v.sub_d, &v.sub_hit, &v.sub_tr, &v.w0, &v.w1, &v.w2, &v.w3, &v.w4};
     for (float4 **a : arrs) if ((rc = dupload<float4>(ctx, pool, nullptr, n, a))) return rc;
     ctx->vw_capacity = capacity;
+    return GNX_OK;
+}
+
+static int ensure_queue_sort(gnx_ctx *ctx, int capacity) {
+    const size_t words = ((size_t)capacity + 31) / 32;
+    if (words <= ctx->qs_words) return GNX_OK;
+    free_pool(ctx->qs_allocs);
+    ctx->qs_words = 0;
+    int rc;
+    if ((rc = dupload<unsigned>(ctx, ctx->qs_allocs, nullptr, words, &ctx->qs_bits))) return rc;   // zeroed; k_qs_emit leaves it zeroed
+    if ((rc = dupload<int>(ctx, ctx->qs_allocs, nullptr, (words + kQsBlock - 1) / kQsBlock, &ctx->qs_blocks))) return rc;
+    if (!ctx->qs_probe_dev) {
+        GNX_CUDA(ctx, cudaMalloc((void **)&ctx->qs_probe_dev, sizeof(int)));
+        GNX_CUDA(ctx, cudaMallocHost((void **)&ctx->qs_probe_host, 2 * sizeof(int)));
+        ctx->qs_probe_host[0] = ctx->qs_probe_host[1] = 0;
+    }
+    ctx->qs_words = words;
     return GNX_OK;
 }
 
@@ -965,6 +998,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     const bool tex = ctx->n_textures_host > 0;  // image textures: integrators with a RayDifferential filter them through the MIPMap
     if (volWave && (rc = ensure_volwave(ctx, ctx->capacity))) return rc;
     if (whittedStaged && (rc = ensure_whitted(ctx, ctx->capacity, ctx->sc.n_lights))) return rc;
+    if (ctx->sort_queues && p->integrator == GNX_INTEGRATOR_PATH && (rc = ensure_queue_sort(ctx, ctx->capacity))) return rc;
 
     // escaped rays of scenes with a SkyBoxLight are queued for k_escape
     if (ctx->sc.skybox.present && (p->integrator == GNX_INTEGRATOR_PATH || whittedStaged) && !ctx->q.miss_q && ctx->capacity > 0)
@@ -1175,6 +1209,9 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         const bool mixed = ctx->merge_extend && psv.La && psv.Lb && !hasNull && sc.n_lights > 0;
         // any-hit rays through the compressed 8-wide tree (both queue halves in one launch: needs the second accumulator)
         const bool close8 = sc.wide_closest && sc.nodes8 != nullptr;
+        // (decided once per call, from what the previous call saw)
+        const bool sortQueues = ctx->sort_queues && ctx->qs_bits &&
+                                (ctx->qs_probe_host[1] == 0 || (long long)ctx->qs_probe_host[0] * kQsMinDensity >= ctx->qs_probe_host[1]);
         const bool any8 = sc.wide_any && sc.nodes8 != nullptr && ctx->merge_shadow && (psv.Lb || !sc.env.present);
         // bounces 0..maxDepth; surfaces without a material do not count as bounces, so scenes that
         // have them keep iterating until the queue drains.
@@ -1224,7 +1261,26 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             ++extendLaunches;
             if (qv.miss_q) { k_escape<<<gridWide, 256, 0, st>>>(sc, psv, qv); ++launches; }
             if (mixed && iter > 0) { k_reset_ray_counts<<<1, 32, 0, st>>>(qv.counts); ++launches; }
+            if (ctx->sort_queues && iter == 0 && done == 0) {  // for the NEXT call's decision (no synchronisation)
+                k_qs_probe<<<1, 32, 0, st>>>(qv.counts, ctx->qs_probe_dev);
+                GNX_CUDA(ctx, cudaMemcpyAsync((void *)ctx->qs_probe_host, ctx->qs_probe_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+                ctx->qs_probe_host[1] = rcn.npix * rcn.batch_spp;
+            }
             tm.begin(ST_SHADE);
+            if (sortQueues) {
+                // the shade queues back into slot order (the traversal kernel filled them in completion order)
+                const int nSlots = rcn.npix * rcn.batch_spp, nWords = (nSlots + 31) / 32, nBlocks = (nWords + kQsBlock - 1) / kQsBlock;
+                for (int t = 0; t < kNumShadeTypes; ++t) {
+                    if (!((ctx->shade_type_mask >> t) & 1u)) continue;
+                    int *list = qv.shade_q + (size_t)t * qv.capacity;
+                    const int *cnt = qv.counts + kCntShade0 + t;
+                    k_qs_mark<<<gridWide, 256, 0, st>>>(list, cnt, ctx->qs_bits, nSlots);
+                    k_qs_count<<<nBlocks, kQsBlock, 0, st>>>(ctx->qs_bits, nWords, ctx->qs_blocks, cnt, nSlots);
+                    k_qs_scan<<<1, 1024, 0, st>>>(ctx->qs_blocks, nBlocks, cnt, nSlots);
+                    k_qs_emit<<<nBlocks, kQsBlock, 0, st>>>(ctx->qs_bits, nWords, ctx->qs_blocks, list, cnt, nSlots);
+                    launches += 4;
+                }
+            }
             for (int t = 0; t < kNumShadeTypes - 1; ++t) {
                 if (!((ctx->shade_type_mask >> t) & 1u)) continue;
                 if (ctx->has_next_lights) {  // point / spot / distant / skybox records: the variant with every Light::Sample_Li
