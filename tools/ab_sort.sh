@@ -4,7 +4,7 @@ set -u
 O=gpurun_out
 mkdir -p $O
 Q="--no-cpu-baseline --no-bridge --no-strong-record"
-for w in c2 c3 u1p; do
+for w in c4 u1w w1; do
   for s in 1 0; do
     GNX_SORT_QUEUES=$s python bench.py --workload $w --steps 5 --warmup 3 $Q > $O/r2s_${w}_s$s.json 2>> $O/r2s.err
     python - $O/r2s_${w}_s$s.json "$w sorted=$s" <<'PY'
