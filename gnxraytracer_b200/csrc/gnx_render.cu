@@ -837,11 +837,9 @@ static int ensure_volwave(gnx_ctx *ctx, int capacity) {
     std::vector<void *> &pool = ctx->vw_allocs;
     const size_t n = (size_t)capacity;
     int rc;
-    VolWave &v = ctx->vw;
-    if ((rc = dupload<uint2>(ctx, pool, nullptr, n, &v.rng))) return rc;
-    if ((rc = dupload<float>(ctx, pool, nullptr, n, &v.tmi))) return rc;
-    float4 **arrs[] = {&v.sub_o, &v.sub_d, &v.sub_hit, &v.sub_tr, &v.w0, &v.w1, &v.w2, &v.w3, &v.w4};
-    for (float4 **a : arrs) if ((rc = dupload<float4>(ctx, pool, nullptr, n, a))) return rc;
+    char *records = nullptr;  // one 160-byte record per path (gnx_volwave.cuh)
+    if ((rc = dupload<char>(ctx, pool, nullptr, n * kVolRecordBytes, &records))) return rc;
+    ctx->vw.bind(records);
     ctx->vw_capacity = capacity;
     return GNX_OK;
 }

@@ -20,18 +20,40 @@
 
 namespace gnx {
 
+// One field of the per-path walk record.  On the device the eleven fields of a path share ONE 160-byte record (five full
+// 32-byte sectors): the phase queues name path slots in no particular order, so with one array per field every access of
+// a lane touched its own half-used sector (ncu: the vertex kernel moved 2.2 x its algorithmic bytes through DRAM).  A
+// plain pointer converts to a field with the element's own stride (host emulation: one record at a time).
+template <class T>
+struct VolField {
+    char *base;
+    int stride;
+    VolField() = default;
+    GNX_HD VolField(T *p) : base((char *)p), stride((int)sizeof(T)) {}
+    GNX_HD VolField(void *recordBase, int offset, int recordBytes) : base((char *)recordBase + offset), stride(recordBytes) {}
+    GNX_HD T &operator[](size_t slot) const { return *(T *)(base + slot * (size_t)stride); }
+    GNX_HD VolField &operator-=(long n) { base -= n * (long)stride; return *this; }
+};
+constexpr int kVolRecordBytes = 160;
 struct VolWave {        // per path slot, next to PathState
-    uint2 *rng;         // PCG32 state (lo, hi); Halton: x = dimension counter (index in PathState::hidx)
-    float *tmi;         // medium sample on the current path segment: t of the interaction (ray parametrisation), -1 none
-    float4 *sub_o;      // walk (shadow / MIS) ray: origin, tMax
-    float4 *sub_d;      //   direction, bits(medium)
-    float4 *sub_hit;    //   hit of its current segment: b0 b1 b2 bits(prim), prim -1 = none
-    float4 *sub_tr;     //   transmittance so far xyz, bits(light number)
-    float4 *w0;         // shadow walk: f xyz, MIS weight      MIS walk: f xyz, MIS weight
-    float4 *w1;         // shadow walk: Li xyz, light pdf      MIS walk: Ld of the light-sampling half xyz, scattering pdf
-    float4 *w2;         // shadow walk: target point xyz       both: w = pdf of the light choice
-    float4 *w3;         // shadow walk: target normal xyz, uScattering.x
-    float4 *w4;         // shadow walk: target error xyz, uScattering.y
+    VolField<uint2> rng;       // PCG32 state (lo, hi); Halton: x = dimension counter (index in PathState::hidx)
+    VolField<float> tmi;       // medium sample on the current path segment: t of the interaction (ray parametrisation), -1 none
+    VolField<float4> sub_o;    // walk (shadow / MIS) ray: origin, tMax
+    VolField<float4> sub_d;    //   direction, bits(medium)
+    VolField<float4> sub_hit;  //   hit of its current segment: b0 b1 b2 bits(prim), prim -1 = none
+    VolField<float4> sub_tr;   //   transmittance so far xyz, bits(light number)
+    VolField<float4> w0;       // shadow walk: f xyz, MIS weight      MIS walk: f xyz, MIS weight
+    VolField<float4> w1;       // shadow walk: Li xyz, light pdf      MIS walk: Ld of the light-sampling half xyz, scattering pdf
+    VolField<float4> w2;       // shadow walk: target point xyz       both: w = pdf of the light choice
+    VolField<float4> w3;       // shadow walk: target normal xyz, uScattering.x
+    VolField<float4> w4;       // shadow walk: target error xyz, uScattering.y
+    // device layout: sub_o 0, sub_d 16, sub_hit 32, sub_tr 48, w0 64, w1 80, w2 96, w3 112, w4 128, rng 144, tmi 152
+    void bind(void *records) {
+        VolField<float4> *f4[] = {&sub_o, &sub_d, &sub_hit, &sub_tr, &w0, &w1, &w2, &w3, &w4};
+        for (int k = 0; k < 9; ++k) *f4[k] = VolField<float4>(records, 16 * k, kVolRecordBytes);
+        rng = VolField<uint2>(records, 144, kVolRecordBytes);
+        tmi = VolField<float>(records, 152, kVolRecordBytes);
+    }
 };
 
 // Phases of a path, and which logic kernel owns them.  A path that reaches a phase of ANOTHER kernel is stored and
