@@ -806,8 +806,8 @@ __global__ void k_accumulate(PathState ps, float4 *accum, RenderConsts rc) {
 }
 #endif
 
-// Gaussian film, step 1 (per path slot): the sample's radiance summed into L.xyz and its film offset written into the
-// slot's ray-origin record, which is dead once the bounce loop has ended.
+// Gaussian film, step 1 (per path slot): the sample's radiance summed into L.xyz and its film offset written into
+// ps.film_off (dense in slot order).
 #ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts rc) {
     const int n = rc.npix * rc.batch_spp;
@@ -816,13 +816,13 @@ __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts 
         slot_to_sample(rc, slot, &pixel, &sample);
         float u0, u1;
         film_sample_offset(sc, rc.width, pixel % rc.width, pixel / rc.width, sample, &u0, &u1);  // (no tile partition with the Gaussian film)
-        ps.ray_o[slot] = make_float4(u0, u1, 0.f, 0.f);
         float4 L = ps.L[slot];
         if (L.w != 0.f) {
             if (ps.La) { const float4 La = ps.La[slot]; L.x += La.x; L.y += La.y; L.z += La.z; }
             if (ps.Lb) { const float4 Lb = ps.Lb[slot]; L.x += Lb.x; L.y += Lb.y; L.z += Lb.z; }
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
+        ps.film_off[slot] = make_float4(u0, u1, 0.f, 0.f);  // (shares Lb's storage: written after Lb has been folded in)
     }
 }
 #endif
@@ -831,7 +831,7 @@ __global__ void k_film_prepare(const DeviceScene sc, PathState ps, RenderConsts 
 #ifndef GNX_KERNELS_TEMPLATES_ONLY
 __global__ void k_accumulate_gauss(PathState ps, float4 *accum, RenderConsts rc, FilmFilter f) {
     for (int pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < rc.npix; pixel += gridDim.x * blockDim.x) {
-        const float4 g = gaussian_gather(ps.L, ps.ray_o, rc, f, pixel % rc.width, pixel / rc.width);
+        const float4 g = gaussian_gather(ps.L, ps.film_off, rc, f, pixel % rc.width, pixel / rc.width);
         float4 a = accum[pixel];
         a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
         accum[pixel] = a;
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(kFilmTW * kFilmTH) k_accumulate_gauss_tiled(Pa
                 if (in) {
                     const size_t slot = ((size_t)sy * rc.width + sx) * rc.batch_spp + s0 + s;
                     l = ps.L[slot];
-                    o = ps.ray_o[slot];
+                    o = ps.film_off[slot];
                 }
                 sLx[idx] = l.x; sLy[idx] = l.y; sLz[idx] = l.z;
                 const float pdx = ((float)sx + o.x) - 0.5f, pdy = ((float)sy + o.y) - 0.5f;

@@ -796,16 +796,13 @@ static int ensure_wavefront(gnx_ctx *ctx, int capacity, int npix, int npixFrame)
         std::vector<void *> &pool = ctx->wave_allocs;
         int rc;
         size_t n = (size_t)capacity;
-        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.ray_o))) return rc;
-        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.ray_d))) return rc;
-        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.beta))) return rc;
+        char *records = nullptr;  // one 96-byte record per path slot (gnx_scene.cuh), the accumulators as arrays next to it
+        if ((rc = dupload<char>(ctx, pool, nullptr, n * kPathRecordBytes, &records))) return rc;
+        ctx->ps.bind(records);
         if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.L))) return rc;
-        if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.hit))) return rc;
-        if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.hidx))) return rc;
-        if ((rc = dupload<uint32_t>(ctx, pool, nullptr, n, &ctx->ps.meta))) return rc;
-        if ((rc = dupload<int32_t>(ctx, pool, nullptr, n, &ctx->ps.medium))) return rc;
         if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.Lb))) return rc;
         if ((rc = dupload<float4>(ctx, pool, nullptr, n, &ctx->ps.La))) return rc;
+        ctx->ps.film_off = ctx->ps.Lb;  // dead by the time the film kernels run (k_film_prepare folds Lb into L first)
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[0]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n, &ctx->q.extend_q[1]))) return rc;
         if ((rc = dupload<int>(ctx, pool, nullptr, n * kNumShadeTypes, &ctx->q.shade_q))) return rc;
@@ -981,7 +978,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
         // (cudaMemGetInfo costs ~0.5 ms: only asked when the buffers of an earlier call do not already cover the batch)
         const long long want = std::min(slots, (long long)npix * p->spp);
         if ((long long)ctx->capacity < want && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            // PathState 124 B + queues 180 B, rounded up; the VolPath wavefront keeps 156 B more per path
+            // path record 96 B + accumulators 48 B + queues 180 B, rounded up; the VolPath wavefront keeps 160 B more per path
             long long bytesPerSlot = (p->integrator == GNX_INTEGRATOR_VOLPATH && !ctx->vol_megakernel) ? 480 : 320;
             if (whittedStaged) bytesPerSlot += 64ll * ctx->sc.n_lights;  // a shadow item and a contribution per light
             long long avail = (long long)((freeB + (size_t)ctx->capacity * bytesPerSlot) / 4 / bytesPerSlot);

@@ -111,21 +111,48 @@ struct DeviceScene {
     DevSampler smp;
 };
 
-// ---- wavefront state: structure of arrays over the path slots of one batch ------------------------
+// ---- wavefront state over the path slots of one batch ------------------------------------------------------------
+// One field of a per-slot record.  The queues name path slots in no particular order, so with one array per field every
+// access of a lane touches its own half-used 32-byte sector (a float4) or an eighth-used one (a 4-byte field); with the
+// fields of a slot side by side the sectors a kernel fetches are used in full.  A plain pointer converts to a field with
+// the element's own stride (the host emulation works on one record at a time).
+template <class T>
+struct SlotField {
+    char *base;
+    int stride;
+    SlotField() = default;
+    GNX_HD SlotField(T *p) : base((char *)p), stride((int)sizeof(T)) {}
+    GNX_HD SlotField(void *recordBase, int offset, int recordBytes) : base((char *)recordBase + offset), stride(recordBytes) {}
+    GNX_HD T &operator[](size_t slot) const { return *(T *)(base + slot * (size_t)stride); }
+    GNX_HD SlotField &operator-=(long n) { base -= n * (long)stride; return *this; }
+};
+// Device layout of a path record (96 bytes = three sectors): ray_o 0, ray_d 16, beta 32, hit 48, hidx 64, meta 68,
+// medium 72.  The radiance accumulators stay arrays of their own: the film kernels read them densely, in slot order.
+constexpr int kPathRecordBytes = 96;
 struct PathState {
-    float4 *ray_o;     // xyz origin, w = tMax
-    float4 *ray_d;     // xyz direction, w = etaScale
-    float4 *beta;      // xyz throughput, w unused
+    SlotField<float4> ray_o;   // xyz origin, w = tMax
+    SlotField<float4> ray_d;   // xyz direction, w = etaScale
+    SlotField<float4> beta;    // xyz throughput, w unused
     float4 *L;         // xyz radiance accumulated by this path; w != 0: Lb[slot] is live as well
-    float4 *hit;       // b0 b1 b2 bits(prim) written by extend
-    uint32_t *hidx;    // Halton sample index (low 32 bits; the reference's int64 never exceeds 2^32 at the configs)
-    uint32_t *meta;    // dimension (16 bits) | bounces (8) | flags (8)
-    int32_t *medium;   // current ray medium (VolPath), -1 none
+    SlotField<float4> hit;     // b0 b1 b2 bits(prim) written by extend
+    SlotField<uint32_t> hidx;  // Halton sample index (low 32 bits; the reference's int64 never exceeds 2^32 at the configs)
+    SlotField<uint32_t> meta;  // dimension (16 bits) | bounces (8) | flags (8)
+    SlotField<int32_t> medium; // current ray medium (VolPath), -1 none
     float4 *Lb;        // contributions of the environment-MIS (shadow B) rays, kept apart from L so that the shadow A
                        // and shadow B rays of a path can be traced in the same launch without racing on one float4
                        // (null: they go to L, sequential callers)
     float4 *La;        // likewise for the shadow (A) rays, needed when they share a launch with the next bounce's
                        // extension rays, whose escape adds the environment radiance to L (null: they go to L)
+    float4 *film_off;  // Gaussian film: the samples' film offsets, dense in slot order (k_film_prepare)
+    void bind(void *records) {
+        ray_o = SlotField<float4>(records, 0, kPathRecordBytes);
+        ray_d = SlotField<float4>(records, 16, kPathRecordBytes);
+        beta = SlotField<float4>(records, 32, kPathRecordBytes);
+        hit = SlotField<float4>(records, 48, kPathRecordBytes);
+        hidx = SlotField<uint32_t>(records, 64, kPathRecordBytes);
+        meta = SlotField<uint32_t>(records, 68, kPathRecordBytes);
+        medium = SlotField<int32_t>(records, 72, kPathRecordBytes);
+    }
 };
 constexpr uint32_t kFlagSpecular = 1u;
 constexpr uint32_t kFlagCameraDiff = 2u;  // VolPath: the path segment is still the camera's RayDifferential
