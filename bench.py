@@ -470,9 +470,17 @@ def run_ours(args, wl, name):
                           "frac": (by[k] / (ms[k] * 1e-3) / 1e9 / peak) if ms[k] > 0 else None} for k in range(5)]
             dom = max(range(5), key=lambda k: ms[k])
             achieved, ext_ms, ext_bytes = vp_stages[dom]["achieved"], ms[dom] / max(1, st.vp_rounds), by[dom] / max(1, st.vp_rounds)
+        whitted_any = None
+        if integ == WHITTED and st.ms_shadow > st.ms_extend:
+            # staged first vertex (csrc/gnx_whitted.cuh): the any-hit launch over the vertices' shadow items is the largest stage
+            any_bytes = 32.0 * (st.nodes_visited - st.extend_nodes) + 48.0 * (st.tris_tested - st.extend_tris) + 48.0 * (st.rays_shadow + st.rays_mis)
+            ext_ms, ext_bytes = st.ms_shadow, any_bytes
+            achieved = (any_bytes / (st.ms_shadow * 1e-3)) / 1e9
+            whitted_any = "k_anyhit8<0> (+ k_whitted_sum): the shadow rays of the staged first vertices, one per light and vertex, on the compressed 8-wide tree (the step's largest stage)"
         kernel = {PATH: "k_trace<3|0> + k_anyhit8<1> (the extend stage: closest-hit extension launches on the two-child tree and, on a second stream next to them, the previous bounce's any-hit rays on the compressed 8-wide tree)",
                   VOLPATH: (vp_stages[dom]["kernel"] + " (the stage with the largest share of the step; every stage under `stages`)") if vp_stages else "k_volpath",
-                  }.get(integ, "k_recursive (Whitted / DirectLighting, one launch per batch)")
+                  WHITTED: whitted_any or "k_trace<3> + k_recursive<0> (camera rays, then the per-lane recursion over the samples whose first vertex has specular lobes; the other first vertices are staged: k_whitted_vertex -> k_anyhit8 -> k_whitted_sum)",
+                  }.get(integ, "k_recursive (DirectLighting, one launch per batch)")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
