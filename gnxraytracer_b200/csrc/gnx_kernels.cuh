@@ -571,7 +571,10 @@ __global__ void k_vp_reset(int *counts, int consumed) {
 #ifndef GNX_VP_LOGIC_BLOCKS
 #define GNX_VP_LOGIC_BLOCKS 4  // measured on C4: 4 blocks (128 registers) 148 ms, 6: 158 ms, 8: 177 ms — the spills cost more than the warps hide
 #endif
-template <int KERNEL, bool TEX = false>
+// MAXL: lobe capacity of the BSDFs the kernel builds — 8 with a DisneyMaterial in the scene, 2 otherwise (like k_shade<2 | 8>).
+// The per-thread frame (Surface, Bsdf, walk state) lives in local memory; across all resident threads it is larger than
+// L2, so its size is DRAM traffic: the vertex kernel of C4 takes 54.8 ms with MAXL 8 and 49.8 ms with MAXL 2.
+template <int KERNEL, bool TEX = false, int MAXL = GNX_VOL_MAXL>
 __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const DeviceScene sc, PathState ps, VolWave vw, Queues q, RenderConsts rc, int queue,
                                                         DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(kBlock, GNX_VP_LOGIC_BLOCKS) k_vp_logic(const 
         int slot = 0, y = VY_DONE;
         if (i < n) {
             slot = list ? list[i] : i;
-            y = vol_advance<GNX_VOL_MAXL, TEX>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
+            y = vol_advance<MAXL, TEX>(sc, rc, ps, vw, slot, entry, KERNEL, stack, kBlock, cnt, vc);
         }
         __syncwarp();
         int idx = warp_push(&q.counts[kCntExtend0], y == VY_TRACK_MAIN || y == VY_TRACK_SUB);
@@ -1046,6 +1049,10 @@ extern template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, 
 extern template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_MIS, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_VERTEX, false, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_VERTEX, true, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_MIS, false, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+extern template __global__ void k_vp_logic<VK_MIS, true, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_EXTEND, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_EXTEND, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 extern template __global__ void k_vp_logic<VK_SHADOW, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
@@ -1088,6 +1095,14 @@ template __global__ void k_recursive<2, true>(const DeviceScene, PathState, Queu
 #if defined(GNX_TU_VOL1)
 template __global__ void k_vp_logic<VK_VERTEX, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 template __global__ void k_vp_logic<VK_VERTEX, true>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+#endif
+#if defined(GNX_TU_VOL4)
+template __global__ void k_vp_logic<VK_VERTEX, false, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_VERTEX, true, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+#endif
+#if defined(GNX_TU_VOL5)
+template __global__ void k_vp_logic<VK_MIS, false, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
+template __global__ void k_vp_logic<VK_MIS, true, 2>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);
 #endif
 #if defined(GNX_TU_VOL2)
 template __global__ void k_vp_logic<VK_MIS, false>(const DeviceScene, PathState, VolWave, Queues, RenderConsts, int, DevStats *);

@@ -84,6 +84,13 @@ struct gnx_ctx {
     int sm_count = 148;
     void *geom_base = nullptr;
     size_t geom_bytes = 0;
+    // GNX_L2_ENV=1: the environment light's tables (texels, Distribution2D, guides: one slab) get a persisting L2 window —
+    // every shaded vertex samples them at a random row, while the path state streams through L2 in between
+    int l2_env = 0;
+    void *env_base = nullptr;
+    long long l2_persist_max = -1, l2_window_max = 0;
+    size_t l2_set_aside = 0;
+    size_t env_bytes = 0;
     int l2_persist = 0;  // measured on B200/C2: 52.1 ms with the window vs 46.1 ms without (set-aside starves the rest)
     int grid_trace = 148 * 8, grid_shade = 148 * 4, grid_shade8 = 148 * 4, grid_volpath = 148 * 2, grid_recursive = 148 * 2;  // SM count x resident blocks (occupancy query at create)
     // scene
@@ -141,6 +148,7 @@ struct gnx_ctx {
     int grid_whitted_vertex = 148 * 4;
     bool vol_megakernel = false;   // GNX_VOLPATH_MEGAKERNEL=1: the per-lane kernel k_volpath instead of the staged wavefront
     int grid_vp_logic = 148 * 4, grid_vp_track = 148 * 8;
+    int grid_vp_kernel[4] = {148 * 4, 148 * 4, 148 * 4, 148 * 4};  // per logic kernel (VolKernel): each is sized from its own occupancy
     std::vector<void *> wave_allocs;
     float4 *accum = nullptr, *rgba = nullptr;
     int film_pixels = 0;
@@ -273,6 +281,11 @@ int gnx_create(gnx_ctx **out, int device) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_recursive<0, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_recursive = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_whitted_vertex<false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_whitted_vertex = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_logic = ctx->sm_count * b;
+        for (int k = 0; k < 4; ++k) ctx->grid_vp_kernel[k] = ctx->grid_vp_logic;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_EXTEND, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_kernel[VK_EXTEND] = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_VERTEX, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_kernel[VK_VERTEX] = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_SHADOW, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_kernel[VK_SHADOW] = ctx->sm_count * b;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_logic<VK_MIS, false>, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_kernel[VK_MIS] = ctx->sm_count * b;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_vp_track, kBlock, 0) == cudaSuccess && b > 0) ctx->grid_vp_track = ctx->sm_count * b;
     }
     // the tiled Gaussian-film gather stages up to 72 KB per block (above the 48 KB a kernel gets without asking)
@@ -283,6 +296,7 @@ int gnx_create(gnx_ctx **out, int device) {
     cudaFuncSetAttribute(k_accumulate_gauss_tiled<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     cudaGetLastError();
     if (const char *l2 = getenv("GNX_L2_PERSIST")) ctx->l2_persist = l2[0] != '0';
+    if (const char *l2 = getenv("GNX_L2_ENV")) ctx->l2_env = l2[0] != '0';
     if (const char *ms = getenv("GNX_MERGE_SHADOW")) ctx->merge_shadow = ms[0] != '0';
     if (const char *fs = getenv("GNX_FILM_SIMPLE")) ctx->film_simple = fs[0] == '1';
     if (const char *fc = getenv("GNX_FILM_CHUNK")) ctx->film_chunk = atoi(fc);
@@ -398,6 +412,8 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
     if (d_in->abi_version != GNX_ABI_VERSION) return fail(ctx, GNX_ERR_INVALID, "abi_version mismatch");
     GNX_CUDA(ctx, cudaSetDevice(ctx->device));
     free_pool(ctx->scene_allocs);
+    ctx->env_base = nullptr;
+    ctx->env_bytes = 0;
     ctx->has_scene = false;
     ctx->spatial_built = false;
     ctx->has_next_lights = false;
@@ -609,33 +625,51 @@ static int upload_one(gnx_ctx *ctx, const gnx_scene_desc *d_in) {
         DevEnv &de = sc.env;
         de.present = 1; de.light_index = e.light_index;
         de.w = e.width; de.h = e.height; de.dw = e.dist_w; de.dh = e.dist_h;
-        {
-            std::vector<float4> tex;
-            pack_env_texels(e.texels, (size_t)e.width * e.height, tex);
-            float4 *d4;
-            if ((rc = dupload(ctx, pool, tex.data(), tex.size(), &d4))) return rc; de.texels = d4;
-        }
-        if ((rc = dupload(ctx, pool, e.cond_func, (size_t)e.dist_w * e.dist_h, &df))) return rc; de.cond_func = df;
-        if ((rc = dupload(ctx, pool, e.cond_cdf, (size_t)(e.dist_w + 1) * e.dist_h, &df))) return rc; de.cond_cdf = df;
-        if ((rc = dupload(ctx, pool, e.cond_int, (size_t)e.dist_h, &df))) return rc; de.cond_int = df;
-        if ((rc = dupload(ctx, pool, e.marg_func, (size_t)e.dist_h, &df))) return rc; de.marg_func = df;
-        if ((rc = dupload(ctx, pool, e.marg_cdf, (size_t)e.dist_h + 1, &df))) return rc; de.marg_cdf = df;
+        // all of the light's tables in ONE allocation (a single L2 access-policy window can cover them, set_l2_window)
+        std::vector<float4> tex;
+        pack_env_texels(e.texels, (size_t)e.width * e.height, tex);
         de.marg_int = e.marg_int;
         de.cond_guide = de.marg_guide = nullptr;
         de.cond_g = de.marg_g = 0;
+        std::vector<uint16_t> cg, mg;
         if (e.dist_w < 65536 && e.dist_h < 65536 && !getenv("GNX_NO_CDF_GUIDE")) {
             // guide tables for the two inverse-cdf searches of InfiniteAreaLight::Sample_Li (same results, ~half the
             // dependent loads)
             de.cond_g = guide_buckets(e.dist_w);
             de.marg_g = guide_buckets(e.dist_h);
-            std::vector<uint16_t> cg((size_t)e.dist_h * (de.cond_g + 1)), mg((size_t)de.marg_g + 1);
+            cg.resize((size_t)e.dist_h * (de.cond_g + 1));
+            mg.resize((size_t)de.marg_g + 1);
             for (int v = 0; v < e.dist_h; ++v)
                 make_cdf_guide(e.cond_cdf + (size_t)v * (e.dist_w + 1), e.dist_w + 1, de.cond_g, cg.data() + (size_t)v * (de.cond_g + 1));
             make_cdf_guide(e.marg_cdf, e.dist_h + 1, de.marg_g, mg.data());
-            uint16_t *du;
-            if ((rc = dupload(ctx, pool, cg.data(), cg.size(), &du))) return rc; de.cond_guide = du;
-            if ((rc = dupload(ctx, pool, mg.data(), mg.size(), &du))) return rc; de.marg_guide = du;
         }
+        struct Piece { const void *src; size_t bytes; size_t off; };
+        Piece pieces[] = {{tex.data(), tex.size() * sizeof(float4), 0},
+                          {e.cond_func, (size_t)e.dist_w * e.dist_h * sizeof(float), 0},
+                          {e.cond_cdf, (size_t)(e.dist_w + 1) * e.dist_h * sizeof(float), 0},
+                          {e.cond_int, (size_t)e.dist_h * sizeof(float), 0},
+                          {e.marg_func, (size_t)e.dist_h * sizeof(float), 0},
+                          {e.marg_cdf, ((size_t)e.dist_h + 1) * sizeof(float), 0},
+                          {cg.data(), cg.size() * sizeof(uint16_t), 0},
+                          {mg.data(), mg.size() * sizeof(uint16_t), 0}};
+        size_t total = 0;
+        for (Piece &pc : pieces) { pc.off = total; total += (pc.bytes + 255) & ~(size_t)255; }
+        char *slab = nullptr;
+        if ((rc = dupload<char>(ctx, pool, nullptr, total, &slab))) return rc;
+        for (const Piece &pc : pieces)
+            if (pc.bytes) GNX_CUDA(ctx, cudaMemcpy(slab + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice));
+        de.texels = (const float4 *)(slab + pieces[0].off);
+        de.cond_func = (const float *)(slab + pieces[1].off);
+        de.cond_cdf = (const float *)(slab + pieces[2].off);
+        de.cond_int = (const float *)(slab + pieces[3].off);
+        de.marg_func = (const float *)(slab + pieces[4].off);
+        de.marg_cdf = (const float *)(slab + pieces[5].off);
+        if (!cg.empty()) {
+            de.cond_guide = (const uint16_t *)(slab + pieces[6].off);
+            de.marg_guide = (const uint16_t *)(slab + pieces[7].off);
+        }
+        ctx->env_base = slab;
+        ctx->env_bytes = total;
         memcpy(de.l2w.m, e.light_to_world, 64);
         memcpy(de.w2l.m, e.world_to_light, 64);
         de.world_radius = e.world_radius;
@@ -916,6 +950,30 @@ static int validate_params(gnx_ctx *ctx, const gnx_render_params *p) {
 // the traversal then compete less with the streaming path-state / queue traffic (C2: 98 MB of geometry
 // against ~1 GB of state per bounce, 126 MB of L2).
 static void set_l2_window(gnx_ctx *ctx, cudaStream_t st) {
+    if (ctx->l2_env && ctx->env_base && ctx->sc.env.present) {
+        if (ctx->l2_persist_max < 0) {  // (the property query takes milliseconds: once per context)
+            int a = 0, b = 0;
+            cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            cudaDeviceGetAttribute(&b, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            ctx->l2_persist_max = a;
+            ctx->l2_window_max = b;
+            cudaGetLastError();
+        }
+        if (ctx->l2_persist_max <= 0) return;
+        const size_t setAside = std::min<size_t>((size_t)ctx->l2_persist_max, ctx->env_bytes);
+        if (ctx->l2_set_aside != setAside) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside); ctx->l2_set_aside = setAside; }
+        cudaStreamAttrValue attr{};
+        const size_t win = std::min<size_t>(ctx->env_bytes, (size_t)ctx->l2_window_max);
+        attr.accessPolicyWindow.base_ptr = ctx->env_base;
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = win > 0 ? std::min(1.0f, (float)setAside / (float)win) : 0.f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        if (ctx->stream_any) cudaStreamSetAttribute(ctx->stream_any, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+        return;
+    }
     if (!ctx->l2_persist || !ctx->geom_base) return;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
@@ -1091,19 +1149,27 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             else k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, -1, ctx->d_stats);
             tm.end();
             launches += 2;
+            // no DisneyMaterial in the scene: no BSDF has more than two lobes (the k_shade<2> / <8> split of the PathIntegrator)
+            const bool fewLobes = !((ctx->shade_type_mask >> GNX_MAT_DISNEY) & 1u) && !getenv("GNX_VOL_MAXL8");
             auto logic = [&](int queue) {
                 tm.begin(ST_VP_EXTEND + vol_queue_kernel(queue));
                 k_vp_reset<<<1, 32, 0, st>>>(qv.counts, -2);  // (the cursor only)
                 switch (vol_queue_kernel(queue)) {
-                case VK_EXTEND: k_vp_logic<VK_EXTEND><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                case VK_EXTEND: k_vp_logic<VK_EXTEND><<<ctx->grid_vp_kernel[VK_EXTEND], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
                 case VK_VERTEX:
-                    if (tex) k_vp_logic<VK_VERTEX, true><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
-                    else k_vp_logic<VK_VERTEX><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    if (fewLobes) {
+                        if (tex) k_vp_logic<VK_VERTEX, true, 2><<<ctx->grid_vp_kernel[VK_VERTEX], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                        else k_vp_logic<VK_VERTEX, false, 2><<<ctx->grid_vp_kernel[VK_VERTEX], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    } else if (tex) k_vp_logic<VK_VERTEX, true><<<ctx->grid_vp_kernel[VK_VERTEX], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    else k_vp_logic<VK_VERTEX><<<ctx->grid_vp_kernel[VK_VERTEX], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
                     break;
-                case VK_SHADOW: k_vp_logic<VK_SHADOW><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
+                case VK_SHADOW: k_vp_logic<VK_SHADOW><<<ctx->grid_vp_kernel[VK_SHADOW], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats); break;
                 default:
-                    if (tex) k_vp_logic<VK_MIS, true><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
-                    else k_vp_logic<VK_MIS><<<gl, kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    if (fewLobes) {
+                        if (tex) k_vp_logic<VK_MIS, true, 2><<<ctx->grid_vp_kernel[VK_MIS], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                        else k_vp_logic<VK_MIS, false, 2><<<ctx->grid_vp_kernel[VK_MIS], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    } else if (tex) k_vp_logic<VK_MIS, true><<<ctx->grid_vp_kernel[VK_MIS], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
+                    else k_vp_logic<VK_MIS><<<ctx->grid_vp_kernel[VK_MIS], kBlock, 0, st>>>(sc, psv, ctx->vw, qv, rcn, queue, ctx->d_stats);
                     break;
                 }
                 k_vp_reset<<<1, 32, 0, st>>>(qv.counts, kCntShade0 + queue);
