@@ -1,6 +1,6 @@
 // scenekit.cpp — host-side scene kit (include/gnx_scenekit.h): builds the BASELINE.json configs
 // directly as gnx_scene_desc buffers.  Plain C++ (g++), no CUDA, no dependency on the reference or on
-// the oracle.  tests/test_scenekit_parity.py checks that these scenes render like the ones the
+// the oracle.  tests/test_scenekit.py and tests/test_gpu_parity.py check that these scenes render like the ones the
 // bridge flattens out of the reference's own objects.
 #include <omp.h>
 
