@@ -533,3 +533,47 @@ def test_whitted_staged_first_vertex_is_bit_equal_to_the_recursion(scene, args, 
     assert np.array_equal(out[0][0], out[1][0])
     assert out[0][2] > 0
     sk.close()
+
+
+def _render_with_env(sk, p, **env):
+    """One render on a fresh context created under the given environment switches (read at gnx_create)."""
+    import os
+    os.environ.update(env)
+    try:
+        c = Context(0)
+    finally:
+        for k in env:
+            del os.environ[k]
+    c.upload(sk.desc)
+    c.render(p)             # (the queue sort decides from the previous call's hit density: render twice)
+    img, st = c.render(p)
+    c.close()
+    return img, st
+
+
+def test_sorted_shade_queues_do_not_change_a_bit():
+    """The PathIntegrator puts dense shade queues back into slot order before shading (k_qs_mark / count / scan / emit,
+    csrc/gnx_kernels.cuh): the paths are independent and every per-path sum keeps its order, so the image must be bit-equal
+    to the completion-order render (GNX_SORT_QUEUES=0).  `ui` = the reference UI's closed scene, every camera ray hits."""
+    res, spp = 160, 4
+    sk = SceneKit("ui", res, res, spp, 0, 0, 0)
+    p = RenderParams.make(res, res, spp, max_depth=15)
+    a, sa = _render_with_env(sk, p)
+    b, sb = _render_with_env(sk, p, GNX_SORT_QUEUES="0")
+    assert np.array_equal(a, b)
+    assert int(sa.rays_extend) == int(sb.rays_extend) and int(sa.rays_shadow) == int(sb.rays_shadow)
+    assert int(sa.kernel_launches) > int(sb.kernel_launches)  # the sort really ran
+    sk.close()
+
+
+def test_volpath_two_lobe_kernels_equal_the_eight_lobe_ones():
+    """Scenes without a DisneyMaterial run the VolPath vertex / MIS kernels with two-lobe BSDFs (smaller local frame);
+    GNX_VOL_MAXL8 forces the eight-lobe instantiations: same image, bit for bit."""
+    from gnxraytracer_b200.api import INTEGRATOR_VOLPATH
+    res, spp = 96, 4
+    sk = SceneKit("smoke", res, res, spp, 0, 0, 0)
+    p = RenderParams.make(res, res, spp, max_depth=5, integrator=INTEGRATOR_VOLPATH)
+    a, _ = _render_with_env(sk, p)
+    b, _ = _render_with_env(sk, p, GNX_VOL_MAXL8="1")
+    assert np.array_equal(a, b)
+    sk.close()
