@@ -2,7 +2,13 @@
 // walks its input queue with a block-uniform grid-stride loop so that every lane of a warp reaches
 // the warp-aggregated queue pushes (__ballot_sync + one atomicAdd per warp and queue).
 //
-//   k_trace<3> (ray-gen + first extension) -> k_shade<type> ... -> k_trace<1> x2, k_trace<2> -> k_trace<0> -> k_shade ... -> k_trace<1> x2, k_trace<2> -> (next bounce) ... -> k_accumulate -> k_film
+//   PathIntegrator:  k_trace<3> (ray-gen + first extension) -> [k_qs_* : dense shade queues back into slot order] -> k_shade<type> ...
+//                    -> k_trace<2> (area-light MIS probes) -> { k_trace<0> (extension rays, reference-order two-child tree)  ||
+//                    k_anyhit8<1> (the previous bounce's shadow / environment-MIS rays, compressed 8-wide tree, second stream) }
+//                    -> k_shade ... -> (next bounce) ... -> k_anyhit8<0> (last bounce's any-hit rays) -> k_accumulate -> k_film
+//   VolPath:         k_vp_logic<extend> -> rounds of { k_vp_track, k_vp_logic<vertex | shadow | MIS | extend> } -> k_accumulate -> k_film
+//   Whitted:         k_trace<3> -> k_whitted_vertex -> k_anyhit8<0> -> k_whitted_sum -> k_recursive<0> over the listed samples -> ...
+//   DirectLighting:  k_recursive<1 | 2> (one camera sample per lane)
 //
 // Grids are sized from the occupancy query: SM count (148 on B200) x resident blocks per SM, so a
 // persistent kernel never has a partial second wave.  The traversal kernel keeps its stacks in shared
