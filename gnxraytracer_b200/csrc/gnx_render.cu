@@ -133,6 +133,12 @@ struct gnx_ctx {
     int *qs_blocks = nullptr;
     size_t qs_words = 0;
     std::vector<void *> qs_allocs;
+    bool rebin = false;            // GNX_REBIN=1 (experiment): extension queue sorted by origin Morton code + direction octant
+    uint32_t *rb_keys[2] = {nullptr, nullptr};
+    int *rb_vals[2] = {nullptr, nullptr};
+    void *rb_tmp = nullptr;
+    size_t rb_tmp_bytes = 0, rb_slots = 0;
+    std::vector<void *> rb_allocs;
     bool sort_queues = true;       // GNX_SORT_QUEUES=0: shade in the completion order of the traversal kernel
     // Sorting pays on dense queues only (kQsMinDensity).  The kernels check that themselves, but in a scene where few camera
     // rays hit anything even their empty launches cost ~1 %: the previous render call's hit count of the first batch (copied
@@ -211,6 +217,42 @@ struct StageTimer {
 static int fail(gnx_ctx *ctx, int code, const std::string &msg) {
     ctx->err = msg;
     return code;
+}
+
+// ---- experiment (GNX_REBIN=1, off by default): the extension queue re-binned by the Morton code of the ray origins and the
+// direction octant between bounces ("measure ray re-binning by hit-point Morton code").  The sort is
+// cub's radix sort over the whole batch (queue lengths are not known on the host); see DESIGN.md section 11 for the numbers.
+__device__ __forceinline__ uint32_t rebin_spread3(uint32_t v) {  // 9 bits -> every third bit
+    v &= 0x1ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_rebin_keys(const DeviceScene sc, PathState ps, const int *list, const int *count, uint32_t *keys, int *vals, int nPad) {
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
+        uint32_t key = 0xffffffffu;
+        int slot = 0;
+        if (i < n) {
+            slot = list[i];
+            const float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
+            const float p[3] = {o.x, o.y, o.z};
+            uint32_t q[3];
+            for (int a = 0; a < 3; ++a) {
+                const float ext = sc.wb_max[a] - sc.wb_min[a];
+                float t = ext > 0.f ? (p[a] - sc.wb_min[a]) / ext : 0.f;
+                t = fminf(fmaxf(t, 0.f), 1.f);
+                q[a] = (uint32_t)(t * 511.f);
+            }
+            const uint32_t morton = rebin_spread3(q[0]) | (rebin_spread3(q[1]) << 1) | (rebin_spread3(q[2]) << 2);
+            const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+            key = (morton << 3) | oct;
+        }
+        keys[i] = key;
+        vals[i] = slot;
+    }
 }
 
 template <typename T>
@@ -307,6 +349,7 @@ int gnx_create(gnx_ctx **out, int device) {
     if (const char *vm = getenv("GNX_VOLPATH_MEGAKERNEL")) ctx->vol_megakernel = vm[0] == '1';
     if (const char *ws = getenv("GNX_WHITTED_STAGED")) ctx->whitted_staged = ws[0] != '0';
     if (const char *sq = getenv("GNX_SORT_QUEUES")) ctx->sort_queues = sq[0] != '0';
+    if (const char *rb = getenv("GNX_REBIN")) ctx->rebin = rb[0] == '1';
     if (const char *rm = getenv("GNX_REDUCE")) ctx->reduce_mode = !strcmp(rm, "nccl") ? 1 : (!strcmp(rm, "p2p") ? 2 : 0);
     const char *t = getenv("GNX_STAGE_TIMERS");
     ctx->stage_timers = !(t && t[0] == '0');
@@ -338,6 +381,7 @@ void gnx_destroy(gnx_ctx *ctx) {
     free_pool(ctx->vw_allocs);
     free_pool(ctx->ww_allocs);
     free_pool(ctx->qs_allocs);
+    free_pool(ctx->rb_allocs);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->rgba) cudaFree(ctx->rgba);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
@@ -875,6 +919,25 @@ static int ensure_volwave(gnx_ctx *ctx, int capacity) {
     return GNX_OK;
 }
 
+static int ensure_rebin(gnx_ctx *ctx, int capacity) {
+    if ((size_t)capacity <= ctx->rb_slots) return GNX_OK;
+    free_pool(ctx->rb_allocs);
+    ctx->rb_slots = 0;
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dupload<uint32_t>(ctx, ctx->rb_allocs, nullptr, (size_t)capacity, &ctx->rb_keys[k]))) return rc;
+        if ((rc = dupload<int>(ctx, ctx->rb_allocs, nullptr, (size_t)capacity, &ctx->rb_vals[k]))) return rc;
+    }
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->rb_keys[0], ctx->rb_keys[1], ctx->rb_vals[0], ctx->rb_vals[1], capacity, 0, 31);
+    char *tmp = nullptr;
+    if ((rc = dupload<char>(ctx, ctx->rb_allocs, nullptr, bytes, &tmp))) return rc;
+    ctx->rb_tmp = tmp;
+    ctx->rb_tmp_bytes = bytes;
+    ctx->rb_slots = (size_t)capacity;
+    return GNX_OK;
+}
+
 static int ensure_queue_sort(gnx_ctx *ctx, int capacity) {
     const size_t words = ((size_t)capacity + 31) / 32;
     if (words <= ctx->qs_words) return GNX_OK;
@@ -1052,6 +1115,7 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
     if (volWave && (rc = ensure_volwave(ctx, ctx->capacity))) return rc;
     if (whittedStaged && (rc = ensure_whitted(ctx, ctx->capacity, ctx->sc.n_lights))) return rc;
     if (ctx->sort_queues && p->integrator == GNX_INTEGRATOR_PATH && (rc = ensure_queue_sort(ctx, ctx->capacity))) return rc;
+    if (ctx->rebin && p->integrator == GNX_INTEGRATOR_PATH && (rc = ensure_rebin(ctx, ctx->capacity))) return rc;
 
     // escaped rays of scenes with a SkyBoxLight are queued for k_escape
     if (ctx->sc.skybox.present && (p->integrator == GNX_INTEGRATOR_PATH || whittedStaged) && !ctx->q.miss_q && ctx->capacity > 0)
@@ -1293,6 +1357,13 @@ static int render_impl(gnx_ctx *ctx, const gnx_render_params *p_in, float *rgba_
             const int out = 1 - in;
             if (mixed && iter > 0) k_reset_counts_keep_rays<<<1, 32, 0, st>>>(qv.counts, out);
             else k_reset_counts<<<1, 32, 0, st>>>(qv.counts, out);
+            if (ctx->rebin && iter > 0 && ctx->rb_tmp) {
+                const int nPad = rcn.npix * rcn.batch_spp;
+                k_rebin_keys<<<gridWide, 256, 0, st>>>(sc, psv, qv.extend_q[in], qv.counts + in, ctx->rb_keys[0], ctx->rb_vals[0], nPad);
+                size_t bytes = ctx->rb_tmp_bytes;
+                cub::DeviceRadixSort::SortPairs(ctx->rb_tmp, bytes, ctx->rb_keys[0], ctx->rb_keys[1], ctx->rb_vals[0], ctx->rb_vals[1], nPad, 0, 31, st);
+                GNX_CUDA(ctx, cudaMemcpyAsync(qv.extend_q[in], ctx->rb_vals[1], (size_t)nPad * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            }
             tm.begin(ST_EXTEND);
             // Closest hits through the compressed 8-wide tree (k_trace<., true>); the rays it flags (two candidates within
             // the tie band: the reference's answer depends on its visiting order) are traced again in reference order by a
