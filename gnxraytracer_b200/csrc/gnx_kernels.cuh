@@ -705,6 +705,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_vp_track(const DeviceScene sc, Pa
 
 // WhittedIntegrator / DirectLightingIntegrator: one camera sample per lane, the recursion as a depth-first frame
 // stack (gnx_whitted.cuh).  Same dynamic fetch as k_volpath.
+#ifndef GNX_REC_MAXL
+#define GNX_REC_MAXL 8
+#endif
 template <int DIRECT, bool TEX>  // DIRECT: 0 Whitted, 1 DirectLighting UniformSampleOne, 2 UniformSampleAll; TEX: carry ray differentials
 __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, PathState ps, Queues q, RenderConsts rc, DevStats *st) {
     __shared__ int2 s_stack[kSmemStack * kBlock];
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_recursive(const DeviceScene sc, P
             int pixel, sample, px, py;
             slot_to_sample(rc, slot, &pixel, &sample);
             V3 L(0.f);
-            if (pixel_xy(rc, pixel, &px, &py)) L = recursive_li<8, DIRECT, TEX>(sc, rc, px, py, sample, stack, kBlock, cnt, rcnt);
+            if (pixel_xy(rc, pixel, &px, &py)) L = recursive_li<GNX_REC_MAXL, DIRECT, TEX>(sc, rc, px, py, sample, stack, kBlock, cnt, rcnt);
             ps.L[slot] = make_float4(L.x, L.y, L.z, 0.f);
         }
         __syncwarp();
