@@ -105,3 +105,25 @@ def test_restate_and_emulated_kernels_agree_on_counters(ref, restate, emul):
     # the very same leaves in the very same order (triangle counts above are identical).
     assert 0.6 * ca["nodes_visited"] <= int(sb.nodes_visited) <= ca["nodes_visited"]
     r.close()
+
+
+def test_wide_tree_constrains_rays_parallel_to_an_axis(emul):
+    """The camera ray through the exact image centre has d = (0, 0, -1): 1 / d is infinite on two axes.  The compressed
+    8-wide tree's slab test once turned that into NaN = "no constraint" and the ray visited every node (gnx_bvh8.cuh caps
+    |1 / d|).  A 2 x 2 image's pixel (1, 1), sample 0, is that ray: the wide traversal must not visit more node bytes than
+    the two-child tree does, and must find the same hits."""
+    sk = SceneKit("dragon", 2, 2, 1, 0, 96, 24)
+    p = RenderParams.make(2, 2, 1, max_depth=0)
+    res = {}
+    for wide in ("0", "1"):
+        os.environ["GNX_CLOSEST_BVH8"] = wide
+        try:
+            es = emul.scene(sk.desc)
+        finally:
+            del os.environ["GNX_CLOSEST_BVH8"]
+        img, st = es.render(p)
+        res[wide] = (img, int(st.nodes_visited), es.primary_hits(2, 2, 0))
+    assert np.array_equal(res["0"][0], res["1"][0])
+    assert np.array_equal(res["0"][2], res["1"][2])
+    assert res["1"][1] <= 1.5 * res["0"][1] + 64, (res["0"][1], res["1"][1])
+    sk.close()
